@@ -1,0 +1,330 @@
+"""Python host mirror of ABC's ciphertext boundary, over the C ABI (include/abc_b200.h).
+
+`CudaCiphertextFactory` / `CudaCiphertext` carry the same method names, argument meaning and error
+behaviour as the reference's SealCiphertextFactory / SealCiphertext
+(/root/reference/include/ast_opt/runtime/SealCiphertextFactory.h:59-123,
+ /root/reference/include/ast_opt/runtime/SealCiphertext.h:46-112), so parity tests read like the
+reference's own (test/runtime/SealCiphertextFactoryTest.cpp).  The C++ drop-in that ABC's RuntimeVisitor
+drives lives in abc_b200/cpp/ (CudaCiphertextFactory.h); this module is the binding used by tests and bench.py.
+
+Everything here only sequences calls into libabc_b200.so — no arithmetic on ciphertext data in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+KEY_SECRET, KEY_PUBLIC, KEY_RELIN, KEY_GALOIS = 0, 1, 2, 3
+
+
+class AbcError(RuntimeError):
+    """std::runtime_error of the reference (every failure on this path is one:
+    /root/reference/src/runtime/SealCiphertext.cpp:40,137,242)."""
+
+
+class CudaCiphertextFactory:
+    """Owns one device context: parameters, tables, keys, stream (SealCiphertextFactory.cpp:72-100)."""
+
+    def __init__(self, numElementsPerCiphertextSlot=16384, primes=None, plain_modulus=0, device=0, batch=1,
+                 seed=4673838, keygen=True):
+        self._lib = _capi.load()
+        p = _capi.AbcParams()
+        p.poly_degree = numElementsPerCiphertextSlot
+        self._primes_arr = None
+        if primes:
+            self._primes_arr = (C.c_uint64 * len(primes))(*primes)
+            p.n_primes, p.primes = len(primes), self._primes_arr
+        p.plain_modulus, p.device, p.batch, p.seed = plain_modulus, device, batch, seed
+        h = C.c_void_p()
+        st = self._lib.abc_ctx_create(C.byref(p), C.byref(h))
+        if st != 0:
+            raise AbcError("abc_ctx_create failed (%d): %s" % (st, self._lib.abc_last_error(None).decode()))
+        self._h = h
+        self.N = self._lib.abc_poly_degree(h)
+        self.k = self._lib.abc_n_primes(h)
+        self.L = self._lib.abc_n_limbs(h)
+        self.batch = self._lib.abc_batch(h)
+        self.t = self._lib.abc_plain_modulus(h)
+        q = np.zeros(self.k, dtype=np.uint64)
+        self._ck(self._lib.abc_get_primes(h, q.ctypes.data))
+        self.primes = [int(v) for v in q]
+        if keygen:
+            self.keygen()
+
+    # -- plumbing
+    def _ck(self, st):
+        if st != 0:
+            raise AbcError(self._lib.abc_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.abc_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._ck(self._lib.abc_sync(self._h))
+
+    def getCiphertextSlotSize(self):
+        return self.N
+
+    def aux_primes(self):
+        out = np.zeros(self.L + 3, dtype=np.uint64)
+        n = C.c_uint32()
+        self._ck(self._lib.abc_get_aux_primes(self._h, out.ctypes.data, C.byref(n)))
+        return int(out[0]), int(out[1]), [int(v) for v in out[2:n.value]]
+
+    # -- keys
+    def keygen(self):
+        self._ck(self._lib.abc_keygen(self._h))
+
+    def key_shape(self, kind):
+        return {KEY_SECRET: (self.k, self.N), KEY_PUBLIC: (2, self.k, self.N),
+                KEY_RELIN: (self.L, 2, self.k, self.N), KEY_GALOIS: (self.L, 2, self.k, self.N)}[kind]
+
+    def export_key(self, kind, galois_elt=0):
+        out = np.zeros(self.key_shape(kind), dtype=np.uint64)
+        self._ck(self._lib.abc_key_export(self._h, kind, galois_elt, out.ctypes.data, out.size))
+        return out
+
+    def import_key(self, kind, data, galois_elt=0):
+        data = np.ascontiguousarray(data, dtype=np.uint64)
+        self._ck(self._lib.abc_key_import(self._h, kind, galois_elt, data.ctypes.data, data.size))
+
+    def has_galois_key(self, elt):
+        return bool(self._lib.abc_has_galois_key(self._h, elt))
+
+    def set_encrypt_nonce(self, nonce):
+        self._ck(self._lib.abc_set_encrypt_nonce(self._h, nonce))
+
+    # -- ciphertext creation (AbstractCiphertextFactory.h:19-38)
+    def _slots(self, data):
+        """Returns (int64 array, n per instance, broadcast flag)."""
+        if np.isscalar(data):
+            data = [data]
+        arr = np.ascontiguousarray(data, dtype=np.int64)
+        if arr.ndim == 1:
+            if arr.size == 0:
+                raise AbcError("Cannot encode an empty vector.")
+            return arr, arr.size, 1
+        if arr.ndim == 2 and arr.shape[0] == self.batch:
+            return arr, arr.shape[1], 0
+        raise AbcError("slot data must be 1-D (broadcast) or [batch][n]")
+
+    def createCiphertext(self, data):
+        arr, n, bc = self._slots(data)
+        h = C.c_void_p()
+        self._ck(self._lib.abc_encode_encrypt(self._h, arr.ctypes.data, n, bc, C.byref(h)))
+        return CudaCiphertext(self, h)
+
+    def createPlaintext(self, data):
+        arr, n, bc = self._slots(data)
+        h = C.c_void_p()
+        self._ck(self._lib.abc_pt_encode(self._h, arr.ctypes.data, n, bc, C.byref(h)))
+        return CudaPlaintext(self, h)
+
+    def encryptPlaintext(self, pt):
+        h = C.c_void_p()
+        self._ck(self._lib.abc_encrypt_pt(self._h, pt._h, C.byref(h)))
+        return CudaCiphertext(self, h)
+
+    def allocCiphertext(self):
+        h = C.c_void_p()
+        self._ck(self._lib.abc_ct_alloc(self._h, C.byref(h)))
+        return CudaCiphertext(self, h)
+
+    def importCiphertext(self, words):
+        """words: uint64 [batch][2][L][N] (per instance: seal::Ciphertext's coefficient layout)."""
+        ct = self.allocCiphertext()
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        self._ck(self._lib.abc_ct_import(self._h, ct._h, words.ctypes.data, words.size))
+        return ct
+
+    def decryptCiphertext(self, ct):
+        """Returns int64 [batch][N] ([N] when batch == 1), like decryptCiphertext fills its out-vector
+        (SealCiphertextFactory.cpp:146-152)."""
+        out = np.zeros((self.batch, self.N), dtype=np.int64)
+        self._ck(self._lib.abc_decrypt_decode(self._h, ct._h, out.ctypes.data))
+        return out[0] if self.batch == 1 else out
+
+    def getString(self, ct):
+        vals = np.atleast_2d(self.decryptCiphertext(ct))[0]
+        return "[" + ",".join(" %d" % v for v in vals) + " ]"
+
+    # -- probes / measurement
+    def probe_ntt(self, mod_index, rows, inverse=False):
+        rows = np.ascontiguousarray(rows, dtype=np.uint64).copy()
+        r2 = rows.reshape(-1, self.N)
+        self._ck(self._lib.abc_probe_ntt(self._h, int(inverse), mod_index, r2.ctypes.data, r2.shape[0]))
+        return rows
+
+    def probe_multiply(self, a, b):
+        out = np.zeros((self.batch, 3, self.L, self.N), dtype=np.uint64)
+        self._ck(self._lib.abc_probe_multiply(self._h, a._h, b._h, out.ctypes.data, out.size))
+        return out
+
+    def timer_start(self):
+        self._ck(self._lib.abc_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self._lib.abc_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self, nbytes=256 << 20):
+        self._ck(self._lib.abc_flush_l2(self._h, nbytes))
+
+    def launch_count(self):
+        return int(self._lib.abc_launch_count(self._h))
+
+    def profile_enable(self, on=True):
+        self._ck(self._lib.abc_profile_enable(self._h, int(on)))
+
+    def profile(self):
+        import json
+        return json.loads(self._lib.abc_profile_json(self._h).decode())
+
+    def measure_int_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self._lib.abc_measure_int_peak(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+class CudaPlaintext:
+    def __init__(self, factory, handle):
+        self.factory, self._h = factory, handle
+
+    def __del__(self):
+        if getattr(self, "_h", None) and getattr(self.factory, "_h", None):
+            self.factory._lib.abc_pt_free(self._h)
+        self._h = None
+
+
+class CudaCiphertext:
+    """Mirror of SealCiphertext (src/runtime/SealCiphertext.cpp): out-of-place ops return a new object and
+    leave operands untouched; *Inplace ops overwrite self."""
+
+    def __init__(self, factory, handle):
+        self.factory, self._h = factory, handle
+
+    def __del__(self):
+        if getattr(self, "_h", None) and getattr(self.factory, "_h", None):
+            self.factory._lib.abc_ct_free(self._h)
+        self._h = None
+
+    def getFactory(self):
+        return self.factory
+
+    def _other(self, operand):
+        if not isinstance(operand, CudaCiphertext) or operand.factory is not self.factory:
+            raise AbcError("Cast of AbstractCiphertext to CudaCiphertext failed!")
+        return operand
+
+    def _new(self):
+        return self.factory.allocCiphertext()
+
+    def export(self):
+        f = self.factory
+        out = np.zeros((f.batch, 2, f.L, f.N), dtype=np.uint64)
+        f._ck(f._lib.abc_ct_export(f._h, self._h, out.ctypes.data, out.size))
+        return out
+
+    def clone(self):
+        f = self.factory
+        h = C.c_void_p()
+        f._ck(f._lib.abc_ct_clone(f._h, self._h, C.byref(h)))
+        return CudaCiphertext(f, h)
+
+    # ctxt-ctxt
+    def _cc(self, fn, operand, dst):
+        f = self.factory
+        f._ck(fn(f._h, dst._h, self._h, self._other(operand)._h))
+        return dst
+
+    def add(self, operand):
+        return self._cc(self.factory._lib.abc_add, operand, self._new())
+
+    def addInplace(self, operand):
+        self._cc(self.factory._lib.abc_add, operand, self)
+
+    def subtract(self, operand):
+        return self._cc(self.factory._lib.abc_sub, operand, self._new())
+
+    def subtractInplace(self, operand):
+        self._cc(self.factory._lib.abc_sub, operand, self)
+
+    def multiply(self, operand):
+        return self._cc(self.factory._lib.abc_mul_relin, operand, self._new())
+
+    def multiplyInplace(self, operand):
+        self._cc(self.factory._lib.abc_mul_relin, operand, self)
+
+    def negate(self):
+        f, dst = self.factory, self._new()
+        f._ck(f._lib.abc_negate(f._h, dst._h, self._h))
+        return dst
+
+    def negateInplace(self):
+        f = self.factory
+        f._ck(f._lib.abc_negate(f._h, self._h, self._h))
+
+    def rotateRows(self, steps):
+        f, dst = self.factory, self._new()
+        f._ck(f._lib.abc_rotate_rows(f._h, dst._h, self._h, steps))
+        return dst
+
+    def rotateRowsInplace(self, steps):
+        f = self.factory
+        f._ck(f._lib.abc_rotate_rows(f._h, self._h, self._h, steps))
+
+    # ctxt-plain; operand: list/array of ints (Cleartext<int>::getData()) or a CudaPlaintext
+    def _cp(self, fn_slots, fn_pt, operand, dst):
+        f = self.factory
+        if isinstance(operand, CudaPlaintext):
+            f._ck(fn_pt(f._h, dst._h, self._h, operand._h))
+        else:
+            arr, n, bc = f._slots(operand)
+            f._ck(fn_slots(f._h, dst._h, self._h, arr.ctypes.data, n, bc))
+        return dst
+
+    @staticmethod
+    def _all_minus_one(operand):
+        if isinstance(operand, CudaPlaintext):
+            return False
+        a = np.asarray(operand)
+        return a.size > 0 and bool((a == -1).all())
+
+    def addPlain(self, operand):
+        L = self.factory._lib
+        return self._cp(L.abc_add_plain, L.abc_add_plain_pt, operand, self._new())
+
+    def addPlainInplace(self, operand):
+        L = self.factory._lib
+        self._cp(L.abc_add_plain, L.abc_add_plain_pt, operand, self)
+
+    def subtractPlain(self, operand):
+        L = self.factory._lib
+        return self._cp(L.abc_sub_plain, L.abc_sub_plain_pt, operand, self._new())
+
+    def subtractPlainInplace(self, operand):
+        L = self.factory._lib
+        self._cp(L.abc_sub_plain, L.abc_sub_plain_pt, operand, self)
+
+    def multiplyPlain(self, operand):
+        # Cleartext<int>::allEqual(-1) -> negate fast path (SealCiphertext.cpp:156-157)
+        if self._all_minus_one(operand):
+            return self.negate()
+        L = self.factory._lib
+        return self._cp(L.abc_mul_plain, L.abc_mul_plain_pt, operand, self._new())
+
+    def multiplyPlainInplace(self, operand):
+        if self._all_minus_one(operand):
+            return self.negateInplace()
+        L = self.factory._lib
+        self._cp(L.abc_mul_plain, L.abc_mul_plain_pt, operand, self)

@@ -1,0 +1,521 @@
+// kernels.cuh — sm_100a kernels of the BFV hot path.  Each kernel names the SEAL 3.6.5 routine it
+// replaces and the ABC call site (paths relative to /root/reference) that reaches it.
+// Layouts: ciphertext [inst][poly][limb][N]; keys [J][comp][k][N] (NTT form); all u64, canonical residues.
+// No tensor cores: this is 64-bit modular integer work; kernels are bound by the INT pipes (NTT, base
+// conversion, key inner product) or by HBM (add/sub/negate/permute/moddown).
+#pragma once
+#include "ntt.cuh"
+
+#define ABC_MAXL 16  // max data limbs with register-resident base conversion
+
+// Per-context constants (device copy).  Index convention for `mods`: 0..k-1 key-level primes,
+// k..k+nbsk-1 Bsk = (B_0..B_{nB-1}, m_sk), k+nbsk = plain modulus t, k+nbsk+1 = gamma.
+struct DevConst {
+  int N, logN, k, L, nB, nbsk;
+  u64 q[ABC_MAXL + 1];                       // key-level primes (q[L] = special prime p)
+  u64 q_mu_hi[ABC_MAXL + 1], q_mu_lo[ABC_MAXL + 1];
+  u64 t, t_half_up, q_mod_t, t_mu_hi, t_mu_lo;
+  u64 delta[ABC_MAXL];                       // floor(Q/t) mod q_i
+  u64 p, p_half, p_mu_hi;
+  u64 inv_p[ABC_MAXL], inv_p_s[ABC_MAXL], p_half_mod_q[ABC_MAXL], p_mod_q[ABC_MAXL];
+  // decryption
+  u64 gamma, gamma_half, g_mu_hi, g_mu_lo;
+  u64 dec_c[ABC_MAXL], dec_c_s[ABC_MAXL];    // (t*gamma) * (Q/q_i)^-1 mod q_i
+  u64 punct_t[ABC_MAXL], punct_g[ABC_MAXL];  // (Q/q_i) mod t, mod gamma
+  u64 neg_inv_q_t, neg_inv_q_t_s, neg_inv_q_g, neg_inv_q_g_s, inv_g_t, inv_g_t_s;
+  // BEHZ
+  u64 bsk[ABC_MAXL + 1], bsk_mu_hi[ABC_MAXL + 1], bsk_mu_lo[ABC_MAXL + 1];
+  u64 lift_c[ABC_MAXL], lift_c_s[ABC_MAXL];        // m~ * (Q/q_i)^-1 mod q_i
+  u64 punct_q_bsk[ABC_MAXL + 1][ABC_MAXL];         // (Q/q_i) mod bsk_j
+  u32 punct_q_mt[ABC_MAXL];                        // (Q/q_i) mod 2^32
+  u32 neg_inv_q_mt;                                // -Q^-1 mod 2^32
+  u64 q_mod_bsk[ABC_MAXL + 1];
+  u64 inv_mt_bsk[ABC_MAXL + 1], inv_mt_bsk_s[ABC_MAXL + 1];
+  u64 scale_c[ABC_MAXL], scale_c_s[ABC_MAXL];      // t * (Q/q_i)^-1 mod q_i
+  u64 t_mod_bsk[ABC_MAXL + 1], t_mod_bsk_s[ABC_MAXL + 1];
+  u64 inv_q_bsk[ABC_MAXL + 1], inv_q_bsk_s[ABC_MAXL + 1];
+  u64 inv_punct_B[ABC_MAXL], inv_punct_B_s[ABC_MAXL];
+  u64 punct_B_q[ABC_MAXL][ABC_MAXL];               // (B/B_j) mod q_i   [i][j]
+  u64 punct_B_msk[ABC_MAXL];
+  u64 inv_B_msk, inv_B_msk_s;
+  u64 B_mod_q[ABC_MAXL], B_mod_q_s[ABC_MAXL];
+};
+
+// ------------------------------------------------------------------------------------------------
+// add / sub / negate.  Evaluator::add_inplace / sub_inplace / negate_inplace
+// (src/runtime/SealCiphertext.cpp:92,98,114,118,157,193).  HBM-bound: 24 B per coefficient.
+// grid: (ceil(N/2/256), polys*L, B); 16-byte accesses.
+template <int OP>  // 0 add, 1 sub, 2 negate
+__global__ void __launch_bounds__(256) k_addsub(u64 *__restrict__ dst, const u64 *__restrict__ a,
+                                                const u64 *__restrict__ b, const DevConst *__restrict__ C, int N,
+                                                int L, long long istride) {
+  const int e2 = blockIdx.x * 256 + threadIdx.x;
+  if (e2 >= N / 2) return;
+  const int row = blockIdx.y;
+  const u64 q = C->q[row % L];
+  const size_t off = (size_t)blockIdx.z * istride + (size_t)row * N;
+  ulonglong2 x = reinterpret_cast<const ulonglong2 *>(a + off)[e2], r;
+  if (OP == 2) {
+    r.x = neg_mod(x.x, q); r.y = neg_mod(x.y, q);
+  } else {
+    ulonglong2 y = reinterpret_cast<const ulonglong2 *>(b + off)[e2];
+    if (OP == 0) { r.x = add_mod(x.x, y.x, q); r.y = add_mod(x.y, y.y, q); }
+    else { r.x = sub_mod(x.x, y.x, q); r.y = sub_mod(x.y, y.y, q); }
+  }
+  reinterpret_cast<ulonglong2 *>(dst + off)[e2] = r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The limb pipeline: one CTA = one limb staged whole in shared memory:
+//   load (with a pre-op) -> [forward NTT] -> [pointwise * mul row] -> [inverse NTT] -> store (with a post-op)
+enum { PRE_LOAD = 0, PRE_REDUCE = 1, PRE_PLAIN_LIFT = 2, PRE_TERNARY = 3, PRE_CBD = 4, PRE_ENCODE = 5 };
+enum { POST_STORE = 0, POST_ADD = 1, POST_DECODE = 2 };
+
+struct LimbJob {
+  u64 *dst; const u64 *src; const u64 *mul; const u64 *add;
+  long long dst_is, src_is, mul_is, add_is;  // per-instance strides in words (0 = shared by all instances)
+  const int *rowmod;                          // [W] modulus index of row w
+  const int *rowsrc;                          // [W] source row, or nullptr = w
+  const int *rowmul;                          // [W] row of `mul`/`add`, or nullptr = w
+  // sampler (PRE_TERNARY / PRE_CBD): stream = stream_key(seed, domain, a0 + inst, b)
+  u64 seed, domain, a0, b;
+  // PRE_ENCODE / POST_DECODE
+  const long long *slots_in; long long *slots_out; const u32 *index_map; int n_slots; long long slots_is;
+};
+
+__device__ __forceinline__ u64 small_to_mod(int v, u64 q) { return v < 0 ? q - (u64)(-v) : (u64)v; }
+__device__ __forceinline__ int sample_ternary(u64 h, u64 idx) {
+  u64 r = mix64(h ^ idx);
+  return (int)(((r >> 32) * 3) >> 32) - 1;
+}
+__device__ __forceinline__ int sample_cbd(u64 h, u64 idx) {
+  u64 r = mix64(h ^ idx);
+  return __popcll(r & 0x1fffffULL) - __popcll((r >> 21) & 0x1fffffULL);
+}
+
+template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST>
+__global__ void __launch_bounds__(NttDims<LOGN>::T) k_limb(LimbJob job, const ModInfo *__restrict__ mods,
+                                                           const DevConst *__restrict__ C) {
+  typedef NttDims<LOGN> D;
+  extern __shared__ __align__(16) u64 sm[];
+  const int tid = threadIdx.x, w = blockIdx.x, inst = blockIdx.y;
+  const ModInfo M = mods[job.rowmod[w]];
+  const u64 q = M.q;
+  const int srow = job.rowsrc ? job.rowsrc[w] : w;
+
+  // ---- load
+  if (PRE == PRE_TERNARY || PRE == PRE_CBD) {
+    const u64 h = stream_key(job.seed, job.domain, job.a0 + (u64)inst, job.b);
+    for (int e = tid; e < D::N; e += D::T) {
+      int v = (PRE == PRE_TERNARY) ? sample_ternary(h, (u64)e) : sample_cbd(h, (u64)e);
+      sm[swz(e)] = small_to_mod(v, q);
+    }
+  } else if (PRE == PRE_ENCODE) {
+    // BatchEncoder::encode (SealCiphertextFactory.cpp:102-132): pad with the last value, scatter by the index map
+    const long long *sl = job.slots_in + (size_t)inst * job.slots_is;
+    for (int e = tid; e < D::N; e += D::T) {
+      long long v = sl[e < job.n_slots ? e : job.n_slots - 1];
+      sm[swz((int)job.index_map[e])] = v < 0 ? q + (u64)v : (u64)v;
+    }
+  } else {
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(job.src + (size_t)inst * job.src_is + (size_t)srow * D::N);
+    for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
+      ulonglong2 v = src[e2];
+      if (PRE == PRE_REDUCE) { v.x = barrett64(v.x, q, M.mu_hi); v.y = barrett64(v.y, q, M.mu_hi); }
+      if (PRE == PRE_PLAIN_LIFT) {
+        // multiply_plain_normal: centred lift of a mod-t coefficient into [0,q)
+        const u64 th = C->t_half_up, inc = q - C->t;
+        v.x = v.x >= th ? v.x + inc : v.x;
+        v.y = v.y >= th ? v.y + inc : v.y;
+      }
+      *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = v;
+    }
+  }
+  __syncthreads();
+
+  if (FWD) ntt_fwd_smem<LOGN>(sm, M, 1u, tid);
+
+  if (MUL) {
+    const int mrow = job.rowmul ? job.rowmul[w] : w;
+    const ulonglong2 *mp = reinterpret_cast<const ulonglong2 *>(job.mul + (size_t)inst * job.mul_is + (size_t)mrow * D::N);
+    for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
+      ulonglong2 m = mp[e2];
+      ulonglong2 *p = reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]);
+      ulonglong2 v = *p;
+      v.x = mul_mod(v.x, m.x, q, M.mu_hi, M.mu_lo);
+      v.y = mul_mod(v.y, m.y, q, M.mu_hi, M.mu_lo);
+      *p = v;
+    }
+    __syncthreads();
+  }
+
+  if (INV) ntt_inv_smem<LOGN, true>(sm, M, 1u, tid);
+
+  // ---- store
+  if (POST == POST_DECODE) {
+    // BatchEncoder::decode (SealCiphertextFactory.cpp:151): gather by the index map, centre to signed
+    long long *out = job.slots_out + (size_t)inst * D::N;
+    const u64 half = q >> 1;
+    for (int e = tid; e < D::N; e += D::T) {
+      u64 v = sm[swz((int)job.index_map[e])];
+      out[e] = v > half ? (long long)v - (long long)q : (long long)v;
+    }
+  } else {
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(job.dst + (size_t)inst * job.dst_is + (size_t)w * D::N);
+    const ulonglong2 *ad = nullptr;
+    if (POST == POST_ADD) {
+      const int arow = job.rowmul ? job.rowmul[w] : w;
+      ad = reinterpret_cast<const ulonglong2 *>(job.add + (size_t)inst * job.add_is + (size_t)arow * D::N);
+    }
+    for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
+      ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
+      if (INV) { v.x = csub(v.x, q); v.y = csub(v.y, q); }
+      if (POST == POST_ADD) {
+        ulonglong2 a = ad[e2];
+        v.x = add_mod(v.x, a.x, q); v.y = add_mod(v.y, a.y, q);
+      }
+      dst[e2] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BEHZ step 1: x*m~ -> FastBConv q -> Bsk U {m~} -> SmMRq.  RNSTool::fastbconv_m_tilde + sm_mrq
+// (Evaluator::bfv_multiply, reached from src/runtime/SealCiphertext.cpp:104,122).
+// X layout [inst][4][W=2L+1][N]; this kernel fills all W rows (q rows are a copy of the input).
+// grid: (N/128, 4, B).  INT-bound: L Shoup products + L*(L+2) 128-bit MACs per coefficient.
+template <int L>
+__global__ void __launch_bounds__(128) k_behz_lift(const u64 *__restrict__ a, const u64 *__restrict__ b,
+                                                   u64 *__restrict__ X, const DevConst *__restrict__ C, int N) {
+  const int n = blockIdx.x * 128 + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
+  constexpr int W = 2 * L + 1;
+  const u64 *src = (poly < 2 ? a : b) + ((size_t)inst * 2 + (poly & 1)) * L * N + n;
+  u64 *dst = X + ((size_t)inst * 4 + poly) * W * N + n;
+  u64 z[L];
+  u32 xm = 0;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    u64 x = src[(size_t)i * N];
+    dst[(size_t)i * N] = x;
+    z[i] = mul_shoup(x, C->lift_c[i], C->lift_c_s[i], C->q[i]);
+    xm += (u32)z[i] * C->punct_q_mt[i];
+  }
+  const u32 r = xm * C->neg_inv_q_mt;  // [-x * Q^-1] mod 2^32
+#pragma unroll
+  for (int j = 0; j <= L; ++j) {
+    const u64 pm = C->bsk[j], mh = C->bsk_mu_hi[j], ml = C->bsk_mu_lo[j];
+    u64 lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < L; ++i) mac128(lo, hi, z[i], C->punct_q_bsk[j][i]);
+    const u64 xb = barrett128(lo, hi, pm, mh, ml);
+    // centred r (m~ is a power of two, hence '>='), then (x + Q*r) * m~^-1 mod p_j
+    const u64 rc = (r >= 0x80000000u) ? (u64)r + (pm - 0x100000000ULL) : (u64)r;
+    lo = xb; hi = 0;
+    mac128(lo, hi, rc, C->q_mod_bsk[j]);
+    const u64 v = barrett128(lo, hi, pm, mh, ml);
+    dst[(size_t)(L + j) * N] = mul_shoup(v, C->inv_mt_bsk[j], C->inv_mt_bsk_s[j], pm);
+  }
+}
+
+// BEHZ tensor product in q and Bsk (Evaluator::bfv_multiply "behz_ciphertext_product"), in place on X:
+// (X0,X1,X2,X3) = (a0,a1,b0,b1) -> (a0*b0, a0*b1+a1*b0, a1*b1).  grid: (N/256, W, B)
+__global__ void __launch_bounds__(256) k_behz_tensor(u64 *__restrict__ X, const ModInfo *__restrict__ mods,
+                                                     const int *__restrict__ rowmod, int N, int W) {
+  const int n = blockIdx.x * 256 + threadIdx.x, w = blockIdx.y, inst = blockIdx.z;
+  const ModInfo *Mp = mods + rowmod[w];
+  const u64 q = Mp->q, mh = Mp->mu_hi, ml = Mp->mu_lo;
+  u64 *p = X + ((size_t)inst * 4 * W + w) * N + n;
+  const size_t ps = (size_t)W * N;
+  const u64 a0 = p[0], a1 = p[ps], b0 = p[2 * ps], b1 = p[3 * ps];
+  p[0] = mul_mod(a0, b0, q, mh, ml);
+  u64 lo = a0 * b1, hi = __umul64hi(a0, b1);
+  mac128(lo, hi, a1, b0);
+  p[ps] = barrett128(lo, hi, q, mh, ml);
+  p[2 * ps] = mul_mod(a1, b1, q, mh, ml);
+}
+
+// BEHZ steps 6-8: *t, fast_floor (q U Bsk -> Bsk), fastbconv_sk (Bsk -> q).  RNSTool::fast_floor + fastbconv_sk.
+// X [inst][4][W][N] (polys 0..2, coefficient form) -> dst3 [inst][3][L][N].  grid: (N/128, 3, B)
+template <int L>
+__global__ void __launch_bounds__(128) k_behz_scale(const u64 *__restrict__ X, u64 *__restrict__ dst,
+                                                    const DevConst *__restrict__ C, int N) {
+  const int n = blockIdx.x * 128 + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
+  constexpr int W = 2 * L + 1;
+  const u64 *src = X + ((size_t)inst * 4 + poly) * W * N + n;
+  u64 *out = dst + ((size_t)inst * 3 + poly) * L * N + n;
+  u64 z[L], zb[L];
+#pragma unroll
+  for (int i = 0; i < L; ++i) z[i] = mul_shoup(src[(size_t)i * N], C->scale_c[i], C->scale_c_s[i], C->q[i]);
+  u64 ysk = 0;
+#pragma unroll
+  for (int j = 0; j <= L; ++j) {
+    const u64 pm = C->bsk[j];
+    u64 lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < L; ++i) mac128(lo, hi, z[i], C->punct_q_bsk[j][i]);
+    const u64 conv = barrett128(lo, hi, pm, C->bsk_mu_hi[j], C->bsk_mu_lo[j]);
+    const u64 xb = mul_shoup(src[(size_t)(L + j) * N], C->t_mod_bsk[j], C->t_mod_bsk_s[j], pm);
+    const u64 y = mul_shoup(sub_mod(xb, conv, pm), C->inv_q_bsk[j], C->inv_q_bsk_s[j], pm);
+    if (j < L) zb[j] = mul_shoup(y, C->inv_punct_B[j], C->inv_punct_B_s[j], pm);
+    else ysk = y;
+  }
+  // Shenoy-Kumaresan: alpha = (FastBConv_{B->m_sk}(y) - y_sk) * B^-1 mod m_sk, centred
+  const u64 msk = C->bsk[L];
+  u64 lo = 0, hi = 0;
+#pragma unroll
+  for (int j = 0; j < L; ++j) mac128(lo, hi, zb[j], C->punct_B_msk[j]);
+  const u64 conv_sk = barrett128(lo, hi, msk, C->bsk_mu_hi[L], C->bsk_mu_lo[L]);
+  const u64 alpha = mul_shoup(sub_mod(conv_sk, ysk, msk), C->inv_B_msk, C->inv_B_msk_s, msk);
+  const bool negative = alpha > (msk >> 1);
+  const u64 amag = negative ? msk - alpha : alpha;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const u64 q = C->q[i];
+    lo = 0; hi = 0;
+#pragma unroll
+    for (int j = 0; j < L; ++j) mac128(lo, hi, zb[j], C->punct_B_q[i][j]);
+    const u64 conv = barrett128(lo, hi, q, C->q_mu_hi[i], C->q_mu_lo[i]);
+    const u64 corr = mul_shoup(barrett64(amag, q, C->q_mu_hi[i]), C->B_mod_q[i], C->B_mod_q_s[i], q);
+    out[(size_t)i * N] = negative ? add_mod(conv, corr, q) : sub_mod(conv, corr, q);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Key switching (Evaluator::switch_key_inplace; relinearize at SealCiphertext.cpp:105,123, rotate at :55,60).
+// ModUp + NTT is k_limb<PRE_REDUCE,FWD> into T [inst][k][L][N].
+// Inner product: acc[inst][comp][I][n] = sum_J T[inst][I][J][n] * key[J][comp][I][n] mod q_I.
+// grid: (N/256, k, B).  128-bit lazy accumulation, one Barrett reduction per output.
+__global__ void __launch_bounds__(256) k_ks_inner(const u64 *__restrict__ T, const u64 *__restrict__ key,
+                                                  u64 *__restrict__ acc, const ModInfo *__restrict__ mods, int N,
+                                                  int L, int k) {
+  const int n = blockIdx.x * 256 + threadIdx.x, I = blockIdx.y, inst = blockIdx.z;
+  const ModInfo *Mp = mods + I;
+  const u64 *t = T + (((size_t)inst * k + I) * L) * N + n;
+  const u64 *kp = key + (size_t)I * N + n;
+  u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+  for (int J = 0; J < L; ++J) {
+    const u64 tv = t[(size_t)J * N];
+    mac128(lo0, hi0, tv, __ldg(kp + (size_t)(J * 2 + 0) * k * N));
+    mac128(lo1, hi1, tv, __ldg(kp + (size_t)(J * 2 + 1) * k * N));
+  }
+  u64 *o = acc + ((size_t)inst * 2 * k + I) * N + n;
+  o[0] = barrett128(lo0, hi0, Mp->q, Mp->mu_hi, Mp->mu_lo);
+  o[(size_t)k * N] = barrett128(lo1, hi1, Mp->q, Mp->mu_hi, Mp->mu_lo);
+}
+
+// ModDown with rounding and accumulate (tail of switch_key_inplace): acc is in coefficient form.
+// dst[inst][comp][i][n] = base + p^-1 * (acc_i - ([acc_L + p/2]_p mod q_i) + [p/2]_{q_i}) mod q_i
+// base0/base1: polynomial added into component 0 / 1 (nullptr = zero).  grid: (N/256, 2, B)
+__global__ void __launch_bounds__(256) k_ks_moddown(const u64 *__restrict__ acc, const u64 *__restrict__ base0,
+                                                    long long base0_is, const u64 *__restrict__ base1,
+                                                    long long base1_is, u64 *__restrict__ dst,
+                                                    const DevConst *__restrict__ C, int N, int L, int k) {
+  const int n = blockIdx.x * 256 + threadIdx.x, comp = blockIdx.y, inst = blockIdx.z;
+  const u64 *ac = acc + ((size_t)inst * 2 + comp) * k * N + n;
+  const u64 *base = comp == 0 ? base0 : base1;
+  const long long bis = comp == 0 ? base0_is : base1_is;
+  if (base) base += (size_t)inst * bis + n;
+  u64 *o = dst + ((size_t)inst * 2 + comp) * L * N + n;
+  const u64 tl = add_mod(ac[(size_t)L * N], C->p_half, C->p);
+  for (int i = 0; i < L; ++i) {
+    const u64 q = C->q[i];
+    const u64 r = sub_mod(barrett64(tl, q, C->q_mu_hi[i]), C->p_half_mod_q[i], q);
+    u64 v = mul_shoup(sub_mod(ac[(size_t)i * N], r, q), C->inv_p[i], C->inv_p_s[i], q);
+    if (base) v = add_mod(v, base[(size_t)i * N], q);
+    o[(size_t)i * N] = v;
+  }
+}
+
+// Galois automorphism in coefficient form (GaloisTool::apply_galois), gather formulation so that writes
+// are coalesced: out[j] = +-in[j * elt^-1 mod 2N].  c0 -> out0 [inst][L][N] (stride out0_is), c1 -> out1.
+// grid: (N/256, 2L, B)
+__global__ void __launch_bounds__(256) k_galois(const u64 *__restrict__ ct, u64 *__restrict__ out0, long long out0_is,
+                                                u64 *__restrict__ out1, long long out1_is, u32 elt_inv,
+                                                const DevConst *__restrict__ C, int N, int L) {
+  const int j = blockIdx.x * 256 + threadIdx.x, row = blockIdx.y, inst = blockIdx.z;
+  const int poly = row / L, i = row % L;
+  const u64 q = C->q[i];
+  const u32 raw = ((u32)j * elt_inv) & (2u * N - 1);
+  const u64 v = ct[((size_t)inst * 2 * L + row) * N + (raw & (N - 1))];
+  u64 *o = poly == 0 ? out0 + (size_t)inst * out0_is : out1 + (size_t)inst * out1_is;
+  o[(size_t)i * N + j] = (raw >= (u32)N) ? neg_mod(v, q) : v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plain add/sub with Delta-scaling (util::multiply_add/sub_plain_with_scaling_variant;
+// SealCiphertext.cpp:134,145,175,184).  plain: [inst or 1][N] mod t.  grid: (N/256, 1, B)
+// floor(x / t) for 128-bit x via the Barrett quotient
+__device__ __forceinline__ u64 div128_by(u64 lo, u64 hi, u64 t, u64 mu_hi, u64 mu_lo) {
+  u64 carry = __umul64hi(lo, mu_lo);
+  u64 t2lo = lo * mu_hi, t2hi = __umul64hi(lo, mu_hi);
+  u64 t1 = t2lo + carry;
+  u64 t3 = t2hi + (t1 < t2lo);
+  u64 t4lo = hi * mu_lo, t4hi = __umul64hi(hi, mu_lo);
+  u64 t5 = t1 + t4lo;
+  u64 c2 = t4hi + (t5 < t1);
+  u64 qhat = hi * mu_hi + t3 + c2;
+  u64 r = lo - qhat * t;
+  return qhat + (r >= t);
+}
+__device__ __forceinline__ u64 scaled_plain(u64 m, u64 fix, int i, const DevConst *__restrict__ C) {
+  u64 lo = fix, hi = 0;
+  mac128(lo, hi, m, C->delta[i]);
+  return barrett128(lo, hi, C->q[i], C->q_mu_hi[i], C->q_mu_lo[i]);
+}
+template <int SUB>
+__global__ void __launch_bounds__(256) k_plain_addsub(u64 *__restrict__ dst, const u64 *__restrict__ a,
+                                                      const u64 *__restrict__ plain, long long plain_is,
+                                                      const DevConst *__restrict__ C, int N, int L) {
+  const int n = blockIdx.x * 256 + threadIdx.x, inst = blockIdx.z;
+  const u64 m = plain[(size_t)inst * plain_is + n];
+  u64 lo = C->t_half_up, hi = 0;
+  mac128(lo, hi, m, C->q_mod_t);
+  const u64 fix = div128_by(lo, hi, C->t, C->t_mu_hi, C->t_mu_lo);
+  const size_t base = (size_t)inst * 2 * L * N + n;
+  for (int i = 0; i < L; ++i) {
+    const u64 q = C->q[i], s = scaled_plain(m, fix, i, C);
+    const u64 x = a[base + (size_t)i * N];
+    dst[base + (size_t)i * N] = SUB ? sub_mod(x, s, q) : add_mod(x, s, q);
+    if (dst != a) dst[base + (size_t)(L + i) * N] = a[base + (size_t)(L + i) * N];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Encryption tail (Encryptor::encrypt_zero_internal + RNSTool::divide_and_round_q_last_inplace +
+// multiply_add_plain_with_scaling_variant; SealCiphertextFactory.cpp:12).
+// tmp [inst][2][k][N] = INTT(pk_j * NTT(u)) in coefficient form.  Adds e_j ~ CBD, divides by p with
+// rounding, adds the scaled plaintext to component 0.  grid: (N/256, 2, B)
+__global__ void __launch_bounds__(256) k_enc_finish(const u64 *__restrict__ tmp, const u64 *__restrict__ plain,
+                                                    long long plain_is, u64 *__restrict__ ct, u64 seed, u64 nonce0,
+                                                    const DevConst *__restrict__ C, int N, int L, int k) {
+  const int n = blockIdx.x * 256 + threadIdx.x, comp = blockIdx.y, inst = blockIdx.z;
+  const u64 h = stream_key(seed, 4 /*DOM_ENC*/, nonce0 + (u64)inst, 1 + (u64)comp);
+  const int e = sample_cbd(h, (u64)n);
+  const u64 *tp = tmp + ((size_t)inst * 2 + comp) * k * N + n;
+  u64 last = add_mod(tp[(size_t)L * N], small_to_mod(e, C->p), C->p);
+  last = add_mod(last, C->p_half, C->p);
+  u64 m = 0, fix = 0;
+  if (comp == 0) {
+    m = plain[(size_t)inst * plain_is + n];
+    u64 lo = C->t_half_up, hi = 0;
+    mac128(lo, hi, m, C->q_mod_t);
+    fix = div128_by(lo, hi, C->t, C->t_mu_hi, C->t_mu_lo);
+  }
+  u64 *o = ct + ((size_t)inst * 2 + comp) * L * N + n;
+  for (int i = 0; i < L; ++i) {
+    const u64 q = C->q[i];
+    const u64 d = add_mod(tp[(size_t)i * N], small_to_mod(e, q), q);
+    const u64 r = sub_mod(barrett64(last, q, C->q_mu_hi[i]), C->p_half_mod_q[i], q);
+    u64 v = mul_shoup(sub_mod(d, r, q), C->inv_p[i], C->inv_p_s[i], q);
+    if (comp == 0) v = add_mod(v, scaled_plain(m, fix, i, C), q);
+    o[(size_t)i * N] = v;
+  }
+}
+
+// Decryption tail: RNSTool::decrypt_scale_and_round (Decryptor::bfv_decrypt; SealCiphertextFactory.cpp:150).
+// x [inst][L][N] = c0 + c1*s (coefficient form) -> plain [inst][N] mod t.  grid: (N/128, 1, B)
+template <int L>
+__global__ void __launch_bounds__(128) k_dec_finish(const u64 *__restrict__ x, u64 *__restrict__ plain,
+                                                    const DevConst *__restrict__ C, int N) {
+  const int n = blockIdx.x * 128 + threadIdx.x, inst = blockIdx.z;
+  const u64 *src = x + (size_t)inst * L * N + n;
+  const u64 t = C->t, g = C->gamma;
+  u64 lt = 0, ht = 0, lg = 0, hg = 0;
+#pragma unroll
+  for (int i = 0; i < L; ++i) {
+    const u64 z = mul_shoup(src[(size_t)i * N], C->dec_c[i], C->dec_c_s[i], C->q[i]);
+    mac128(lt, ht, z, C->punct_t[i]);
+    mac128(lg, hg, z, C->punct_g[i]);
+  }
+  const u64 yt = mul_shoup(barrett128(lt, ht, t, C->t_mu_hi, C->t_mu_lo), C->neg_inv_q_t, C->neg_inv_q_t_s, t);
+  const u64 yg = mul_shoup(barrett128(lg, hg, g, C->g_mu_hi, C->g_mu_lo), C->neg_inv_q_g, C->neg_inv_q_g_s, g);
+  u64 d;
+  if (yg > C->gamma_half) d = add_mod(yt, barrett64(g - yg, t, C->t_mu_hi), t);
+  else d = sub_mod(yt, barrett64(yg, t, C->t_mu_hi), t);
+  plain[(size_t)inst * N + n] = d ? mul_shoup(d, C->inv_g_t, C->inv_g_t_s, t) : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Key generation helpers (KeyGenerator; SealCiphertextFactory.cpp:89-93)
+// uniform a_i mod q_i for all key-level limbs of one polynomial.  grid: (N/256, k)
+__global__ void __launch_bounds__(256) k_sample_uniform(u64 *__restrict__ dst, u64 seed, u64 domain, u64 a,
+                                                        u64 b_base, const DevConst *__restrict__ C, int N) {
+  const int n = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
+  const u64 q = C->q[i];
+  const u64 h = stream_key(seed, domain, a, ((b_base | (u64)i) << 2) | 0);
+  const u64 max_random = ~0ULL, max_multiple = max_random - (max_random % q) - 1;
+  u64 r;
+  for (u64 attempt = 0;; ++attempt) {
+    r = mix64(h ^ ((u64)n | (attempt << 32)));
+    if (r < max_multiple) break;
+  }
+  dst[(size_t)i * N + n] = r % q;
+}
+// c0 = -(a*s + e) [+ factor * newkey at limb J]  (encrypt_zero_symmetric + generate_one_kswitch_key)
+// key block layout [2][k][N]: c0 rows then c1 = a rows.  grid: (N/256, k)
+__global__ void __launch_bounds__(256) k_ksk_finish(u64 *__restrict__ keyblk, const u64 *__restrict__ e_ntt,
+                                                    const u64 *__restrict__ sk, const u64 *__restrict__ newkey, int J,
+                                                    const ModInfo *__restrict__ mods, const DevConst *__restrict__ C,
+                                                    int N, int k) {
+  const int n = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
+  const ModInfo *Mp = mods + i;
+  const u64 q = Mp->q;
+  const size_t o = (size_t)i * N + n;
+  const u64 a = keyblk[(size_t)k * N + o];
+  u64 v = neg_mod(add_mod(mul_mod(a, sk[o], q, Mp->mu_hi, Mp->mu_lo), e_ntt[o], q), q);
+  if (newkey && i == J) v = add_mod(v, mul_mod(newkey[o], C->p_mod_q[i], q, Mp->mu_hi, Mp->mu_lo), q);
+  keyblk[o] = v;
+}
+// new key material: relin (sk^2) or Galois (NTT-domain permutation, GaloisTool::apply_galois_ntt).  grid: (N/256, k)
+__global__ void __launch_bounds__(256) k_newkey(u64 *__restrict__ nk, const u64 *__restrict__ sk, u32 galois_elt,
+                                                const ModInfo *__restrict__ mods, int N, int logN) {
+  const int n = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
+  const size_t o = (size_t)i * N;
+  if (galois_elt == 0) {
+    const ModInfo *Mp = mods + i;
+    const u64 s = sk[o + n];
+    nk[o + n] = mul_mod(s, s, Mp->q, Mp->mu_hi, Mp->mu_lo);
+  } else {
+    const u32 rev = __brev((u32)(n + N)) >> (32 - (logN + 1));
+    const u32 idx = (u32)((((u64)galois_elt * rev) >> 1) & (u64)(N - 1));
+    nk[o + n] = sk[o + (__brev(idx) >> (32 - logN))];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// integer-pipe issue-rate microbenchmarks (the INT roofline denominator)
+__global__ void __launch_bounds__(1024) k_peak_imad(u32 *out, int iters) {
+  u32 a = threadIdx.x, b = blockIdx.x | 1, c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      c0 = c0 * a + b; c1 = c1 * a + b; c2 = c2 * a + b; c3 = c3 * a + b;
+      c4 = c4 * a + b; c5 = c5 * a + b; c6 = c6 * a + b; c7 = c7 * a + b;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+}
+__global__ void __launch_bounds__(1024) k_peak_iadd(u32 *out, int iters) {
+  u32 a = threadIdx.x, b = blockIdx.x | 1, c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      c0 = (c0 + a) ^ b; c1 = (c1 + a) ^ b; c2 = (c2 + a) ^ b; c3 = (c3 + a) ^ b;
+      c4 = (c4 + a) ^ b; c5 = (c5 + a) ^ b; c6 = (c6 + a) ^ b; c7 = (c7 + a) ^ b;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+}
+// 64-bit Shoup butterflies per second (the unit the NTT roofline is quoted in)
+__global__ void __launch_bounds__(1024) k_peak_butterfly(u64 *out, int iters, u64 q, u64 w, u64 ws) {
+  u64 x0 = threadIdx.x, y0 = blockIdx.x, x1 = x0 + 1, y1 = y0 + 2, x2 = x0 + 3, y2 = y0 + 4, x3 = x0 + 5, y3 = y0 + 6;
+  const ulonglong2 tw = make_ulonglong2(w, ws);
+  const u64 q2 = 2 * q;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      bf_fwd(x0, y0, tw, q, q2); bf_fwd(x1, y1, tw, q, q2); bf_fwd(x2, y2, tw, q, q2); bf_fwd(x3, y3, tw, q, q2);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ y0 ^ x1 ^ y1 ^ x2 ^ y2 ^ x3 ^ y3;
+}

@@ -1,0 +1,940 @@
+// lib.cu — context, handles and op orchestration behind the C ABI of include/abc_b200.h.
+// Host code only sequences kernels on the context's stream; all arithmetic on ciphertexts, keys and
+// plaintexts happens in the sm_100a kernels of kernels.cuh.  There is no CPU fallback.
+#include "../../include/abc_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "hostmath.hpp"
+#include "kernels.cuh"
+
+namespace {
+thread_local std::string g_create_error;
+
+struct ProfRec { const char *name; cudaEvent_t a, b; };
+
+enum { DOM_SK = 1, DOM_PK = 2, DOM_KSK = 3, DOM_ENC = 4 };
+}  // namespace
+
+struct abc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int N = 0, logN = 0, k = 0, L = 0, nB = 0, nbsk = 0, B = 1, W = 0;
+  u64 t = 0, seed = 0, enc_nonce = 0, gamma = 0, msk = 0;
+  std::vector<u64> primes, bsk;
+  DevConst hC;
+  DevConst *dC = nullptr;
+  ModInfo *d_mods = nullptr;
+  int idx_t = 0;
+  std::vector<void *> owned;  // device allocations freed at destroy
+  u32 *d_index_map = nullptr;
+  int *rm_ct = nullptr;     // [3L]  w % L
+  int *rm_key = nullptr;    // [2k]  w % k
+  int *rm_behz = nullptr;   // [4W]  q / Bsk modulus of X row
+  int *rm_modup = nullptr;  // [kL]  I
+  int *rs_modup = nullptr;  // [kL]  J
+  int *rm_t = nullptr;      // [1]   idx_t
+  int *rs_c1 = nullptr;     // [L]   L + w
+  int *rs_zero = nullptr;   // [2k]  0
+  u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;
+  std::map<u32, u64 *> galois;
+  bool have_keys = false;
+  std::string err;
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool prof = false;
+  std::vector<ProfRec> prof_recs;
+  std::string prof_json;
+  size_t flush_bytes = 0;
+  void *flush_buf = nullptr;
+};
+struct abc_ct { abc_ctx *ctx; u64 *d; };
+struct abc_pt { abc_ctx *ctx; u64 *d; int broadcast; };
+
+namespace {
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) {                                                                          \
+      c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                    \
+      return ABC_ERR_CUDA;                                                                            \
+    }                                                                                                 \
+  } while (0)
+#define TRY(call)                                                                                     \
+  do {                                                                                                \
+    abc_status s_ = (call);                                                                           \
+    if (s_ != ABC_OK) return s_;                                                                      \
+  } while (0)
+
+abc_status fail(abc_ctx *c, abc_status s, const std::string &msg) { c->err = msg; return s; }
+
+struct Launch {
+  abc_ctx *c; const char *name; cudaEvent_t a = nullptr, b = nullptr;
+  Launch(abc_ctx *c_, const char *n) : c(c_), name(n) {
+    c->launches++;
+    if (c->prof) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
+  }
+  ~Launch() {
+    if (c->prof) { cudaEventRecord(b, c->stream); c->prof_recs.push_back({name, a, b}); }
+  }
+};
+
+abc_status salloc(abc_ctx *c, u64 **p, size_t words) {
+  CK(cudaMallocAsync((void **)p, words * sizeof(u64), c->stream));
+  return ABC_OK;
+}
+void sfree(abc_ctx *c, void *p) { if (p) cudaFreeAsync(p, c->stream); }
+
+template <typename T> abc_status upload(abc_ctx *c, T **dst, const std::vector<T> &v) {
+  CK(cudaMalloc((void **)dst, v.size() * sizeof(T)));
+  c->owned.push_back(*dst);
+  CK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return ABC_OK;
+}
+
+// ---- limb-pipeline launcher
+template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST>
+abc_status launch_limb_n(abc_ctx *c, const LimbJob &job, int W, int B, const char *name) {
+  typedef NttDims<LOGN> D;
+  auto kern = k_limb<LOGN, PRE, FWD, MUL, INV, POST>;
+  static bool attr_done[64] = {false};
+  if (D::SMEM > 48 * 1024 && !attr_done[c->device & 63]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::SMEM));
+    attr_done[c->device & 63] = true;
+  }
+  Launch l(c, name);
+  kern<<<dim3(W, B), D::T, D::SMEM, c->stream>>>(job, c->d_mods, c->dC);
+  CK(cudaGetLastError());
+  return ABC_OK;
+}
+template <int PRE, bool FWD, bool MUL, bool INV, int POST>
+abc_status launch_limb(abc_ctx *c, const LimbJob &job, int W, int B, const char *name) {
+  switch (c->logN) {
+    case 10: return launch_limb_n<10, PRE, FWD, MUL, INV, POST>(c, job, W, B, name);
+    case 11: return launch_limb_n<11, PRE, FWD, MUL, INV, POST>(c, job, W, B, name);
+    case 12: return launch_limb_n<12, PRE, FWD, MUL, INV, POST>(c, job, W, B, name);
+    case 13: return launch_limb_n<13, PRE, FWD, MUL, INV, POST>(c, job, W, B, name);
+    case 14: return launch_limb_n<14, PRE, FWD, MUL, INV, POST>(c, job, W, B, name);
+    default: return fail(c, ABC_ERR_UNSUPPORTED, "poly_degree not supported by the shared-memory NTT");
+  }
+}
+LimbJob blank_job() { LimbJob j; memset(&j, 0, sizeof j); return j; }
+
+#define DISPATCH_L(c, EXPR)                                                        \
+  switch ((c)->L) {                                                                \
+    case 1: { constexpr int LL = 1; EXPR; } break;                                 \
+    case 2: { constexpr int LL = 2; EXPR; } break;                                 \
+    case 3: { constexpr int LL = 3; EXPR; } break;                                 \
+    case 4: { constexpr int LL = 4; EXPR; } break;                                 \
+    case 5: { constexpr int LL = 5; EXPR; } break;                                 \
+    case 6: { constexpr int LL = 6; EXPR; } break;                                 \
+    case 7: { constexpr int LL = 7; EXPR; } break;                                 \
+    case 8: { constexpr int LL = 8; EXPR; } break;                                 \
+    case 9: { constexpr int LL = 9; EXPR; } break;                                 \
+    case 10: { constexpr int LL = 10; EXPR; } break;                               \
+    case 11: { constexpr int LL = 11; EXPR; } break;                               \
+    case 12: { constexpr int LL = 12; EXPR; } break;                               \
+    case 13: { constexpr int LL = 13; EXPR; } break;                               \
+    case 14: { constexpr int LL = 14; EXPR; } break;                               \
+    case 15: { constexpr int LL = 15; EXPR; } break;                               \
+    default: return fail(c, ABC_ERR_UNSUPPORTED, "limb count not supported");      \
+  }
+
+// ---- context construction --------------------------------------------------------------------
+void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, std::vector<ulonglong2> &itw) {
+  using hm::mulmod; using hm::invmod; using hm::shoup; using hm::prod_mod; using hm::barrett_ratio; using hm::bit_reverse; using hm::minimal_2nth_root; using hm::get_primes; using hm::bits_of; using hm::prod_bits;
+  m.q = q;
+  barrett_ratio(q, m.mu_hi, m.mu_lo);
+  m.ninv = invmod((u64)N % q, q);
+  m.ninv_s = shoup(m.ninv, q);
+  const u64 psi = minimal_2nth_root(q, (u64)N), ipsi = invmod(psi, q);
+  tw.assign(N, make_ulonglong2(0, 0));
+  itw.assign(N, make_ulonglong2(0, 0));
+  u64 pw = 1, ipw = 1;
+  for (int i = 0; i < N; ++i) {
+    const uint32_t j = bit_reverse((uint32_t)i, logN);
+    tw[j] = make_ulonglong2(pw, shoup(pw, q));
+    itw[j] = make_ulonglong2(ipw, shoup(ipw, q));
+    pw = mulmod(pw, psi, q);
+    ipw = mulmod(ipw, ipsi, q);
+  }
+  m.wl_ninv = mulmod(itw[1].x, m.ninv, q);
+  m.wl_ninv_s = shoup(m.wl_ninv, q);
+}
+
+abc_status build_tables(abc_ctx *c) {
+  using hm::mulmod; using hm::invmod; using hm::shoup; using hm::prod_mod; using hm::barrett_ratio; using hm::bit_reverse; using hm::minimal_2nth_root; using hm::get_primes; using hm::bits_of; using hm::prod_bits;
+  const int N = c->N, logN = c->logN, k = c->k, L = c->L;
+  const u64 t = c->t;
+  std::vector<u64> Q(c->primes.begin(), c->primes.begin() + L);  // data-level base
+  // auxiliary bases (RNSTool::initialize)
+  int nB = L;
+  if (32 + bits_of(t) + prod_bits(Q) >= 61 * L + 61) nB++;
+  if (nB != L) return fail(c, ABC_ERR_UNSUPPORTED, "parameter set needs |B| = L+1 (not supported)");
+  std::vector<u64> aux = get_primes((u64)N, 61, (size_t)nB + 2);
+  c->msk = aux[0]; c->gamma = aux[1];
+  std::vector<u64> Bv(aux.begin() + 2, aux.end());
+  c->bsk = Bv; c->bsk.push_back(c->msk);
+  c->nB = nB; c->nbsk = nB + 1; c->W = L + c->nbsk;
+  c->idx_t = k + c->nbsk;
+
+  // ---- per-modulus tables
+  const int nmods = k + c->nbsk + 1;
+  std::vector<ModInfo> mods(nmods);
+  std::vector<ulonglong2> tw, itw;
+  for (int i = 0; i < nmods; ++i) {
+    const u64 q = i < k ? c->primes[i] : (i < k + c->nbsk ? c->bsk[i - k] : t);
+    fill_mod(mods[i], q, N, logN, tw, itw);
+    ulonglong2 *d_tw = nullptr, *d_itw = nullptr;
+    TRY(upload(c, &d_tw, tw));
+    TRY(upload(c, &d_itw, itw));
+    mods[i].tw = d_tw; mods[i].itw = d_itw;
+  }
+  TRY(upload(c, &c->d_mods, mods));
+
+  // ---- constants
+  DevConst &C = c->hC;
+  memset(&C, 0, sizeof C);
+  C.N = N; C.logN = logN; C.k = k; C.L = L; C.nB = nB; C.nbsk = c->nbsk;
+  for (int i = 0; i < k; ++i) { C.q[i] = c->primes[i]; barrett_ratio(C.q[i], C.q_mu_hi[i], C.q_mu_lo[i]); }
+  C.t = t; C.t_half_up = (t + 1) >> 1; C.q_mod_t = prod_mod(Q, t);
+  barrett_ratio(t, C.t_mu_hi, C.t_mu_lo);
+  const u64 p = c->primes[k - 1];
+  C.p = p; C.p_half = p >> 1; C.p_mu_hi = C.q_mu_hi[k - 1];
+  C.gamma = c->gamma; C.gamma_half = c->gamma >> 1;
+  barrett_ratio(c->gamma, C.g_mu_hi, C.g_mu_lo);
+  const u64 mt = 1ull << 32;
+  for (int i = 0; i < L; ++i) {
+    const u64 qi = Q[i];
+    const u64 inv_punct = invmod(prod_mod(Q, qi, i), qi);
+    C.delta[i] = mulmod((qi - C.q_mod_t % qi) % qi, invmod(t % qi, qi), qi);
+    C.inv_p[i] = invmod(p % qi, qi); C.inv_p_s[i] = shoup(C.inv_p[i], qi);
+    C.p_half_mod_q[i] = C.p_half % qi; C.p_mod_q[i] = p % qi;
+    C.dec_c[i] = mulmod(mulmod(t % qi, c->gamma % qi, qi), inv_punct, qi); C.dec_c_s[i] = shoup(C.dec_c[i], qi);
+    C.punct_t[i] = prod_mod(Q, t, i); C.punct_g[i] = prod_mod(Q, c->gamma, i);
+    C.lift_c[i] = mulmod(mt % qi, inv_punct, qi); C.lift_c_s[i] = shoup(C.lift_c[i], qi);
+    C.punct_q_mt[i] = (u32)prod_mod(Q, mt, i);
+    C.scale_c[i] = mulmod(t % qi, inv_punct, qi); C.scale_c_s[i] = shoup(C.scale_c[i], qi);
+    C.B_mod_q[i] = prod_mod(Bv, qi); C.B_mod_q_s[i] = shoup(C.B_mod_q[i], qi);
+    for (int j = 0; j < nB; ++j) C.punct_B_q[i][j] = prod_mod(Bv, qi, j);
+  }
+  C.p_mod_q[L] = 0;
+  C.neg_inv_q_t = (t - invmod(prod_mod(Q, t), t)) % t; C.neg_inv_q_t_s = shoup(C.neg_inv_q_t, t);
+  C.neg_inv_q_g = (c->gamma - invmod(prod_mod(Q, c->gamma), c->gamma)) % c->gamma;
+  C.neg_inv_q_g_s = shoup(C.neg_inv_q_g, c->gamma);
+  C.inv_g_t = invmod(c->gamma % t, t); C.inv_g_t_s = shoup(C.inv_g_t, t);
+  C.neg_inv_q_mt = (u32)(mt - invmod(prod_mod(Q, mt), mt));
+  for (int j = 0; j < c->nbsk; ++j) {
+    const u64 pj = c->bsk[j];
+    C.bsk[j] = pj; barrett_ratio(pj, C.bsk_mu_hi[j], C.bsk_mu_lo[j]);
+    for (int i = 0; i < L; ++i) C.punct_q_bsk[j][i] = prod_mod(Q, pj, i);
+    C.q_mod_bsk[j] = prod_mod(Q, pj);
+    C.inv_mt_bsk[j] = invmod(mt % pj, pj); C.inv_mt_bsk_s[j] = shoup(C.inv_mt_bsk[j], pj);
+    C.t_mod_bsk[j] = t % pj; C.t_mod_bsk_s[j] = shoup(C.t_mod_bsk[j], pj);
+    C.inv_q_bsk[j] = invmod(C.q_mod_bsk[j], pj); C.inv_q_bsk_s[j] = shoup(C.inv_q_bsk[j], pj);
+  }
+  for (int j = 0; j < nB; ++j) {
+    C.inv_punct_B[j] = invmod(prod_mod(Bv, Bv[j], j), Bv[j]); C.inv_punct_B_s[j] = shoup(C.inv_punct_B[j], Bv[j]);
+    C.punct_B_msk[j] = prod_mod(Bv, c->msk, j);
+  }
+  C.inv_B_msk = invmod(prod_mod(Bv, c->msk), c->msk); C.inv_B_msk_s = shoup(C.inv_B_msk, c->msk);
+  CK(cudaMalloc((void **)&c->dC, sizeof(DevConst)));
+  c->owned.push_back(c->dC);
+  CK(cudaMemcpy(c->dC, &C, sizeof(DevConst), cudaMemcpyHostToDevice));
+
+  // ---- BatchEncoder index map (populate_matrix_reps_index_map)
+  std::vector<u32> imap(N);
+  {
+    const u64 m = 2ull * N; u64 pos = 1; const int row = N >> 1;
+    for (int i = 0; i < row; ++i) {
+      imap[i] = bit_reverse((uint32_t)((pos - 1) >> 1), logN);
+      imap[row | i] = bit_reverse((uint32_t)((m - pos - 1) >> 1), logN);
+      pos = (pos * 3) & (m - 1);
+    }
+  }
+  TRY(upload(c, &c->d_index_map, imap));
+
+  // ---- row maps
+  const int W = c->W;
+  std::vector<int> v;
+  v.resize(3 * L); for (int w = 0; w < 3 * L; ++w) v[w] = w % L;
+  TRY(upload(c, &c->rm_ct, v));
+  v.resize(2 * k); for (int w = 0; w < 2 * k; ++w) v[w] = w % k;
+  TRY(upload(c, &c->rm_key, v));
+  v.resize(4 * W); for (int w = 0; w < 4 * W; ++w) { int r = w % W; v[w] = r < L ? r : k + (r - L); }
+  TRY(upload(c, &c->rm_behz, v));
+  v.resize(k * L); for (int w = 0; w < k * L; ++w) v[w] = w / L;
+  TRY(upload(c, &c->rm_modup, v));
+  for (int w = 0; w < k * L; ++w) v[w] = w % L;
+  TRY(upload(c, &c->rs_modup, v));
+  v.assign(1, c->idx_t);
+  TRY(upload(c, &c->rm_t, v));
+  v.resize(L); for (int w = 0; w < L; ++w) v[w] = L + w;
+  TRY(upload(c, &c->rs_c1, v));
+  v.assign(2 * k, 0);
+  TRY(upload(c, &c->rs_zero, v));
+  return ABC_OK;
+}
+
+// ---- op building blocks ------------------------------------------------------------------------
+size_t ct_words1(const abc_ctx *c) { return (size_t)2 * c->L * c->N; }
+
+// Evaluator::switch_key_inplace: dst[inst][2][L][N] = (base0, base1) + KeySwitch(target)
+abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u64 *key, const u64 *base0,
+                     long long base0_is, const u64 *base1, long long base1_is, u64 *dst) {
+  const int N = c->N, L = c->L, k = c->k, B = c->B;
+  u64 *T = nullptr, *acc = nullptr;
+  TRY(salloc(c, &T, (size_t)B * k * L * N));
+  TRY(salloc(c, &acc, (size_t)B * 2 * k * N));
+  LimbJob j = blank_job();
+  j.dst = T; j.dst_is = (long long)k * L * N; j.src = target; j.src_is = target_is;
+  j.rowmod = c->rm_modup; j.rowsrc = c->rs_modup;
+  TRY((launch_limb<PRE_REDUCE, true, false, false, POST_STORE>(c, j, k * L, B, "ks_modup_ntt")));
+  {
+    Launch l(c, "ks_inner");
+    k_ks_inner<<<dim3(N / 256, k, B), 256, 0, c->stream>>>(T, key, acc, c->d_mods, N, L, k);
+    CK(cudaGetLastError());
+  }
+  j = blank_job();
+  j.dst = acc; j.src = acc; j.dst_is = j.src_is = (long long)2 * k * N; j.rowmod = c->rm_key;
+  TRY((launch_limb<PRE_LOAD, false, false, true, POST_STORE>(c, j, 2 * k, B, "ks_intt")));
+  {
+    Launch l(c, "ks_moddown");
+    k_ks_moddown<<<dim3(N / 256, 2, B), 256, 0, c->stream>>>(acc, base0, base0_is, base1, base1_is, dst, c->dC, N, L, k);
+    CK(cudaGetLastError());
+  }
+  sfree(c, T); sfree(c, acc);
+  return ABC_OK;
+}
+
+// Evaluator::bfv_multiply (size 2 x size 2 -> size 3): out3 [B][3][L][N]
+abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
+  const int N = c->N, L = c->L, B = c->B, W = c->W;
+  u64 *X = nullptr;
+  TRY(salloc(c, &X, (size_t)B * 4 * W * N));
+  {
+    Launch l(c, "behz_lift");
+    DISPATCH_L(c, (k_behz_lift<LL><<<dim3(N / 128, 4, B), 128, 0, c->stream>>>(a, b, X, c->dC, N)));
+    CK(cudaGetLastError());
+  }
+  LimbJob j = blank_job();
+  j.dst = X; j.src = X; j.dst_is = j.src_is = (long long)4 * W * N; j.rowmod = c->rm_behz;
+  TRY((launch_limb<PRE_LOAD, true, false, false, POST_STORE>(c, j, 4 * W, B, "behz_ntt")));
+  {
+    Launch l(c, "behz_tensor");
+    k_behz_tensor<<<dim3(N / 256, W, B), 256, 0, c->stream>>>(X, c->d_mods, c->rm_behz, N, W);
+    CK(cudaGetLastError());
+  }
+  TRY((launch_limb<PRE_LOAD, false, false, true, POST_STORE>(c, j, 3 * W, B, "behz_intt")));
+  {
+    Launch l(c, "behz_scale");
+    DISPATCH_L(c, (k_behz_scale<LL><<<dim3(N / 128, 3, B), 128, 0, c->stream>>>(X, out3, c->dC, N)));
+    CK(cudaGetLastError());
+  }
+  sfree(c, X);
+  return ABC_OK;
+}
+
+// one Galois automorphism + key switch (Evaluator::apply_galois_inplace)
+abc_status apply_galois(abc_ctx *c, const u64 *src, u64 *dst, u32 elt) {
+  auto it = c->galois.find(elt);
+  if (it == c->galois.end()) return fail(c, ABC_ERR_STATE, "Galois key not present");
+  const int N = c->N, L = c->L, B = c->B;
+  u64 *g = nullptr;
+  TRY(salloc(c, &g, (size_t)B * 2 * L * N));
+  const u32 elt_inv = (u32)hm::invmod(elt, 2ull * N);
+  {
+    Launch l(c, "galois_permute");
+    k_galois<<<dim3(N / 256, 2 * L, B), 256, 0, c->stream>>>(src, g, 2ll * L * N, g + (size_t)L * N, 2ll * L * N, elt_inv,
+                                                            c->dC, N, L);
+    CK(cudaGetLastError());
+  }
+  TRY(keyswitch(c, g + (size_t)L * N, 2ll * L * N, it->second, g, 2ll * L * N, nullptr, 0, dst));
+  sfree(c, g);
+  return ABC_OK;
+}
+
+u32 elt_from_step(const abc_ctx *c, int step) {
+  const u32 n = (u32)c->N, m = 2 * n;
+  const u32 pos = (u32)(step < 0 ? -step : step);
+  const u32 e = step < 0 ? (n >> 1) - pos : pos;
+  u64 elt = 1;
+  for (u32 i = 0; i < e; ++i) elt = (elt * 3) & (m - 1);
+  return (u32)elt;
+}
+
+// Evaluator::rotate_internal, in place on d
+abc_status rotate_internal(abc_ctx *c, u64 *d, int steps) {
+  if (steps == 0) return ABC_OK;
+  const u32 elt = elt_from_step(c, steps);
+  if (c->galois.count(elt)) return apply_galois(c, d, d, elt);
+  // util::naf, least significant digit first
+  std::vector<int> naf;
+  {
+    int v = steps < 0 ? -steps : steps; const bool neg = steps < 0;
+    for (int i = 0; v; ++i) {
+      int zi = (v & 1) ? 2 - (v & 3) : 0;
+      v = (v - zi) >> 1;
+      if (zi) naf.push_back((neg ? -zi : zi) * (1 << i));
+    }
+  }
+  if (naf.size() == 1) return fail(c, ABC_ERR_STATE, "Galois key not present");
+  for (int s : naf) {
+    if ((s < 0 ? -s : s) == (c->N >> 1)) continue;
+    TRY(rotate_internal(c, d, s));
+  }
+  return ABC_OK;
+}
+
+abc_status encode_device(abc_ctx *c, const int64_t *slots, size_t n, int broadcast, u64 **plain_out) {
+  const int N = c->N, Bp = broadcast ? 1 : c->B;
+  if (!slots || n == 0) return fail(c, ABC_ERR_PARAM, "Cannot encode an empty vector.");
+  if (n > (size_t)N)
+    return fail(c, ABC_ERR_PARAM, "Cannot encode " + std::to_string(n) + " elements in a ciphertext of size " +
+                                      std::to_string(N) + ". ");
+  long long *d_slots = nullptr;
+  u64 *plain = nullptr;
+  CK(cudaMallocAsync((void **)&d_slots, (size_t)Bp * n * sizeof(long long), c->stream));
+  CK(cudaMemcpyAsync(d_slots, slots, (size_t)Bp * n * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  TRY(salloc(c, &plain, (size_t)Bp * N));
+  LimbJob j = blank_job();
+  j.dst = plain; j.dst_is = N; j.rowmod = c->rm_t;
+  j.slots_in = d_slots; j.slots_is = (long long)n; j.n_slots = (int)n; j.index_map = c->d_index_map;
+  TRY((launch_limb<PRE_ENCODE, false, false, true, POST_STORE>(c, j, 1, Bp, "encode_intt")));
+  sfree(c, d_slots);
+  *plain_out = plain;
+  return ABC_OK;
+}
+
+abc_status encrypt_device(abc_ctx *c, const u64 *plain, int broadcast, u64 *ct) {
+  if (!c->have_keys) return fail(c, ABC_ERR_STATE, "keys not generated");
+  const int N = c->N, L = c->L, k = c->k, B = c->B;
+  const u64 nonce0 = c->enc_nonce * (u64)B;
+  c->enc_nonce++;
+  u64 *u = nullptr, *tmp = nullptr;
+  TRY(salloc(c, &u, (size_t)B * k * N));
+  TRY(salloc(c, &tmp, (size_t)B * 2 * k * N));
+  LimbJob j = blank_job();
+  j.dst = u; j.dst_is = (long long)k * N; j.rowmod = c->rm_key;
+  j.seed = c->seed; j.domain = DOM_ENC; j.a0 = nonce0; j.b = 0;
+  TRY((launch_limb<PRE_TERNARY, true, false, false, POST_STORE>(c, j, k, B, "enc_sample_u_ntt")));
+  j = blank_job();
+  j.src = u; j.src_is = (long long)k * N; j.rowsrc = c->rm_key;
+  j.mul = c->d_pk; j.mul_is = 0;
+  j.dst = tmp; j.dst_is = (long long)2 * k * N; j.rowmod = c->rm_key;
+  TRY((launch_limb<PRE_LOAD, false, true, true, POST_STORE>(c, j, 2 * k, B, "enc_mul_pk_intt")));
+  {
+    Launch l(c, "enc_finish");
+    k_enc_finish<<<dim3(N / 256, 2, B), 256, 0, c->stream>>>(tmp, plain, broadcast ? 0 : N, ct, c->seed, nonce0, c->dC, N,
+                                                           L, k);
+    CK(cudaGetLastError());
+  }
+  sfree(c, u); sfree(c, tmp);
+  return ABC_OK;
+}
+
+abc_status mul_plain_device(abc_ctx *c, u64 *dst, const u64 *a, const u64 *plain, int broadcast) {
+  const int N = c->N, L = c->L, B = c->B, Bp = broadcast ? 1 : B;
+  u64 *P = nullptr;
+  TRY(salloc(c, &P, (size_t)Bp * L * N));
+  LimbJob j = blank_job();
+  j.src = plain; j.src_is = N; j.rowsrc = c->rs_zero; j.dst = P; j.dst_is = (long long)L * N; j.rowmod = c->rm_ct;
+  TRY((launch_limb<PRE_PLAIN_LIFT, true, false, false, POST_STORE>(c, j, L, Bp, "plain_lift_ntt")));
+  j = blank_job();
+  j.src = a; j.dst = dst; j.src_is = j.dst_is = (long long)2 * L * N; j.rowmod = c->rm_ct;
+  j.mul = P; j.mul_is = broadcast ? 0 : (long long)L * N; j.rowmul = c->rm_ct;
+  TRY((launch_limb<PRE_LOAD, true, true, true, POST_STORE>(c, j, 2 * L, B, "ct_mul_plain")));
+  sfree(c, P);
+  return ABC_OK;
+}
+
+template <int SUB> abc_status plain_addsub_device(abc_ctx *c, u64 *dst, const u64 *a, const u64 *plain, int broadcast) {
+  Launch l(c, SUB ? "plain_sub" : "plain_add");
+  k_plain_addsub<SUB><<<dim3(c->N / 256, 1, c->B), 256, 0, c->stream>>>(dst, a, plain, broadcast ? 0 : c->N, c->dC, c->N,
+                                                                      c->L);
+  CK(cudaGetLastError());
+  return ABC_OK;
+}
+
+// one key-switching-key block [2][k][N]: c1 = a uniform, c0 = -(a s + e) (+ p * newkey at limb J)
+abc_status gen_key_block(abc_ctx *c, u64 *blk, u64 dom, u64 a_id, u64 b_base, const u64 *newkey, int J, u64 *e_ntt) {
+  const int N = c->N, k = c->k;
+  {
+    Launch l(c, "keygen_uniform");
+    k_sample_uniform<<<dim3(N / 256, k), 256, 0, c->stream>>>(blk + (size_t)k * N, c->seed, dom, a_id, b_base, c->dC, N);
+    CK(cudaGetLastError());
+  }
+  LimbJob j = blank_job();
+  j.dst = e_ntt; j.dst_is = 0; j.rowmod = c->rm_key;
+  j.seed = c->seed; j.domain = dom; j.a0 = a_id; j.b = (b_base << 2) | 1;
+  TRY((launch_limb<PRE_CBD, true, false, false, POST_STORE>(c, j, k, 1, "keygen_noise_ntt")));
+  {
+    Launch l(c, "keygen_finish");
+    k_ksk_finish<<<dim3(N / 256, k), 256, 0, c->stream>>>(blk, e_ntt, c->d_sk, newkey, J, c->d_mods, c->dC, N, k);
+    CK(cudaGetLastError());
+  }
+  return ABC_OK;
+}
+abc_status gen_kswitch_key(abc_ctx *c, u64 *key, u64 key_id, u32 galois_elt, u64 *nk, u64 *e_ntt) {
+  const int N = c->N, k = c->k, L = c->L;
+  {
+    Launch l(c, "keygen_newkey");
+    k_newkey<<<dim3(N / 256, k), 256, 0, c->stream>>>(nk, c->d_sk, galois_elt, c->d_mods, N, c->logN);
+    CK(cudaGetLastError());
+  }
+  for (int J = 0; J < L; ++J)
+    TRY(gen_key_block(c, key + (size_t)J * 2 * k * N, DOM_KSK, key_id, (u64)J << 8, nk, J, e_ntt));
+  return ABC_OK;
+}
+
+std::vector<u32> galois_elts_all(const abc_ctx *c) {
+  const u64 m = 2ull * c->N;
+  std::vector<u32> v;
+  v.push_back((u32)(m - 1));
+  u64 pos = 3, neg = hm::invmod(3, m);
+  for (int i = 0; i < c->logN - 1; ++i) {
+    v.push_back((u32)pos); pos = (pos * pos) & (m - 1);
+    v.push_back((u32)neg); neg = (neg * neg) & (m - 1);
+  }
+  return v;
+}
+
+bool valid_ct(const abc_ctx *c, const abc_ct *x) { return x && x->ctx == c && x->d; }
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+abc_status abc_ctx_create(const abc_params *p, abc_ctx **out) {
+  if (out) *out = nullptr;
+  if (!p || !out) { g_create_error = "null argument"; return ABC_ERR_PARAM; }
+  abc_ctx *c = new abc_ctx();
+  auto bail = [&](abc_status s, const std::string &m) {
+    g_create_error = m.empty() ? c->err : m;
+    abc_ctx_destroy(c);
+    return s;
+  };
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return bail(ABC_ERR_CUDA, "no CUDA device: libabc_b200 has no CPU fallback");
+  if (p->device < 0 || p->device >= ndev) return bail(ABC_ERR_PARAM, "invalid device ordinal");
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, p->device);
+  if (prop.major < 10) return bail(ABC_ERR_CUDA, "device is not sm_100-class: kernels are built for sm_100a only");
+  c->device = p->device;
+  if (cudaSetDevice(c->device) != cudaSuccess) return bail(ABC_ERR_CUDA, "cudaSetDevice failed");
+  const u64 N = p->poly_degree;
+  int logN = 0;
+  while ((1ull << logN) < N) ++logN;
+  if ((1ull << logN) != N || logN < 10 || logN > 15) return bail(ABC_ERR_PARAM, "poly_degree must be a power of two in [1024, 32768]");
+  c->N = (int)N; c->logN = logN; c->B = p->batch ? (int)p->batch : 1; c->seed = p->seed;
+  try {
+    if (p->n_primes == 0) c->primes = hm::bfv_default_primes(N);
+    else c->primes.assign(p->primes, p->primes + p->n_primes);
+    c->t = p->plain_modulus ? p->plain_modulus : hm::get_primes(N, 20, 1)[0];
+    c->k = (int)c->primes.size(); c->L = c->k - 1;
+    if (c->k < 2 || c->L > 15) return bail(ABC_ERR_PARAM, "need 2..16 coefficient primes (incl. the special prime)");
+    for (u64 q : c->primes)
+      if (!hm::is_prime(q) || (q - 1) % (2 * N) || q >> 60) return bail(ABC_ERR_PARAM, "coefficient primes must be < 2^60 and = 1 mod 2N");
+    for (size_t i = 0; i < c->primes.size(); ++i)
+      for (size_t j = 0; j < i; ++j)
+        if (c->primes[i] == c->primes[j]) return bail(ABC_ERR_PARAM, "coefficient primes must be distinct");
+    if (!hm::is_prime(c->t) || (c->t - 1) % (2 * N)) return bail(ABC_ERR_PARAM, "plain_modulus must be a prime = 1 mod 2N (batching)");
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ABC_ERR_CUDA, "stream creation failed");
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    abc_status s = build_tables(c);
+    if (s != ABC_OK) return bail(s, "");
+  } catch (const std::exception &e) {
+    return bail(ABC_ERR_PARAM, e.what());
+  }
+  *out = c;
+  return ABC_OK;
+}
+
+void abc_ctx_destroy(abc_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto &kv : c->galois) cudaFree(kv.second);
+  cudaFree(c->d_sk); cudaFree(c->d_pk); cudaFree(c->d_relin);
+  for (void *p : c->owned) cudaFree(p);
+  if (c->flush_buf) cudaFree(c->flush_buf);
+  for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char *abc_last_error(const abc_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+abc_status abc_sync(abc_ctx *c) { CK(cudaStreamSynchronize(c->stream)); return ABC_OK; }
+uint32_t abc_poly_degree(const abc_ctx *c) { return (uint32_t)c->N; }
+uint32_t abc_n_primes(const abc_ctx *c) { return (uint32_t)c->k; }
+uint32_t abc_n_limbs(const abc_ctx *c) { return (uint32_t)c->L; }
+uint32_t abc_batch(const abc_ctx *c) { return (uint32_t)c->B; }
+uint64_t abc_plain_modulus(const abc_ctx *c) { return c->t; }
+abc_status abc_get_primes(const abc_ctx *c, uint64_t *out) {
+  for (int i = 0; i < c->k; ++i) out[i] = c->primes[i];
+  return ABC_OK;
+}
+abc_status abc_get_aux_primes(const abc_ctx *c, uint64_t *out, uint32_t *count) {
+  out[0] = c->msk; out[1] = c->gamma;
+  for (int j = 0; j < c->nB; ++j) out[2 + j] = c->bsk[j];
+  if (count) *count = (uint32_t)c->nB + 2;
+  return ABC_OK;
+}
+
+// ---- keys
+abc_status abc_keygen(abc_ctx *c) {
+  const int N = c->N, k = c->k, L = c->L;
+  CK(cudaSetDevice(c->device));
+  const size_t kw = (size_t)L * 2 * k * N;
+  if (!c->d_sk) CK(cudaMalloc((void **)&c->d_sk, (size_t)k * N * 8));
+  if (!c->d_pk) CK(cudaMalloc((void **)&c->d_pk, (size_t)2 * k * N * 8));
+  if (!c->d_relin) CK(cudaMalloc((void **)&c->d_relin, kw * 8));
+  LimbJob j = blank_job();
+  j.dst = c->d_sk; j.rowmod = c->rm_key; j.seed = c->seed; j.domain = DOM_SK;
+  TRY((launch_limb<PRE_TERNARY, true, false, false, POST_STORE>(c, j, k, 1, "keygen_sk_ntt")));
+  u64 *nk = nullptr, *e_ntt = nullptr;
+  TRY(salloc(c, &nk, (size_t)k * N));
+  TRY(salloc(c, &e_ntt, (size_t)k * N));
+  TRY(gen_key_block(c, c->d_pk, DOM_PK, 0, 0, nullptr, -1, e_ntt));
+  TRY(gen_kswitch_key(c, c->d_relin, 0, 0, nk, e_ntt));
+  for (u32 elt : galois_elts_all(c)) {
+    if (c->galois.count(elt)) continue;
+    u64 *key = nullptr;
+    CK(cudaMalloc((void **)&key, kw * 8));
+    c->galois[elt] = key;
+    TRY(gen_kswitch_key(c, key, elt, elt, nk, e_ntt));
+  }
+  sfree(c, nk); sfree(c, e_ntt);
+  c->have_keys = true;
+  return ABC_OK;
+}
+size_t abc_key_words(const abc_ctx *c, int kind) {
+  const size_t kn = (size_t)c->k * c->N;
+  switch (kind) {
+    case ABC_KEY_SECRET: return kn;
+    case ABC_KEY_PUBLIC: return 2 * kn;
+    case ABC_KEY_RELIN: case ABC_KEY_GALOIS: return (size_t)c->L * 2 * kn;
+    default: return 0;
+  }
+}
+static u64 **key_slot(abc_ctx *c, int kind, uint32_t elt, bool create) {
+  switch (kind) {
+    case ABC_KEY_SECRET: return &c->d_sk;
+    case ABC_KEY_PUBLIC: return &c->d_pk;
+    case ABC_KEY_RELIN: return &c->d_relin;
+    case ABC_KEY_GALOIS: {
+      if (!(elt & 1) || elt >= 2u * c->N) return nullptr;
+      auto it = c->galois.find(elt);
+      if (it != c->galois.end()) return &it->second;
+      if (!create) return nullptr;
+      c->galois[elt] = nullptr;
+      return &c->galois[elt];
+    }
+    default: return nullptr;
+  }
+}
+abc_status abc_key_export(abc_ctx *c, int kind, uint32_t elt, uint64_t *host, size_t words) {
+  u64 **slot = key_slot(c, kind, elt, false);
+  if (!slot || !*slot) return fail(c, ABC_ERR_STATE, "key not present");
+  if (words != abc_key_words(c, kind)) return fail(c, ABC_ERR_PARAM, "key size mismatch");
+  CK(cudaMemcpyAsync(host, *slot, words * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ABC_OK;
+}
+abc_status abc_key_import(abc_ctx *c, int kind, uint32_t elt, const uint64_t *host, size_t words) {
+  CK(cudaSetDevice(c->device));
+  u64 **slot = key_slot(c, kind, elt, true);
+  if (!slot) return fail(c, ABC_ERR_PARAM, "invalid key kind / Galois element");
+  if (words != abc_key_words(c, kind)) return fail(c, ABC_ERR_PARAM, "key size mismatch");
+  if (!*slot) CK(cudaMalloc((void **)slot, words * 8));
+  CK(cudaMemcpyAsync(*slot, host, words * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->d_sk && c->d_pk && c->d_relin) c->have_keys = true;
+  return ABC_OK;
+}
+int abc_has_galois_key(const abc_ctx *c, uint32_t elt) { return c->galois.count(elt) ? 1 : 0; }
+
+// ---- handles
+abc_status abc_ct_alloc(abc_ctx *c, abc_ct **out) {
+  CK(cudaSetDevice(c->device));
+  u64 *d = nullptr;
+  TRY(salloc(c, &d, abc_ct_words(c)));
+  *out = new abc_ct{c, d};
+  return ABC_OK;
+}
+void abc_ct_free(abc_ct *ct) {
+  if (!ct) return;
+  sfree(ct->ctx, ct->d);
+  delete ct;
+}
+size_t abc_ct_words(const abc_ctx *c) { return (size_t)c->B * ct_words1(c); }
+abc_status abc_ct_clone(abc_ctx *c, const abc_ct *src, abc_ct **out) {
+  if (!valid_ct(c, src)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+  TRY(abc_ct_alloc(c, out));
+  c->launches++;
+  CK(cudaMemcpyAsync((*out)->d, src->d, abc_ct_words(c) * 8, cudaMemcpyDeviceToDevice, c->stream));
+  return ABC_OK;
+}
+abc_status abc_ct_export(abc_ctx *c, const abc_ct *ct, uint64_t *host, size_t words) {
+  if (!valid_ct(c, ct) || words != abc_ct_words(c)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle or size");
+  CK(cudaMemcpyAsync(host, ct->d, words * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ABC_OK;
+}
+abc_status abc_ct_import(abc_ctx *c, abc_ct *ct, const uint64_t *host, size_t words) {
+  if (!valid_ct(c, ct) || words != abc_ct_words(c)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle or size");
+  CK(cudaMemcpyAsync(ct->d, host, words * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ABC_OK;
+}
+
+// ---- encode / encrypt / decrypt
+abc_status abc_pt_encode(abc_ctx *c, const int64_t *slots, size_t n, int broadcast, abc_pt **out) {
+  CK(cudaSetDevice(c->device));
+  u64 *plain = nullptr;
+  TRY(encode_device(c, slots, n, broadcast, &plain));
+  *out = new abc_pt{c, plain, broadcast};
+  return ABC_OK;
+}
+void abc_pt_free(abc_pt *pt) {
+  if (!pt) return;
+  sfree(pt->ctx, pt->d);
+  delete pt;
+}
+abc_status abc_encrypt_pt(abc_ctx *c, const abc_pt *pt, abc_ct **out) {
+  if (!pt || pt->ctx != c) return fail(c, ABC_ERR_PARAM, "invalid plaintext handle");
+  TRY(abc_ct_alloc(c, out));
+  abc_status s = encrypt_device(c, pt->d, pt->broadcast, (*out)->d);
+  if (s != ABC_OK) { abc_ct_free(*out); *out = nullptr; }
+  return s;
+}
+abc_status abc_encode_encrypt(abc_ctx *c, const int64_t *slots, size_t n, int broadcast, abc_ct **out) {
+  abc_pt *pt = nullptr;
+  TRY(abc_pt_encode(c, slots, n, broadcast, &pt));
+  abc_status s = abc_encrypt_pt(c, pt, out);
+  abc_pt_free(pt);
+  return s;
+}
+abc_status abc_set_encrypt_nonce(abc_ctx *c, uint64_t nonce) { c->enc_nonce = nonce; return ABC_OK; }
+
+abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) {
+  if (!valid_ct(c, ct)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+  if (!c->d_sk) return fail(c, ABC_ERR_STATE, "secret key not present");
+  CK(cudaSetDevice(c->device));
+  const int N = c->N, L = c->L, B = c->B;
+  u64 *x = nullptr, *plain = nullptr;
+  long long *d_out = nullptr;
+  TRY(salloc(c, &x, (size_t)B * L * N));
+  TRY(salloc(c, &plain, (size_t)B * N));
+  CK(cudaMallocAsync((void **)&d_out, (size_t)B * N * sizeof(long long), c->stream));
+  LimbJob j = blank_job();
+  j.src = ct->d; j.src_is = (long long)2 * L * N; j.rowsrc = c->rs_c1;
+  j.mul = c->d_sk; j.mul_is = 0;
+  j.add = ct->d; j.add_is = (long long)2 * L * N;
+  j.dst = x; j.dst_is = (long long)L * N; j.rowmod = c->rm_ct;
+  TRY((launch_limb<PRE_LOAD, true, true, true, POST_ADD>(c, j, L, B, "dec_c1s_plus_c0")));
+  {
+    Launch l(c, "dec_scale_round");
+    DISPATCH_L(c, (k_dec_finish<LL><<<dim3(N / 128, 1, B), 128, 0, c->stream>>>(x, plain, c->dC, N)));
+    CK(cudaGetLastError());
+  }
+  j = blank_job();
+  j.src = plain; j.src_is = N; j.rowmod = c->rm_t; j.slots_out = d_out; j.index_map = c->d_index_map;
+  TRY((launch_limb<PRE_LOAD, true, false, false, POST_DECODE>(c, j, 1, B, "decode_ntt")));
+  CK(cudaMemcpyAsync(out_slots, d_out, (size_t)B * N * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  sfree(c, x); sfree(c, plain); sfree(c, d_out);
+  return ABC_OK;
+}
+
+// ---- ciphertext ops
+static abc_status addsub(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct *b, int op) {
+  if (!valid_ct(c, dst) || !valid_ct(c, a) || (op != 2 && !valid_ct(c, b)))
+    return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+  const int N = c->N, L = c->L;
+  Launch l(c, op == 0 ? "add" : op == 1 ? "sub" : "negate");
+  dim3 grid((N / 2 + 255) / 256, 2 * L, c->B);
+  const long long is = 2ll * L * N;
+  if (op == 0) k_addsub<0><<<grid, 256, 0, c->stream>>>(dst->d, a->d, b->d, c->dC, N, L, is);
+  else if (op == 1) k_addsub<1><<<grid, 256, 0, c->stream>>>(dst->d, a->d, b->d, c->dC, N, L, is);
+  else k_addsub<2><<<grid, 256, 0, c->stream>>>(dst->d, a->d, nullptr, c->dC, N, L, is);
+  CK(cudaGetLastError());
+  return ABC_OK;
+}
+abc_status abc_add(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct *b) { return addsub(c, dst, a, b, 0); }
+abc_status abc_sub(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct *b) { return addsub(c, dst, a, b, 1); }
+abc_status abc_negate(abc_ctx *c, abc_ct *dst, const abc_ct *a) { return addsub(c, dst, a, nullptr, 2); }
+
+abc_status abc_mul_relin(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct *b) {
+  if (!valid_ct(c, dst) || !valid_ct(c, a) || !valid_ct(c, b)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+  if (!c->d_relin) return fail(c, ABC_ERR_STATE, "relinearisation key not present");
+  const size_t LN = (size_t)c->L * c->N;
+  u64 *out3 = nullptr;
+  TRY(salloc(c, &out3, (size_t)c->B * 3 * LN));
+  TRY(behz_multiply(c, a->d, b->d, out3));
+  TRY(keyswitch(c, out3 + 2 * LN, 3ll * LN, c->d_relin, out3, 3ll * LN, out3 + LN, 3ll * LN, dst->d));
+  sfree(c, out3);
+  return ABC_OK;
+}
+
+abc_status abc_rotate_rows(abc_ctx *c, abc_ct *dst, const abc_ct *a, int steps) {
+  if (!valid_ct(c, dst) || !valid_ct(c, a)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+  const int as = steps < 0 ? -steps : steps;
+  if (as >= (c->N >> 1)) return fail(c, ABC_ERR_PARAM, "step count too large");
+  if (dst != a) {
+    c->launches++;
+    CK(cudaMemcpyAsync(dst->d, a->d, abc_ct_words(c) * 8, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return rotate_internal(c, dst->d, steps);
+}
+
+// ---- plaintext operands
+abc_status abc_add_plain_pt(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_pt *pt) {
+  if (!valid_ct(c, dst) || !valid_ct(c, a) || !pt || pt->ctx != c) return fail(c, ABC_ERR_PARAM, "invalid handle");
+  return plain_addsub_device<0>(c, dst->d, a->d, pt->d, pt->broadcast);
+}
+abc_status abc_sub_plain_pt(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_pt *pt) {
+  if (!valid_ct(c, dst) || !valid_ct(c, a) || !pt || pt->ctx != c) return fail(c, ABC_ERR_PARAM, "invalid handle");
+  return plain_addsub_device<1>(c, dst->d, a->d, pt->d, pt->broadcast);
+}
+abc_status abc_mul_plain_pt(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_pt *pt) {
+  if (!valid_ct(c, dst) || !valid_ct(c, a) || !pt || pt->ctx != c) return fail(c, ABC_ERR_PARAM, "invalid handle");
+  return mul_plain_device(c, dst->d, a->d, pt->d, pt->broadcast);
+}
+#define PLAIN_OP(NAME, PTFN)                                                                                      \
+  abc_status NAME(abc_ctx *c, abc_ct *dst, const abc_ct *a, const int64_t *slots, size_t n, int broadcast) {      \
+    abc_pt *pt = nullptr;                                                                                         \
+    TRY(abc_pt_encode(c, slots, n, broadcast, &pt));                                                              \
+    abc_status s = PTFN(c, dst, a, pt);                                                                           \
+    abc_pt_free(pt);                                                                                              \
+    return s;                                                                                                     \
+  }
+PLAIN_OP(abc_add_plain, abc_add_plain_pt)
+PLAIN_OP(abc_sub_plain, abc_sub_plain_pt)
+PLAIN_OP(abc_mul_plain, abc_mul_plain_pt)
+
+// ---- probes
+abc_status abc_probe_ntt(abc_ctx *c, int inverse, uint32_t mod_index, uint64_t *host_rows, size_t n_rows) {
+  CK(cudaSetDevice(c->device));
+  if ((int)mod_index > c->idx_t || n_rows == 0 || n_rows > 65535) return fail(c, ABC_ERR_PARAM, "invalid probe arguments");
+  const int N = c->N;
+  u64 *d = nullptr; int *rm = nullptr;
+  TRY(salloc(c, &d, n_rows * N));
+  CK(cudaMallocAsync((void **)&rm, n_rows * sizeof(int), c->stream));
+  std::vector<int> v(n_rows, (int)mod_index);
+  CK(cudaMemcpyAsync(rm, v.data(), n_rows * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d, host_rows, n_rows * N * 8, cudaMemcpyHostToDevice, c->stream));
+  LimbJob j = blank_job();
+  j.dst = d; j.src = d; j.rowmod = rm;
+  if (inverse) TRY((launch_limb<PRE_LOAD, false, false, true, POST_STORE>(c, j, (int)n_rows, 1, "probe_intt")));
+  else TRY((launch_limb<PRE_LOAD, true, false, false, POST_STORE>(c, j, (int)n_rows, 1, "probe_ntt")));
+  CK(cudaMemcpyAsync(host_rows, d, n_rows * N * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  sfree(c, d); sfree(c, rm);
+  return ABC_OK;
+}
+abc_status abc_probe_multiply(abc_ctx *c, const abc_ct *a, const abc_ct *b, uint64_t *host_out3, size_t words) {
+  if (!valid_ct(c, a) || !valid_ct(c, b)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+  const size_t need = (size_t)c->B * 3 * c->L * c->N;
+  if (words != need) return fail(c, ABC_ERR_PARAM, "size mismatch");
+  u64 *out3 = nullptr;
+  TRY(salloc(c, &out3, need));
+  TRY(behz_multiply(c, a->d, b->d, out3));
+  CK(cudaMemcpyAsync(host_out3, out3, need * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  sfree(c, out3);
+  return ABC_OK;
+}
+
+// ---- timing / profiling
+abc_status abc_timer_start(abc_ctx *c) { CK(cudaEventRecord(c->ev0, c->stream)); return ABC_OK; }
+abc_status abc_timer_stop(abc_ctx *c, float *ms) {
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaEventSynchronize(c->ev1));
+  CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  return ABC_OK;
+}
+abc_status abc_flush_l2(abc_ctx *c, size_t bytes) {
+  if (bytes > c->flush_bytes) {
+    if (c->flush_buf) cudaFree(c->flush_buf);
+    c->flush_buf = nullptr; c->flush_bytes = 0;
+    CK(cudaMalloc(&c->flush_buf, bytes));
+    c->flush_bytes = bytes;
+  }
+  CK(cudaMemsetAsync(c->flush_buf, 0x5a, bytes, c->stream));
+  return ABC_OK;
+}
+uint64_t abc_launch_count(const abc_ctx *c) { return c->launches; }
+abc_status abc_profile_enable(abc_ctx *c, int on) {
+  CK(cudaStreamSynchronize(c->stream));
+  for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  c->prof_recs.clear();
+  c->prof = on != 0;
+  return ABC_OK;
+}
+const char *abc_profile_json(abc_ctx *c) {
+  cudaStreamSynchronize(c->stream);
+  std::map<std::string, std::pair<long, double>> agg;
+  std::vector<std::string> order;
+  for (auto &r : c->prof_recs) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (!agg.count(r.name)) order.push_back(r.name);
+    agg[r.name].first++; agg[r.name].second += ms;
+  }
+  std::string s = "[";
+  for (size_t i = 0; i < order.size(); ++i) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s{\"kernel\": \"%s\", \"launches\": %ld, \"ms\": %.6f}", i ? ", " : "", order[i].c_str(),
+             agg[order[i]].first, agg[order[i]].second);
+    s += buf;
+  }
+  s += "]";
+  c->prof_json = s;
+  return c->prof_json.c_str();
+}
+
+abc_status abc_measure_int_peak(abc_ctx *c, double *imad_per_s, double *iadd_per_s) {
+  CK(cudaSetDevice(c->device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  const int grid = sms * 2, iters = 2048;
+  u32 *out = nullptr;
+  CK(cudaMallocAsync((void **)&out, (size_t)grid * 1024 * 8, c->stream));
+  const double ops = (double)grid * 1024 * iters * 16 * 8;
+  float ms = 0;
+  for (int rep = 0; rep < 2; ++rep) {
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_peak_imad<<<grid, 1024, 0, c->stream>>>(out, iters);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  }
+  if (imad_per_s) *imad_per_s = ops / (ms * 1e-3);
+  for (int rep = 0; rep < 2; ++rep) {
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_peak_iadd<<<grid, 1024, 0, c->stream>>>(out, iters);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  }
+  if (iadd_per_s) *iadd_per_s = 2.0 * ops / (ms * 1e-3);  // one IADD + one LOP3 per step
+  sfree(c, out);
+  return ABC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,248 @@
+// ntt.cuh — negacyclic NTT of one RNS limb staged whole in shared memory (N <= 16384), sm_100a.
+//
+// Replaces SEAL 3.6.5 ntt_negacyclic_harvey / inverse_ntt_negacyclic_harvey (util/ntt.cpp,
+// util/dwthandler.h), which ABC reaches inside every multiply / relinearize / rotate / multiply_plain /
+// encrypt / decrypt (src/runtime/SealCiphertext.cpp:55,104,105,159; SealCiphertextFactory.cpp:12,150).
+// Same transform: forward = Cooley-Tukey, natural in, bit-reversed out, tw[bitrev(i)] = psi^i;
+// inverse = Gentleman-Sande, bit-reversed in, natural out, N^-1 folded into the last stage.
+//
+// Mapping: T = min(N/8, 1024) threads; every thread owns 8 coefficients per pass and does up to three
+// butterfly stages on them in registers (radix-8), so a limb makes 3-4 trips through shared memory
+// instead of log2(N).  The last forward pass (first inverse pass) owns 8 CONTIGUOUS coefficients: the
+// stages with gaps 4,2,1 are in-register and the stages with gaps 8 (and 16) are warp-shuffle
+// butterflies between lane pairs, each lane computing half of the pair's butterflies.
+// Shared memory is XOR-swizzled at 16-byte granularity so both the strided passes and the
+// contiguous pass are bank-conflict free.
+#pragma once
+#include "modarith.cuh"
+
+// element index -> physical index; keeps (even, odd) pairs adjacent so 16-byte accesses stay legal
+__device__ __forceinline__ int swz(int e) { return e ^ ((e >> 3) & 14); }
+
+template <int LOGN> struct NttPlan;
+template <> struct NttPlan<10> { static constexpr int R0 = 3, R1 = 3, R2 = 0, NSH = 1; };
+template <> struct NttPlan<11> { static constexpr int R0 = 3, R1 = 3, R2 = 1, NSH = 1; };
+template <> struct NttPlan<12> { static constexpr int R0 = 3, R1 = 3, R2 = 2, NSH = 1; };
+template <> struct NttPlan<13> { static constexpr int R0 = 3, R1 = 3, R2 = 3, NSH = 1; };
+template <> struct NttPlan<14> { static constexpr int R0 = 3, R1 = 3, R2 = 3, NSH = 2; };
+
+template <int LOGN> struct NttDims {
+  static constexpr int N = 1 << LOGN;
+  static constexpr int T = (N / 8 < 1024) ? N / 8 : 1024;
+  static constexpr int IT = N / 8 / T;
+  static constexpr size_t SMEM = (size_t)N * 8;
+};
+
+// Harvey forward butterfly: x,y in [0,4q) -> [0,4q)
+__device__ __forceinline__ void bf_fwd(u64 &x, u64 &y, ulonglong2 w, u64 q, u64 q2) {
+  u64 u = csub(x, q2);
+  u64 v = mul_shoup_lazy(y, w.x, w.y, q);
+  x = u + v;
+  y = u + q2 - v;
+}
+// Gentleman-Sande inverse butterfly: x,y in [0,2q) -> [0,2q)
+__device__ __forceinline__ void bf_inv(u64 &x, u64 &y, ulonglong2 w, u64 q, u64 q2) {
+  u64 u = x, v = y;
+  x = csub(u + v, q2);
+  y = mul_shoup_lazy(u + q2 - v, w.x, w.y, q);
+}
+
+// ---- strided pass: stages S0 .. S0+R-1 (stage s has 2^s groups, gap N >> (s+1)); twbase = 1 for a whole
+// transform, (2^a + block) when this limb is block `block` of the tail of a larger 2^(a+LOGN) transform.
+template <int LOGN, int S0, int R>
+__device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 q2,
+                                            int tid) {
+  typedef NttDims<LOGN> D;
+  constexpr int LG = LOGN - S0 - R;
+#pragma unroll
+  for (int it = 0; it < D::IT; ++it) {
+    const int vt = tid + it * D::T;
+    const int off = vt & ((1 << LG) - 1), blk = vt >> LG;
+    const int base = (blk << (LG + 3)) | off;
+    const int pbase = swz(base);
+    u64 x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) x[r] = sm[LG >= 7 ? pbase + (r << LG) : swz(base + (r << LG))];
+#pragma unroll
+    for (int b = R - 1; b >= 0; --b) {
+      const int s = S0 + R - 1 - b;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r & (1 << b)) continue;
+        const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)((blk << 3) + r) >> (b + 1))]);
+        bf_fwd(x[r], x[r | (1 << b)], w, q, q2);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[LG >= 7 ? pbase + (r << LG) : swz(base + (r << LG))] = x[r];
+  }
+}
+
+template <int LOGN, int S0, int R, bool FOLD>
+__device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 q2, int tid) {
+  typedef NttDims<LOGN> D;
+  constexpr int LG = LOGN - S0 - R;
+  const ulonglong2 *__restrict__ tw = M.itw;
+#pragma unroll
+  for (int it = 0; it < D::IT; ++it) {
+    const int vt = tid + it * D::T;
+    const int off = vt & ((1 << LG) - 1), blk = vt >> LG;
+    const int base = (blk << (LG + 3)) | off;
+    const int pbase = swz(base);
+    u64 x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) x[r] = sm[LG >= 7 ? pbase + (r << LG) : swz(base + (r << LG))];
+#pragma unroll
+    for (int b = 0; b < R; ++b) {
+      const int s = S0 + R - 1 - b;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r & (1 << b)) continue;
+        if (FOLD && s == 0) {
+          // last stage of the whole transform: fold N^-1 into both outputs
+          u64 u = x[r], v = x[r | (1 << b)];
+          x[r] = mul_shoup_lazy(u + v, M.ninv, M.ninv_s, q);
+          x[r | (1 << b)] = mul_shoup_lazy(u + q2 - v, M.wl_ninv, M.wl_ninv_s, q);
+        } else {
+          const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)((blk << 3) + r) >> (b + 1))]);
+          bf_inv(x[r], x[r | (1 << b)], w, q, q2);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sm[LG >= 7 ? pbase + (r << LG) : swz(base + (r << LG))] = x[r];
+  }
+}
+
+// ---- contiguous pass: 8 consecutive coefficients per thread; NSH shuffle stages + gaps 4,2,1 in registers
+template <int LOGN, int NSH>
+__device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 q2,
+                                             int tid) {
+  typedef NttDims<LOGN> D;
+#pragma unroll
+  for (int it = 0; it < D::IT; ++it) {
+    const int vt = tid + it * D::T;
+    u64 x[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(8 * vt + 2 * i)]);
+      x[2 * i] = v.x; x[2 * i + 1] = v.y;
+    }
+#pragma unroll
+    for (int j = NSH - 1; j >= 0; --j) {
+      const int s = LOGN - 4 - j;
+      const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)vt >> (1 + j))]);
+      const bool hi = (vt >> j) & 1;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        u64 recv = __shfl_xor_sync(0xffffffffu, hi ? x[r] : x[4 + r], 1 << j);
+        u64 a = hi ? recv : x[r];
+        u64 b = hi ? x[4 + r] : recv;
+        bf_fwd(a, b, w, q, q2);
+        u64 got = __shfl_xor_sync(0xffffffffu, hi ? a : b, 1 << j);
+        x[r] = hi ? got : a;
+        x[4 + r] = hi ? b : got;
+      }
+    }
+#pragma unroll
+    for (int b = 2; b >= 0; --b) {
+      const int s = LOGN - 1 - b;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r & (1 << b)) continue;
+        const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)(8 * vt + r) >> (b + 1))]);
+        bf_fwd(x[r], x[r | (1 << b)], w, q, q2);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ulonglong2 v;
+      v.x = csub(csub(x[2 * i], q2), q);
+      v.y = csub(csub(x[2 * i + 1], q2), q);
+      *reinterpret_cast<ulonglong2 *>(&sm[swz(8 * vt + 2 * i)]) = v;
+    }
+  }
+}
+
+template <int LOGN, int NSH>
+__device__ __forceinline__ void ntt_inv_first(u64 *sm, const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 q2,
+                                              int tid) {
+  typedef NttDims<LOGN> D;
+#pragma unroll
+  for (int it = 0; it < D::IT; ++it) {
+    const int vt = tid + it * D::T;
+    u64 x[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(8 * vt + 2 * i)]);
+      x[2 * i] = v.x; x[2 * i + 1] = v.y;
+    }
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+      const int s = LOGN - 1 - b;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r & (1 << b)) continue;
+        const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)(8 * vt + r) >> (b + 1))]);
+        bf_inv(x[r], x[r | (1 << b)], w, q, q2);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NSH; ++j) {
+      const int s = LOGN - 4 - j;
+      const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)vt >> (1 + j))]);
+      const bool hi = (vt >> j) & 1;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        u64 recv = __shfl_xor_sync(0xffffffffu, hi ? x[r] : x[4 + r], 1 << j);
+        u64 a = hi ? recv : x[r];
+        u64 b = hi ? x[4 + r] : recv;
+        bf_inv(a, b, w, q, q2);
+        u64 got = __shfl_xor_sync(0xffffffffu, hi ? a : b, 1 << j);
+        x[r] = hi ? got : a;
+        x[4 + r] = hi ? b : got;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ulonglong2 v; v.x = x[2 * i]; v.y = x[2 * i + 1];
+      *reinterpret_cast<ulonglong2 *>(&sm[swz(8 * vt + 2 * i)]) = v;
+    }
+  }
+}
+
+// ---- whole-limb transforms on a swizzled shared-memory limb.  Caller has filled sm[swz(e)] and synced.
+// Forward: input < 4q, output canonical.  On return all threads have passed a barrier after the last write.
+template <int LOGN>
+__device__ __forceinline__ void ntt_fwd_smem(u64 *sm, const ModInfo &M, u32 twbase, int tid) {
+  typedef NttPlan<LOGN> P;
+  const u64 q = M.q, q2 = 2 * q;
+  const ulonglong2 *tw = M.tw;
+  ntt_fwd_mid<LOGN, 0, P::R0>(sm, tw, twbase, q, q2, tid);
+  __syncthreads();
+  ntt_fwd_mid<LOGN, P::R0, P::R1>(sm, tw, twbase, q, q2, tid);
+  __syncthreads();
+  if constexpr (P::R2 > 0) {
+    ntt_fwd_mid<LOGN, P::R0 + P::R1, (P::R2 > 0 ? P::R2 : 1)>(sm, tw, twbase, q, q2, tid);
+    __syncthreads();
+  }
+  ntt_fwd_last<LOGN, P::NSH>(sm, tw, twbase, q, q2, tid);
+  __syncthreads();
+}
+// Inverse: input < 2q, output in [0,2q) (the caller's copy-out does the final conditional subtract).
+// WHOLE folds N^-1 into the last stage; for a tail block (WHOLE=false) a head pass finishes the transform.
+template <int LOGN, bool WHOLE>
+__device__ __forceinline__ void ntt_inv_smem(u64 *sm, const ModInfo &M, u32 twbase, int tid) {
+  typedef NttPlan<LOGN> P;
+  const u64 q = M.q, q2 = 2 * q;
+  ntt_inv_first<LOGN, P::NSH>(sm, M.itw, twbase, q, q2, tid);
+  __syncthreads();
+  if constexpr (P::R2 > 0) {
+    ntt_inv_mid<LOGN, P::R0 + P::R1, (P::R2 > 0 ? P::R2 : 1), false>(sm, M, twbase, q, q2, tid);
+    __syncthreads();
+  }
+  ntt_inv_mid<LOGN, P::R0, P::R1, false>(sm, M, twbase, q, q2, tid);
+  __syncthreads();
+  ntt_inv_mid<LOGN, 0, P::R0, WHOLE>(sm, M, twbase, q, q2, tid);
+  __syncthreads();
+}

@@ -1,0 +1,139 @@
+/*
+ * abc_b200.h — C ABI of libabc_b200.so, the B200 (sm_100a) BFV ciphertext backend for MarbleHE/ABC.
+ *
+ * This is the drop-in boundary for the path ABC reaches through
+ *   include/ast_opt/runtime/AbstractCiphertextFactory.h:19-49  and
+ *   include/ast_opt/runtime/AbstractCiphertext.h:27-98
+ * (paths relative to /root/reference).  Each entry point names the reference interface it replaces.
+ * Plain pointers and sizes only; no C++ or torch types.  Every call returns an abc_status; on
+ * failure abc_last_error() holds a message (the C++ wrapper rethrows it as std::runtime_error,
+ * the reference's error convention: src/runtime/SealCiphertext.cpp:40,137,242).
+ *
+ * Execution model: a context owns ONE device and ONE CUDA stream.  Ciphertext ops only enqueue
+ * kernels and return; abc_decrypt_decode, the export calls and abc_sync are the sync points.
+ * There is no CPU fallback: without a usable sm_100-class device abc_ctx_create fails.
+ *
+ * Batch: a context is created for `batch` independent program instances.  Every abc_ct handle
+ * holds `batch` ciphertexts, laid out [batch][poly][limb][N] (u64, coefficient form, canonical
+ * residues — per instance this is exactly seal::Ciphertext's layout), and every op runs on all
+ * instances in one launch sequence with shared keys.
+ */
+#ifndef ABC_B200_H
+#define ABC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int abc_status; /* 0 = ok */
+enum { ABC_OK = 0, ABC_ERR_PARAM = 1, ABC_ERR_CUDA = 2, ABC_ERR_STATE = 3, ABC_ERR_UNSUPPORTED = 4 };
+
+typedef struct abc_ctx abc_ctx;
+typedef struct abc_ct abc_ct;
+
+typedef struct abc_params {
+  uint32_t poly_degree;     /* N: 1024..32768, power of two */
+  uint32_t n_primes;        /* k, incl. the special prime (last); 0 -> SEAL CoeffModulus::BFVDefault(N) */
+  const uint64_t *primes;   /* k primes = 1 (mod 2N), each < 2^60; ignored when n_primes == 0 */
+  uint64_t plain_modulus;   /* t; 0 -> SEAL PlainModulus::Batching(N, 20) */
+  int32_t device;           /* CUDA device ordinal */
+  uint32_t batch;           /* independent instances per handle (>= 1) */
+  uint64_t seed;            /* sampler seed for keys and encryption randomness */
+} abc_params;
+
+/* --- context: replaces SealCiphertextFactory::setupSealContext (src/runtime/SealCiphertextFactory.cpp:72-100)
+ * up to, not including, key generation. */
+abc_status abc_ctx_create(const abc_params *params, abc_ctx **out);
+void abc_ctx_destroy(abc_ctx *ctx);
+const char *abc_last_error(const abc_ctx *ctx); /* ctx may be NULL: error of the failed abc_ctx_create */
+abc_status abc_sync(abc_ctx *ctx);
+
+/* parameter queries (SealCiphertextFactory::getCiphertextSlotSize, include/ast_opt/runtime/SealCiphertextFactory.h:90) */
+uint32_t abc_poly_degree(const abc_ctx *ctx);
+uint32_t abc_n_primes(const abc_ctx *ctx);        /* k */
+uint32_t abc_n_limbs(const abc_ctx *ctx);         /* L = k-1 */
+uint32_t abc_batch(const abc_ctx *ctx);
+uint64_t abc_plain_modulus(const abc_ctx *ctx);
+abc_status abc_get_primes(const abc_ctx *ctx, uint64_t *out_k);
+/* auxiliary BEHZ bases chosen by SEAL's rule: out = [m_sk, gamma, B_0..B_{nB-1}]; returns nB+2 via *count */
+abc_status abc_get_aux_primes(const abc_ctx *ctx, uint64_t *out, uint32_t *count);
+
+/* --- keys: replaces KeyGenerator usage at src/runtime/SealCiphertextFactory.cpp:89-93
+ * (secret key, public key, relinearisation key, the default Galois key set). Runs on the device. */
+abc_status abc_keygen(abc_ctx *ctx);
+enum { ABC_KEY_SECRET = 0, ABC_KEY_PUBLIC = 1, ABC_KEY_RELIN = 2, ABC_KEY_GALOIS = 3 };
+/* words: secret k*N, public 2*k*N, relin/galois L*2*k*N (layout [J][component][limb][N], NTT form) */
+size_t abc_key_words(const abc_ctx *ctx, int kind);
+abc_status abc_key_export(abc_ctx *ctx, int kind, uint32_t galois_elt, uint64_t *host, size_t words);
+abc_status abc_key_import(abc_ctx *ctx, int kind, uint32_t galois_elt, const uint64_t *host, size_t words);
+int abc_has_galois_key(const abc_ctx *ctx, uint32_t galois_elt);
+
+/* --- ciphertext handles (SealCiphertext ctor/copy/clone: src/runtime/SealCiphertext.cpp:10-34,71-78) */
+abc_status abc_ct_alloc(abc_ctx *ctx, abc_ct **out);            /* uninitialised size-2 ciphertexts */
+void abc_ct_free(abc_ct *ct);                                   /* stream-ordered; safe right after enqueue */
+abc_status abc_ct_clone(abc_ctx *ctx, const abc_ct *src, abc_ct **out);
+size_t abc_ct_words(const abc_ctx *ctx);                        /* batch*2*L*N */
+abc_status abc_ct_export(abc_ctx *ctx, const abc_ct *ct, uint64_t *host, size_t words);
+abc_status abc_ct_import(abc_ctx *ctx, abc_ct *ct, const uint64_t *host, size_t words);
+
+/* --- encode+encrypt / decrypt+decode
+ * replaces createCiphertext (src/runtime/SealCiphertextFactory.cpp:9-24: expandVector pad-with-last :102-115,
+ * BatchEncoder::encode :127-132, Encryptor::encrypt :12) and decryptCiphertext (:146-152).
+ * slots: n values per instance (1 <= n <= N); instance b reads slots[b*n .. b*n+n) unless `broadcast`,
+ * in which case all instances read slots[0..n).  Values are padded to N with the last one. */
+abc_status abc_encode_encrypt(abc_ctx *ctx, const int64_t *slots, size_t n, int broadcast, abc_ct **out);
+abc_status abc_decrypt_decode(abc_ctx *ctx, const abc_ct *ct, int64_t *out_slots /* batch*N */);
+/* encryption randomness counter: instance b of the next encryption uses nonce*batch + b */
+abc_status abc_set_encrypt_nonce(abc_ctx *ctx, uint64_t nonce);
+
+/* --- ciphertext-ciphertext ops.  dst may alias a (the *Inplace variants of the reference).
+ * add/sub: Evaluator::add/sub          (src/runtime/SealCiphertext.cpp:90-100,113-119)
+ * negate:  Evaluator::negate            (:157,193)
+ * mul_relin: multiply + relinearize_inplace (:102-107,121-124)
+ * rotate_rows: Evaluator::rotate_rows   (:52-61); |steps| >= N/2 is an error; NAF path when no direct key */
+abc_status abc_add(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, const abc_ct *b);
+abc_status abc_sub(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, const abc_ct *b);
+abc_status abc_negate(abc_ctx *ctx, abc_ct *dst, const abc_ct *a);
+abc_status abc_mul_relin(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, const abc_ct *b);
+abc_status abc_rotate_rows(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, int steps);
+
+/* --- ciphertext-plaintext ops (src/runtime/SealCiphertext.cpp:130-202). slots/n/broadcast as above.
+ * The reference's all-(-1) negate fast path for multiplyPlain lives in the C++ wrapper. */
+abc_status abc_add_plain(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, const int64_t *slots, size_t n, int broadcast);
+abc_status abc_sub_plain(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, const int64_t *slots, size_t n, int broadcast);
+abc_status abc_mul_plain(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, const int64_t *slots, size_t n, int broadcast);
+
+/* --- device-resident plaintext operands (so a benchmark loop need not re-upload slots) */
+typedef struct abc_pt abc_pt;
+abc_status abc_pt_encode(abc_ctx *ctx, const int64_t *slots, size_t n, int broadcast, abc_pt **out);
+void abc_pt_free(abc_pt *pt);
+abc_status abc_add_plain_pt(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, const abc_pt *pt);
+abc_status abc_sub_plain_pt(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, const abc_pt *pt);
+abc_status abc_mul_plain_pt(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, const abc_pt *pt);
+abc_status abc_encrypt_pt(abc_ctx *ctx, const abc_pt *pt, abc_ct **out);
+
+/* --- kernel-level probes used by the parity tests and the profiler (one limb-row = N words)
+ * mod_index: 0..k-1 key-level primes, k..k+nbsk-1 the Bsk primes (B..., m_sk), k+nbsk the plain modulus t */
+abc_status abc_probe_ntt(abc_ctx *ctx, int inverse, uint32_t mod_index, uint64_t *host_rows, size_t n_rows);
+/* BEHZ multiply without relinearisation: out3 gets batch*3*L*N words */
+abc_status abc_probe_multiply(abc_ctx *ctx, const abc_ct *a, const abc_ct *b, uint64_t *host_out3, size_t words);
+
+/* --- timing on the context's stream (CUDA events; torch.cuda.Event cannot see this stream) */
+abc_status abc_timer_start(abc_ctx *ctx);
+abc_status abc_timer_stop(abc_ctx *ctx, float *ms);            /* synchronises */
+/* writes `bytes` of scratch to evict L2 between timed iterations */
+abc_status abc_flush_l2(abc_ctx *ctx, size_t bytes);
+/* kernels launched by this context so far */
+uint64_t abc_launch_count(const abc_ctx *ctx);
+/* per-kernel-family device time: enable, then read {name, launches, total ms} rows as a JSON string */
+abc_status abc_profile_enable(abc_ctx *ctx, int on);
+const char *abc_profile_json(abc_ctx *ctx);
+
+/* integer-pipe issue-rate microbenchmark (IMAD / IADD3-class ops per second, whole GPU) */
+abc_status abc_measure_int_peak(abc_ctx *ctx, double *imad_per_s, double *iadd_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
