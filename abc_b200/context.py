@@ -195,6 +195,11 @@ class CudaCiphertextFactory:
         self._ck(self._lib.abc_measure_int_peak(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def measure_butterfly_peak(self):
+        a = C.c_double()
+        self._ck(self._lib.abc_measure_butterfly_peak(self._h, C.byref(a)))
+        return a.value
+
 
 class CudaPlaintext:
     def __init__(self, factory, handle):

@@ -132,6 +132,8 @@ const char *abc_profile_json(abc_ctx *ctx);
 
 /* integer-pipe issue-rate microbenchmark (IMAD / IADD3-class ops per second, whole GPU) */
 abc_status abc_measure_int_peak(abc_ctx *ctx, double *imad_per_s, double *iadd_per_s);
+/* dependent-chain-free 64-bit Harvey/Shoup butterflies per second, whole GPU: the unit NTT rooflines are quoted in */
+abc_status abc_measure_butterfly_peak(abc_ctx *ctx, double *butterflies_per_s);
 
 #ifdef __cplusplus
 }

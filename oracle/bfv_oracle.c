@@ -6,6 +6,7 @@
  * site that reaches it.  Everything is canonical-residue in/out; lazy ranges are internal.
  */
 #include "bfv_oracle.h"
+#include <malloc.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -38,6 +39,34 @@ static inline u64 mul_shoup_lazy(u64 x, u64 w, u64 ws, u64 q) {
   u64 h = (u64)(((u128)x * ws) >> 64);
   return x * w - h * q;
 }
+
+/* SEAL Modulus + barrett_reduce_128 / barrett_reduce_64 (util/uintarithsmallmod.h): const_ratio = floor(2^128/q) */
+typedef struct { u64 q, mu_hi, mu_lo; } bmod;
+static bmod bmod_init(u64 q) {
+  bmod m; m.q = q;
+  u128 all = ~(u128)0, r = all / q;
+  if (all % q == q - 1) r += 1;
+  m.mu_hi = (u64)(r >> 64); m.mu_lo = (u64)r;
+  return m;
+}
+static inline u64 bred128(u128 x, const bmod *m) {
+  u64 lo = (u64)x, hi = (u64)(x >> 64);
+  u64 carry = (u64)(((u128)lo * m->mu_lo) >> 64);
+  u128 t2 = (u128)lo * m->mu_hi;
+  u64 t1 = (u64)t2 + carry;
+  u64 t3 = (u64)(t2 >> 64) + (t1 < (u64)t2);
+  u128 t4 = (u128)hi * m->mu_lo;
+  u64 t5 = t1 + (u64)t4;
+  u64 c2 = (u64)(t4 >> 64) + (t5 < t1);
+  u64 qhat = hi * m->mu_hi + t3 + c2;
+  u64 r = lo - qhat * m->q;
+  return r >= m->q ? r - m->q : r;
+}
+static inline u64 bred64(u64 x, const bmod *m) {
+  u64 r = x - (u64)(((u128)x * m->mu_hi) >> 64) * m->q;
+  return r >= m->q ? r - m->q : r;
+}
+static inline u64 bmul(u64 a, u64 b, const bmod *m) { return bred128((u128)a * b, m); }
 
 /* deterministic Miller-Rabin for 64-bit */
 static int is_prime64(u64 n) {
@@ -154,6 +183,7 @@ static void ntt_inv(const ntt_tab *T, u64 *x, size_t N) {
 struct obfv_ctx {
   size_t N; int logN; size_t k, L; u64 t;
   u64 q[MAXK]; ntt_tab nq[MAXK]; ntt_tab nt;
+  bmod bq[MAXK], bbsk[MAXK], bt, bgamma;                  /* Barrett forms of the moduli */
   u32 *index_map;                                   /* BatchEncoder matrix_reps_index_map */
   /* plain scaling (SEAL ContextData: coeff_div_plain_modulus, coeff_modulus_mod_plain_modulus) */
   u64 q_mod_t, delta_mod_q[MAXK], t_half_up;
@@ -218,10 +248,14 @@ obfv_ctx *obfv_create(size_t N, const u64 *primes, size_t k, u64 t) {
   for (size_t i = 0; i < k; i++) if (!is_prime64(primes[i]) || (primes[i] - 1) % (2 * N)) return NULL;
   if (!is_prime64(t) || (t - 1) % (2 * N)) return NULL;
 
+  /* keep large scratch buffers on the per-thread heaps: mmap/munmap per op serialises threads on the mm lock */
+  mallopt(M_MMAP_THRESHOLD, 1 << 30);
+  mallopt(M_TRIM_THRESHOLD, 1 << 30);
   obfv_ctx *c = calloc(1, sizeof *c);
   c->N = N; c->logN = logN; c->k = k; c->L = k - 1; c->t = t;
   const size_t L = c->L;
-  for (size_t i = 0; i < k; i++) { c->q[i] = primes[i]; ntt_tab_init(&c->nq[i], primes[i], N, logN); }
+  for (size_t i = 0; i < k; i++) { c->q[i] = primes[i]; c->bq[i] = bmod_init(primes[i]); ntt_tab_init(&c->nq[i], primes[i], N, logN); }
+  c->bt = bmod_init(t);
   ntt_tab_init(&c->nt, t, N, logN);
 
   /* BatchEncoder::populate_matrix_reps_index_map (batchencoder.cpp) */
@@ -255,7 +289,8 @@ obfv_ctx *obfv_create(size_t N, const u64 *primes, size_t k, u64 t) {
   c->nB = nB; c->nbsk = nB + 1; c->msk = aux[0]; c->gamma = aux[1];
   for (size_t i = 0; i < nB; i++) { c->B[i] = aux[2 + i]; c->bsk[i] = aux[2 + i]; }
   c->bsk[nB] = c->msk;
-  for (size_t j = 0; j < c->nbsk; j++) ntt_tab_init(&c->nbskt[j], c->bsk[j], N, logN);
+  for (size_t j = 0; j < c->nbsk; j++) { c->bbsk[j] = bmod_init(c->bsk[j]); ntt_tab_init(&c->nbskt[j], c->bsk[j], N, logN); }
+  c->bgamma = bmod_init(c->gamma);
   c->mtilde = (u64)1 << 32;
   for (size_t i = 0; i < L; i++) {
     u64 qi = c->q[i];
@@ -523,7 +558,7 @@ void obfv_encrypt(const obfv_ctx *c, const u64 *plain, u64 nonce, u64 *ct) {
       const u64 q = c->q[i];
       u64 *d = tmp + (pidx * k + i) * N;
       const u64 *pkp = c->pk + (pidx * k + i) * N;
-      for (size_t j = 0; j < N; j++) d[j] = mulmod(u[i * N + j], pkp[j], q);
+      for (size_t j = 0; j < N; j++) d[j] = bmul(u[i * N + j], pkp[j], &c->bq[i]);
       ntt_inv(&c->nq[i], d, N);
       for (size_t j = 0; j < N; j++) d[j] = addmod(d[j], small_to_mod(sample_cbd(he, j), q), q);
     }
@@ -534,8 +569,8 @@ void obfv_encrypt(const obfv_ctx *c, const u64 *plain, u64 nonce, u64 *ct) {
       const u64 q = c->q[i];
       u64 *d = tmp + (pidx * k + i) * N, *o = ct + (pidx * L + i) * N;
       for (size_t j = 0; j < N; j++) {
-        u64 tl = submod(last[j] % q, c->p_half_mod_q[i], q);
-        o[j] = mulmod(submod(d[j], tl, q), c->inv_p_mod_q[i], q);
+        u64 tl = submod(bred64(last[j], &c->bq[i]), c->p_half_mod_q[i], q);
+        o[j] = bmul(submod(d[j], tl, q), c->inv_p_mod_q[i], &c->bq[i]);
       }
     }
   }
@@ -545,10 +580,11 @@ void obfv_encrypt(const obfv_ctx *c, const u64 *plain, u64 nonce, u64 *ct) {
 
 /* FastBConv (BaseConverter::fast_convert_array) on one coefficient:
  * out = sum_i z_i * punct_i mod m, with z_i = x_i * inv_punct_i mod base_i supplied by the caller */
-static inline u64 dot_mod(const u64 *z, const u64 *punct, size_t n, u64 m) {
+static inline u64 dot_mod(const u64 *z, const u64 *punct, size_t n, const bmod *m) {
+  /* SEAL dot_product_mod: lazy 128-bit accumulation (products < 2^122, n < 64), one Barrett reduction */
   u128 acc = 0;
-  for (size_t i = 0; i < n; i++) acc += (u128)(((u128)z[i] * punct[i]) % m);
-  return (u64)(acc % m);
+  for (size_t i = 0; i < n; i++) acc += (u128)z[i] * punct[i];
+  return bred128(acc, m);
 }
 
 /* ------------------------------------------------------------------ decryption (decryptor.cpp, rns.cpp)
@@ -564,8 +600,8 @@ void obfv_decrypt(const obfv_ctx *c, const u64 *ct, size_t size, u64 *plain) {
     for (size_t pidx = 1; pidx < size; pidx++) {
       memcpy(tmp, ct + (pidx * L + i) * N, N * 8);
       ntt_fwd(&c->nq[i], tmp, N);
-      for (size_t j = 0; j < N; j++) x[i * N + j] = addmod(x[i * N + j], mulmod(tmp[j], spow[j], q), q);
-      for (size_t j = 0; j < N; j++) spow[j] = mulmod(spow[j], c->sk[i * N + j], q);
+      for (size_t j = 0; j < N; j++) x[i * N + j] = addmod(x[i * N + j], bmul(tmp[j], spow[j], &c->bq[i]), q);
+      if (pidx + 1 < size) for (size_t j = 0; j < N; j++) spow[j] = bmul(spow[j], c->sk[i * N + j], &c->bq[i]);
     }
     ntt_inv(&c->nq[i], x + i * N, N);
     for (size_t j = 0; j < N; j++) x[i * N + j] = addmod(x[i * N + j], ct[i * N + j], q);
@@ -575,13 +611,13 @@ void obfv_decrypt(const obfv_ctx *c, const u64 *ct, size_t size, u64 *plain) {
   u64 z[MAXK];
   for (size_t j = 0; j < N; j++) {
     for (size_t i = 0; i < L; i++)
-      z[i] = mulmod(mulmod(x[i * N + j], c->tgamma_mod_q[i], c->q[i]), c->inv_punct_q[i], c->q[i]);
-    u64 yt = mulmod(dot_mod(z, c->punct_q_mod_t, L, t), c->neg_inv_q_mod_t, t);
-    u64 yg = mulmod(dot_mod(z, c->punct_q_mod_gamma, L, g), c->neg_inv_q_mod_gamma, g);
+      z[i] = bmul(bmul(x[i * N + j], c->tgamma_mod_q[i], &c->bq[i]), c->inv_punct_q[i], &c->bq[i]);
+    u64 yt = bmul(dot_mod(z, c->punct_q_mod_t, L, &c->bt), c->neg_inv_q_mod_t, &c->bt);
+    u64 yg = bmul(dot_mod(z, c->punct_q_mod_gamma, L, &c->bgamma), c->neg_inv_q_mod_gamma, &c->bgamma);
     u64 d;
-    if (yg > g_half) d = addmod(yt, (g - yg) % t, t);
-    else d = submod(yt, yg % t, t);
-    plain[j] = d ? mulmod(d, c->inv_gamma_mod_t, t) : 0;
+    if (yg > g_half) d = addmod(yt, bred64(g - yg, &c->bt), t);
+    else d = submod(yt, bred64(yg, &c->bt), t);
+    plain[j] = d ? bmul(d, c->inv_gamma_mod_t, &c->bt) : 0;
   }
   free(x); free(tmp); free(spow);
 }
@@ -627,7 +663,7 @@ void obfv_multiply_plain(const obfv_ctx *c, const u64 *a, const u64 *plain, u64 
     for (size_t p = 0; p < 2; p++) {
       memcpy(tmp, a + (p * L + i) * N, N * 8);
       ntt_fwd(&c->nq[i], tmp, N);
-      for (size_t j = 0; j < N; j++) tmp[j] = mulmod(tmp[j], pl[j], q);
+      for (size_t j = 0; j < N; j++) tmp[j] = bmul(tmp[j], pl[j], &c->bq[i]);
       ntt_inv(&c->nq[i], tmp, N);
       memcpy(out + (p * L + i) * N, tmp, N * 8);
     }
@@ -643,15 +679,17 @@ void obfv_behz_lift(const obfv_ctx *c, const u64 *x, u64 *out) {
   u64 z[MAXK];
   for (size_t j = 0; j < N; j++) {
     for (size_t i = 0; i < L; i++)
-      z[i] = mulmod(mulmod(x[i * N + j], c->mtilde_mod_q[i], c->q[i]), c->inv_punct_q[i], c->q[i]);
-    u64 xm = dot_mod(z, c->punct_q_mod_mtilde, L, mt);
+      z[i] = bmul(bmul(x[i * N + j], c->mtilde_mod_q[i], &c->bq[i]), c->inv_punct_q[i], &c->bq[i]);
+    u64 xm = 0;
+    for (size_t i = 0; i < L; i++) xm += z[i] * c->punct_q_mod_mtilde[i];
+    xm &= mt - 1;
     u64 r = (xm * c->neg_inv_q_mod_mtilde) & (mt - 1);
     for (size_t b = 0; b < nb; b++) {
       const u64 pm = c->bsk[b];
-      u64 xb = dot_mod(z, c->punct_q_mod_bsk[b], L, pm);
+      u64 xb = dot_mod(z, c->punct_q_mod_bsk[b], L, &c->bbsk[b]);
       u64 rc = r >= mt_half ? r + (pm - mt) : r;
-      u64 v = (u64)(((u128)rc * c->q_mod_bsk[b] + xb) % pm);
-      out[b * N + j] = mulmod(v, c->inv_mtilde_mod_bsk[b], pm);
+      u64 v = bred128((u128)rc * c->q_mod_bsk[b] + xb, &c->bbsk[b]);
+      out[b * N + j] = bmul(v, c->inv_mtilde_mod_bsk[b], &c->bbsk[b]);
     }
   }
 }
@@ -662,21 +700,21 @@ void obfv_behz_scale(const obfv_ctx *c, const u64 *in_q, const u64 *in_bsk, u64 
   u64 z[MAXK], y[MAXK], zb[MAXK];
   for (size_t j = 0; j < N; j++) {
     for (size_t i = 0; i < L; i++)
-      z[i] = mulmod(mulmod(in_q[i * N + j], t % c->q[i], c->q[i]), c->inv_punct_q[i], c->q[i]);
+      z[i] = bmul(bmul(in_q[i * N + j], t % c->q[i], &c->bq[i]), c->inv_punct_q[i], &c->bq[i]);
     for (size_t b = 0; b < nb; b++) {
       const u64 pm = c->bsk[b];
-      u64 conv = dot_mod(z, c->punct_q_mod_bsk[b], L, pm);
-      u64 xb = mulmod(in_bsk[b * N + j], t % pm, pm);
-      y[b] = mulmod(submod(xb, conv, pm), c->inv_q_mod_bsk[b], pm);
+      u64 conv = dot_mod(z, c->punct_q_mod_bsk[b], L, &c->bbsk[b]);
+      u64 xb = bmul(in_bsk[b * N + j], t, &c->bbsk[b]);
+      y[b] = bmul(submod(xb, conv, pm), c->inv_q_mod_bsk[b], &c->bbsk[b]);
     }
-    for (size_t b = 0; b < nB; b++) zb[b] = mulmod(y[b], c->inv_punct_B[b], c->B[b]);
-    u64 conv_sk = dot_mod(zb, c->punct_B_mod_msk, nB, msk);
-    u64 alpha = mulmod(submod(conv_sk, y[nB], msk), c->inv_B_mod_msk, msk);
+    for (size_t b = 0; b < nB; b++) zb[b] = bmul(y[b], c->inv_punct_B[b], &c->bbsk[b]);
+    u64 conv_sk = dot_mod(zb, c->punct_B_mod_msk, nB, &c->bbsk[nB]);
+    u64 alpha = bmul(submod(conv_sk, y[nB], msk), c->inv_B_mod_msk, &c->bbsk[nB]);
     for (size_t i = 0; i < L; i++) {
       const u64 q = c->q[i];
-      u64 conv = dot_mod(zb, c->punct_B_mod_q[i], nB, q);
-      if (alpha > msk_half) out[i * N + j] = addmod(conv, mulmod((msk - alpha) % q, c->B_mod_q[i], q), q);
-      else out[i * N + j] = submod(conv, mulmod(alpha % q, c->B_mod_q[i], q), q);
+      u64 conv = dot_mod(zb, c->punct_B_mod_q[i], nB, &c->bq[i]);
+      if (alpha > msk_half) out[i * N + j] = addmod(conv, bmul(bred64(msk - alpha, &c->bq[i]), c->B_mod_q[i], &c->bq[i]), q);
+      else out[i * N + j] = submod(conv, bmul(bred64(alpha, &c->bq[i]), c->B_mod_q[i], &c->bq[i]), q);
     }
   }
 }
@@ -695,14 +733,14 @@ void obfv_multiply(const obfv_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
     for (size_t j = 0; j < nb; j++) ntt_fwd(&c->nbskt[j], d + (L + j) * N, N);
   }
   for (size_t w = 0; w < W; w++) {
-    const u64 m = w < L ? c->q[w] : c->bsk[w - L];
+    const bmod *bm = w < L ? &c->bq[w] : &c->bbsk[w - L];
     const u64 *a0 = in + (0 * W + w) * N, *a1 = in + (1 * W + w) * N;
     const u64 *b0 = in + (2 * W + w) * N, *b1 = in + (3 * W + w) * N;
     u64 *d0 = prod + (0 * W + w) * N, *d1 = prod + (1 * W + w) * N, *d2 = prod + (2 * W + w) * N;
     for (size_t j = 0; j < N; j++) {
-      d0[j] = mulmod(a0[j], b0[j], m);
-      d1[j] = addmod(mulmod(a0[j], b1[j], m), mulmod(a1[j], b0[j], m), m);
-      d2[j] = mulmod(a1[j], b1[j], m);
+      d0[j] = bmul(a0[j], b0[j], bm);
+      d1[j] = bred128((u128)a0[j] * b1[j] + (u128)a1[j] * b0[j], bm);
+      d2[j] = bmul(a1[j], b1[j], bm);
     }
     const ntt_tab *T = w < L ? &c->nq[w] : &c->nbskt[w - L];
     ntt_inv(T, d0, N); ntt_inv(T, d1, N); ntt_inv(T, d2, N);
@@ -720,12 +758,13 @@ void obfv_switch_key(const obfv_ctx *c, u64 *ct, const u64 *target, const u64 *k
   for (size_t I = 0; I < k; I++) { /* I == L is the special prime */
     const u64 q = c->q[I];
     for (size_t J = 0; J < L; J++) {
-      for (size_t j = 0; j < N; j++) tn[j] = target[J * N + j] % q;
+      if (c->q[J] <= q) memcpy(tn, target + J * N, N * 8);
+      else for (size_t j = 0; j < N; j++) tn[j] = bred64(target[J * N + j], &c->bq[I]);
       ntt_fwd(&c->nq[I], tn, N);
       for (size_t comp = 0; comp < 2; comp++) {
         const u64 *kk = key + ((J * 2 + comp) * k + I) * N;
         u64 *ac = acc + (comp * k + I) * N;
-        for (size_t j = 0; j < N; j++) ac[j] = addmod(ac[j], mulmod(tn[j], kk[j], q), q);
+        for (size_t j = 0; j < N; j++) ac[j] = addmod(ac[j], bmul(tn[j], kk[j], &c->bq[I]), q);
       }
     }
   }
@@ -738,8 +777,8 @@ void obfv_switch_key(const obfv_ctx *c, u64 *ct, const u64 *target, const u64 *k
       u64 *ai = acc + (comp * k + i) * N, *o = ct + (comp * L + i) * N;
       ntt_inv(&c->nq[i], ai, N);
       for (size_t j = 0; j < N; j++) {
-        u64 tl = submod(last[j] % q, c->p_half_mod_q[i], q);
-        o[j] = addmod(o[j], mulmod(submod(ai[j], tl, q), c->inv_p_mod_q[i], q), q);
+        u64 tl = submod(bred64(last[j], &c->bq[i]), c->p_half_mod_q[i], q);
+        o[j] = addmod(o[j], bmul(submod(ai[j], tl, q), c->inv_p_mod_q[i], &c->bq[i]), q);
       }
     }
   }
