@@ -61,6 +61,7 @@ SYMBOLS = {
     "abc_encrypt_pt": (i32, [vp, vp, vpp]),
     "abc_probe_ntt": (i32, [vp, i32, u32, vp, sz]),
     "abc_probe_multiply": (i32, [vp, vp, vp, vp, sz]),
+    "abc_bench_ntt": (i32, [vp, i32, u32, sz, i32, f32p]),
     "abc_timer_start": (i32, [vp]),
     "abc_timer_stop": (i32, [vp, f32p]),
     "abc_flush_l2": (i32, [vp, sz]),

@@ -169,6 +169,11 @@ class CudaCiphertextFactory:
         self._ck(self._lib.abc_probe_multiply(self._h, a._h, b._h, out.ctypes.data, out.size))
         return out
 
+    def bench_ntt(self, mod_index, n_rows, iters=10, inverse=False):
+        ms = C.c_float()
+        self._ck(self._lib.abc_bench_ntt(self._h, int(inverse), mod_index, n_rows, iters, C.byref(ms)))
+        return ms.value
+
     def timer_start(self):
         self._ck(self._lib.abc_timer_start(self._h))
 

@@ -94,7 +94,7 @@ __device__ __forceinline__ int sample_cbd(u64 h, u64 idx) {
 }
 
 template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST>
-__global__ void __launch_bounds__(NttDims<LOGN>::T) k_limb(LimbJob job, const ModInfo *__restrict__ mods,
+__global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(LimbJob job, const ModInfo *__restrict__ mods,
                                                            const DevConst *__restrict__ C) {
   typedef NttDims<LOGN> D;
   extern __shared__ __align__(16) u64 sm[];

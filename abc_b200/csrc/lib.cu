@@ -847,6 +847,30 @@ abc_status abc_probe_ntt(abc_ctx *c, int inverse, uint32_t mod_index, uint64_t *
   sfree(c, d); sfree(c, rm);
   return ABC_OK;
 }
+abc_status abc_bench_ntt(abc_ctx *c, int inverse, uint32_t mod_index, size_t n_rows, int iters, float *ms) {
+  CK(cudaSetDevice(c->device));
+  if ((int)mod_index > c->idx_t || n_rows == 0) return fail(c, ABC_ERR_PARAM, "invalid arguments");
+  const int N = c->N;
+  const int W = n_rows > 32768 ? 32768 : (int)n_rows, By = (int)((n_rows + W - 1) / W);
+  u64 *d = nullptr; int *rm = nullptr;
+  TRY(salloc(c, &d, (size_t)W * By * N));
+  CK(cudaMemsetAsync(d, 0, (size_t)W * By * N * 8, c->stream));
+  CK(cudaMallocAsync((void **)&rm, W * sizeof(int), c->stream));
+  std::vector<int> v(W, (int)mod_index);
+  CK(cudaMemcpyAsync(rm, v.data(), W * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  LimbJob j = blank_job();
+  j.dst = d; j.src = d; j.rowmod = rm; j.dst_is = j.src_is = (long long)W * N;
+  for (int it = -1; it < iters; ++it) {
+    if (it == 0) CK(cudaEventRecord(c->ev0, c->stream));
+    if (inverse) TRY((launch_limb<PRE_LOAD, false, false, true, POST_STORE>(c, j, W, By, "bench_intt")));
+    else TRY((launch_limb<PRE_LOAD, true, false, false, POST_STORE>(c, j, W, By, "bench_ntt")));
+  }
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaEventSynchronize(c->ev1));
+  CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+  sfree(c, d); sfree(c, rm);
+  return ABC_OK;
+}
 abc_status abc_probe_multiply(abc_ctx *c, const abc_ct *a, const abc_ct *b, uint64_t *host_out3, size_t words) {
   if (!valid_ct(c, a) || !valid_ct(c, b)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
   const size_t need = (size_t)c->B * 3 * c->L * c->N;

@@ -28,7 +28,10 @@ template <> struct NttPlan<14> { static constexpr int R0 = 3, R1 = 3, R2 = 3, NS
 
 template <int LOGN> struct NttDims {
   static constexpr int N = 1 << LOGN;
-  static constexpr int T = (N / 8 < 1024) ? N / 8 : 1024;
+  // <= 8192: 512 threads x 2 passes so that two CTAs share an SM (64 regs/thread, 64 KiB smem each) and
+  // one CTA's barriers / global-memory phases overlap the other's butterflies.
+  static constexpr int T = (LOGN >= 14) ? 1024 : ((N / 8 < 512) ? N / 8 : 512);
+  static constexpr int MINB = (LOGN >= 14) ? 1 : 2;
   static constexpr int IT = N / 8 / T;
   static constexpr size_t SMEM = (size_t)N * 8;
 };

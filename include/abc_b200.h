@@ -118,6 +118,8 @@ abc_status abc_encrypt_pt(abc_ctx *ctx, const abc_pt *pt, abc_ct **out);
 abc_status abc_probe_ntt(abc_ctx *ctx, int inverse, uint32_t mod_index, uint64_t *host_rows, size_t n_rows);
 /* BEHZ multiply without relinearisation: out3 gets batch*3*L*N words */
 abc_status abc_probe_multiply(abc_ctx *ctx, const abc_ct *a, const abc_ct *b, uint64_t *host_out3, size_t words);
+/* device-time of `iters` launches of the limb NTT kernel over n_rows resident rows (microbenchmark) */
+abc_status abc_bench_ntt(abc_ctx *ctx, int inverse, uint32_t mod_index, size_t n_rows, int iters, float *ms);
 
 /* --- timing on the context's stream (CUDA events; torch.cuda.Event cannot see this stream) */
 abc_status abc_timer_start(abc_ctx *ctx);
