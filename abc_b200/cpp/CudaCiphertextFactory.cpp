@@ -1,0 +1,123 @@
+#include "CudaCiphertextFactory.h"
+
+#include <sstream>
+#include <stdexcept>
+
+#include "CudaCiphertext.h"
+#include "abc_b200.h"
+#include "ast_opt/runtime/Cleartext.h"
+
+void CudaCiphertextFactory::check(int status) const {
+  if (status != ABC_OK) throw std::runtime_error(abc_last_error(ctx));
+}
+
+void CudaCiphertextFactory::setup(int device, unsigned int batch, uint64_t seed) {
+  // SealCiphertextFactory::setupSealContext (src/runtime/SealCiphertextFactory.cpp:72-100): BFVDefault(N),
+  // Batching(N, 20), then secret/public/Galois/relin keys.  n_primes = 0 and plain_modulus = 0 select the
+  // same SEAL defaults inside the library.
+  abc_params p{};
+  p.poly_degree = ciphertextSlotSize;
+  p.device = device;
+  p.batch = batch;
+  p.seed = seed;
+  if (abc_ctx_create(&p, &ctx) != ABC_OK) {
+    throw std::runtime_error(std::string("CudaCiphertextFactory: ") + abc_last_error(nullptr));
+  }
+  check(abc_keygen(ctx));
+}
+
+CudaCiphertextFactory::CudaCiphertextFactory() { setup(0, 1, 4673838); }
+
+CudaCiphertextFactory::CudaCiphertextFactory(unsigned int numElementsPerCiphertextSlot)
+    : ciphertextSlotSize(numElementsPerCiphertextSlot) {
+  setup(0, 1, 4673838);
+}
+
+CudaCiphertextFactory::CudaCiphertextFactory(unsigned int numElementsPerCiphertextSlot, int device,
+                                             unsigned int batch, uint64_t seed)
+    : ciphertextSlotSize(numElementsPerCiphertextSlot) {
+  setup(device, batch, seed);
+}
+
+CudaCiphertextFactory::~CudaCiphertextFactory() { abc_ctx_destroy(ctx); }
+
+unsigned int CudaCiphertextFactory::getCiphertextSlotSize() const { return ciphertextSlotSize; }
+unsigned int CudaCiphertextFactory::getBatchSize() const { return abc_batch(ctx); }
+void CudaCiphertextFactory::synchronize() const { check(abc_sync(ctx)); }
+uint64_t CudaCiphertextFactory::launchCount() const { return abc_launch_count(ctx); }
+
+std::unique_ptr<AbstractCiphertext> CudaCiphertextFactory::createCiphertext(const std::vector<int64_t> &data) const {
+  // expandVector + BatchEncoder::encode + Encryptor::encrypt, all on the device; an empty vector is an
+  // error here (the reference calls .back() on it, SealCiphertextFactory.cpp:112).
+  abc_ct *h = nullptr;
+  check(abc_encode_encrypt(ctx, data.data(), data.size(), /*broadcast=*/1, &h));
+  return std::make_unique<CudaCiphertext>(*this, h);
+}
+
+std::unique_ptr<AbstractCiphertext> CudaCiphertextFactory::createCiphertext(const std::vector<int> &data) const {
+  std::vector<int64_t> ciphertextData(data.begin(), data.end());
+  return createCiphertext(ciphertextData);
+}
+
+std::unique_ptr<AbstractCiphertext> CudaCiphertextFactory::createCiphertext(int64_t data) const {
+  std::vector<int64_t> values = {data};
+  return createCiphertext(values);
+}
+
+std::unique_ptr<AbstractCiphertext> CudaCiphertextFactory::createCiphertext(
+    std::unique_ptr<AbstractValue> &&abstractValue) const {
+  if (auto castedCleartext = dynamic_cast<Cleartext<int> *>(abstractValue.get())) {
+    auto castedCleartextData = castedCleartext->getData();
+    std::vector<int64_t> data(castedCleartextData.begin(), castedCleartextData.end());
+    return createCiphertext(data);
+  }
+  throw std::runtime_error("Cannot create ciphertext from any other than a Cleartext<int> as used ciphertext factory "
+                           "(CudaCiphertextFactory) uses BFV that only supports integers.");
+}
+
+std::unique_ptr<AbstractCiphertext> CudaCiphertextFactory::createCiphertextBatch(const std::vector<int64_t> &data,
+                                                                                 size_t n) const {
+  if (n == 0 || data.size() != n * getBatchSize()) throw std::runtime_error("createCiphertextBatch: need batch*n values");
+  abc_ct *h = nullptr;
+  check(abc_encode_encrypt(ctx, data.data(), n, /*broadcast=*/0, &h));
+  return std::make_unique<CudaCiphertext>(*this, h);
+}
+
+static CudaCiphertext &castCuda(AbstractCiphertext &abstractCiphertext) {
+  if (auto c = dynamic_cast<CudaCiphertext *>(&abstractCiphertext)) return *c;
+  throw std::runtime_error("Cast of AbstractCiphertext to CudaCiphertext failed!");
+}
+
+void CudaCiphertextFactory::decryptCiphertextBatch(AbstractCiphertext &abstractCiphertext,
+                                                   std::vector<int64_t> &out) const {
+  auto &ctxt = castCuda(abstractCiphertext);
+  out.assign(static_cast<size_t>(getBatchSize()) * ciphertextSlotSize, 0);
+  check(abc_decrypt_decode(ctx, ctxt.getHandle(), out.data()));
+}
+
+void CudaCiphertextFactory::decryptCiphertext(AbstractCiphertext &abstractCiphertext,
+                                              std::vector<int64_t> &ciphertextData) const {
+  // Decryptor::decrypt + BatchEncoder::decode: overwrites the vector with exactly N signed values
+  // (instance 0 when the factory was built with a batch).
+  decryptCiphertextBatch(abstractCiphertext, ciphertextData);
+  ciphertextData.resize(ciphertextSlotSize);
+}
+
+std::vector<uint64_t> CudaCiphertextFactory::exportCoefficients(const AbstractCiphertext &abstractCiphertext) const {
+  auto c = dynamic_cast<const CudaCiphertext *>(&abstractCiphertext);
+  if (!c) throw std::runtime_error("Cast of AbstractCiphertext to CudaCiphertext failed!");
+  std::vector<uint64_t> out(abc_ct_words(ctx));
+  check(abc_ct_export(ctx, c->getHandle(), out.data(), out.size()));
+  return out;
+}
+
+std::string CudaCiphertextFactory::getString(AbstractCiphertext &abstractCiphertext) const {
+  std::vector<int64_t> plainValues;
+  decryptCiphertext(abstractCiphertext, plainValues);
+  std::stringstream ss;
+  ss << "[";
+  for (const auto value : plainValues) ss << " " << value << ", ";
+  ss.seekp(-1, ss.cur);
+  ss << " ]";
+  return ss.str();
+}

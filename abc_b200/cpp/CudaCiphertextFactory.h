@@ -1,0 +1,69 @@
+// CudaCiphertextFactory — B200 drop-in for ABC's SealCiphertextFactory.
+//
+// Implements AbstractCiphertextFactory (/root/reference/include/ast_opt/runtime/AbstractCiphertextFactory.h:19-49)
+// with the same public surface as SealCiphertextFactory (include/ast_opt/runtime/SealCiphertextFactory.h:59-123):
+// same constructor argument (slot count; SEAL's BFVDefault coefficient modulus and Batching(N,20) plain modulus),
+// same pad-with-last / oversize-throws behaviour, same decrypt semantics.  RuntimeVisitor drives it unchanged.
+// All arithmetic runs in libabc_b200.so (include/abc_b200.h); there is no CPU path in this class.
+#ifndef ABC_B200_CPP_CUDACIPHERTEXTFACTORY_H_
+#define ABC_B200_CPP_CUDACIPHERTEXTFACTORY_H_
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "ast_opt/runtime/AbstractCiphertextFactory.h"
+
+struct abc_ctx;
+struct abc_ct;
+class CudaCiphertext;
+
+class CudaCiphertextFactory : public AbstractCiphertextFactory {
+ private:
+  /// The number of slots (= polynomial degree N) of every ciphertext created by this factory.
+  const unsigned int ciphertextSlotSize = 16'384;  // same default as SealCiphertextFactory.h:13
+  /// Device context: parameters, NTT tables, keys, stream.  All factory virtuals are const, so the
+  /// mutable device state lives behind this pointer.
+  abc_ctx *ctx = nullptr;
+
+  void setup(int device, unsigned int batch, uint64_t seed);
+
+ public:
+  CudaCiphertextFactory();
+  /// \param numElementsPerCiphertextSlot slot count N (4096, 8192, 16384 use SEAL's default parameter sets).
+  explicit CudaCiphertextFactory(unsigned int numElementsPerCiphertextSlot);
+  /// Extended constructor: device ordinal, instances per handle (lock-step batch), sampler seed.
+  CudaCiphertextFactory(unsigned int numElementsPerCiphertextSlot, int device, unsigned int batch, uint64_t seed);
+  ~CudaCiphertextFactory();
+
+  CudaCiphertextFactory(const CudaCiphertextFactory &) = delete;  // keys live on one device: not copyable
+  CudaCiphertextFactory &operator=(const CudaCiphertextFactory &) = delete;
+
+  std::unique_ptr<AbstractCiphertext> createCiphertext(const std::vector<int64_t> &data) const override;
+  std::unique_ptr<AbstractCiphertext> createCiphertext(const std::vector<int> &data) const override;
+  std::unique_ptr<AbstractCiphertext> createCiphertext(int64_t data) const override;
+  std::unique_ptr<AbstractCiphertext> createCiphertext(std::unique_ptr<AbstractValue> &&cleartext) const override;
+  void decryptCiphertext(AbstractCiphertext &abstractCiphertext, std::vector<int64_t> &ciphertextData) const override;
+  std::string getString(AbstractCiphertext &abstractCiphertext) const override;
+
+  /// Gets the number of slots of a ciphertext (SealCiphertextFactory::getCiphertextSlotSize).
+  [[nodiscard]] unsigned int getCiphertextSlotSize() const;
+  /// Instances carried by every ciphertext handle (1 unless constructed with a batch).
+  [[nodiscard]] unsigned int getBatchSize() const;
+  /// Batched variants: data holds batch*n slot values (instance-major); out gets batch*N values.
+  std::unique_ptr<AbstractCiphertext> createCiphertextBatch(const std::vector<int64_t> &data, size_t n) const;
+  void decryptCiphertextBatch(AbstractCiphertext &abstractCiphertext, std::vector<int64_t> &out) const;
+  /// Raw coefficients [batch][2][L][N] of a ciphertext (the bit-exactness probe).
+  std::vector<uint64_t> exportCoefficients(const AbstractCiphertext &abstractCiphertext) const;
+  /// Blocks until all enqueued work of this factory has finished.
+  void synchronize() const;
+  /// Kernels launched so far.
+  [[nodiscard]] uint64_t launchCount() const;
+
+  [[nodiscard]] abc_ctx *context() const { return ctx; }
+  /// Throws std::runtime_error(abc_last_error) when status != 0 (the reference's error convention).
+  void check(int status) const;
+};
+
+#endif  // ABC_B200_CPP_CUDACIPHERTEXTFACTORY_H_

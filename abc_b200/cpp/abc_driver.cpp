@@ -1,0 +1,297 @@
+// abc_driver — runs ABC programs through the reference's own Parser / TypeCheckingVisitor / RuntimeVisitor
+// (compiled unchanged from /root/reference/src) with CudaCiphertextFactory as the ciphertext backend.
+//
+//   abc_driver kats            the SEAL-backed cases of test/runtime/RuntimeVisitorTest.cpp and
+//                              test/runtime/SealCiphertextFactoryTest.cpp with the factory swapped (N=4096)
+//   abc_driver programs [N]    the hand-written batched programs of SURVEY.md 8(d) at N (default 8192), secret
+//                              inputs: HammingDistance, L2Distance (n = N/2), BoxBlur, GxKernel (64x64 image),
+//                              checked against plain C++ evaluations of the same functions
+// Prints one line per case and a JSON summary; exit code 1 on any mismatch.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <functional>
+#include <iostream>
+#include <random>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "CudaCiphertext.h"
+#include "CudaCiphertextFactory.h"
+#include "ast_opt/parser/Parser.h"
+#include "ast_opt/runtime/Cleartext.h"
+#include "ast_opt/runtime/RuntimeVisitor.h"
+#include "ast_opt/visitor/TypeCheckingVisitor.h"
+
+namespace {
+int failures = 0, cases = 0;
+
+void report(const std::string &name, bool ok, const std::string &detail = "") {
+  ++cases;
+  if (!ok) ++failures;
+  std::cout << (ok ? "[ ok ] " : "[FAIL] ") << name << (detail.empty() ? "" : "  " + detail) << std::endl;
+}
+
+std::string listOf(const std::vector<int> &v) {
+  std::stringstream ss;
+  ss << "{";
+  for (size_t i = 0; i < v.size(); ++i) ss << (i ? "," : "") << v[i];
+  ss << "}";
+  return ss.str();
+}
+
+struct Var { std::string name; bool secret; };
+
+using Results = std::unordered_map<std::string, std::vector<int64_t>>;
+
+// The flow of test/runtime/RuntimeVisitorTest.cpp:224-262: parse inputs/program/outputs, pre-seed the type
+// checker with the input variables, run, decrypt.
+Results runProgram(CudaCiphertextFactory &factory, const std::string &inputs, const std::string &program,
+                   const std::string &outputs, const std::vector<Var> &inputVars, double *seconds = nullptr) {
+  auto astInput = Parser::parse(inputs);
+  auto astProgram = Parser::parse(program);
+  auto astOutput = Parser::parse(outputs);
+  TypeCheckingVisitor tcv;
+  auto rootScope = std::make_unique<Scope>(*astProgram);
+  for (const auto &v : inputVars) {
+    auto scopedIdentifier = std::make_unique<ScopedIdentifier>(*rootScope, v.name);
+    rootScope->addIdentifier(v.name);
+    tcv.addVariableDatatype(*scopedIdentifier, Datatype(Type::INT, v.secret));
+  }
+  tcv.setRootScope(std::move(rootScope));
+  astProgram->accept(tcv);
+  auto secretTaintedNodesMap = tcv.getSecretTaintedNodes();
+  auto t0 = std::chrono::steady_clock::now();
+  RuntimeVisitor srv(factory, *astInput, secretTaintedNodesMap);
+  srv.executeAst(*astProgram);
+  auto output = srv.getOutput(*astOutput);
+  Results res;
+  for (const auto &[identifier, value] : output) {
+    std::vector<int64_t> plainValues;
+    if (auto ciphertext = dynamic_cast<AbstractCiphertext *>(value.get())) {
+      factory.decryptCiphertext(*ciphertext, plainValues);
+    } else if (auto cleartextInt = dynamic_cast<Cleartext<int> *>(value.get())) {
+      auto d = cleartextInt->getData();
+      plainValues.assign(d.begin(), d.end());
+    } else if (auto cleartextBool = dynamic_cast<Cleartext<bool> *>(value.get())) {
+      auto d = cleartextBool->getData();
+      plainValues.assign(d.begin(), d.end());
+    } else {
+      throw std::runtime_error("Could not determine type of result.");
+    }
+    res[identifier] = plainValues;
+  }
+  if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return res;
+}
+
+bool prefixEquals(const std::vector<int64_t> &got, const std::vector<int64_t> &want) {
+  if (got.size() < want.size()) return false;
+  for (size_t i = 0; i < want.size(); ++i)
+    if (got[i] != want[i]) return false;
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------ kats
+void checkCiphertextData(CudaCiphertextFactory &f, AbstractCiphertext &ct, const std::vector<int64_t> &expected,
+                         const std::string &name) {
+  // SealCiphertextFactoryTest.cpp:22-41: first values as given, every remaining slot = last value, size = N
+  std::vector<int64_t> result;
+  f.decryptCiphertext(ct, result);
+  bool ok = result.size() == f.getCiphertextSlotSize() && prefixEquals(result, expected);
+  for (size_t i = expected.size(); ok && i < result.size(); ++i) ok = result[i] == expected.back();
+  report(name, ok);
+}
+
+void runKats() {
+  CudaCiphertextFactory f(4096);
+  const std::vector<int64_t> data1 = {3, 3, 1, 4, 5, 9}, data2 = {0, 1, 2, 1, 10, 21};
+  const std::vector<int64_t> sum = {3, 4, 3, 5, 15, 30}, diff = {3, 2, -1, 3, -5, -12}, prod = {0, 3, 2, 4, 50, 189};
+  {
+    auto c = f.createCiphertext(data1);
+    checkCiphertextData(f, *c, data1, "factory.createCiphertext");
+    auto c1 = f.createCiphertext(data1), c2 = f.createCiphertext(data2);
+    auto r = c1->add(*c2); checkCiphertextData(f, *r, sum, "factory.add");
+    r = c1->subtract(*c2); checkCiphertextData(f, *r, diff, "factory.sub");
+    r = c1->multiply(*c2); checkCiphertextData(f, *r, prod, "factory.multiply");
+    checkCiphertextData(f, *c1, data1, "factory.operand1 unchanged");
+    checkCiphertextData(f, *c2, data2, "factory.operand2 unchanged");
+    auto a = c1->clone(); a->addInplace(*c2); checkCiphertextData(f, *a, sum, "factory.addInplace");
+    a = c1->clone(); a->subtractInplace(*c2); checkCiphertextData(f, *a, diff, "factory.subInplace");
+    a = c1->clone(); a->multiplyInplace(*c2); checkCiphertextData(f, *a, prod, "factory.multiplyInplace");
+    Cleartext<int> pt(std::vector<int>{0, 1, 2, 1, 10, 21});
+    r = c1->addPlain(pt); checkCiphertextData(f, *r, sum, "factory.addPlain");
+    r = c1->subtractPlain(pt); checkCiphertextData(f, *r, diff, "factory.subPlain");
+    r = c1->multiplyPlain(pt); checkCiphertextData(f, *r, prod, "factory.multiplyPlain");
+    a = c1->clone(); a->addPlainInplace(pt); checkCiphertextData(f, *a, sum, "factory.addPlainInplace");
+    a = c1->clone(); a->subtractPlainInplace(pt); checkCiphertextData(f, *a, diff, "factory.subPlainInplace");
+    a = c1->clone(); a->multiplyPlainInplace(pt); checkCiphertextData(f, *a, prod, "factory.multiplyPlainInplace");
+    Cleartext<int> minusOne(std::vector<int>{-1});
+    r = c1->multiplyPlain(minusOne); checkCiphertextData(f, *r, {-3, -3, -1, -4, -5, -9}, "factory.multiplyPlain(-1) negates");
+    // rotation incl. wrap-around at N/2 (SealCiphertextFactoryTest.cpp:51-140)
+    const std::vector<int64_t> rd = {123456, 3, 1, 4, 5, 9, 5, 2, 1, 5};
+    auto rc = f.createCiphertext(rd);
+    const size_t half = f.getCiphertextSlotSize() / 2;
+    for (int steps : {4, -24}) {
+      auto rot = rc->rotateRows(steps);
+      std::vector<int64_t> dv, full(rd);
+      full.resize(f.getCiphertextSlotSize(), rd.back());
+      f.decryptCiphertext(*rot, dv);
+      bool ok = true;
+      for (size_t row = 0; row < 2; ++row)
+        for (size_t i = 0; i < half; ++i)
+          ok = ok && dv[row * half + i] == full[row * half + ((i + half + steps) % half)];
+      report("factory.rotateRows(" + std::to_string(steps) + ")", ok);
+    }
+    bool threw = false;
+    try { auto big = f.createCiphertext(std::vector<int64_t>(4097, 1)); } catch (std::runtime_error &) { threw = true; }
+    report("factory.createCiphertext(> N values) throws std::runtime_error", threw);
+  }
+  const std::vector<Var> in0 = {{"__input0__", true}}, in01 = {{"__input0__", true}, {"__input1__", true}};
+  {
+    auto r = runProgram(f, "secret int __input0__ = {43, 1, 1, 1, 22, 11, 425, 0, 1, 7};",
+                        "__input0__ = rotate(__input0__, -4);", "y = __input0__;", in0);
+    report("visitor.testRotateNegative", prefixEquals(r["y"], {7, 7, 7, 7, 43, 1, 1, 1, 22, 11, 425, 0, 1, 7}));
+    r = runProgram(f, "secret int __input0__ = {43, 1, 1, 1, 22, 11, 425, 0, 1, 7};",
+                   "__input0__ = rotate(__input0__, 6);", "y = __input0__;", in0);
+    report("visitor.testRotatePositive", prefixEquals(r["y"], {425, 0, 1, 7, 7, 7, 7, 7, 7}));
+    r = runProgram(f,
+                   "secret int __input0__ = {43,  1,   1,   1,  22, 11, 425,  0, 1, 7};\n"
+                   "secret int __input1__ = {24, 34, 222,   4,    1, 4,   9, 22, 1, 3};",
+                   "secret int result = __input0__ *** __input1__;\nreturn result;", "y = result;", in01);
+    report("visitor.testFheMultCtxtCtxt", prefixEquals(r["y"], {1032, 34, 222, 4, 22, 44, 3825, 0, 1, 21}));
+    r = runProgram(f, "secret int __input0__ = {43,  1,   1,  22, 11, 7};",
+                   "int i = 19;\nsecret int result = __input0__ *** i;\nreturn result;", "y = result;\nx = result[3];", in0);
+    report("visitor.testFheMultCtxtPlain", prefixEquals(r["y"], {817, 19, 19, 418, 209, 133}) && prefixEquals(r["x"], {418}));
+    r = runProgram(f, "secret int __input0__ = {43,  1,   1,  22, 11, 7};",
+                   "int i = 19;\nsecret int result = i *** __input0__;\nreturn result;", "y = result;\nx = result[3];", in0);
+    report("visitor.testFheMultPlainCtxt", prefixEquals(r["y"], {817, 19, 19, 418, 209, 133}) && prefixEquals(r["x"], {418}));
+    r = runProgram(f, "secret int __input0__ = {43, 1, 1, 1, 22, 11, 425, 0, 1, 7};",
+                   "int LIMIT = 10;\nsecret int result = 0;\nfor (int i = 0; i < LIMIT; i = i + 1) {\n"
+                   "  result = result + __input0__;\n}\nreturn;",
+                   "y = result;", in0);
+    report("visitor.testForLoop", prefixEquals(r["y"], {430, 10, 10, 10, 220, 110, 4250, 0, 10, 70}));
+    bool threw = false;
+    try {
+      runProgram(f, "secret int sum = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10};", "secret int result = sum / sum;\nreturn result;",
+                 "y = result;", {{"sum", true}});
+    } catch (std::runtime_error &) { threw = true; }
+    report("visitor.unsupported '/' on ciphertexts throws std::runtime_error", threw);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ programs
+std::vector<int> randomVector(size_t n, unsigned seed) {
+  // the reference's generator: std::default_random_engine(4673838), uniform ints in [0,1024]
+  // (test/end-to-end/BoxBlurTest.cpp:111-124)
+  std::default_random_engine engine(seed);
+  std::uniform_int_distribution<int> dist(0, 1024);
+  std::vector<int> v(n);
+  for (auto &x : v) x = dist(engine);
+  return v;
+}
+
+// plain evaluation of a 3x3 wrap-around stencil, pixel (x,y) at x*size + y
+std::vector<int64_t> stencil(const std::vector<int> &img, int size, const int w[3][3]) {
+  std::vector<int64_t> out(img.size());
+  const long total = (long)img.size();
+  for (int x = 0; x < size; ++x)
+    for (int y = 0; y < size; ++y) {
+      int64_t acc = 0;
+      for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy) {
+          long idx = (((long)(x + dx) * size + (y + dy)) % total + total) % total;
+          acc += (int64_t)w[dx + 1][dy + 1] * img[idx];
+        }
+      out[(size_t)x * size + y] = acc;
+    }
+  return out;
+}
+
+// batched form: one rotation per non-zero tap, ciphertext on the left of every binary op
+std::string stencilProgram(int size, const int w[3][3]) {
+  std::stringstream p;
+  // acc starts as the first tap (not as img --- img: SEAL rejects that transparent result)
+  p << "secret int acc = img;\nsecret int r = img;\n";
+  bool first = true;
+  for (int dx = -1; dx <= 1; ++dx)
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int weight = w[dx + 1][dy + 1], k = dx * size + dy;
+      if (weight == 0) continue;
+      if (k == 0) p << "r = img;\n";
+      else p << "r = rotate(img, " << k << ");\n";
+      if (std::abs(weight) != 1) p << "r = r *** " << std::abs(weight) << ";\n";
+      if (first && weight > 0) p << "acc = r;\n";
+      else p << "acc = acc " << (weight > 0 ? "+++" : "---") << " r;\n";
+      first = false;
+    }
+  p << "return acc;\n";
+  return p.str();
+}
+
+void runPrograms(unsigned N) {
+  CudaCiphertextFactory f(N);
+  const size_t n = N / 2;  // one batching row
+  const int64_t t = N <= 8192 ? 1032193 : 786433;
+  auto centre = [&](int64_t v) { v %= t; if (v < 0) v += t; return v > t / 2 ? v - t : v; };
+  auto x = randomVector(n, 4673838), y = randomVector(n, 4673839);
+  std::vector<int> bx(n), by(n);
+  for (size_t i = 0; i < n; ++i) { bx[i] = x[i] & 1; by[i] = y[i] & 1; }
+
+  // rotate-and-sum ladder: log2(n) rotations, result in slot 0 (and every slot of the row)
+  std::stringstream ladder;
+  ladder << "secret int d = x --- y;\nsecret int s = d *** d;\n";
+  for (size_t k = n / 2; k >= 1; k /= 2) ladder << "s = s +++ rotate(s, " << k << ");\n";
+  ladder << "return s;\n";
+  const std::vector<Var> xy = {{"x", true}, {"y", true}};
+  double secs = 0;
+  {
+    auto r = runProgram(f, "secret int x = " + listOf(bx) + ";\nsecret int y = " + listOf(by) + ";", ladder.str(), "s = s;", xy, &secs);
+    int64_t want = 0;
+    for (size_t i = 0; i < n; ++i) want += (bx[i] - by[i]) * (bx[i] - by[i]);
+    report("program.HammingDistance n=" + std::to_string(n), !r["s"].empty() && r["s"][0] == centre(want),
+           "expected " + std::to_string(centre(want)) + " got " + std::to_string(r["s"].empty() ? -1 : r["s"][0]) +
+               " in " + std::to_string(secs) + " s");
+  }
+  {
+    auto r = runProgram(f, "secret int x = " + listOf(x) + ";\nsecret int y = " + listOf(y) + ";", ladder.str(), "s = s;", xy, &secs);
+    int64_t want = 0;
+    for (size_t i = 0; i < n; ++i) want += (int64_t)(x[i] - y[i]) * (x[i] - y[i]);
+    report("program.L2Distance n=" + std::to_string(n), !r["s"].empty() && r["s"][0] == centre(want),
+           "expected " + std::to_string(centre(want)) + " got " + std::to_string(r["s"].empty() ? -1 : r["s"][0]) +
+               " in " + std::to_string(secs) + " s");
+  }
+  {
+    const int size = (int)std::lround(std::sqrt((double)n));
+    auto img = randomVector((size_t)size * size, 4673838);
+    const int box[3][3] = {{1, 1, 1}, {1, 1, 1}, {1, 1, 1}};
+    const int gx[3][3] = {{1, 2, 1}, {0, 0, 0}, {-1, -2, -1}};  // weightMatrix of GxKernelTest.cpp:22
+    for (int which = 0; which < 2; ++which) {
+      const auto &w = which == 0 ? box : gx;
+      auto r = runProgram(f, "secret int img = " + listOf(img) + ";", stencilProgram(size, w), "acc = acc;", {{"img", true}}, &secs);
+      auto want = stencil(img, size, w);
+      bool ok = r["acc"].size() >= want.size();
+      for (size_t i = 0; ok && i < want.size(); ++i) ok = r["acc"][i] == centre(want[i]);
+      report(std::string("program.") + (which == 0 ? "BoxBlur " : "GxKernel ") + std::to_string(size) + "x" + std::to_string(size), ok,
+             "in " + std::to_string(secs) + " s");
+    }
+  }
+  std::cout << "launches=" << f.launchCount() << std::endl;
+}
+}  // namespace
+
+int main(int argc, char **argv) {
+  const std::string mode = argc > 1 ? argv[1] : "kats";
+  try {
+    if (mode == "kats") runKats();
+    else if (mode == "programs") runPrograms(argc > 2 ? (unsigned)std::stoul(argv[2]) : 8192);
+    else { std::cerr << "usage: abc_driver kats|programs [N]" << std::endl; return 2; }
+  } catch (const std::exception &e) {
+    std::cout << "[FAIL] uncaught exception: " << e.what() << std::endl;
+    ++failures;
+  }
+  std::cout << "{\"mode\": \"" << mode << "\", \"cases\": " << cases << ", \"failures\": " << failures << "}" << std::endl;
+  return failures ? 1 : 0;
+}

@@ -284,23 +284,28 @@ __global__ void __launch_bounds__(128) k_behz_scale(const u64 *__restrict__ X, u
 // Key switching (Evaluator::switch_key_inplace; relinearize at SealCiphertext.cpp:105,123, rotate at :55,60).
 // ModUp + NTT is k_limb<PRE_REDUCE,FWD> into T [inst][k][L][N].
 // Inner product: acc[inst][comp][I][n] = sum_J T[inst][I][J][n] * key[J][comp][I][n] mod q_I.
-// grid: (N/256, k, B).  128-bit lazy accumulation, one Barrett reduction per output.
+// grid: (N/512, k, B).  128-bit lazy accumulation, one Barrett reduction per output.
+template <int L>
 __global__ void __launch_bounds__(256) k_ks_inner(const u64 *__restrict__ T, const u64 *__restrict__ key,
-                                                  u64 *__restrict__ acc, const ModInfo *__restrict__ mods, int N,
-                                                  int L, int k) {
-  const int n = blockIdx.x * 256 + threadIdx.x, I = blockIdx.y, inst = blockIdx.z;
+                                                  u64 *__restrict__ acc, const ModInfo *__restrict__ mods, int N, int k) {
+  // two adjacent coefficients per thread (16-byte accesses), J loop unrolled
+  const int n2 = blockIdx.x * 256 + threadIdx.x, I = blockIdx.y, inst = blockIdx.z;
   const ModInfo *Mp = mods + I;
-  const u64 *t = T + (((size_t)inst * k + I) * L) * N + n;
-  const u64 *kp = key + (size_t)I * N + n;
-  u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+  const u64 q = Mp->q, mh = Mp->mu_hi, ml = Mp->mu_lo;
+  const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(T + ((size_t)(inst * k + I) * L) * N) + n2;
+  const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(key + (size_t)I * N) + n2;
+  const int rowv = N >> 1, keyv = k * rowv;  // row / key-component strides in 16-byte units
+  u64 lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+#pragma unroll
   for (int J = 0; J < L; ++J) {
-    const u64 tv = t[(size_t)J * N];
-    mac128(lo0, hi0, tv, __ldg(kp + (size_t)(J * 2 + 0) * k * N));
-    mac128(lo1, hi1, tv, __ldg(kp + (size_t)(J * 2 + 1) * k * N));
+    const ulonglong2 tv = t[J * rowv];
+    const ulonglong2 k0 = __ldg(kp + (2 * J) * keyv), k1 = __ldg(kp + (2 * J + 1) * keyv);
+    mac128(lo[0], hi[0], tv.x, k0.x); mac128(lo[1], hi[1], tv.y, k0.y);
+    mac128(lo[2], hi[2], tv.x, k1.x); mac128(lo[3], hi[3], tv.y, k1.y);
   }
-  u64 *o = acc + ((size_t)inst * 2 * k + I) * N + n;
-  o[0] = barrett128(lo0, hi0, Mp->q, Mp->mu_hi, Mp->mu_lo);
-  o[(size_t)k * N] = barrett128(lo1, hi1, Mp->q, Mp->mu_hi, Mp->mu_lo);
+  ulonglong2 *o = reinterpret_cast<ulonglong2 *>(acc + ((size_t)inst * 2 * k + I) * N) + n2;
+  o[0] = make_ulonglong2(barrett128(lo[0], hi[0], q, mh, ml), barrett128(lo[1], hi[1], q, mh, ml));
+  o[keyv] = make_ulonglong2(barrett128(lo[2], hi[2], q, mh, ml), barrett128(lo[3], hi[3], q, mh, ml));
 }
 
 // ModDown with rounding and accumulate (tail of switch_key_inplace): acc is in coefficient form.

@@ -297,7 +297,7 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   TRY((launch_limb<PRE_REDUCE, true, false, false, POST_STORE>(c, j, k * L, B, "ks_modup_ntt")));
   {
     Launch l(c, "ks_inner");
-    k_ks_inner<<<dim3(N / 256, k, B), 256, 0, c->stream>>>(T, key, acc, c->d_mods, N, L, k);
+    DISPATCH_L(c, (k_ks_inner<LL><<<dim3(N / 512, k, B), 256, 0, c->stream>>>(T, key, acc, c->d_mods, N, k)));
     CK(cudaGetLastError());
   }
   j = blank_job();
