@@ -4,42 +4,7 @@
 // No tensor cores: this is 64-bit modular integer work; kernels are bound by the INT pipes (NTT, base
 // conversion, key inner product) or by HBM (add/sub/negate/permute/moddown).
 #pragma once
-#include "ntt.cuh"
-
-#define ABC_MAXL 16  // max data limbs with register-resident base conversion
-
-// Per-context constants (device copy).  Index convention for `mods`: 0..k-1 key-level primes,
-// k..k+nbsk-1 Bsk = (B_0..B_{nB-1}, m_sk), k+nbsk = plain modulus t, k+nbsk+1 = gamma.
-struct DevConst {
-  int N, logN, k, L, nB, nbsk;
-  u64 q[ABC_MAXL + 1];                       // key-level primes (q[L] = special prime p)
-  u64 q_mu_hi[ABC_MAXL + 1], q_mu_lo[ABC_MAXL + 1];
-  u64 t, t_half_up, q_mod_t, t_mu_hi, t_mu_lo;
-  u64 delta[ABC_MAXL];                       // floor(Q/t) mod q_i
-  u64 p, p_half, p_mu_hi;
-  u64 inv_p[ABC_MAXL], inv_p_s[ABC_MAXL], p_half_mod_q[ABC_MAXL], p_mod_q[ABC_MAXL];
-  // decryption
-  u64 gamma, gamma_half, g_mu_hi, g_mu_lo;
-  u64 dec_c[ABC_MAXL], dec_c_s[ABC_MAXL];    // (t*gamma) * (Q/q_i)^-1 mod q_i
-  u64 punct_t[ABC_MAXL], punct_g[ABC_MAXL];  // (Q/q_i) mod t, mod gamma
-  u64 neg_inv_q_t, neg_inv_q_t_s, neg_inv_q_g, neg_inv_q_g_s, inv_g_t, inv_g_t_s;
-  // BEHZ
-  u64 bsk[ABC_MAXL + 1], bsk_mu_hi[ABC_MAXL + 1], bsk_mu_lo[ABC_MAXL + 1];
-  u64 lift_c[ABC_MAXL], lift_c_s[ABC_MAXL];        // m~ * (Q/q_i)^-1 mod q_i
-  u64 punct_q_bsk[ABC_MAXL + 1][ABC_MAXL];         // (Q/q_i) mod bsk_j
-  u32 punct_q_mt[ABC_MAXL];                        // (Q/q_i) mod 2^32
-  u32 neg_inv_q_mt;                                // -Q^-1 mod 2^32
-  u64 q_mod_bsk[ABC_MAXL + 1];
-  u64 inv_mt_bsk[ABC_MAXL + 1], inv_mt_bsk_s[ABC_MAXL + 1];
-  u64 scale_c[ABC_MAXL], scale_c_s[ABC_MAXL];      // t * (Q/q_i)^-1 mod q_i
-  u64 t_mod_bsk[ABC_MAXL + 1], t_mod_bsk_s[ABC_MAXL + 1];
-  u64 inv_q_bsk[ABC_MAXL + 1], inv_q_bsk_s[ABC_MAXL + 1];
-  u64 inv_punct_B[ABC_MAXL], inv_punct_B_s[ABC_MAXL];
-  u64 punct_B_q[ABC_MAXL][ABC_MAXL];               // (B/B_j) mod q_i   [i][j]
-  u64 punct_B_msk[ABC_MAXL];
-  u64 inv_B_msk, inv_B_msk_s;
-  u64 B_mod_q[ABC_MAXL], B_mod_q_s[ABC_MAXL];
-};
+#include "limb.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // add / sub / negate.  Evaluator::add_inplace / sub_inplace / negate_inplace
@@ -63,120 +28,6 @@ __global__ void __launch_bounds__(256) k_addsub(u64 *__restrict__ dst, const u64
     else { r.x = sub_mod(x.x, y.x, q); r.y = sub_mod(x.y, y.y, q); }
   }
   reinterpret_cast<ulonglong2 *>(dst + off)[e2] = r;
-}
-
-// ------------------------------------------------------------------------------------------------
-// The limb pipeline: one CTA = one limb staged whole in shared memory:
-//   load (with a pre-op) -> [forward NTT] -> [pointwise * mul row] -> [inverse NTT] -> store (with a post-op)
-enum { PRE_LOAD = 0, PRE_REDUCE = 1, PRE_PLAIN_LIFT = 2, PRE_TERNARY = 3, PRE_CBD = 4, PRE_ENCODE = 5 };
-enum { POST_STORE = 0, POST_ADD = 1, POST_DECODE = 2 };
-
-struct LimbJob {
-  u64 *dst; const u64 *src; const u64 *mul; const u64 *add;
-  long long dst_is, src_is, mul_is, add_is;  // per-instance strides in words (0 = shared by all instances)
-  const int *rowmod;                          // [W] modulus index of row w
-  const int *rowsrc;                          // [W] source row, or nullptr = w
-  const int *rowmul;                          // [W] row of `mul`/`add`, or nullptr = w
-  // sampler (PRE_TERNARY / PRE_CBD): stream = stream_key(seed, domain, a0 + inst, b)
-  u64 seed, domain, a0, b;
-  // PRE_ENCODE / POST_DECODE
-  const long long *slots_in; long long *slots_out; const u32 *index_map; int n_slots; long long slots_is;
-};
-
-__device__ __forceinline__ u64 small_to_mod(int v, u64 q) { return v < 0 ? q - (u64)(-v) : (u64)v; }
-__device__ __forceinline__ int sample_ternary(u64 h, u64 idx) {
-  u64 r = mix64(h ^ idx);
-  return (int)(((r >> 32) * 3) >> 32) - 1;
-}
-__device__ __forceinline__ int sample_cbd(u64 h, u64 idx) {
-  u64 r = mix64(h ^ idx);
-  return __popcll(r & 0x1fffffULL) - __popcll((r >> 21) & 0x1fffffULL);
-}
-
-template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST>
-__global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(LimbJob job, const ModInfo *__restrict__ mods,
-                                                           const DevConst *__restrict__ C) {
-  typedef NttDims<LOGN> D;
-  extern __shared__ __align__(16) u64 sm[];
-  const int tid = threadIdx.x, w = blockIdx.x, inst = blockIdx.y;
-  const ModInfo M = mods[job.rowmod[w]];
-  const u64 q = M.q;
-  const int srow = job.rowsrc ? job.rowsrc[w] : w;
-
-  // ---- load
-  if (PRE == PRE_TERNARY || PRE == PRE_CBD) {
-    const u64 h = stream_key(job.seed, job.domain, job.a0 + (u64)inst, job.b);
-    for (int e = tid; e < D::N; e += D::T) {
-      int v = (PRE == PRE_TERNARY) ? sample_ternary(h, (u64)e) : sample_cbd(h, (u64)e);
-      sm[swz(e)] = small_to_mod(v, q);
-    }
-  } else if (PRE == PRE_ENCODE) {
-    // BatchEncoder::encode (SealCiphertextFactory.cpp:102-132): pad with the last value, scatter by the index map
-    const long long *sl = job.slots_in + (size_t)inst * job.slots_is;
-    for (int e = tid; e < D::N; e += D::T) {
-      long long v = sl[e < job.n_slots ? e : job.n_slots - 1];
-      sm[swz((int)job.index_map[e])] = v < 0 ? q + (u64)v : (u64)v;
-    }
-  } else {
-    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(job.src + (size_t)inst * job.src_is + (size_t)srow * D::N);
-    for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
-      ulonglong2 v = src[e2];
-      if (PRE == PRE_REDUCE) { v.x = barrett64(v.x, q, M.mu_hi); v.y = barrett64(v.y, q, M.mu_hi); }
-      if (PRE == PRE_PLAIN_LIFT) {
-        // multiply_plain_normal: centred lift of a mod-t coefficient into [0,q)
-        const u64 th = C->t_half_up, inc = q - C->t;
-        v.x = v.x >= th ? v.x + inc : v.x;
-        v.y = v.y >= th ? v.y + inc : v.y;
-      }
-      *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = v;
-    }
-  }
-  __syncthreads();
-
-  if (FWD) ntt_fwd_smem<LOGN>(sm, M, 1u, tid);
-
-  if (MUL) {
-    const int mrow = job.rowmul ? job.rowmul[w] : w;
-    const ulonglong2 *mp = reinterpret_cast<const ulonglong2 *>(job.mul + (size_t)inst * job.mul_is + (size_t)mrow * D::N);
-    for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
-      ulonglong2 m = mp[e2];
-      ulonglong2 *p = reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]);
-      ulonglong2 v = *p;
-      v.x = mul_mod(v.x, m.x, q, M.mu_hi, M.mu_lo);
-      v.y = mul_mod(v.y, m.y, q, M.mu_hi, M.mu_lo);
-      *p = v;
-    }
-    __syncthreads();
-  }
-
-  if (INV) ntt_inv_smem<LOGN, true>(sm, M, 1u, tid);
-
-  // ---- store
-  if (POST == POST_DECODE) {
-    // BatchEncoder::decode (SealCiphertextFactory.cpp:151): gather by the index map, centre to signed
-    long long *out = job.slots_out + (size_t)inst * D::N;
-    const u64 half = q >> 1;
-    for (int e = tid; e < D::N; e += D::T) {
-      u64 v = sm[swz((int)job.index_map[e])];
-      out[e] = v > half ? (long long)v - (long long)q : (long long)v;
-    }
-  } else {
-    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(job.dst + (size_t)inst * job.dst_is + (size_t)w * D::N);
-    const ulonglong2 *ad = nullptr;
-    if (POST == POST_ADD) {
-      const int arow = job.rowmul ? job.rowmul[w] : w;
-      ad = reinterpret_cast<const ulonglong2 *>(job.add + (size_t)inst * job.add_is + (size_t)arow * D::N);
-    }
-    for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
-      ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
-      if (INV) { v.x = csub(v.x, q); v.y = csub(v.y, q); }
-      if (POST == POST_ADD) {
-        ulonglong2 a = ad[e2];
-        v.x = add_mod(v.x, a.x, q); v.y = add_mod(v.y, a.y, q);
-      }
-      dst[e2] = v;
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -282,7 +133,7 @@ __global__ void __launch_bounds__(128) k_behz_scale(const u64 *__restrict__ X, u
 
 // ------------------------------------------------------------------------------------------------
 // Key switching (Evaluator::switch_key_inplace; relinearize at SealCiphertext.cpp:105,123, rotate at :55,60).
-// ModUp + NTT is k_limb<PRE_REDUCE,FWD> into T [inst][k][L][N].
+// ModUp + NTT is the limb pipeline (LIMB_REDUCE_FWD) into T [inst][k][L][N].
 // Inner product: acc[inst][comp][I][n] = sum_J T[inst][I][J][n] * key[J][comp][I][n] mod q_I.
 // grid: (N/512, k, B).  128-bit lazy accumulation, one Barrett reduction per output.
 template <int L>
@@ -519,7 +370,7 @@ __global__ void __launch_bounds__(1024) k_peak_butterfly(u64 *out, int iters, u6
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      bf_fwd(x0, y0, tw, q, q2); bf_fwd(x1, y1, tw, q, q2); bf_fwd(x2, y2, tw, q, q2); bf_fwd(x3, y3, tw, q, q2);
+      bf_fwd<AR_SHOUP>(x0, y0, tw, q, q2); bf_fwd<AR_SHOUP>(x1, y1, tw, q, q2); bf_fwd<AR_SHOUP>(x2, y2, tw, q, q2); bf_fwd<AR_SHOUP>(x3, y3, tw, q, q2);
     }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ y0 ^ x1 ^ y1 ^ x2 ^ y2 ^ x3 ^ y3;

@@ -3,7 +3,9 @@
 // plaintexts happens in the sm_100a kernels of kernels.cuh.  There is no CPU fallback.
 #include "../../include/abc_b200.h"
 
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -29,16 +31,22 @@ struct abc_ctx {
   DevConst hC;
   DevConst *dC = nullptr;
   ModInfo *d_mods = nullptr;
+  std::vector<ModInfo> hmods;
+  int ar_q = 0, ar_t = 0, force_ar = -1;  // NTT arithmetic class of the key-level primes / of t (ntt.cuh)
   int idx_t = 0;
   std::vector<void *> owned;  // device allocations freed at destroy
   u32 *d_index_map = nullptr;
   int *rm_ct = nullptr;     // [3L]  w % L
   int *rm_key = nullptr;    // [2k]  w % k
   int *rm_behz = nullptr;   // [4W]  q / Bsk modulus of X row
+  int *rm_behz_q = nullptr, *rd_behz_q = nullptr;  // [4L]    q rows of X: modulus, row
+  int *rm_behz_b = nullptr, *rd_behz_b = nullptr;  // [4nbsk] Bsk rows of X: modulus, row
   int *rm_modup = nullptr;  // [kL]  I
   int *rs_modup = nullptr;  // [kL]  J
   int *rm_t = nullptr;      // [1]   idx_t
   int *rs_c1 = nullptr;     // [L]   L + w
+  int *rm_special = nullptr, *rd_special = nullptr;  // [2] special-prime rows of an accumulator block
+  int *rs_accq = nullptr;   // [2L]  comp*k + i: data rows of an accumulator block
   int *rs_zero = nullptr;   // [2k]  0
   u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;
   std::map<u32, u64 *> galois;
@@ -97,31 +105,19 @@ template <typename T> abc_status upload(abc_ctx *c, T **dst, const std::vector<T
   return ABC_OK;
 }
 
-// ---- limb-pipeline launcher
-template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST>
-abc_status launch_limb_n(abc_ctx *c, const LimbJob &job, int W, int B, const char *name) {
-  typedef NttDims<LOGN> D;
-  auto kern = k_limb<LOGN, PRE, FWD, MUL, INV, POST>;
-  static bool attr_done[64] = {false};
-  if (D::SMEM > 48 * 1024 && !attr_done[c->device & 63]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::SMEM));
-    attr_done[c->device & 63] = true;
-  }
+// ---- limb-pipeline launcher (kernels live in limb_12/13/14.cu)
+abc_status launch_limb(abc_ctx *c, int combo, int ar, const LimbJob &job, int W, int B, const char *name) {
+  if (c->force_ar >= 0 && c->force_ar < ar) ar = c->force_ar;
   Launch l(c, name);
-  kern<<<dim3(W, B), D::T, D::SMEM, c->stream>>>(job, c->d_mods, c->dC);
-  CK(cudaGetLastError());
-  return ABC_OK;
-}
-template <int PRE, bool FWD, bool MUL, bool INV, int POST>
-abc_status launch_limb(abc_ctx *c, const LimbJob &job, int W, int B, const char *name) {
+  int e;
   switch (c->logN) {
-    case 10: return launch_limb_n<10, PRE, FWD, MUL, INV, POST>(c, job, W, B, name);
-    case 11: return launch_limb_n<11, PRE, FWD, MUL, INV, POST>(c, job, W, B, name);
-    case 12: return launch_limb_n<12, PRE, FWD, MUL, INV, POST>(c, job, W, B, name);
-    case 13: return launch_limb_n<13, PRE, FWD, MUL, INV, POST>(c, job, W, B, name);
-    case 14: return launch_limb_n<14, PRE, FWD, MUL, INV, POST>(c, job, W, B, name);
-    default: return fail(c, ABC_ERR_UNSUPPORTED, "poly_degree not supported by the shared-memory NTT");
+    case 12: e = limb_dispatch<12>(combo, ar, job, c->d_mods, W, B, c->stream); break;
+    case 13: e = limb_dispatch<13>(combo, ar, job, c->d_mods, W, B, c->stream); break;
+    case 14: e = limb_dispatch<14>(combo, ar, job, c->d_mods, W, B, c->stream); break;
+    default: return fail(c, ABC_ERR_UNSUPPORTED, "poly_degree not supported by the shared-memory NTT (4096, 8192, 16384)");
   }
+  if (e != 0) { c->err = std::string(name) + ": " + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
+  return ABC_OK;
 }
 LimbJob blank_job() { LimbJob j; memset(&j, 0, sizeof j); return j; }
 
@@ -146,7 +142,8 @@ LimbJob blank_job() { LimbJob j; memset(&j, 0, sizeof j); return j; }
   }
 
 // ---- context construction --------------------------------------------------------------------
-void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, std::vector<ulonglong2> &itw) {
+void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, std::vector<ulonglong2> &itw,
+              std::vector<ulonglong2> &twf, std::vector<ulonglong2> &itwf) {
   using hm::mulmod; using hm::invmod; using hm::shoup; using hm::prod_mod; using hm::barrett_ratio; using hm::bit_reverse; using hm::minimal_2nth_root; using hm::get_primes; using hm::bits_of; using hm::prod_bits;
   m.q = q;
   barrett_ratio(q, m.mu_hi, m.mu_lo);
@@ -165,6 +162,21 @@ void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, s
   }
   m.wl_ninv = mulmod(itw[1].x, m.ninv, q);
   m.wl_ninv_s = shoup(m.wl_ninv, q);
+  // FP64-assisted class: companion = double(w/q) (correctly rounded: both operands are exact doubles)
+  auto dbits = [q](u64 w) { double d = (double)w / (double)q; u64 b; memcpy(&b, &d, 8); return b; };
+  m.ar_class = AR_SHOUP;
+  if ((q >> 49) == 0) m.ar_class = ((unsigned __int128)q * (unsigned)(2 * logN + 1) < ((unsigned __int128)1 << 51)) ? AR_FP_LAZY : AR_FP;
+  twf.clear(); itwf.clear();
+  m.ninv_f = m.wl_ninv_f = m.qinv_bits = 0;
+  if (m.ar_class != AR_SHOUP) {
+    twf.resize(N); itwf.resize(N);
+    for (int j = 0; j < N; ++j) {
+      twf[j] = make_ulonglong2(tw[j].x, dbits(tw[j].x));
+      itwf[j] = make_ulonglong2(itw[j].x, dbits(itw[j].x));
+    }
+    m.ninv_f = dbits(m.ninv); m.wl_ninv_f = dbits(m.wl_ninv);
+    double qi = 1.0 / (double)q; memcpy(&m.qinv_bits, &qi, 8);
+  }
 }
 
 abc_status build_tables(abc_ctx *c) {
@@ -186,16 +198,22 @@ abc_status build_tables(abc_ctx *c) {
   // ---- per-modulus tables
   const int nmods = k + c->nbsk + 1;
   std::vector<ModInfo> mods(nmods);
-  std::vector<ulonglong2> tw, itw;
+  std::vector<ulonglong2> tw, itw, twf, itwf;
   for (int i = 0; i < nmods; ++i) {
     const u64 q = i < k ? c->primes[i] : (i < k + c->nbsk ? c->bsk[i - k] : t);
-    fill_mod(mods[i], q, N, logN, tw, itw);
-    ulonglong2 *d_tw = nullptr, *d_itw = nullptr;
+    fill_mod(mods[i], q, N, logN, tw, itw, twf, itwf);
+    ulonglong2 *d_tw = nullptr, *d_itw = nullptr, *d_twf = nullptr, *d_itwf = nullptr;
     TRY(upload(c, &d_tw, tw));
     TRY(upload(c, &d_itw, itw));
-    mods[i].tw = d_tw; mods[i].itw = d_itw;
+    if (!twf.empty()) { TRY(upload(c, &d_twf, twf)); TRY(upload(c, &d_itwf, itwf)); }
+    mods[i].tw = d_tw; mods[i].itw = d_itw; mods[i].twf = d_twf; mods[i].itwf = d_itwf;
   }
   TRY(upload(c, &c->d_mods, mods));
+  c->hmods = mods;
+  c->ar_q = AR_FP_LAZY;
+  for (int i = 0; i < k; ++i) c->ar_q = std::min(c->ar_q, mods[i].ar_class);
+  c->ar_t = mods[c->idx_t].ar_class;
+  if (const char *e = getenv("ABC_FORCE_AR")) c->force_ar = atoi(e);
 
   // ---- constants
   DevConst &C = c->hC;
@@ -268,6 +286,15 @@ abc_status build_tables(abc_ctx *c) {
   TRY(upload(c, &c->rm_key, v));
   v.resize(4 * W); for (int w = 0; w < 4 * W; ++w) { int r = w % W; v[w] = r < L ? r : k + (r - L); }
   TRY(upload(c, &c->rm_behz, v));
+  {
+    std::vector<int> mq, dq, mb, db;
+    for (int p = 0; p < 4; ++p) {
+      for (int i = 0; i < L; ++i) { mq.push_back(i); dq.push_back(p * W + i); }
+      for (int j = 0; j < c->nbsk; ++j) { mb.push_back(k + j); db.push_back(p * W + L + j); }
+    }
+    TRY(upload(c, &c->rm_behz_q, mq)); TRY(upload(c, &c->rd_behz_q, dq));
+    TRY(upload(c, &c->rm_behz_b, mb)); TRY(upload(c, &c->rd_behz_b, db));
+  }
   v.resize(k * L); for (int w = 0; w < k * L; ++w) v[w] = w / L;
   TRY(upload(c, &c->rm_modup, v));
   for (int w = 0; w < k * L; ++w) v[w] = w % L;
@@ -278,36 +305,49 @@ abc_status build_tables(abc_ctx *c) {
   TRY(upload(c, &c->rs_c1, v));
   v.assign(2 * k, 0);
   TRY(upload(c, &c->rs_zero, v));
+  v = {L, L};
+  TRY(upload(c, &c->rm_special, v));
+  v = {L, k + L};
+  TRY(upload(c, &c->rd_special, v));
+  v.resize(2 * L); for (int w = 0; w < 2 * L; ++w) v[w] = (w / L) * k + (w % L);
+  TRY(upload(c, &c->rs_accq, v));
   return ABC_OK;
 }
 
 // ---- op building blocks ------------------------------------------------------------------------
 size_t ct_words1(const abc_ctx *c) { return (size_t)2 * c->L * c->N; }
 
-// Evaluator::switch_key_inplace: dst[inst][2][L][N] = (base0, base1) + KeySwitch(target)
+// Evaluator::switch_key_inplace: dst[inst][2][L][N] = sigma(base0, base1) + KeySwitch(sigma(target)), where sigma is the
+// Galois automorphism with inverse element einv (0: identity).  dst must not alias target/base when einv != 0.
+//   1. ModUp: every target limb J reduced mod every key-level prime I (+ automorphism gather), forward NTT   [limb pipeline]
+//   2. inner product with the key over J, 128-bit lazy accumulation                                          [k_ks_inner]
+//   3. INTT of the two special-prime rows                                                                    [limb pipeline]
+//   4. INTT of the 2L data rows fused with ModDown (rounded division by p) and the base accumulate            [limb pipeline]
 abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u64 *key, const u64 *base0,
-                     long long base0_is, const u64 *base1, long long base1_is, u64 *dst) {
+                     long long base0_is, const u64 *base1, long long base1_is, u32 einv, u64 *dst) {
   const int N = c->N, L = c->L, k = c->k, B = c->B;
   u64 *T = nullptr, *acc = nullptr;
   TRY(salloc(c, &T, (size_t)B * k * L * N));
   TRY(salloc(c, &acc, (size_t)B * 2 * k * N));
   LimbJob j = blank_job();
   j.dst = T; j.dst_is = (long long)k * L * N; j.src = target; j.src_is = target_is;
-  j.rowmod = c->rm_modup; j.rowsrc = c->rs_modup;
-  TRY((launch_limb<PRE_REDUCE, true, false, false, POST_STORE>(c, j, k * L, B, "ks_modup_ntt")));
+  j.rowmod = c->rm_modup; j.rowsrc = c->rs_modup; j.galois_einv = einv;
+  TRY(launch_limb(c, einv ? LIMB_GALOIS_REDUCE_FWD : LIMB_REDUCE_FWD, c->ar_q, j, k * L, B, "ks_modup_ntt"));
   {
     Launch l(c, "ks_inner");
     DISPATCH_L(c, (k_ks_inner<LL><<<dim3(N / 512, k, B), 256, 0, c->stream>>>(T, key, acc, c->d_mods, N, k)));
     CK(cudaGetLastError());
   }
   j = blank_job();
-  j.dst = acc; j.src = acc; j.dst_is = j.src_is = (long long)2 * k * N; j.rowmod = c->rm_key;
-  TRY((launch_limb<PRE_LOAD, false, false, true, POST_STORE>(c, j, 2 * k, B, "ks_intt")));
-  {
-    Launch l(c, "ks_moddown");
-    k_ks_moddown<<<dim3(N / 256, 2, B), 256, 0, c->stream>>>(acc, base0, base0_is, base1, base1_is, dst, c->dC, N, L, k);
-    CK(cudaGetLastError());
-  }
+  j.dst = acc; j.src = acc; j.dst_is = j.src_is = (long long)2 * k * N;
+  j.rowmod = c->rm_special; j.rowdst = c->rd_special;
+  TRY(launch_limb(c, LIMB_INV, c->ar_q, j, 2, B, "ks_intt_special"));
+  j = blank_job();
+  j.src = acc; j.src_is = (long long)2 * k * N; j.rowsrc = c->rs_accq; j.rowmod = c->rm_ct;
+  j.dst = dst; j.dst_is = (long long)2 * L * N;
+  j.C = c->dC; j.tl = acc; j.tl_is = (long long)2 * k * N; j.L = L; j.k = k;
+  j.base0 = base0; j.base0_is = base0_is; j.base1 = base1; j.base1_is = base1_is; j.base_einv = einv;
+  TRY(launch_limb(c, LIMB_INV_MODDOWN, c->ar_q, j, 2 * L, B, "ks_intt_moddown"));
   sfree(c, T); sfree(c, acc);
   return ABC_OK;
 }
@@ -324,13 +364,26 @@ abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
   }
   LimbJob j = blank_job();
   j.dst = X; j.src = X; j.dst_is = j.src_is = (long long)4 * W * N; j.rowmod = c->rm_behz;
-  TRY((launch_limb<PRE_LOAD, true, false, false, POST_STORE>(c, j, 4 * W, B, "behz_ntt")));
+  LimbJob jq = j, jb = j;
+  jq.rowmod = c->rm_behz_q; jq.rowdst = c->rd_behz_q;
+  jb.rowmod = c->rm_behz_b; jb.rowdst = c->rd_behz_b;
+  if (c->ar_q == AR_SHOUP) {
+    TRY(launch_limb(c, LIMB_FWD, AR_SHOUP, j, 4 * W, B, "behz_ntt"));
+  } else {  // q rows on the FP64-assisted class, the 61-bit Bsk rows on the Shoup class
+    TRY(launch_limb(c, LIMB_FWD, c->ar_q, jq, 4 * L, B, "behz_ntt_q"));
+    TRY(launch_limb(c, LIMB_FWD, AR_SHOUP, jb, 4 * c->nbsk, B, "behz_ntt_bsk"));
+  }
   {
     Launch l(c, "behz_tensor");
     k_behz_tensor<<<dim3(N / 256, W, B), 256, 0, c->stream>>>(X, c->d_mods, c->rm_behz, N, W);
     CK(cudaGetLastError());
   }
-  TRY((launch_limb<PRE_LOAD, false, false, true, POST_STORE>(c, j, 3 * W, B, "behz_intt")));
+  if (c->ar_q == AR_SHOUP) {
+    TRY(launch_limb(c, LIMB_INV, AR_SHOUP, j, 3 * W, B, "behz_intt"));
+  } else {
+    TRY(launch_limb(c, LIMB_INV, c->ar_q, jq, 3 * L, B, "behz_intt_q"));
+    TRY(launch_limb(c, LIMB_INV, AR_SHOUP, jb, 3 * c->nbsk, B, "behz_intt_bsk"));
+  }
   {
     Launch l(c, "behz_scale");
     DISPATCH_L(c, (k_behz_scale<LL><<<dim3(N / 128, 3, B), 128, 0, c->stream>>>(X, out3, c->dC, N)));
@@ -340,23 +393,14 @@ abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
   return ABC_OK;
 }
 
-// one Galois automorphism + key switch (Evaluator::apply_galois_inplace)
+// one Galois automorphism + key switch (Evaluator::apply_galois_inplace): dst = (sigma(c0), 0) + KeySwitch(sigma(c1)).
+// The coefficient permutation is never materialised: it is a gather in the ModUp load and in the ModDown base read.
 abc_status apply_galois(abc_ctx *c, const u64 *src, u64 *dst, u32 elt) {
   auto it = c->galois.find(elt);
   if (it == c->galois.end()) return fail(c, ABC_ERR_STATE, "Galois key not present");
-  const int N = c->N, L = c->L, B = c->B;
-  u64 *g = nullptr;
-  TRY(salloc(c, &g, (size_t)B * 2 * L * N));
-  const u32 elt_inv = (u32)hm::invmod(elt, 2ull * N);
-  {
-    Launch l(c, "galois_permute");
-    k_galois<<<dim3(N / 256, 2 * L, B), 256, 0, c->stream>>>(src, g, 2ll * L * N, g + (size_t)L * N, 2ll * L * N, elt_inv,
-                                                            c->dC, N, L);
-    CK(cudaGetLastError());
-  }
-  TRY(keyswitch(c, g + (size_t)L * N, 2ll * L * N, it->second, g, 2ll * L * N, nullptr, 0, dst));
-  sfree(c, g);
-  return ABC_OK;
+  const long long LN = (long long)c->L * c->N;
+  const u32 elt_inv = (u32)hm::invmod(elt, 2ull * c->N);
+  return keyswitch(c, src + LN, 2 * LN, it->second, src, 2 * LN, nullptr, 0, elt_inv, dst);
 }
 
 u32 elt_from_step(const abc_ctx *c, int step) {
@@ -368,13 +412,13 @@ u32 elt_from_step(const abc_ctx *c, int step) {
   return (u32)elt;
 }
 
-// Evaluator::rotate_internal, in place on d
-abc_status rotate_internal(abc_ctx *c, u64 *d, int steps) {
+// Evaluator::rotate_internal flattened into the list of Galois elements it applies, in order:
+// a direct key when one exists, else one step per non-zero NAF digit (least significant first, |digit| = N/2 skipped).
+abc_status rotation_plan(abc_ctx *c, int steps, std::vector<u32> &plan) {
   if (steps == 0) return ABC_OK;
   const u32 elt = elt_from_step(c, steps);
-  if (c->galois.count(elt)) return apply_galois(c, d, d, elt);
-  // util::naf, least significant digit first
-  std::vector<int> naf;
+  if (c->galois.count(elt)) { plan.push_back(elt); return ABC_OK; }
+  std::vector<int> naf;  // util::naf
   {
     int v = steps < 0 ? -steps : steps; const bool neg = steps < 0;
     for (int i = 0; v; ++i) {
@@ -386,7 +430,7 @@ abc_status rotate_internal(abc_ctx *c, u64 *d, int steps) {
   if (naf.size() == 1) return fail(c, ABC_ERR_STATE, "Galois key not present");
   for (int s : naf) {
     if ((s < 0 ? -s : s) == (c->N >> 1)) continue;
-    TRY(rotate_internal(c, d, s));
+    TRY(rotation_plan(c, s, plan));
   }
   return ABC_OK;
 }
@@ -405,7 +449,7 @@ abc_status encode_device(abc_ctx *c, const int64_t *slots, size_t n, int broadca
   LimbJob j = blank_job();
   j.dst = plain; j.dst_is = N; j.rowmod = c->rm_t;
   j.slots_in = d_slots; j.slots_is = (long long)n; j.n_slots = (int)n; j.index_map = c->d_index_map;
-  TRY((launch_limb<PRE_ENCODE, false, false, true, POST_STORE>(c, j, 1, Bp, "encode_intt")));
+  TRY(launch_limb(c, LIMB_ENCODE_INV, c->ar_t, j, 1, Bp, "encode_intt"));
   sfree(c, d_slots);
   *plain_out = plain;
   return ABC_OK;
@@ -422,12 +466,12 @@ abc_status encrypt_device(abc_ctx *c, const u64 *plain, int broadcast, u64 *ct) 
   LimbJob j = blank_job();
   j.dst = u; j.dst_is = (long long)k * N; j.rowmod = c->rm_key;
   j.seed = c->seed; j.domain = DOM_ENC; j.a0 = nonce0; j.b = 0;
-  TRY((launch_limb<PRE_TERNARY, true, false, false, POST_STORE>(c, j, k, B, "enc_sample_u_ntt")));
+  TRY(launch_limb(c, LIMB_TERNARY_FWD, c->ar_q, j, k, B, "enc_sample_u_ntt"));
   j = blank_job();
   j.src = u; j.src_is = (long long)k * N; j.rowsrc = c->rm_key;
   j.mul = c->d_pk; j.mul_is = 0;
   j.dst = tmp; j.dst_is = (long long)2 * k * N; j.rowmod = c->rm_key;
-  TRY((launch_limb<PRE_LOAD, false, true, true, POST_STORE>(c, j, 2 * k, B, "enc_mul_pk_intt")));
+  TRY(launch_limb(c, LIMB_MUL_INV, c->ar_q, j, 2 * k, B, "enc_mul_pk_intt"));
   {
     Launch l(c, "enc_finish");
     k_enc_finish<<<dim3(N / 256, 2, B), 256, 0, c->stream>>>(tmp, plain, broadcast ? 0 : N, ct, c->seed, nonce0, c->dC, N,
@@ -443,12 +487,13 @@ abc_status mul_plain_device(abc_ctx *c, u64 *dst, const u64 *a, const u64 *plain
   u64 *P = nullptr;
   TRY(salloc(c, &P, (size_t)Bp * L * N));
   LimbJob j = blank_job();
+  j.t = c->t; j.t_half_up = (c->t + 1) >> 1;
   j.src = plain; j.src_is = N; j.rowsrc = c->rs_zero; j.dst = P; j.dst_is = (long long)L * N; j.rowmod = c->rm_ct;
-  TRY((launch_limb<PRE_PLAIN_LIFT, true, false, false, POST_STORE>(c, j, L, Bp, "plain_lift_ntt")));
+  TRY(launch_limb(c, LIMB_PLAINLIFT_FWD, c->ar_q, j, L, Bp, "plain_lift_ntt"));
   j = blank_job();
   j.src = a; j.dst = dst; j.src_is = j.dst_is = (long long)2 * L * N; j.rowmod = c->rm_ct;
   j.mul = P; j.mul_is = broadcast ? 0 : (long long)L * N; j.rowmul = c->rm_ct;
-  TRY((launch_limb<PRE_LOAD, true, true, true, POST_STORE>(c, j, 2 * L, B, "ct_mul_plain")));
+  TRY(launch_limb(c, LIMB_FWD_MUL_INV, c->ar_q, j, 2 * L, B, "ct_mul_plain"));
   sfree(c, P);
   return ABC_OK;
 }
@@ -472,7 +517,7 @@ abc_status gen_key_block(abc_ctx *c, u64 *blk, u64 dom, u64 a_id, u64 b_base, co
   LimbJob j = blank_job();
   j.dst = e_ntt; j.dst_is = 0; j.rowmod = c->rm_key;
   j.seed = c->seed; j.domain = dom; j.a0 = a_id; j.b = (b_base << 2) | 1;
-  TRY((launch_limb<PRE_CBD, true, false, false, POST_STORE>(c, j, k, 1, "keygen_noise_ntt")));
+  TRY(launch_limb(c, LIMB_CBD_FWD, c->ar_q, j, k, 1, "keygen_noise_ntt"));
   {
     Launch l(c, "keygen_finish");
     k_ksk_finish<<<dim3(N / 256, k), 256, 0, c->stream>>>(blk, e_ntt, c->d_sk, newkey, J, c->d_mods, c->dC, N, k);
@@ -605,7 +650,7 @@ abc_status abc_keygen(abc_ctx *c) {
   if (!c->d_relin) CK(cudaMalloc((void **)&c->d_relin, kw * 8));
   LimbJob j = blank_job();
   j.dst = c->d_sk; j.rowmod = c->rm_key; j.seed = c->seed; j.domain = DOM_SK;
-  TRY((launch_limb<PRE_TERNARY, true, false, false, POST_STORE>(c, j, k, 1, "keygen_sk_ntt")));
+  TRY(launch_limb(c, LIMB_TERNARY_FWD, c->ar_q, j, k, 1, "keygen_sk_ntt"));
   u64 *nk = nullptr, *e_ntt = nullptr;
   TRY(salloc(c, &nk, (size_t)k * N));
   TRY(salloc(c, &e_ntt, (size_t)k * N));
@@ -746,7 +791,7 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
   j.mul = c->d_sk; j.mul_is = 0;
   j.add = ct->d; j.add_is = (long long)2 * L * N;
   j.dst = x; j.dst_is = (long long)L * N; j.rowmod = c->rm_ct;
-  TRY((launch_limb<PRE_LOAD, true, true, true, POST_ADD>(c, j, L, B, "dec_c1s_plus_c0")));
+  TRY(launch_limb(c, LIMB_FWD_MUL_INV_ADD, c->ar_q, j, L, B, "dec_c1s_plus_c0"));
   {
     Launch l(c, "dec_scale_round");
     DISPATCH_L(c, (k_dec_finish<LL><<<dim3(N / 128, 1, B), 128, 0, c->stream>>>(x, plain, c->dC, N)));
@@ -754,7 +799,7 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
   }
   j = blank_job();
   j.src = plain; j.src_is = N; j.rowmod = c->rm_t; j.slots_out = d_out; j.index_map = c->d_index_map;
-  TRY((launch_limb<PRE_LOAD, true, false, false, POST_DECODE>(c, j, 1, B, "decode_ntt")));
+  TRY(launch_limb(c, LIMB_FWD_DECODE, c->ar_t, j, 1, B, "decode_ntt"));
   CK(cudaMemcpyAsync(out_slots, d_out, (size_t)B * N * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   sfree(c, x); sfree(c, plain); sfree(c, d_out);
@@ -786,7 +831,7 @@ abc_status abc_mul_relin(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct 
   u64 *out3 = nullptr;
   TRY(salloc(c, &out3, (size_t)c->B * 3 * LN));
   TRY(behz_multiply(c, a->d, b->d, out3));
-  TRY(keyswitch(c, out3 + 2 * LN, 3ll * LN, c->d_relin, out3, 3ll * LN, out3 + LN, 3ll * LN, dst->d));
+  TRY(keyswitch(c, out3 + 2 * LN, 3ll * LN, c->d_relin, out3, 3ll * LN, out3 + LN, 3ll * LN, 0, dst->d));
   sfree(c, out3);
   return ABC_OK;
 }
@@ -795,11 +840,29 @@ abc_status abc_rotate_rows(abc_ctx *c, abc_ct *dst, const abc_ct *a, int steps) 
   if (!valid_ct(c, dst) || !valid_ct(c, a)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
   const int as = steps < 0 ? -steps : steps;
   if (as >= (c->N >> 1)) return fail(c, ABC_ERR_PARAM, "step count too large");
-  if (dst != a) {
-    c->launches++;
-    CK(cudaMemcpyAsync(dst->d, a->d, abc_ct_words(c) * 8, cudaMemcpyDeviceToDevice, c->stream));
+  std::vector<u32> plan;
+  TRY(rotation_plan(c, steps, plan));
+  if (plan.empty()) {
+    if (dst != a) {
+      c->launches++;
+      CK(cudaMemcpyAsync(dst->d, a->d, abc_ct_words(c) * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return ABC_OK;
   }
-  return rotate_internal(c, dst->d, steps);
+  // each key switch writes a fresh buffer (its gathers read the previous one); the last one becomes dst's storage
+  const u64 *cur = a->d;
+  u64 *owned = nullptr;
+  for (u32 elt : plan) {
+    u64 *out = nullptr;
+    TRY(salloc(c, &out, abc_ct_words(c)));
+    abc_status s = apply_galois(c, cur, out, elt);
+    if (owned) sfree(c, owned);
+    if (s != ABC_OK) { sfree(c, out); return s; }
+    cur = owned = out;
+  }
+  sfree(c, dst->d);  // stream-ordered: after the kernels that read it
+  dst->d = owned;
+  return ABC_OK;
 }
 
 // ---- plaintext operands
@@ -840,8 +903,8 @@ abc_status abc_probe_ntt(abc_ctx *c, int inverse, uint32_t mod_index, uint64_t *
   CK(cudaMemcpyAsync(d, host_rows, n_rows * N * 8, cudaMemcpyHostToDevice, c->stream));
   LimbJob j = blank_job();
   j.dst = d; j.src = d; j.rowmod = rm;
-  if (inverse) TRY((launch_limb<PRE_LOAD, false, false, true, POST_STORE>(c, j, (int)n_rows, 1, "probe_intt")));
-  else TRY((launch_limb<PRE_LOAD, true, false, false, POST_STORE>(c, j, (int)n_rows, 1, "probe_ntt")));
+  if (inverse) TRY(launch_limb(c, LIMB_INV, c->hmods[mod_index].ar_class, j, (int)n_rows, 1, "probe_intt"));
+  else TRY(launch_limb(c, LIMB_FWD, c->hmods[mod_index].ar_class, j, (int)n_rows, 1, "probe_ntt"));
   CK(cudaMemcpyAsync(host_rows, d, n_rows * N * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   sfree(c, d); sfree(c, rm);
@@ -862,8 +925,8 @@ abc_status abc_bench_ntt(abc_ctx *c, int inverse, uint32_t mod_index, size_t n_r
   j.dst = d; j.src = d; j.rowmod = rm; j.dst_is = j.src_is = (long long)W * N;
   for (int it = -1; it < iters; ++it) {
     if (it == 0) CK(cudaEventRecord(c->ev0, c->stream));
-    if (inverse) TRY((launch_limb<PRE_LOAD, false, false, true, POST_STORE>(c, j, W, By, "bench_intt")));
-    else TRY((launch_limb<PRE_LOAD, true, false, false, POST_STORE>(c, j, W, By, "bench_ntt")));
+    if (inverse) TRY(launch_limb(c, LIMB_INV, c->hmods[mod_index].ar_class, j, W, By, "bench_intt"));
+    else TRY(launch_limb(c, LIMB_FWD, c->hmods[mod_index].ar_class, j, W, By, "bench_ntt"));
   }
   CK(cudaEventRecord(c->ev1, c->stream));
   CK(cudaEventSynchronize(c->ev1));

@@ -1,0 +1,4 @@
+// limb pipeline kernels for N = 2^13 (one translation unit per size so the sizes compile in parallel)
+#define ABC_LIMB_IMPL
+#include "limb.cuh"
+template int limb_dispatch<13>(int, int, const LimbJob &, const ModInfo *, int, int, cudaStream_t);

@@ -16,6 +16,11 @@ struct ModInfo {
   u64 wl_ninv, wl_ninv_s;    // irp[1] * N^-1 (last inverse stage folded with the scaling)
   const ulonglong2 *tw;      // forward twiddles {w, w'} : tw[bitrev(i)] = psi^i
   const ulonglong2 *itw;     // inverse twiddles at the same index: itw[j] = tw[j]^-1
+  // FP64-assisted class (q < 2^49, see ntt.cuh): companions are the bit patterns of double(w/q)
+  const ulonglong2 *twf, *itwf;
+  u64 ninv_f, wl_ninv_f;     // bits of double(ninv/q), double(wl_ninv/q)
+  u64 qinv_bits;             // bits of double(1/q)
+  int ar_class;              // AR_SHOUP / AR_FP / AR_FP_LAZY: the fastest class this modulus allows
 };
 
 __device__ __forceinline__ u64 csub(u64 x, u64 q) { return x >= q ? x - q : x; }

@@ -188,7 +188,7 @@ def run_ours(args):
         r = program_gpu(cx, cy)
         f._ck(lib.abc_decrypt_decode(f._h, r._h, hout.data_ptr()))
 
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(1, args.warmup)):
         e2e_step()
     assert np.array_equal(hout[:, 0].numpy(), want0), "e2e result mismatch"
     barrier()
@@ -205,6 +205,7 @@ def run_ours(args):
         tt = torch.tensor([ms, e2e_ms, e2e_wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms, e2e_ms, e2e_wall = [float(v) for v in tt.tolist()]
+    e2e_dev = e2e_ms
     e2e_ms = max(e2e_ms, e2e_wall)
 
     line = None
@@ -219,19 +220,21 @@ def run_ours(args):
         L, k = f.L, f.k
         row = N_POLY * 8
         # algorithmic bytes per launch of each kernel family (DESIGN.md "kernels")
+        nb = L + 1
         alg = {"ks_modup_ntt": B * (L + k * L) * row, "ks_inner": B * (k * L + 2 * k) * row + 2 * k * L * row,
-               "ks_intt": B * 4 * k * row, "ks_moddown": B * (2 * k + 4 * L) * row,
-               "behz_ntt": B * 8 * (2 * L + 1) * row, "behz_intt": B * 6 * (2 * L + 1) * row,
+               "ks_intt_special": B * 4 * row, "ks_intt_moddown": B * (2 * L + 2 + 2 * L + 2 * L) * row,
+               "behz_ntt_q": B * 8 * L * row, "behz_ntt_bsk": B * 8 * nb * row,
+               "behz_intt_q": B * 6 * L * row, "behz_intt_bsk": B * 6 * nb * row,
                "behz_lift": B * 4 * (L + 2 * L + 1) * row, "behz_tensor": B * 7 * (2 * L + 1) * row,
-               "behz_scale": B * 3 * (3 * L + 1) * row, "galois_permute": B * 4 * L * row,
-               "add": B * 6 * L * row, "sub": B * 6 * L * row}
+               "behz_scale": B * 3 * (3 * L + 1) * row, "add": B * 6 * L * row, "sub": B * 6 * L * row}
         peaks, how = measured_peaks()
         per_launch_ms = top["ms"] / top["launches"]
         ach = alg.get(top["kernel"], 0) / (per_launch_ms * 1e-3) / 1e9
         bf_peak = f.measure_butterfly_peak()
         imad, iadd = f.measure_int_peak()
         logn = N_POLY.bit_length() - 1
-        ntt_rows = {"ks_modup_ntt": k * L, "ks_intt": 2 * k, "behz_ntt": 4 * (2 * L + 1), "behz_intt": 3 * (2 * L + 1)}
+        ntt_rows = {"ks_modup_ntt": k * L, "ks_intt_special": 2, "ks_intt_moddown": 2 * L, "behz_ntt_q": 4 * L,
+                    "behz_ntt_bsk": 4 * nb, "behz_intt_q": 3 * L, "behz_intt_bsk": 3 * nb}
         ntt_ms = sum(r["ms"] for r in prof if r["kernel"] in ntt_rows)
         ntt_bf = sum(r["launches"] * ntt_rows[r["kernel"]] for r in prof if r["kernel"] in ntt_rows) * B * (N_POLY // 2) * logn
         ops_total = B * OPS_PER_INSTANCE * world
@@ -246,6 +249,7 @@ def run_ours(args):
                        "l2": "inputs+intermediates exceed L2 (%.0f MiB of ciphertext per operand)" % (B * 2 * L * row / 2**20)},
             "e2e": {"value": ops_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": 2 * B * N_VEC * 8, "d2h_bytes_per_step": B * N_POLY * 8,
+                    "device_ms_per_step": e2e_dev / args.steps, "wall_ms_per_step": e2e_wall / args.steps,
                     "includes": "createCiphertext(x), createCiphertext(y) from pinned host slots, program, decryptCiphertext to host"},
             "gpu_launches": launches,
             "clocks": clocks,

@@ -1,0 +1,39 @@
+"""GPU: the reference's own RuntimeVisitor (compiled unchanged from /root/reference/src into oracle/_ref/libabc_ref.a)
+driving the C++ drop-in CudaCiphertextFactory (abc_b200/cpp) — the reference's SEAL-backed test cases with the
+factory swapped, and the batched end-to-end programs of SURVEY.md 8(d)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "abc_b200", "bin", "abc_driver")
+
+
+def run(*args):
+    assert os.path.exists(DRIVER), "abc_driver is not built (python -c 'import __graft_entry__ as g; g.build()')"
+    p = subprocess.run([DRIVER, *args], capture_output=True, text=True, timeout=600)
+    print(p.stdout[-4000:], p.stderr[-2000:])
+    summary = json.loads(p.stdout.strip().splitlines()[-1])
+    assert p.returncode == 0 and summary["failures"] == 0, p.stdout[-4000:]
+    return summary, p.stdout
+
+
+def test_reference_runtime_visitor_and_factory_kats():
+    summary, _ = run("kats")
+    assert summary["cases"] >= 25
+
+
+def test_batched_programs_n8192():
+    summary, out = run("programs", "8192")
+    assert summary["cases"] == 4
+    for name in ("HammingDistance", "L2Distance", "BoxBlur", "GxKernel"):
+        assert "[ ok ] program." + name in out
+
+
+def test_batched_programs_n16384():
+    # 8192 slots per row is not a square image: distance programs only
+    summary, _ = run("programs", "16384")
+    assert summary["cases"] == 2
