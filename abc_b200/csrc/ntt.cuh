@@ -32,9 +32,10 @@ enum { AR_SHOUP = 0, AR_FP = 1, AR_FP_LAZY = 2 };
 __device__ __forceinline__ int swz(int e) { return e ^ ((e >> 3) & 14); }
 
 template <int LOGN> struct NttPlan;
-template <> struct NttPlan<12> { static constexpr int R0 = 3, R1 = 3, R2 = 2, NSH = 1; };
-template <> struct NttPlan<13> { static constexpr int R0 = 3, R1 = 3, R2 = 3, NSH = 1; };
-template <> struct NttPlan<14> { static constexpr int R0 = 3, R1 = 3, R2 = 3, NSH = 2; };
+// strided passes (radix 2^R each); the contiguous pass (NttLast) takes the remaining stages
+template <> struct NttPlan<12> { static constexpr int R0 = 3, R1 = 3, R2 = 2; };   // + 1 shuffle + 3 in-register
+template <> struct NttPlan<13> { static constexpr int R0 = 3, R1 = 3, R2 = 3; };   // + 4 in-register (16 per thread)
+template <> struct NttPlan<14> { static constexpr int R0 = 3, R1 = 3, R2 = 3; };   // + 1 shuffle + 4 in-register
 
 template <int LOGN> struct NttDims {
   static constexpr int N = 1 << LOGN;
@@ -46,6 +47,17 @@ template <int LOGN> struct NttDims {
 
 // ---- modular product y*w with a precomputed companion c: lazy result in [0,2q)
 // AR_SHOUP: c = floor(w*2^64/q), any 64-bit y.   AR_FP*: c = bits of double(w/q), y < 2^51, result in (0,2q).
+// lo64(a*b + c) as one IMAD.WIDE + two IMAD (no separate carry adds): the shape ptxas keeps on the fma pipe
+__device__ __forceinline__ u64 mad_lo64(u64 a, u64 b, u64 c) {
+  u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), lo, hi;
+  u64 t;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t) : "r"(a0), "r"(b0), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(t));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(a0), "r"(b1));
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(a1), "r"(b0));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "r"(lo), "r"(hi));
+  return t;
+}
 template <int AR> __device__ __forceinline__ u64 mul_tw(u64 y, u64 w, u64 c, u64 q) {
   if (AR == AR_SHOUP) {
     return y * w - __umul64hi(y, c) * q;
@@ -53,7 +65,7 @@ template <int AR> __device__ __forceinline__ u64 mul_tw(u64 y, u64 w, u64 c, u64
     const double yd = __longlong_as_double((long long)(y | 0x4330000000000000ULL)) - 4503599627370496.0;
     const double t = fma(yd, __longlong_as_double((long long)c), 4503599627370496.0);
     const u64 qr = (u64)__double_as_longlong(t) & 0x000FFFFFFFFFFFFFULL;  // round(y*w/q), off by <= 1
-    return y * w - qr * q + q;
+    return mad_lo64(qr, 0 - q, mad_lo64(y, w, q));                        // y*w - qr*q + q  (mod 2^64)
   }
 }
 // x mod q for x < 2^51 via the FP64 pipe: result in (0,2q)
@@ -145,106 +157,120 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
   }
 }
 
-// ---- contiguous pass: 8 consecutive coefficients per thread; NSH shuffle stages + gaps 4,2,1 in registers
-template <int LOGN, int NSH, int AR>
+// ---- contiguous pass: every thread owns E = 8*IT CONSECUTIVE coefficients (8 or 16): gaps E/2..1 are in-register,
+// the NSH stages above them (gaps E, 2E) are warp-shuffle butterflies between lane pairs, each lane computing half
+// of the pair's butterflies.  (N = 8192: E = 16 and no shuffle stage at all.)
+template <int LOGN> struct NttLast {
+  // E = 16 (no shuffle stage at N = 8192) was measured slower than two groups of 8 with one shuffle stage
+  // (13.7 vs 15.0 Mrows/s forward): the 32 live data registers cost more than the shuffles save.
+  static constexpr int E = 8, LOGE = (E == 16) ? 4 : 3;
+  static constexpr int GROUPS = 8 * NttDims<LOGN>::IT / E;
+  static constexpr int NSH = LOGN - (NttPlan<LOGN>::R0 + NttPlan<LOGN>::R1 + NttPlan<LOGN>::R2) - LOGE;
+  static_assert(E == 8 || E == 16, "contiguous pass handles 8 or 16 coefficients per thread");
+  static_assert(NSH >= 0 && NSH <= 2, "stage plan does not add up");
+};
+
+template <int LOGN, int AR>
 __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 q2, int tid) {
-  typedef NttDims<LOGN> D;
+  typedef NttLast<LOGN> P;
+  constexpr int E = P::E, H = E / 2;
   const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.tw : M.twf;
 #pragma unroll
-  for (int it = 0; it < D::IT; ++it) {
-    const int vt = tid + it * D::T;
-    u64 x[8];
+  for (int g = 0; g < P::GROUPS; ++g) {
+  const int vt = tid + g * NttDims<LOGN>::T;
+  u64 x[E];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(8 * vt + 2 * i)]);
-      x[2 * i] = v.x; x[2 * i + 1] = v.y;
+  for (int i = 0; i < H; ++i) {
+    ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(E * vt + 2 * i)]);
+    x[2 * i] = v.x; x[2 * i + 1] = v.y;
+  }
+#pragma unroll
+  for (int j = P::NSH - 1; j >= 0; --j) {
+    const int s = LOGN - 1 - P::LOGE - j;
+    const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)vt >> (1 + j))]);
+    const bool hi = (vt >> j) & 1;
+#pragma unroll
+    for (int r = 0; r < H; ++r) {
+      u64 recv = __shfl_xor_sync(0xffffffffu, hi ? x[r] : x[H + r], 1 << j);
+      u64 a = hi ? recv : x[r];
+      u64 b = hi ? x[H + r] : recv;
+      bf_fwd<AR>(a, b, w, q, q2);
+      u64 got = __shfl_xor_sync(0xffffffffu, hi ? a : b, 1 << j);
+      x[r] = hi ? got : a;
+      x[H + r] = hi ? b : got;
     }
+  }
 #pragma unroll
-    for (int j = NSH - 1; j >= 0; --j) {
-      const int s = LOGN - 4 - j;
-      const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)vt >> (1 + j))]);
-      const bool hi = (vt >> j) & 1;
+  for (int b = P::LOGE - 1; b >= 0; --b) {
+    const int s = LOGN - 1 - b;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        u64 recv = __shfl_xor_sync(0xffffffffu, hi ? x[r] : x[4 + r], 1 << j);
-        u64 a = hi ? recv : x[r];
-        u64 b = hi ? x[4 + r] : recv;
-        bf_fwd<AR>(a, b, w, q, q2);
-        u64 got = __shfl_xor_sync(0xffffffffu, hi ? a : b, 1 << j);
-        x[r] = hi ? got : a;
-        x[4 + r] = hi ? b : got;
-      }
+    for (int r = 0; r < E; ++r) {
+      if (r & (1 << b)) continue;
+      const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)(E * vt + r) >> (b + 1))]);
+      bf_fwd<AR>(x[r], x[r | (1 << b)], w, q, q2);
     }
+  }
 #pragma unroll
-    for (int b = 2; b >= 0; --b) {
-      const int s = LOGN - 1 - b;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if (r & (1 << b)) continue;
-        const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)(8 * vt + r) >> (b + 1))]);
-        bf_fwd<AR>(x[r], x[r | (1 << b)], w, q, q2);
-      }
+  for (int i = 0; i < H; ++i) {
+    ulonglong2 v;
+    if (AR == AR_FP_LAZY) {
+      const double qinv = __longlong_as_double((long long)M.qinv_bits);
+      v.x = csub(reduce_fp(x[2 * i], qinv, q), q);
+      v.y = csub(reduce_fp(x[2 * i + 1], qinv, q), q);
+    } else {
+      v.x = csub(csub(x[2 * i], q2), q);
+      v.y = csub(csub(x[2 * i + 1], q2), q);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      ulonglong2 v;
-      if (AR == AR_FP_LAZY) {
-        const double qinv = __longlong_as_double((long long)M.qinv_bits);
-        v.x = csub(reduce_fp(x[2 * i], qinv, q), q);
-        v.y = csub(reduce_fp(x[2 * i + 1], qinv, q), q);
-      } else {
-        v.x = csub(csub(x[2 * i], q2), q);
-        v.y = csub(csub(x[2 * i + 1], q2), q);
-      }
-      *reinterpret_cast<ulonglong2 *>(&sm[swz(8 * vt + 2 * i)]) = v;
-    }
+    *reinterpret_cast<ulonglong2 *>(&sm[swz(E * vt + 2 * i)]) = v;
+  }
   }
 }
 
-template <int LOGN, int NSH, int AR>
-__device__ __forceinline__ void ntt_inv_first(u64 *sm, const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 q2,
-                                              int tid) {
-  typedef NttDims<LOGN> D;
+template <int LOGN, int AR>
+__device__ __forceinline__ void ntt_inv_first(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 q2, int tid) {
+  typedef NttLast<LOGN> P;
+  constexpr int E = P::E, H = E / 2;
+  const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.itw : M.itwf;
 #pragma unroll
-  for (int it = 0; it < D::IT; ++it) {
-    const int vt = tid + it * D::T;
-    u64 x[8];
+  for (int g = 0; g < P::GROUPS; ++g) {
+  const int vt = tid + g * NttDims<LOGN>::T;
+  u64 x[E];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(8 * vt + 2 * i)]);
-      x[2 * i] = v.x; x[2 * i + 1] = v.y;
+  for (int i = 0; i < H; ++i) {
+    ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(E * vt + 2 * i)]);
+    x[2 * i] = v.x; x[2 * i + 1] = v.y;
+  }
+#pragma unroll
+  for (int b = 0; b < P::LOGE; ++b) {
+    const int s = LOGN - 1 - b;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      if (r & (1 << b)) continue;
+      const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)(E * vt + r) >> (b + 1))]);
+      bf_inv<AR>(x[r], x[r | (1 << b)], w, q, q2);
     }
+  }
 #pragma unroll
-    for (int b = 0; b < 3; ++b) {
-      const int s = LOGN - 1 - b;
+  for (int j = 0; j < P::NSH; ++j) {
+    const int s = LOGN - 1 - P::LOGE - j;
+    const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)vt >> (1 + j))]);
+    const bool hi = (vt >> j) & 1;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if (r & (1 << b)) continue;
-        const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)(8 * vt + r) >> (b + 1))]);
-        bf_inv<AR>(x[r], x[r | (1 << b)], w, q, q2);
-      }
+    for (int r = 0; r < H; ++r) {
+      u64 recv = __shfl_xor_sync(0xffffffffu, hi ? x[r] : x[H + r], 1 << j);
+      u64 a = hi ? recv : x[r];
+      u64 b = hi ? x[H + r] : recv;
+      bf_inv<AR>(a, b, w, q, q2);
+      u64 got = __shfl_xor_sync(0xffffffffu, hi ? a : b, 1 << j);
+      x[r] = hi ? got : a;
+      x[H + r] = hi ? b : got;
     }
+  }
 #pragma unroll
-    for (int j = 0; j < NSH; ++j) {
-      const int s = LOGN - 4 - j;
-      const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)vt >> (1 + j))]);
-      const bool hi = (vt >> j) & 1;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        u64 recv = __shfl_xor_sync(0xffffffffu, hi ? x[r] : x[4 + r], 1 << j);
-        u64 a = hi ? recv : x[r];
-        u64 b = hi ? x[4 + r] : recv;
-        bf_inv<AR>(a, b, w, q, q2);
-        u64 got = __shfl_xor_sync(0xffffffffu, hi ? a : b, 1 << j);
-        x[r] = hi ? got : a;
-        x[4 + r] = hi ? b : got;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      ulonglong2 v; v.x = x[2 * i]; v.y = x[2 * i + 1];
-      *reinterpret_cast<ulonglong2 *>(&sm[swz(8 * vt + 2 * i)]) = v;
-    }
+  for (int i = 0; i < H; ++i) {
+    ulonglong2 v; v.x = x[2 * i]; v.y = x[2 * i + 1];
+    *reinterpret_cast<ulonglong2 *>(&sm[swz(E * vt + 2 * i)]) = v;
+  }
   }
 }
 
@@ -263,7 +289,7 @@ __device__ __forceinline__ void ntt_fwd_smem(u64 *sm, const ModInfo &M, u32 twba
     ntt_fwd_mid<LOGN, P::R0 + P::R1, P::R2, AR>(sm, tw, twbase, q, q2, tid);
     __syncthreads();
   }
-  ntt_fwd_last<LOGN, P::NSH, AR>(sm, M, twbase, q, q2, tid);
+  ntt_fwd_last<LOGN, AR>(sm, M, twbase, q, q2, tid);
   __syncthreads();
 }
 // Inverse: input < 2q, output in [0,2q) (the caller's copy-out does the final conditional subtract).
@@ -273,7 +299,7 @@ __device__ __forceinline__ void ntt_inv_smem(u64 *sm, const ModInfo &M, u32 twba
   typedef NttPlan<LOGN> P;
   constexpr int A = (AR == AR_FP_LAZY) ? AR_FP : AR;  // the inverse keeps its guards
   const u64 q = M.q, q2 = 2 * q;
-  ntt_inv_first<LOGN, P::NSH, A>(sm, (A == AR_SHOUP) ? M.itw : M.itwf, twbase, q, q2, tid);
+  ntt_inv_first<LOGN, A>(sm, M, twbase, q, q2, tid);
   __syncthreads();
   if constexpr (P::R2 > 0) {
     ntt_inv_mid<LOGN, P::R0 + P::R1, P::R2, false, A>(sm, M, twbase, q, q2, tid);
