@@ -69,7 +69,8 @@ SYMBOLS = {
     "abc_profile_enable": (i32, [vp, i32]),
     "abc_profile_json": (C.c_char_p, [vp]),
     "abc_measure_int_peak": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
-    "abc_measure_butterfly_peak": (i32, [vp, C.POINTER(C.c_double)]),
+    "abc_measure_butterfly_peak": (i32, [vp, i32, C.POINTER(C.c_double)]),
+    "abc_ntt_arith_class": (i32, [vp]),
 }
 
 _lib = None

@@ -200,9 +200,13 @@ class CudaCiphertextFactory:
         self._ck(self._lib.abc_measure_int_peak(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def measure_butterfly_peak(self):
+    def ntt_arith_class(self):
+        return int(self._lib.abc_ntt_arith_class(self._h))
+
+    def measure_butterfly_peak(self, arith_class=None):
         a = C.c_double()
-        self._ck(self._lib.abc_measure_butterfly_peak(self._h, C.byref(a)))
+        ar = self.ntt_arith_class() if arith_class is None else arith_class
+        self._ck(self._lib.abc_measure_butterfly_peak(self._h, ar, C.byref(a)))
         return a.value
 
 

@@ -362,15 +362,19 @@ __global__ void __launch_bounds__(1024) k_peak_iadd(u32 *out, int iters) {
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
 }
-// 64-bit Shoup butterflies per second (the unit the NTT roofline is quoted in)
-__global__ void __launch_bounds__(1024) k_peak_butterfly(u64 *out, int iters, u64 q, u64 w, u64 ws) {
+// register-resident NTT butterflies per second for one arithmetic class (the ceiling NTT kernels are quoted against)
+template <int AR>
+__global__ void __launch_bounds__(1024) k_peak_butterfly(u64 *out, int iters, u64 q, u64 w, u64 wc) {
   u64 x0 = threadIdx.x, y0 = blockIdx.x, x1 = x0 + 1, y1 = y0 + 2, x2 = x0 + 3, y2 = y0 + 4, x3 = x0 + 5, y3 = y0 + 6;
-  const ulonglong2 tw = make_ulonglong2(w, ws);
+  const ulonglong2 tw = make_ulonglong2(w, wc);
   const u64 q2 = 2 * q;
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      bf_fwd<AR_SHOUP>(x0, y0, tw, q, q2); bf_fwd<AR_SHOUP>(x1, y1, tw, q, q2); bf_fwd<AR_SHOUP>(x2, y2, tw, q, q2); bf_fwd<AR_SHOUP>(x3, y3, tw, q, q2);
+      bf_fwd<AR>(x0, y0, tw, q, q2); bf_fwd<AR>(x1, y1, tw, q, q2); bf_fwd<AR>(x2, y2, tw, q, q2); bf_fwd<AR>(x3, y3, tw, q, q2);
+    }
+    if (AR == AR_FP_LAZY) {  // the unguarded class needs a range reset now and then (amortised: 8 of 32+8)
+      x0 &= q - 1; y0 &= q - 1; x1 &= q - 1; y1 &= q - 1; x2 &= q - 1; y2 &= q - 1; x3 &= q - 1; y3 &= q - 1;
     }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ y0 ^ x1 ^ y1 ^ x2 ^ y2 ^ x3 ^ y3;

@@ -1024,20 +1024,25 @@ abc_status abc_measure_int_peak(abc_ctx *c, double *imad_per_s, double *iadd_per
   return ABC_OK;
 }
 
-abc_status abc_measure_butterfly_peak(abc_ctx *c, double *butterflies_per_s) {
+int abc_ntt_arith_class(const abc_ctx *c) { return c->force_ar >= 0 && c->force_ar < c->ar_q ? c->force_ar : c->ar_q; }
+
+abc_status abc_measure_butterfly_peak(abc_ctx *c, int arith_class, double *butterflies_per_s) {
   CK(cudaSetDevice(c->device));
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
   const int grid = sms * 2, iters = 512;
   u64 *out = nullptr;
   TRY(salloc(c, &out, (size_t)grid * 1024));
-  const u64 q = c->primes[0];
-  const ulonglong2 w = make_ulonglong2(q / 3, hm::shoup(q / 3, q));
+  const u64 q = c->primes[0], w = q / 3;
+  double wd = (double)w / (double)q;
+  u64 wc_fp; memcpy(&wc_fp, &wd, 8);
   const double n = (double)grid * 1024 * iters * 8 * 4;
   float ms = 0;
   for (int rep = 0; rep < 2; ++rep) {
     CK(cudaEventRecord(c->ev0, c->stream));
-    k_peak_butterfly<<<grid, 1024, 0, c->stream>>>(out, iters, q, w.x, w.y);
+    if (arith_class == AR_SHOUP) k_peak_butterfly<AR_SHOUP><<<grid, 1024, 0, c->stream>>>(out, iters, q, w, hm::shoup(w, q));
+    else if (arith_class == AR_FP) k_peak_butterfly<AR_FP><<<grid, 1024, 0, c->stream>>>(out, iters, q, w, wc_fp);
+    else k_peak_butterfly<AR_FP_LAZY><<<grid, 1024, 0, c->stream>>>(out, iters, q, w, wc_fp);
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaEventSynchronize(c->ev1));
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));

@@ -264,10 +264,14 @@ def run_ours(args):
                          "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": how,
                          "share_of_step": top["ms"] / tot,
                          "note": "this kernel family is INT-pipe-bound, see int_roofline"},
-            "int_roofline": {"unit": "64-bit Shoup butterflies/s", "achieved": ntt_bf / (ntt_ms * 1e-3), "peak": bf_peak,
+            "int_roofline": {"unit": "64-bit modular NTT butterflies/s (all limb-pipeline kernels of the step)",
+                             "achieved": ntt_bf / (ntt_ms * 1e-3), "peak": bf_peak,
                              "frac": ntt_bf / (ntt_ms * 1e-3) / bf_peak, "ntt_share_of_step": ntt_ms / tot,
+                             "arith_class": f.ntt_arith_class(), "peak_shoup_class": f.measure_butterfly_peak(0),
                              "imad_per_s": imad, "iadd_lop_per_s": iadd,
-                             "peak_source": "measured in this run (k_peak_butterfly / k_peak_imad / k_peak_iadd)"},
+                             "peak_source": "register-resident butterflies of the same arithmetic class, no memory "
+                                            "traffic, measured in this run (k_peak_butterfly); IMAD / IADD+LOP issue "
+                                            "rates from k_peak_imad / k_peak_iadd"},
             "kernels": [{"kernel": r["kernel"], "launches": r["launches"], "ms": round(r["ms"], 4),
                          "share": round(r["ms"] / tot, 4)} for r in sorted(prof, key=lambda r: -r["ms"])],
             "per_op": {"programs_per_s": B * world * args.steps / (ms * 1e-3)},

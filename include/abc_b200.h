@@ -134,8 +134,11 @@ const char *abc_profile_json(abc_ctx *ctx);
 
 /* integer-pipe issue-rate microbenchmark (IMAD / IADD3-class ops per second, whole GPU) */
 abc_status abc_measure_int_peak(abc_ctx *ctx, double *imad_per_s, double *iadd_per_s);
-/* dependent-chain-free 64-bit Harvey/Shoup butterflies per second, whole GPU: the unit NTT rooflines are quoted in */
-abc_status abc_measure_butterfly_peak(abc_ctx *ctx, double *butterflies_per_s);
+/* register-resident 64-bit NTT butterflies per second, whole GPU (no memory traffic): the ceiling NTT kernels are
+ * quoted against.  arith_class: 0 Shoup, 1 FP64-assisted, 2 FP64-assisted without range guards (see csrc/ntt.cuh) */
+abc_status abc_measure_butterfly_peak(abc_ctx *ctx, int arith_class, double *butterflies_per_s);
+/* arithmetic class the context uses for its key-level primes */
+int abc_ntt_arith_class(const abc_ctx *ctx);
 
 #ifdef __cplusplus
 }
