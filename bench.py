@@ -208,10 +208,8 @@ def run_ours(args):
     barrier()
 
     # max over ranks
-    if world > 1:
-        tt = torch.tensor([ms, e2e_ms, e2e_wall], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, e2e_wall = [float(v) for v in tt.tolist()]
+    from abc_b200.sharding import max_over_ranks
+    ms, e2e_ms, e2e_wall = max_over_ranks([ms, e2e_ms, e2e_wall], dist if world > 1 else None, "cuda")
     e2e_dev = e2e_ms
     e2e_ms = max(e2e_ms, e2e_wall)
 
