@@ -59,6 +59,10 @@ struct abc_ctx {
   std::string prof_json;
   size_t flush_bytes = 0;
   void *flush_buf = nullptr;
+  // grow-only scratch slots reused by every op (one stream: an op's scratch is dead before the next op starts).
+  // Allocating these per op from the stream-ordered pool fragmented it (135 MB / 335 MB / 170 MB blocks) and cost ms.
+  u64 *sc_ptr[12] = {nullptr};
+  size_t sc_words[12] = {0};
 };
 struct abc_ct { abc_ctx *ctx; u64 *d; };
 struct abc_pt { abc_ctx *ctx; u64 *d; int broadcast; };
@@ -97,6 +101,17 @@ abc_status salloc(abc_ctx *c, u64 **p, size_t words) {
   return ABC_OK;
 }
 void sfree(abc_ctx *c, void *p) { if (p) cudaFreeAsync(p, c->stream); }
+enum { SC_T = 0, SC_ACC, SC_X, SC_OUT3, SC_U, SC_TMP, SC_DECX, SC_DECP, SC_P, SC_NK, SC_ENTT };
+abc_status scratch(abc_ctx *c, int slot, u64 **p, size_t words) {
+  if (c->sc_words[slot] < words) {
+    if (c->sc_ptr[slot]) cudaFreeAsync(c->sc_ptr[slot], c->stream);
+    c->sc_ptr[slot] = nullptr; c->sc_words[slot] = 0;
+    CK(cudaMallocAsync((void **)&c->sc_ptr[slot], words * sizeof(u64), c->stream));
+    c->sc_words[slot] = words;
+  }
+  *p = c->sc_ptr[slot];
+  return ABC_OK;
+}
 
 template <typename T> abc_status upload(abc_ctx *c, T **dst, const std::vector<T> &v) {
   CK(cudaMalloc((void **)dst, v.size() * sizeof(T)));
@@ -327,8 +342,8 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
                      long long base0_is, const u64 *base1, long long base1_is, u32 einv, u64 *dst) {
   const int N = c->N, L = c->L, k = c->k, B = c->B;
   u64 *T = nullptr, *acc = nullptr;
-  TRY(salloc(c, &T, (size_t)B * k * L * N));
-  TRY(salloc(c, &acc, (size_t)B * 2 * k * N));
+  TRY(scratch(c, SC_T, &T, (size_t)B * k * L * N));
+  TRY(scratch(c, SC_ACC, &acc, (size_t)B * 2 * k * N));
   LimbJob j = blank_job();
   j.dst = T; j.dst_is = (long long)k * L * N; j.src = target; j.src_is = target_is;
   j.rowmod = c->rm_modup; j.rowsrc = c->rs_modup; j.galois_einv = einv;
@@ -348,7 +363,6 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   j.C = c->dC; j.tl = acc; j.tl_is = (long long)2 * k * N; j.L = L; j.k = k;
   j.base0 = base0; j.base0_is = base0_is; j.base1 = base1; j.base1_is = base1_is; j.base_einv = einv;
   TRY(launch_limb(c, LIMB_INV_MODDOWN, c->ar_q, j, 2 * L, B, "ks_intt_moddown"));
-  sfree(c, T); sfree(c, acc);
   return ABC_OK;
 }
 
@@ -356,7 +370,7 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
 abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
   const int N = c->N, L = c->L, B = c->B, W = c->W;
   u64 *X = nullptr;
-  TRY(salloc(c, &X, (size_t)B * 4 * W * N));
+  TRY(scratch(c, SC_X, &X, (size_t)B * 4 * W * N));
   {
     Launch l(c, "behz_lift");
     DISPATCH_L(c, (k_behz_lift<LL><<<dim3(N / 128, 4, B), 128, 0, c->stream>>>(a, b, X, c->dC, N)));
@@ -389,7 +403,6 @@ abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
     DISPATCH_L(c, (k_behz_scale<LL><<<dim3(N / 128, 3, B), 128, 0, c->stream>>>(X, out3, c->dC, N)));
     CK(cudaGetLastError());
   }
-  sfree(c, X);
   return ABC_OK;
 }
 
@@ -461,8 +474,8 @@ abc_status encrypt_device(abc_ctx *c, const u64 *plain, int broadcast, u64 *ct) 
   const u64 nonce0 = c->enc_nonce * (u64)B;
   c->enc_nonce++;
   u64 *u = nullptr, *tmp = nullptr;
-  TRY(salloc(c, &u, (size_t)B * k * N));
-  TRY(salloc(c, &tmp, (size_t)B * 2 * k * N));
+  TRY(scratch(c, SC_U, &u, (size_t)B * k * N));
+  TRY(scratch(c, SC_TMP, &tmp, (size_t)B * 2 * k * N));
   LimbJob j = blank_job();
   j.dst = u; j.dst_is = (long long)k * N; j.rowmod = c->rm_key;
   j.seed = c->seed; j.domain = DOM_ENC; j.a0 = nonce0; j.b = 0;
@@ -478,14 +491,13 @@ abc_status encrypt_device(abc_ctx *c, const u64 *plain, int broadcast, u64 *ct) 
                                                            L, k);
     CK(cudaGetLastError());
   }
-  sfree(c, u); sfree(c, tmp);
   return ABC_OK;
 }
 
 abc_status mul_plain_device(abc_ctx *c, u64 *dst, const u64 *a, const u64 *plain, int broadcast) {
   const int N = c->N, L = c->L, B = c->B, Bp = broadcast ? 1 : B;
   u64 *P = nullptr;
-  TRY(salloc(c, &P, (size_t)Bp * L * N));
+  TRY(scratch(c, SC_P, &P, (size_t)Bp * L * N));
   LimbJob j = blank_job();
   j.t = c->t; j.t_half_up = (c->t + 1) >> 1;
   j.src = plain; j.src_is = N; j.rowsrc = c->rs_zero; j.dst = P; j.dst_is = (long long)L * N; j.rowmod = c->rm_ct;
@@ -494,7 +506,6 @@ abc_status mul_plain_device(abc_ctx *c, u64 *dst, const u64 *a, const u64 *plain
   j.src = a; j.dst = dst; j.src_is = j.dst_is = (long long)2 * L * N; j.rowmod = c->rm_ct;
   j.mul = P; j.mul_is = broadcast ? 0 : (long long)L * N; j.rowmul = c->rm_ct;
   TRY(launch_limb(c, LIMB_FWD_MUL_INV, c->ar_q, j, 2 * L, B, "ct_mul_plain"));
-  sfree(c, P);
   return ABC_OK;
 }
 
@@ -615,6 +626,7 @@ void abc_ctx_destroy(abc_ctx *c) {
   cudaFree(c->d_sk); cudaFree(c->d_pk); cudaFree(c->d_relin);
   for (void *p : c->owned) cudaFree(p);
   if (c->flush_buf) cudaFree(c->flush_buf);
+  for (u64 *p : c->sc_ptr) if (p) cudaFree(p);
   for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -652,8 +664,8 @@ abc_status abc_keygen(abc_ctx *c) {
   j.dst = c->d_sk; j.rowmod = c->rm_key; j.seed = c->seed; j.domain = DOM_SK;
   TRY(launch_limb(c, LIMB_TERNARY_FWD, c->ar_q, j, k, 1, "keygen_sk_ntt"));
   u64 *nk = nullptr, *e_ntt = nullptr;
-  TRY(salloc(c, &nk, (size_t)k * N));
-  TRY(salloc(c, &e_ntt, (size_t)k * N));
+  TRY(scratch(c, SC_NK, &nk, (size_t)k * N));
+  TRY(scratch(c, SC_ENTT, &e_ntt, (size_t)k * N));
   TRY(gen_key_block(c, c->d_pk, DOM_PK, 0, 0, nullptr, -1, e_ntt));
   TRY(gen_kswitch_key(c, c->d_relin, 0, 0, nk, e_ntt));
   for (u32 elt : galois_elts_all(c)) {
@@ -663,7 +675,6 @@ abc_status abc_keygen(abc_ctx *c) {
     c->galois[elt] = key;
     TRY(gen_kswitch_key(c, key, elt, elt, nk, e_ntt));
   }
-  sfree(c, nk); sfree(c, e_ntt);
   c->have_keys = true;
   return ABC_OK;
 }
@@ -783,8 +794,8 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
   const int N = c->N, L = c->L, B = c->B;
   u64 *x = nullptr, *plain = nullptr;
   long long *d_out = nullptr;
-  TRY(salloc(c, &x, (size_t)B * L * N));
-  TRY(salloc(c, &plain, (size_t)B * N));
+  TRY(scratch(c, SC_DECX, &x, (size_t)B * L * N));
+  TRY(scratch(c, SC_DECP, &plain, (size_t)B * N));
   CK(cudaMallocAsync((void **)&d_out, (size_t)B * N * sizeof(long long), c->stream));
   LimbJob j = blank_job();
   j.src = ct->d; j.src_is = (long long)2 * L * N; j.rowsrc = c->rs_c1;
@@ -802,7 +813,7 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
   TRY(launch_limb(c, LIMB_FWD_DECODE, c->ar_t, j, 1, B, "decode_ntt"));
   CK(cudaMemcpyAsync(out_slots, d_out, (size_t)B * N * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  sfree(c, x); sfree(c, plain); sfree(c, d_out);
+  sfree(c, d_out);
   return ABC_OK;
 }
 
@@ -829,10 +840,9 @@ abc_status abc_mul_relin(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct 
   if (!c->d_relin) return fail(c, ABC_ERR_STATE, "relinearisation key not present");
   const size_t LN = (size_t)c->L * c->N;
   u64 *out3 = nullptr;
-  TRY(salloc(c, &out3, (size_t)c->B * 3 * LN));
+  TRY(scratch(c, SC_OUT3, &out3, (size_t)c->B * 3 * LN));
   TRY(behz_multiply(c, a->d, b->d, out3));
   TRY(keyswitch(c, out3 + 2 * LN, 3ll * LN, c->d_relin, out3, 3ll * LN, out3 + LN, 3ll * LN, 0, dst->d));
-  sfree(c, out3);
   return ABC_OK;
 }
 
@@ -958,6 +968,7 @@ abc_status abc_timer_stop(abc_ctx *c, float *ms) {
 abc_status abc_flush_l2(abc_ctx *c, size_t bytes) {
   if (bytes > c->flush_bytes) {
     if (c->flush_buf) cudaFree(c->flush_buf);
+  for (u64 *p : c->sc_ptr) if (p) cudaFree(p);
     c->flush_buf = nullptr; c->flush_bytes = 0;
     CK(cudaMalloc(&c->flush_buf, bytes));
     c->flush_bytes = bytes;
