@@ -339,6 +339,22 @@ __global__ void __launch_bounds__(256) k_newkey(u64 *__restrict__ nk, const u64 
 }
 
 // ------------------------------------------------------------------------------------------------
+// BatchEncoder scatter / gather as separate kernels for N >= 32768 (below that they are fused into the limb pipeline)
+// grid: (N/256, 1, B)
+__global__ void __launch_bounds__(256) k_encode_scatter(const long long *__restrict__ slots, long long slots_is, int n_slots,
+                                                        const u32 *__restrict__ index_map, u64 *__restrict__ plain, u64 t, int N) {
+  const int e = blockIdx.x * 256 + threadIdx.x, inst = blockIdx.z;
+  const long long v = slots[(size_t)inst * slots_is + (e < n_slots ? e : n_slots - 1)];
+  plain[(size_t)inst * N + index_map[e]] = v < 0 ? t + (u64)v : (u64)v;
+}
+__global__ void __launch_bounds__(256) k_decode_gather(const u64 *__restrict__ vals, const u32 *__restrict__ index_map,
+                                                       long long *__restrict__ out, u64 t, int N) {
+  const int e = blockIdx.x * 256 + threadIdx.x, inst = blockIdx.z;
+  const u64 v = vals[(size_t)inst * N + index_map[e]];
+  out[(size_t)inst * N + e] = v > (t >> 1) ? (long long)v - (long long)t : (long long)v;
+}
+
+// ------------------------------------------------------------------------------------------------
 // integer-pipe issue-rate microbenchmarks (the INT roofline denominator)
 __global__ void __launch_bounds__(1024) k_peak_imad(u32 *out, int iters) {
   u32 a = threadIdx.x, b = blockIdx.x | 1, c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;

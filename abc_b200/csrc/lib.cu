@@ -129,7 +129,8 @@ abc_status launch_limb(abc_ctx *c, int combo, int ar, const LimbJob &job, int W,
     case 12: e = limb_dispatch<12>(combo, ar, job, c->d_mods, W, B, c->stream); break;
     case 13: e = limb_dispatch<13>(combo, ar, job, c->d_mods, W, B, c->stream); break;
     case 14: e = limb_dispatch<14>(combo, ar, job, c->d_mods, W, B, c->stream); break;
-    default: return fail(c, ABC_ERR_UNSUPPORTED, "poly_degree not supported by the shared-memory NTT (4096, 8192, 16384)");
+    case 15: case 16: e = limb_dispatch_big(c->logN - 13, combo, job, c->d_mods, W, B, c->stream); break;
+    default: return fail(c, ABC_ERR_UNSUPPORTED, "poly_degree not supported (4096 .. 65536)");
   }
   if (e != 0) { c->err = std::string(name) + ": " + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
   return ABC_OK;
@@ -462,7 +463,17 @@ abc_status encode_device(abc_ctx *c, const int64_t *slots, size_t n, int broadca
   LimbJob j = blank_job();
   j.dst = plain; j.dst_is = N; j.rowmod = c->rm_t;
   j.slots_in = d_slots; j.slots_is = (long long)n; j.n_slots = (int)n; j.index_map = c->d_index_map;
-  TRY(launch_limb(c, LIMB_ENCODE_INV, c->ar_t, j, 1, Bp, "encode_intt"));
+  if (c->logN >= 15) {  // two-pass sizes: scatter kernel, then INTT mod t in place
+    {
+      Launch l(c, "encode_scatter");
+      k_encode_scatter<<<dim3(N / 256, 1, Bp), 256, 0, c->stream>>>(d_slots, (long long)n, (int)n, c->d_index_map, plain, c->t, N);
+      CK(cudaGetLastError());
+    }
+    j.src = plain; j.src_is = N;
+    TRY(launch_limb(c, LIMB_INV, c->ar_t, j, 1, Bp, "encode_intt"));
+  } else {
+    TRY(launch_limb(c, LIMB_ENCODE_INV, c->ar_t, j, 1, Bp, "encode_intt"));
+  }
   sfree(c, d_slots);
   *plain_out = plain;
   return ABC_OK;
@@ -588,7 +599,7 @@ abc_status abc_ctx_create(const abc_params *p, abc_ctx **out) {
   const u64 N = p->poly_degree;
   int logN = 0;
   while ((1ull << logN) < N) ++logN;
-  if ((1ull << logN) != N || logN < 10 || logN > 15) return bail(ABC_ERR_PARAM, "poly_degree must be a power of two in [1024, 32768]");
+  if ((1ull << logN) != N || logN < 12 || logN > 16) return bail(ABC_ERR_PARAM, "poly_degree must be a power of two in [4096, 65536]");
   c->N = (int)N; c->logN = logN; c->B = p->batch ? (int)p->batch : 1; c->seed = p->seed;
   try {
     if (p->n_primes == 0) c->primes = hm::bfv_default_primes(N);
@@ -810,7 +821,15 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
   }
   j = blank_job();
   j.src = plain; j.src_is = N; j.rowmod = c->rm_t; j.slots_out = d_out; j.index_map = c->d_index_map;
-  TRY(launch_limb(c, LIMB_FWD_DECODE, c->ar_t, j, 1, B, "decode_ntt"));
+  if (c->logN >= 15) {  // two-pass sizes: NTT mod t in place, then gather kernel
+    j.dst = plain; j.dst_is = N;
+    TRY(launch_limb(c, LIMB_FWD, c->ar_t, j, 1, B, "decode_ntt"));
+    Launch l(c, "decode_gather");
+    k_decode_gather<<<dim3(N / 256, 1, B), 256, 0, c->stream>>>(plain, c->d_index_map, d_out, c->t, N);
+    CK(cudaGetLastError());
+  } else {
+    TRY(launch_limb(c, LIMB_FWD_DECODE, c->ar_t, j, 1, B, "decode_ntt"));
+  }
   CK(cudaMemcpyAsync(out_slots, d_out, (size_t)B * N * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   sfree(c, d_out);

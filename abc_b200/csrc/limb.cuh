@@ -1,7 +1,14 @@
-// limb.cuh — the limb pipeline kernel: one CTA = one RNS limb staged whole in shared memory:
-//   load (with a pre-op) -> [forward NTT] -> [pointwise * mul row] -> [inverse NTT] -> store (with a post-op)
-// Every NTT of the BFV path runs through this kernel, fused with the elementwise work either side of it
-// (ModUp reduction, plaintext lift, sampling, BatchEncoder scatter/gather, dyadic product, c0 accumulate).
+// limb.cuh — the limb pipeline: every NTT of the BFV path, fused with the elementwise work either side of it.
+//
+// N <= 16384: one CTA = one RNS limb staged whole in shared memory (k_limb):
+//   load (pre-op) -> [forward NTT] -> [pointwise * mul row] -> [inverse NTT] -> store (post-op)
+// N >= 32768 (a limb is 256-512 KiB, more than an SM's shared memory): two passes.  The first A = log2(N) - 13
+//   stages have gaps >= 8192 and run as register butterflies straight from global memory, 2^A strided
+//   coefficients per thread (k_head_fwd, carrying the pre-op); the remaining 13 stages are confined to 2^A
+//   contiguous blocks of 8192 coefficients, each of which is one k_limb CTA in TAIL mode (twiddle base 2^A + block).
+//   The inverse runs the tail first and k_head_inv last (carrying N^-1 and the post-op).
+// Pre-ops: ModUp reduction, Galois gather + ModUp, plaintext centred lift, ternary / CBD sampling, BatchEncoder
+// scatter.  Post-ops: store, + row, BatchEncoder gather, ModDown with rounding + base accumulate.
 #pragma once
 #include "devconst.cuh"
 #include "ntt.cuh"
@@ -16,6 +23,8 @@ struct LimbJob {
   const int *rowdst;                          // [W] destination row, or nullptr = w
   const int *rowsrc;                          // [W] source row, or nullptr = destination row
   const int *rowmul;                          // [W] row of `mul`/`add`, or nullptr = w
+  int n;                                      // coefficients per limb (row stride); = kernel N except in TAIL mode
+  int sub;                                    // TAIL mode: log2(blocks per limb); blockIdx.x = row << sub | block
   // sampler (PRE_TERNARY / PRE_CBD): stream = stream_key(seed, domain, a0 + inst, b)
   u64 seed, domain, a0, b;
   // PRE_ENCODE / POST_DECODE
@@ -59,66 +68,120 @@ __device__ __forceinline__ int sample_cbd(u64 h, u64 idx) {
   return __popcll(r & 0x1fffffULL) - __popcll((r >> 21) & 0x1fffffULL);
 }
 
-template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST, int AR>
+// ---- pre-op: coefficients (2*e2, 2*e2+1) of source row `srow`, ready for the forward transform (< q)
+// h = sampler stream key (sampling modes); n = coefficients per limb
+template <int PRE>
+__device__ __forceinline__ ulonglong2 limb_load_pair(const LimbJob &job, const ModInfo &M, const ModInfo *__restrict__ mods,
+                                                     int n, int inst, int srow, int e2, u64 h) {
+  const u64 q = M.q;
+  ulonglong2 v;
+  if (PRE == PRE_TERNARY || PRE == PRE_CBD) {
+    const int a = (PRE == PRE_TERNARY) ? sample_ternary(h, (u64)(2 * e2)) : sample_cbd(h, (u64)(2 * e2));
+    const int b = (PRE == PRE_TERNARY) ? sample_ternary(h, (u64)(2 * e2 + 1)) : sample_cbd(h, (u64)(2 * e2 + 1));
+    v.x = small_to_mod(a, q); v.y = small_to_mod(b, q);
+  } else if (PRE == PRE_GALOIS_REDUCE) {
+    // GaloisTool::apply_galois as a gather (negation is modulo the SOURCE limb's prime), then the ModUp reduction
+    const u64 *src = job.src + (size_t)inst * job.src_is + (size_t)srow * n;
+    const u64 qs = mods[srow].q;
+    const u32 einv = job.galois_einv, m2 = 2u * n - 1;
+    const u32 r0 = ((u32)(2 * e2) * einv) & m2, r1 = (r0 + einv) & m2;
+    v.x = src[r0 & (n - 1)]; v.y = src[r1 & (n - 1)];
+    if (r0 >= (u32)n) v.x = neg_mod(v.x, qs);
+    if (r1 >= (u32)n) v.y = neg_mod(v.y, qs);
+    v.x = barrett64(v.x, q, M.mu_hi); v.y = barrett64(v.y, q, M.mu_hi);
+  } else {
+    v = reinterpret_cast<const ulonglong2 *>(job.src + (size_t)inst * job.src_is + (size_t)srow * n)[e2];
+    if (PRE == PRE_REDUCE) { v.x = barrett64(v.x, q, M.mu_hi); v.y = barrett64(v.y, q, M.mu_hi); }
+    if (PRE == PRE_PLAIN_LIFT) {
+      // multiply_plain_normal: centred lift of a mod-t coefficient into [0,q)
+      const u64 th = job.t_half_up, inc = q - job.t;
+      v.x = v.x >= th ? v.x + inc : v.x;
+      v.y = v.y >= th ? v.y + inc : v.y;
+    }
+  }
+  return v;
+}
+
+// ---- post-op on canonical coefficients (2*e2, 2*e2+1) of output row w (destination row drow)
+struct ModDownRow { u64 p, p_half, phm, ip, ips; const ulonglong2 *tl; const u64 *base; };
+__device__ __forceinline__ ModDownRow moddown_row(const LimbJob &job, int n, int inst, int w) {
+  // tail of switch_key_inplace for row (comp, i): dst = base + p^-1 * (acc_i - ([acc_L + p/2]_p mod q_i) + [p/2]_{q_i})
+  const DevConst *C = job.C;
+  const int comp = w / job.L, i = w - comp * job.L;
+  ModDownRow r;
+  r.p = C->p; r.p_half = C->p_half; r.phm = C->p_half_mod_q[i]; r.ip = C->inv_p[i]; r.ips = C->inv_p_s[i];
+  r.tl = reinterpret_cast<const ulonglong2 *>(job.tl + (size_t)inst * job.tl_is + (size_t)(comp * job.k + job.L) * n);
+  r.base = comp == 0 ? job.base0 : job.base1;
+  if (r.base) r.base += (size_t)inst * (comp == 0 ? job.base0_is : job.base1_is) + (size_t)i * n;
+  return r;
+}
+template <int POST>
+__device__ __forceinline__ void limb_store_pair(const LimbJob &job, const ModInfo &M, const ModDownRow &md, int n, int inst,
+                                                int drow, int arow, int e2, ulonglong2 v) {
+  const u64 q = M.q;
+  if (POST == POST_MODDOWN) {
+    const ulonglong2 t = md.tl[e2];
+    const u64 rx = sub_mod(barrett64(add_mod(t.x, md.p_half, md.p), q, M.mu_hi), md.phm, q);
+    const u64 ry = sub_mod(barrett64(add_mod(t.y, md.p_half, md.p), q, M.mu_hi), md.phm, q);
+    v.x = mul_shoup(sub_mod(v.x, rx, q), md.ip, md.ips, q);
+    v.y = mul_shoup(sub_mod(v.y, ry, q), md.ip, md.ips, q);
+    if (md.base) {
+      ulonglong2 b;
+      const u32 einv = job.base_einv;
+      if (einv) {
+        const u32 m2 = 2u * n - 1, r0 = ((u32)(2 * e2) * einv) & m2, r1 = (r0 + einv) & m2;
+        b.x = md.base[r0 & (n - 1)]; b.y = md.base[r1 & (n - 1)];
+        if (r0 >= (u32)n) b.x = neg_mod(b.x, q);
+        if (r1 >= (u32)n) b.y = neg_mod(b.y, q);
+      } else {
+        b = reinterpret_cast<const ulonglong2 *>(md.base)[e2];
+      }
+      v.x = add_mod(v.x, b.x, q); v.y = add_mod(v.y, b.y, q);
+    }
+  } else if (POST == POST_ADD) {
+    const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(job.add + (size_t)inst * job.add_is + (size_t)arow * n)[e2];
+    v.x = add_mod(v.x, a.x, q); v.y = add_mod(v.y, a.y, q);
+  }
+  reinterpret_cast<ulonglong2 *>(job.dst + (size_t)inst * job.dst_is + (size_t)drow * n)[e2] = v;
+}
+
+// ---- one limb (or, TAIL, one 2^LOGN-coefficient block of a larger limb) in shared memory
+template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST, int AR, bool TAIL>
 __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(LimbJob job,
                                                                                const ModInfo *__restrict__ mods) {
   typedef NttDims<LOGN> D;
   extern __shared__ __align__(16) u64 sm[];
-  const int tid = threadIdx.x, w = blockIdx.x, inst = blockIdx.y;
+  const int tid = threadIdx.x, inst = blockIdx.y;
+  const int w = TAIL ? (int)(blockIdx.x >> job.sub) : (int)blockIdx.x;
+  const int blk = TAIL ? (int)(blockIdx.x & ((1u << job.sub) - 1)) : 0;
+  const u32 twbase = TAIL ? ((1u << job.sub) + (u32)blk) : 1u;
+  const int n = TAIL ? job.n : D::N;           // coefficients per limb
+  const int eoff = blk * (D::N / 2);           // this block's offset in 16-byte units
   const ModInfo M = mods[job.rowmod[w]];
   const u64 q = M.q;
   const int drow = job.rowdst ? job.rowdst[w] : w;
   const int srow = job.rowsrc ? job.rowsrc[w] : drow;
+  const int mrow = job.rowmul ? job.rowmul[w] : w;
 
   // ---- load
-  if (PRE == PRE_TERNARY || PRE == PRE_CBD) {
-    const u64 h = stream_key(job.seed, job.domain, job.a0 + (u64)inst, job.b);
-    for (int e = tid; e < D::N; e += D::T) {
-      int v = (PRE == PRE_TERNARY) ? sample_ternary(h, (u64)e) : sample_cbd(h, (u64)e);
-      sm[swz(e)] = small_to_mod(v, q);
-    }
-  } else if (PRE == PRE_ENCODE) {
+  if (PRE == PRE_ENCODE) {
     // BatchEncoder::encode (SealCiphertextFactory.cpp:102-132): pad with the last value, scatter by the index map
     const long long *sl = job.slots_in + (size_t)inst * job.slots_is;
     for (int e = tid; e < D::N; e += D::T) {
       long long v = sl[e < job.n_slots ? e : job.n_slots - 1];
       sm[swz((int)job.index_map[e])] = v < 0 ? q + (u64)v : (u64)v;
     }
-  } else if (PRE == PRE_GALOIS_REDUCE) {
-    // GaloisTool::apply_galois as a gather (negation is modulo the SOURCE limb's prime), then the ModUp reduction
-    const u64 *src = job.src + (size_t)inst * job.src_is + (size_t)srow * D::N;
-    const u64 qs = mods[srow].q;
-    const u32 einv = job.galois_einv, m2 = 2u * D::N - 1;
-    for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
-      const u32 r0 = ((u32)(2 * e2) * einv) & m2, r1 = (r0 + einv) & m2;
-      ulonglong2 v;
-      v.x = src[r0 & (D::N - 1)]; v.y = src[r1 & (D::N - 1)];
-      if (r0 >= (u32)D::N) v.x = neg_mod(v.x, qs);
-      if (r1 >= (u32)D::N) v.y = neg_mod(v.y, qs);
-      v.x = barrett64(v.x, q, M.mu_hi); v.y = barrett64(v.y, q, M.mu_hi);
-      *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = v;
-    }
   } else {
-    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(job.src + (size_t)inst * job.src_is + (size_t)srow * D::N);
-    for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
-      ulonglong2 v = src[e2];
-      if (PRE == PRE_REDUCE) { v.x = barrett64(v.x, q, M.mu_hi); v.y = barrett64(v.y, q, M.mu_hi); }
-      if (PRE == PRE_PLAIN_LIFT) {
-        // multiply_plain_normal: centred lift of a mod-t coefficient into [0,q)
-        const u64 th = job.t_half_up, inc = q - job.t;
-        v.x = v.x >= th ? v.x + inc : v.x;
-        v.y = v.y >= th ? v.y + inc : v.y;
-      }
-      *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = v;
-    }
+    const u64 h = (PRE == PRE_TERNARY || PRE == PRE_CBD) ? stream_key(job.seed, job.domain, job.a0 + (u64)inst, job.b) : 0;
+    for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
+      *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = limb_load_pair<PRE>(job, M, mods, n, inst, srow, eoff + e2, h);
   }
   __syncthreads();
 
-  if (FWD) ntt_fwd_smem<LOGN, AR>(sm, M, 1u, tid);
+  if (FWD) ntt_fwd_smem<LOGN, AR>(sm, M, twbase, tid);
 
   if (MUL) {
-    const int mrow = job.rowmul ? job.rowmul[w] : w;
-    const ulonglong2 *mp = reinterpret_cast<const ulonglong2 *>(job.mul + (size_t)inst * job.mul_is + (size_t)mrow * D::N);
+    const ulonglong2 *mp = reinterpret_cast<const ulonglong2 *>(job.mul + (size_t)inst * job.mul_is + (size_t)mrow * n) + eoff;
     for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
       ulonglong2 m = mp[e2];
       ulonglong2 *p = reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]);
@@ -130,7 +193,7 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
     __syncthreads();
   }
 
-  if (INV) ntt_inv_smem<LOGN, true, AR>(sm, M, 1u, tid);
+  if (INV) ntt_inv_smem<LOGN, !TAIL, AR>(sm, M, twbase, tid);
 
   // ---- store
   if (POST == POST_DECODE) {
@@ -141,66 +204,106 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
       u64 v = sm[swz((int)job.index_map[e])];
       out[e] = v > half ? (long long)v - (long long)q : (long long)v;
     }
-  } else if (POST == POST_MODDOWN) {
-    // tail of switch_key_inplace for row (comp, i): dst = base + p^-1 * (acc_i - ([acc_L + p/2]_p mod q_i) + [p/2]_{q_i})
-    const DevConst *C = job.C;
-    const int comp = w / job.L, i = w - comp * job.L;
-    const u64 p = C->p, p_half = C->p_half, phm = C->p_half_mod_q[i], ip = C->inv_p[i], ips = C->inv_p_s[i];
-    const ulonglong2 *tl = reinterpret_cast<const ulonglong2 *>(job.tl + (size_t)inst * job.tl_is + (size_t)(comp * job.k + job.L) * D::N);
-    const u64 *base = comp == 0 ? job.base0 : job.base1;
-    if (base) base += (size_t)inst * (comp == 0 ? job.base0_is : job.base1_is) + (size_t)i * D::N;
-    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(job.dst + (size_t)inst * job.dst_is + (size_t)drow * D::N);
-    const u32 einv = job.base_einv, m2 = 2u * D::N - 1;
-    for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
-      ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
-      const ulonglong2 t = tl[e2];
-      const u64 rx = sub_mod(barrett64(add_mod(t.x, p_half, p), q, M.mu_hi), phm, q);
-      const u64 ry = sub_mod(barrett64(add_mod(t.y, p_half, p), q, M.mu_hi), phm, q);
-      v.x = mul_shoup(sub_mod(csub(v.x, q), rx, q), ip, ips, q);
-      v.y = mul_shoup(sub_mod(csub(v.y, q), ry, q), ip, ips, q);
-      if (base) {
-        ulonglong2 b;
-        if (einv) {
-          const u32 r0 = ((u32)(2 * e2) * einv) & m2, r1 = (r0 + einv) & m2;
-          b.x = base[r0 & (D::N - 1)]; b.y = base[r1 & (D::N - 1)];
-          if (r0 >= (u32)D::N) b.x = neg_mod(b.x, q);
-          if (r1 >= (u32)D::N) b.y = neg_mod(b.y, q);
-        } else {
-          b = reinterpret_cast<const ulonglong2 *>(base)[e2];
-        }
-        v.x = add_mod(v.x, b.x, q); v.y = add_mod(v.y, b.y, q);
-      }
-      dst[e2] = v;
-    }
   } else {
-    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(job.dst + (size_t)inst * job.dst_is + (size_t)drow * D::N);
-    const ulonglong2 *ad = nullptr;
-    if (POST == POST_ADD) {
-      const int arow = job.rowmul ? job.rowmul[w] : w;
-      ad = reinterpret_cast<const ulonglong2 *>(job.add + (size_t)inst * job.add_is + (size_t)arow * D::N);
-    }
+    ModDownRow md;
+    if (POST == POST_MODDOWN) md = moddown_row(job, n, inst, w);
     for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
       ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
-      if (INV) { v.x = csub(v.x, q); v.y = csub(v.y, q); }
-      if (POST == POST_ADD) {
-        ulonglong2 a = ad[e2];
-        v.x = add_mod(v.x, a.x, q); v.y = add_mod(v.y, a.y, q);
-      }
-      dst[e2] = v;
+      if (INV && !TAIL) { v.x = csub(v.x, q); v.y = csub(v.y, q); }  // a tail block stays in [0,2q) for the head pass
+      limb_store_pair<POST>(job, M, md, n, inst, drow, mrow, eoff + e2, v);
     }
   }
 }
 
-// ---- launcher, instantiated once per LOGN in its own translation unit (limb_12.cu, limb_13.cu, limb_14.cu)
-// returns a cudaError_t as int; W rows x B instances
+// ---- head passes of the two-pass transform (N >= 32768): 2^A coefficients per thread at stride N >> A,
+// two adjacent columns per thread so every access is 16 bytes.  grid: (n / 2^A / 2 / 256, W, B)
+template <int A, int PRE>
+__global__ void __launch_bounds__(256) k_head_fwd(LimbJob job, const ModInfo *__restrict__ mods) {
+  constexpr int R = 1 << A;
+  const int w = blockIdx.y, inst = blockIdx.z, n = job.n;
+  const int c2 = blockIdx.x * 256 + threadIdx.x;  // column pair index, < n / R / 2
+  const int stride2 = n >> (A + 1);               // block stride in 16-byte units
+  const ModInfo M = mods[job.rowmod[w]];
+  const u64 q = M.q, q2 = 2 * q;
+  const int drow = job.rowdst ? job.rowdst[w] : w;
+  const int srow = job.rowsrc ? job.rowsrc[w] : drow;
+  const u64 h = (PRE == PRE_TERNARY || PRE == PRE_CBD) ? stream_key(job.seed, job.domain, job.a0 + (u64)inst, job.b) : 0;
+  u64 x[R], y[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    ulonglong2 v = limb_load_pair<PRE>(job, M, mods, n, inst, srow, c2 + r * stride2, h);
+    x[r] = v.x; y[r] = v.y;
+  }
+#pragma unroll
+  for (int b = A - 1; b >= 0; --b) {  // stage s = A-1-b: 2^s groups, partner r ^ 2^b
+    const int s = A - 1 - b;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (r & (1 << b)) continue;
+      const ulonglong2 tw = __ldg(&M.tw[(1 << s) + (r >> (b + 1))]);
+      bf_fwd<AR_SHOUP>(x[r], x[r | (1 << b)], tw, q, q2);
+      bf_fwd<AR_SHOUP>(y[r], y[r | (1 << b)], tw, q, q2);
+    }
+  }
+  ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(job.dst + (size_t)inst * job.dst_is + (size_t)drow * n) + c2;
+#pragma unroll
+  for (int r = 0; r < R; ++r) dst[r * stride2] = make_ulonglong2(x[r], y[r]);  // < 4q: the tail guards it
+}
+
+template <int A, int POST>
+__global__ void __launch_bounds__(256) k_head_inv(LimbJob job, const ModInfo *__restrict__ mods) {
+  constexpr int R = 1 << A;
+  const int w = blockIdx.y, inst = blockIdx.z, n = job.n;
+  const int c2 = blockIdx.x * 256 + threadIdx.x;
+  const int stride2 = n >> (A + 1);
+  const ModInfo M = mods[job.rowmod[w]];
+  const u64 q = M.q, q2 = 2 * q;
+  const int drow = job.rowdst ? job.rowdst[w] : w;
+  const int srow = job.rowsrc ? job.rowsrc[w] : drow;
+  const int arow = job.rowmul ? job.rowmul[w] : w;
+  const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(job.src + (size_t)inst * job.src_is + (size_t)srow * n) + c2;
+  u64 x[R], y[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { ulonglong2 v = src[r * stride2]; x[r] = v.x; y[r] = v.y; }  // in [0,2q) from the tail
+#pragma unroll
+  for (int b = 0; b < A; ++b) {  // stage s = A-1-b, Gentleman-Sande order: small gaps (in block units) first
+    const int s = A - 1 - b;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (r & (1 << b)) continue;
+      const int r2 = r | (1 << b);
+      if (s == 0) {  // last stage of the whole transform: fold N^-1
+        const u64 ux = x[r], vx = x[r2], uy = y[r], vy = y[r2];
+        x[r] = mul_shoup_lazy(ux + vx, M.ninv, M.ninv_s, q);
+        x[r2] = mul_shoup_lazy(ux + q2 - vx, M.wl_ninv, M.wl_ninv_s, q);
+        y[r] = mul_shoup_lazy(uy + vy, M.ninv, M.ninv_s, q);
+        y[r2] = mul_shoup_lazy(uy + q2 - vy, M.wl_ninv, M.wl_ninv_s, q);
+      } else {
+        const ulonglong2 tw = __ldg(&M.itw[(1 << s) + (r >> (b + 1))]);
+        bf_inv<AR_SHOUP>(x[r], x[r2], tw, q, q2);
+        bf_inv<AR_SHOUP>(y[r], y[r2], tw, q, q2);
+      }
+    }
+  }
+  ModDownRow md;
+  if (POST == POST_MODDOWN) md = moddown_row(job, n, inst, w);
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    limb_store_pair<POST>(job, M, md, n, inst, drow, arow, c2 + r * stride2, make_ulonglong2(csub(x[r], q), csub(y[r], q)));
+}
+
+// ---- launchers, one translation unit per size (limb_12.cu, limb_13.cu, limb_14.cu, limb_big.cu)
+// return a cudaError_t as int; W rows x B instances
 template <int LOGN>
 int limb_dispatch(int combo, int ar, const LimbJob &job, const ModInfo *mods, int W, int B, cudaStream_t stream);
+// N = 2^(13+A), A in {2,3}: every combo as head/tail sequences (Shoup arithmetic; these sizes use 55-60-bit primes)
+int limb_dispatch_big(int A, int combo, const LimbJob &job, const ModInfo *mods, int W, int B, cudaStream_t stream);
 
 #ifdef ABC_LIMB_IMPL
-template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST, int AR>
+template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST, int AR, bool TAIL>
 static int limb_launch(const LimbJob &job, const ModInfo *mods, int W, int B, cudaStream_t stream) {
   typedef NttDims<LOGN> D;
-  auto kern = k_limb<LOGN, PRE, FWD, MUL, INV, POST, AR>;
+  auto kern = k_limb<LOGN, PRE, FWD, MUL, INV, POST, AR, TAIL>;
   if (D::SMEM > 48 * 1024) {
     static bool done[64] = {false};
     int dev = 0;
@@ -214,31 +317,36 @@ static int limb_launch(const LimbJob &job, const ModInfo *mods, int W, int B, cu
   kern<<<dim3(W, B), D::T, D::SMEM, stream>>>(job, mods);
   return (int)cudaGetLastError();
 }
+#endif
+
+#ifdef ABC_LIMB_IMPL_SIZE
 template <int LOGN, int AR>
 static int limb_dispatch_ar(int combo, const LimbJob &j, const ModInfo *m, int W, int B, cudaStream_t s) {
   switch (combo) {
-    case LIMB_FWD: return limb_launch<LOGN, PRE_LOAD, true, false, false, POST_STORE, AR>(j, m, W, B, s);
-    case LIMB_INV: return limb_launch<LOGN, PRE_LOAD, false, false, true, POST_STORE, AR>(j, m, W, B, s);
-    case LIMB_REDUCE_FWD: return limb_launch<LOGN, PRE_REDUCE, true, false, false, POST_STORE, AR>(j, m, W, B, s);
-    case LIMB_PLAINLIFT_FWD: return limb_launch<LOGN, PRE_PLAIN_LIFT, true, false, false, POST_STORE, AR>(j, m, W, B, s);
-    case LIMB_TERNARY_FWD: return limb_launch<LOGN, PRE_TERNARY, true, false, false, POST_STORE, AR>(j, m, W, B, s);
-    case LIMB_CBD_FWD: return limb_launch<LOGN, PRE_CBD, true, false, false, POST_STORE, AR>(j, m, W, B, s);
-    case LIMB_ENCODE_INV: return limb_launch<LOGN, PRE_ENCODE, false, false, true, POST_STORE, AR>(j, m, W, B, s);
-    case LIMB_FWD_DECODE: return limb_launch<LOGN, PRE_LOAD, true, false, false, POST_DECODE, AR>(j, m, W, B, s);
-    case LIMB_FWD_MUL_INV: return limb_launch<LOGN, PRE_LOAD, true, true, true, POST_STORE, AR>(j, m, W, B, s);
-    case LIMB_FWD_MUL_INV_ADD: return limb_launch<LOGN, PRE_LOAD, true, true, true, POST_ADD, AR>(j, m, W, B, s);
-    case LIMB_MUL_INV: return limb_launch<LOGN, PRE_LOAD, false, true, true, POST_STORE, AR>(j, m, W, B, s);
-    case LIMB_GALOIS_REDUCE_FWD: return limb_launch<LOGN, PRE_GALOIS_REDUCE, true, false, false, POST_STORE, AR>(j, m, W, B, s);
-    case LIMB_INV_MODDOWN: return limb_launch<LOGN, PRE_LOAD, false, false, true, POST_MODDOWN, AR>(j, m, W, B, s);
+    case LIMB_FWD: return limb_launch<LOGN, PRE_LOAD, true, false, false, POST_STORE, AR, false>(j, m, W, B, s);
+    case LIMB_INV: return limb_launch<LOGN, PRE_LOAD, false, false, true, POST_STORE, AR, false>(j, m, W, B, s);
+    case LIMB_REDUCE_FWD: return limb_launch<LOGN, PRE_REDUCE, true, false, false, POST_STORE, AR, false>(j, m, W, B, s);
+    case LIMB_PLAINLIFT_FWD: return limb_launch<LOGN, PRE_PLAIN_LIFT, true, false, false, POST_STORE, AR, false>(j, m, W, B, s);
+    case LIMB_TERNARY_FWD: return limb_launch<LOGN, PRE_TERNARY, true, false, false, POST_STORE, AR, false>(j, m, W, B, s);
+    case LIMB_CBD_FWD: return limb_launch<LOGN, PRE_CBD, true, false, false, POST_STORE, AR, false>(j, m, W, B, s);
+    case LIMB_ENCODE_INV: return limb_launch<LOGN, PRE_ENCODE, false, false, true, POST_STORE, AR, false>(j, m, W, B, s);
+    case LIMB_FWD_DECODE: return limb_launch<LOGN, PRE_LOAD, true, false, false, POST_DECODE, AR, false>(j, m, W, B, s);
+    case LIMB_FWD_MUL_INV: return limb_launch<LOGN, PRE_LOAD, true, true, true, POST_STORE, AR, false>(j, m, W, B, s);
+    case LIMB_FWD_MUL_INV_ADD: return limb_launch<LOGN, PRE_LOAD, true, true, true, POST_ADD, AR, false>(j, m, W, B, s);
+    case LIMB_MUL_INV: return limb_launch<LOGN, PRE_LOAD, false, true, true, POST_STORE, AR, false>(j, m, W, B, s);
+    case LIMB_GALOIS_REDUCE_FWD: return limb_launch<LOGN, PRE_GALOIS_REDUCE, true, false, false, POST_STORE, AR, false>(j, m, W, B, s);
+    case LIMB_INV_MODDOWN: return limb_launch<LOGN, PRE_LOAD, false, false, true, POST_MODDOWN, AR, false>(j, m, W, B, s);
     default: return (int)cudaErrorInvalidValue;
   }
 }
 template <int LOGN>
 int limb_dispatch(int combo, int ar, const LimbJob &job, const ModInfo *mods, int W, int B, cudaStream_t stream) {
+  LimbJob j = job;
+  j.n = 1 << LOGN; j.sub = 0;
   switch (ar) {
-    case AR_SHOUP: return limb_dispatch_ar<LOGN, AR_SHOUP>(combo, job, mods, W, B, stream);
-    case AR_FP: return limb_dispatch_ar<LOGN, AR_FP>(combo, job, mods, W, B, stream);
-    case AR_FP_LAZY: return limb_dispatch_ar<LOGN, AR_FP_LAZY>(combo, job, mods, W, B, stream);
+    case AR_SHOUP: return limb_dispatch_ar<LOGN, AR_SHOUP>(combo, j, mods, W, B, stream);
+    case AR_FP: return limb_dispatch_ar<LOGN, AR_FP>(combo, j, mods, W, B, stream);
+    case AR_FP_LAZY: return limb_dispatch_ar<LOGN, AR_FP_LAZY>(combo, j, mods, W, B, stream);
     default: return (int)cudaErrorInvalidValue;
   }
 }

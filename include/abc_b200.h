@@ -33,7 +33,7 @@ typedef struct abc_ctx abc_ctx;
 typedef struct abc_ct abc_ct;
 
 typedef struct abc_params {
-  uint32_t poly_degree;     /* N: 1024..32768, power of two */
+  uint32_t poly_degree;     /* N: 4096..65536, power of two */
   uint32_t n_primes;        /* k, incl. the special prime (last); 0 -> SEAL CoeffModulus::BFVDefault(N) */
   const uint64_t *primes;   /* k primes = 1 (mod 2N), each < 2^60; ignored when n_primes == 0 */
   uint64_t plain_modulus;   /* t; 0 -> SEAL PlainModulus::Batching(N, 20) */

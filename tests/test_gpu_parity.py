@@ -248,3 +248,50 @@ def test_n16384_default_parameters():
         assert np.array_equal(f.decryptCiphertext(a.multiply(b)), (da * db + f.t // 2) % f.t - f.t // 2)
     finally:
         f.close()
+
+
+@pytest.fixture(scope="module")
+def pair32768():
+    from abc_b200 import CudaCiphertextFactory
+    from oracle.bfv_oracle import Oracle
+    o = Oracle(32768, seed=SEED)
+    f = CudaCiphertextFactory(32768, seed=SEED)
+    yield f, o
+    f.close()
+
+
+def test_n32768_two_pass_ntt_bit_exact(pair32768):
+    """N = 32768 (k = 16, 55-bit primes): head passes in registers + 8192-coefficient tail blocks in shared memory."""
+    f, o = pair32768
+    assert f.primes == o.primes and f.t == o.t == 786433 and f.k == 16
+    rng = np.random.default_rng(11)
+    msk, _, B = o.aux_primes()
+    for mi, q, oidx in ((0, f.primes[0], 0), (15, f.primes[15], 15), (16, B[0], 1000), (16 + 15, msk, 1015),
+                        (16 + 16, f.t, -1)):
+        rows = rng.integers(0, q, size=(2, f.N), dtype=np.uint64)
+        got = f.probe_ntt(mi, rows)
+        assert np.array_equal(got[0], o.ntt_fwd(oidx, rows[0])) and np.array_equal(got[1], o.ntt_fwd(oidx, rows[1]))
+        assert np.array_equal(f.probe_ntt(mi, got, inverse=True), rows)
+
+
+def test_n32768_ops_bit_exact(pair32768):
+    from abc_b200 import KEY_PUBLIC, KEY_RELIN, KEY_SECRET
+    f, o = pair32768
+    assert np.array_equal(f.export_key(KEY_SECRET), o.secret_key())
+    assert np.array_equal(f.export_key(KEY_PUBLIC), o.public_key())
+    assert np.array_equal(f.export_key(KEY_RELIN), o.relin_key())
+    rng = np.random.default_rng(12)
+    da, db = rand_slots(rng, f.N), rand_slots(rng, f.N)
+    f.set_encrypt_nonce(7)
+    a = f.createCiphertext(da)
+    a_w, b_w = o.encrypt_slots(da, 7), o.encrypt_slots(db, 8)
+    assert np.array_equal(a.export()[0], a_w)
+    b = f.importCiphertext(b_w[None])
+    assert np.array_equal(f.decryptCiphertext(a), da)
+    assert np.array_equal(a.multiply(b).export()[0], o.mul_relin(a_w, b_w))
+    for steps in (1, -24):
+        assert np.array_equal(a.rotateRows(steps).export()[0], o.rotate_rows(a_w, steps))
+    pl = o.encode(o.expand([5, -3, 7]))
+    assert np.array_equal(a.multiplyPlain([5, -3, 7]).export()[0], o.multiply_plain(a_w, pl))
+    assert np.array_equal(a.addPlain([5, -3, 7]).export()[0], o.add_plain(a_w, pl))
+    assert np.array_equal(f.decryptCiphertext(a.multiply(b)), (da * db + f.t // 2) % f.t - f.t // 2)
