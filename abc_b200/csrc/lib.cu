@@ -987,7 +987,6 @@ abc_status abc_timer_stop(abc_ctx *c, float *ms) {
 abc_status abc_flush_l2(abc_ctx *c, size_t bytes) {
   if (bytes > c->flush_bytes) {
     if (c->flush_buf) cudaFree(c->flush_buf);
-  for (u64 *p : c->sc_ptr) if (p) cudaFree(p);
     c->flush_buf = nullptr; c->flush_bytes = 0;
     CK(cudaMalloc(&c->flush_buf, bytes));
     c->flush_bytes = bytes;
