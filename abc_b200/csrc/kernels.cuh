@@ -383,14 +383,15 @@ template <int AR>
 __global__ void __launch_bounds__(1024) k_peak_butterfly(u64 *out, int iters, u64 q, u64 w, u64 wc) {
   u64 x0 = threadIdx.x, y0 = blockIdx.x, x1 = x0 + 1, y1 = y0 + 2, x2 = x0 + 3, y2 = y0 + 4, x3 = x0 + 5, y3 = y0 + 6;
   const ulonglong2 tw = make_ulonglong2(w, wc);
-  const u64 q2 = 2 * q;
+  const u64 q2 = ar_aux<AR>(q);
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       bf_fwd<AR>(x0, y0, tw, q, q2); bf_fwd<AR>(x1, y1, tw, q, q2); bf_fwd<AR>(x2, y2, tw, q, q2); bf_fwd<AR>(x3, y3, tw, q, q2);
     }
-    if (AR == AR_FP_LAZY) {  // the unguarded class needs a range reset now and then (amortised: 8 of 32+8)
-      x0 &= q - 1; y0 &= q - 1; x1 &= q - 1; y1 &= q - 1; x2 &= q - 1; y2 &= q - 1; x3 &= q - 1; y3 &= q - 1;
+    if (AR == AR_FP_LAZY) {  // the unguarded class needs a range reset now and then (8 ops per 32 butterflies)
+      const u64 m = 0xFFFFFFFFFFULL;
+      x0 &= m; y0 &= m; x1 &= m; y1 &= m; x2 &= m; y2 &= m; x3 &= m; y3 &= m;
     }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ y0 ^ x1 ^ y1 ^ x2 ^ y2 ^ x3 ^ y3;

@@ -181,7 +181,7 @@ void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, s
   // FP64-assisted class: companion = double(w/q) (correctly rounded: both operands are exact doubles)
   auto dbits = [q](u64 w) { double d = (double)w / (double)q; u64 b; memcpy(&b, &d, 8); return b; };
   m.ar_class = AR_SHOUP;
-  if ((q >> 49) == 0) m.ar_class = ((unsigned __int128)q * (unsigned)(2 * logN + 1) < ((unsigned __int128)1 << 51)) ? AR_FP_LAZY : AR_FP;
+  if ((q >> 49) == 0) m.ar_class = (q >> 45) == 0 ? AR_FP_LAZY : AR_FP;  // range plans in ntt.cuh
   twf.clear(); itwf.clear();
   m.ninv_f = m.wl_ninv_f = m.qinv_bits = 0;
   if (m.ar_class != AR_SHOUP) {

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
     if (POST == POST_MODDOWN) md = moddown_row(job, n, inst, w);
     for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
       ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
-      if (INV && !TAIL) { v.x = csub(v.x, q); v.y = csub(v.y, q); }  // a tail block stays in [0,2q) for the head pass
+      if (INV && !TAIL) { v.x = canon_inv<AR>(v.x, q); v.y = canon_inv<AR>(v.y, q); }  // a tail block stays in [0,2q) for the head pass
       limb_store_pair<POST>(job, M, md, n, inst, drow, mrow, eoff + e2, v);
     }
   }

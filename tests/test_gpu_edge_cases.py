@@ -1,0 +1,127 @@
+"""GPU: edge cases the reference tests or SEAL's API define for this path, and non-default parameter sets
+(BASELINE.json configs[2]: 3-16 RNS limbs), all bit-exact against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+SEED = 4673838
+
+
+def make_pair(N, primes=None, t=0):
+    from abc_b200 import CudaCiphertextFactory
+    from oracle.bfv_oracle import Oracle
+    o = Oracle(N, primes=primes, t=t, seed=SEED)
+    f = CudaCiphertextFactory(N, primes=primes, plain_modulus=t, seed=SEED)
+    return f, o
+
+
+def check_ops(f, o, seed=0):
+    rng = np.random.default_rng(seed)
+    da, db = rng.integers(0, 1025, f.N), rng.integers(0, 1025, f.N)
+    a_w, b_w = o.encrypt_slots(da, 1), o.encrypt_slots(db, 2)
+    f.set_encrypt_nonce(1)
+    a = f.createCiphertext(da)
+    assert np.array_equal(a.export()[0], a_w), "encrypt"
+    b = f.importCiphertext(b_w[None])
+    assert np.array_equal(a.add(b).export()[0], o.add(a_w, b_w)), "add"
+    assert np.array_equal(a.multiply(b).export()[0], o.mul_relin(a_w, b_w)), "mul+relin"
+    for steps in (1, -24):
+        assert np.array_equal(a.rotateRows(steps).export()[0], o.rotate_rows(a_w, steps)), "rotate %d" % steps
+    pl = o.encode(o.expand([7, -2, 5]))
+    assert np.array_equal(a.multiplyPlain([7, -2, 5]).export()[0], o.multiply_plain(a_w, pl)), "mul plain"
+    assert np.array_equal(a.subtractPlain([7, -2, 5]).export()[0], o.sub_plain(a_w, pl)), "sub plain"
+    assert np.array_equal(f.decryptCiphertext(a.multiply(b)), o.decrypt_slots(o.mul_relin(a_w, b_w))), "decrypt"
+
+
+@pytest.mark.parametrize("N,bits,k", [(4096, 40, 3), (4096, 50, 4), (8192, 50, 7), (8192, 58, 3), (16384, 45, 6)])
+def test_custom_coefficient_modulus(N, bits, k):
+    """k primes from SEAL's get_primes rule (data primes of `bits` bits + a special prime one bit larger): covers the
+    three NTT arithmetic classes (<2^45 signed-lazy, <2^49 FP64-assisted, larger Shoup) and other limb counts."""
+    from oracle.bfv_oracle import get_primes
+    data = get_primes(N, bits, k - 1)
+    primes = data + [p for p in get_primes(N, bits + 1, 2) if p not in data][:1]
+    f, o = make_pair(N, primes)
+    try:
+        assert f.primes == primes == o.primes and f.k == k
+        check_ops(f, o, seed=k)
+    finally:
+        f.close()
+
+
+def test_sixteen_primes_n8192():
+    """upper end of the 3-16 limb sweep (L = 15 register-resident base conversion)."""
+    from oracle.bfv_oracle import get_primes
+    data = get_primes(8192, 50, 15)
+    primes = data + get_primes(8192, 51, 1)
+    f, o = make_pair(8192, primes)
+    try:
+        check_ops(f, o, seed=16)
+    finally:
+        f.close()
+
+
+def test_value_range_and_padding_edges():
+    f, o = make_pair(4096)
+    try:
+        t = f.t
+        for data in ([t // 2], [-(t // 2)], [0], [-1, 1], list(range(-5, 6)), [t // 2, -(t // 2), 1]):
+            f.set_encrypt_nonce(9)
+            ct = f.createCiphertext(data)
+            assert np.array_equal(ct.export()[0], o.encrypt_slots(data, 9))
+            assert np.array_equal(f.decryptCiphertext(ct), o.expand(data))
+        # exactly N values: no padding
+        full = np.arange(4096, dtype=np.int64) - 2048
+        assert np.array_equal(f.decryptCiphertext(f.createCiphertext(full)), full)
+        # products that wrap around t
+        big = f.createCiphertext([t // 2, -(t // 2), 1000])
+        got = f.decryptCiphertext(big.multiply(big))[:3]
+        want = [((v * v + t // 2) % t) - t // 2 for v in (t // 2, -(t // 2), 1000)]
+        assert list(got) == want
+    finally:
+        f.close()
+
+
+def test_error_behaviour():
+    from abc_b200 import AbcError, CudaCiphertextFactory
+    f, _ = make_pair(4096)
+    g = CudaCiphertextFactory(4096, seed=1)
+    try:
+        with pytest.raises(AbcError):
+            f.createCiphertext([])                      # the reference calls .back() on an empty vector (UB); we throw
+        with pytest.raises(AbcError):
+            f.createCiphertext(list(range(4097)))       # SealCiphertextFactory.cpp:106-110
+        a, b = f.createCiphertext([1, 2]), g.createCiphertext([1, 2])
+        with pytest.raises(AbcError):
+            a.add(b)                                    # ciphertext of another factory (SealCiphertext.cpp:36-50)
+        with pytest.raises(AbcError):
+            a.rotateRows(-2048)
+        with pytest.raises(AbcError):
+            CudaCiphertextFactory(4096, primes=[97, 193])          # not = 1 mod 2N
+        with pytest.raises(AbcError):
+            CudaCiphertextFactory(5000)                             # not a power of two
+        with pytest.raises(AbcError):
+            CudaCiphertextFactory(2048)                             # SEAL's default has no special prime below 4096
+    finally:
+        f.close(); g.close()
+
+
+def test_key_import_round_trip():
+    """abc_key_import: keys produced elsewhere (the oracle here; SEAL's raw key data has the same layout)."""
+    from abc_b200 import CudaCiphertextFactory, KEY_GALOIS, KEY_PUBLIC, KEY_RELIN, KEY_SECRET
+    from oracle.bfv_oracle import Oracle
+    o = Oracle(4096, seed=99)
+    f = CudaCiphertextFactory(4096, seed=1, keygen=False)
+    try:
+        f.import_key(KEY_SECRET, o.secret_key()); f.import_key(KEY_PUBLIC, o.public_key())
+        f.import_key(KEY_RELIN, o.relin_key())
+        for e in o.galois_elts():
+            f.import_key(KEY_GALOIS, o.galois_key(e), e)
+        rng = np.random.default_rng(5)
+        d = rng.integers(0, 1025, 4096)
+        a_w = o.encrypt_slots(d, 3)
+        a = f.importCiphertext(a_w[None])
+        assert np.array_equal(f.decryptCiphertext(a), d)
+        assert np.array_equal(a.multiply(a).export()[0], o.mul_relin(a_w, a_w))
+        assert np.array_equal(a.rotateRows(63).export()[0], o.rotate_rows(a_w, 63))
+    finally:
+        f.close()
