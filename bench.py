@@ -98,6 +98,15 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def traffic_for(kernel, batch):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), else None."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
+        return rec["bytes_per_launch"] if rec and rec["batch"] == batch and rec["N"] == N_POLY else None
+    except Exception:
+        return None
+
+
 def cpu_baseline_port(cores, seconds_budget=20.0):
     """The oracle (SEAL-3.6.5 restatement) running the same program on host cores; bounded sample."""
     from oracle.bfv_oracle import Oracle
@@ -259,7 +268,8 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"kernel": top["kernel"], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": how,
+                         "frac": ach / peaks["hbm_gbs"], "traffic": traffic_for(top["kernel"], B), "peak_source": how,
+                         "algorithmic_bytes_per_launch": alg.get(top["kernel"], 0),
                          "share_of_step": top["ms"] / tot,
                          "note": "this kernel family is INT-pipe-bound, see int_roofline"},
             "int_roofline": {"unit": "64-bit modular NTT butterflies/s (all limb-pipeline kernels of the step)",
