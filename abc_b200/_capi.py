@@ -32,6 +32,8 @@ SYMBOLS = {
     "abc_get_primes": (i32, [vp, vp]),
     "abc_get_aux_primes": (i32, [vp, vp, C.POINTER(u32)]),
     "abc_keygen": (i32, [vp]),
+    "abc_keygen_select": (i32, [vp, vp, sz]),
+    "abc_galois_elt_from_step": (u32, [vp, i32]),
     "abc_key_words": (sz, [vp, i32]),
     "abc_key_export": (i32, [vp, i32, u32, vp, sz]),
     "abc_key_import": (i32, [vp, i32, u32, vp, sz]),

@@ -27,7 +27,7 @@ class CudaCiphertextFactory:
     """Owns one device context: parameters, tables, keys, stream (SealCiphertextFactory.cpp:72-100)."""
 
     def __init__(self, numElementsPerCiphertextSlot=16384, primes=None, plain_modulus=0, device=0, batch=1,
-                 seed=4673838, keygen=True):
+                 seed=4673838, keygen=True, galois_steps=None):
         self._lib = _capi.load()
         p = _capi.AbcParams()
         p.poly_degree = numElementsPerCiphertextSlot
@@ -50,7 +50,7 @@ class CudaCiphertextFactory:
         self._ck(self._lib.abc_get_primes(h, q.ctypes.data))
         self.primes = [int(v) for v in q]
         if keygen:
-            self.keygen()
+            self.keygen(galois_steps)
 
     # -- plumbing
     def _ck(self, st):
@@ -81,8 +81,20 @@ class CudaCiphertextFactory:
         return int(out[0]), int(out[1]), [int(v) for v in out[2:n.value]]
 
     # -- keys
-    def keygen(self):
-        self._ck(self._lib.abc_keygen(self._h))
+    def keygen(self, galois_steps=None):
+        """Default: secret, public, relin and SEAL's default Galois key set.  galois_steps: only the keys for these
+        rotation steps (large parameter sets, where one key is hundreds of MiB)."""
+        if galois_steps is None:
+            self._ck(self._lib.abc_keygen(self._h))
+        else:
+            elts = np.asarray([self.elt_from_step(s) for s in galois_steps], dtype=np.uint32)
+            self._ck(self._lib.abc_keygen_select(self._h, elts.ctypes.data, elts.size))
+
+    def elt_from_step(self, step):
+        e = int(self._lib.abc_galois_elt_from_step(self._h, step))
+        if e == 0:
+            raise AbcError("step count too large")
+        return e
 
     def key_shape(self, kind):
         return {KEY_SECRET: (self.k, self.N), KEY_PUBLIC: (2, self.k, self.N),

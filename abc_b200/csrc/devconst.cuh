@@ -2,7 +2,7 @@
 #pragma once
 #include "modarith.cuh"
 
-#define ABC_MAXL 16  // max data limbs with register-resident base conversion
+#define ABC_MAXL 32  // max data limbs (base conversion is register-resident and fully unrolled up to 15)
 
 // Per-context constants (device copy).  Index convention for `mods`: 0..k-1 key-level primes,
 // k..k+nbsk-1 Bsk = (B_0..B_{nB-1}, m_sk), k+nbsk = plain modulus t, k+nbsk+1 = gamma.

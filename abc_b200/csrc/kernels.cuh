@@ -35,14 +35,18 @@ __global__ void __launch_bounds__(256) k_addsub(u64 *__restrict__ dst, const u64
 // (Evaluator::bfv_multiply, reached from src/runtime/SealCiphertext.cpp:104,122).
 // X layout [inst][4][W=2L+1][N]; this kernel fills all W rows (q rows are a copy of the input).
 // grid: (N/128, 4, B).  INT-bound: L Shoup products + L*(L+2) 128-bit MACs per coefficient.
-template <int L>
+// LT > 0: limb count known at compile time (base conversion fully unrolled, residues in registers);
+// LT = 0: generic limb count Lrt <= ABC_MAXL (loops not unrolled, residues in local memory).
+template <int LT>
 __global__ void __launch_bounds__(128) k_behz_lift(const u64 *__restrict__ a, const u64 *__restrict__ b,
-                                                   u64 *__restrict__ X, const DevConst *__restrict__ C, int N) {
+                                                   u64 *__restrict__ X, const DevConst *__restrict__ C, int N, int Lrt) {
+  constexpr int CAP = LT ? LT : ABC_MAXL;
+  const int L = LT ? LT : Lrt;
   const int n = blockIdx.x * 128 + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
-  constexpr int W = 2 * L + 1;
+  const int W = 2 * L + 1;
   const u64 *src = (poly < 2 ? a : b) + ((size_t)inst * 2 + (poly & 1)) * L * N + n;
   u64 *dst = X + ((size_t)inst * 4 + poly) * W * N + n;
-  u64 z[L];
+  u64 z[CAP];
   u32 xm = 0;
 #pragma unroll
   for (int i = 0; i < L; ++i) {
@@ -87,14 +91,16 @@ __global__ void __launch_bounds__(256) k_behz_tensor(u64 *__restrict__ X, const 
 
 // BEHZ steps 6-8: *t, fast_floor (q U Bsk -> Bsk), fastbconv_sk (Bsk -> q).  RNSTool::fast_floor + fastbconv_sk.
 // X [inst][4][W][N] (polys 0..2, coefficient form) -> dst3 [inst][3][L][N].  grid: (N/128, 3, B)
-template <int L>
+template <int LT>
 __global__ void __launch_bounds__(128) k_behz_scale(const u64 *__restrict__ X, u64 *__restrict__ dst,
-                                                    const DevConst *__restrict__ C, int N) {
+                                                    const DevConst *__restrict__ C, int N, int Lrt) {
+  constexpr int CAP = LT ? LT : ABC_MAXL;
+  const int L = LT ? LT : Lrt;
   const int n = blockIdx.x * 128 + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
-  constexpr int W = 2 * L + 1;
+  const int W = 2 * L + 1;
   const u64 *src = X + ((size_t)inst * 4 + poly) * W * N + n;
   u64 *out = dst + ((size_t)inst * 3 + poly) * L * N + n;
-  u64 z[L], zb[L];
+  u64 z[CAP], zb[CAP];
 #pragma unroll
   for (int i = 0; i < L; ++i) z[i] = mul_shoup(src[(size_t)i * N], C->scale_c[i], C->scale_c_s[i], C->q[i]);
   u64 ysk = 0;
@@ -136,9 +142,11 @@ __global__ void __launch_bounds__(128) k_behz_scale(const u64 *__restrict__ X, u
 // ModUp + NTT is the limb pipeline (LIMB_REDUCE_FWD) into T [inst][k][L][N].
 // Inner product: acc[inst][comp][I][n] = sum_J T[inst][I][J][n] * key[J][comp][I][n] mod q_I.
 // grid: (N/512, k, B).  128-bit lazy accumulation, one Barrett reduction per output.
-template <int L>
+template <int LT>
 __global__ void __launch_bounds__(256) k_ks_inner(const u64 *__restrict__ T, const u64 *__restrict__ key,
-                                                  u64 *__restrict__ acc, const ModInfo *__restrict__ mods, int N, int k) {
+                                                  u64 *__restrict__ acc, const ModInfo *__restrict__ mods, int N, int k,
+                                                  int Lrt) {
+  const int L = LT ? LT : Lrt;
   // two adjacent coefficients per thread (16-byte accesses), J loop unrolled
   const int n2 = blockIdx.x * 256 + threadIdx.x, I = blockIdx.y, inst = blockIdx.z;
   const ModInfo *Mp = mods + I;
@@ -270,9 +278,10 @@ __global__ void __launch_bounds__(256) k_enc_finish(const u64 *__restrict__ tmp,
 
 // Decryption tail: RNSTool::decrypt_scale_and_round (Decryptor::bfv_decrypt; SealCiphertextFactory.cpp:150).
 // x [inst][L][N] = c0 + c1*s (coefficient form) -> plain [inst][N] mod t.  grid: (N/128, 1, B)
-template <int L>
+template <int LT>
 __global__ void __launch_bounds__(128) k_dec_finish(const u64 *__restrict__ x, u64 *__restrict__ plain,
-                                                    const DevConst *__restrict__ C, int N) {
+                                                    const DevConst *__restrict__ C, int N, int Lrt) {
+  const int L = LT ? LT : Lrt;
   const int n = blockIdx.x * 128 + threadIdx.x, inst = blockIdx.z;
   const u64 *src = x + (size_t)inst * L * N + n;
   const u64 t = C->t, g = C->gamma;

@@ -154,7 +154,7 @@ LimbJob blank_job() { LimbJob j; memset(&j, 0, sizeof j); return j; }
     case 13: { constexpr int LL = 13; EXPR; } break;                               \
     case 14: { constexpr int LL = 14; EXPR; } break;                               \
     case 15: { constexpr int LL = 15; EXPR; } break;                               \
-    default: return fail(c, ABC_ERR_UNSUPPORTED, "limb count not supported");      \
+    default: { constexpr int LL = 0; EXPR; } break;                                 \
   }
 
 // ---- context construction --------------------------------------------------------------------
@@ -351,7 +351,7 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   TRY(launch_limb(c, einv ? LIMB_GALOIS_REDUCE_FWD : LIMB_REDUCE_FWD, c->ar_q, j, k * L, B, "ks_modup_ntt"));
   {
     Launch l(c, "ks_inner");
-    DISPATCH_L(c, (k_ks_inner<LL><<<dim3(N / 512, k, B), 256, 0, c->stream>>>(T, key, acc, c->d_mods, N, k)));
+    DISPATCH_L(c, (k_ks_inner<LL><<<dim3(N / 512, k, B), 256, 0, c->stream>>>(T, key, acc, c->d_mods, N, k, c->L)));
     CK(cudaGetLastError());
   }
   j = blank_job();
@@ -374,7 +374,7 @@ abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
   TRY(scratch(c, SC_X, &X, (size_t)B * 4 * W * N));
   {
     Launch l(c, "behz_lift");
-    DISPATCH_L(c, (k_behz_lift<LL><<<dim3(N / 128, 4, B), 128, 0, c->stream>>>(a, b, X, c->dC, N)));
+    DISPATCH_L(c, (k_behz_lift<LL><<<dim3(N / 128, 4, B), 128, 0, c->stream>>>(a, b, X, c->dC, N, c->L)));
     CK(cudaGetLastError());
   }
   LimbJob j = blank_job();
@@ -401,7 +401,7 @@ abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
   }
   {
     Launch l(c, "behz_scale");
-    DISPATCH_L(c, (k_behz_scale<LL><<<dim3(N / 128, 3, B), 128, 0, c->stream>>>(X, out3, c->dC, N)));
+    DISPATCH_L(c, (k_behz_scale<LL><<<dim3(N / 128, 3, B), 128, 0, c->stream>>>(X, out3, c->dC, N, c->L)));
     CK(cudaGetLastError());
   }
   return ABC_OK;
@@ -606,7 +606,7 @@ abc_status abc_ctx_create(const abc_params *p, abc_ctx **out) {
     else c->primes.assign(p->primes, p->primes + p->n_primes);
     c->t = p->plain_modulus ? p->plain_modulus : hm::get_primes(N, 20, 1)[0];
     c->k = (int)c->primes.size(); c->L = c->k - 1;
-    if (c->k < 2 || c->L > 15) return bail(ABC_ERR_PARAM, "need 2..16 coefficient primes (incl. the special prime)");
+    if (c->k < 2 || c->L > ABC_MAXL - 1) return bail(ABC_ERR_PARAM, "need 2..32 coefficient primes (incl. the special prime)");
     for (u64 q : c->primes)
       if (!hm::is_prime(q) || (q - 1) % (2 * N) || q >> 60) return bail(ABC_ERR_PARAM, "coefficient primes must be < 2^60 and = 1 mod 2N");
     for (size_t i = 0; i < c->primes.size(); ++i)
@@ -664,7 +664,7 @@ abc_status abc_get_aux_primes(const abc_ctx *c, uint64_t *out, uint32_t *count) 
 }
 
 // ---- keys
-abc_status abc_keygen(abc_ctx *c) {
+static abc_status keygen_impl(abc_ctx *c, const std::vector<u32> &elts) {
   const int N = c->N, k = c->k, L = c->L;
   CK(cudaSetDevice(c->device));
   const size_t kw = (size_t)L * 2 * k * N;
@@ -679,7 +679,8 @@ abc_status abc_keygen(abc_ctx *c) {
   TRY(scratch(c, SC_ENTT, &e_ntt, (size_t)k * N));
   TRY(gen_key_block(c, c->d_pk, DOM_PK, 0, 0, nullptr, -1, e_ntt));
   TRY(gen_kswitch_key(c, c->d_relin, 0, 0, nk, e_ntt));
-  for (u32 elt : galois_elts_all(c)) {
+  for (u32 elt : elts) {
+    if (!(elt & 1) || elt >= 2u * c->N) return fail(c, ABC_ERR_PARAM, "invalid Galois element");
     if (c->galois.count(elt)) continue;
     u64 *key = nullptr;
     CK(cudaMalloc((void **)&key, kw * 8));
@@ -688,6 +689,16 @@ abc_status abc_keygen(abc_ctx *c) {
   }
   c->have_keys = true;
   return ABC_OK;
+}
+abc_status abc_keygen(abc_ctx *c) { return keygen_impl(c, galois_elts_all(c)); }
+abc_status abc_keygen_select(abc_ctx *c, const uint32_t *galois_elts, size_t n) {
+  return keygen_impl(c, std::vector<u32>(galois_elts, galois_elts + n));
+}
+uint32_t abc_galois_elt_from_step(const abc_ctx *c, int step) {
+  const int as = step < 0 ? -step : step;
+  if (step == 0) return 2u * c->N - 1;
+  if (as >= (c->N >> 1)) return 0;
+  return elt_from_step(c, step);
 }
 size_t abc_key_words(const abc_ctx *c, int kind) {
   const size_t kn = (size_t)c->k * c->N;
@@ -816,7 +827,7 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
   TRY(launch_limb(c, LIMB_FWD_MUL_INV_ADD, c->ar_q, j, L, B, "dec_c1s_plus_c0"));
   {
     Launch l(c, "dec_scale_round");
-    DISPATCH_L(c, (k_dec_finish<LL><<<dim3(N / 128, 1, B), 128, 0, c->stream>>>(x, plain, c->dC, N)));
+    DISPATCH_L(c, (k_dec_finish<LL><<<dim3(N / 128, 1, B), 128, 0, c->stream>>>(x, plain, c->dC, N, c->L)));
     CK(cudaGetLastError());
   }
   j = blank_job();

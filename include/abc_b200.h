@@ -62,6 +62,11 @@ abc_status abc_get_aux_primes(const abc_ctx *ctx, uint64_t *out, uint32_t *count
 /* --- keys: replaces KeyGenerator usage at src/runtime/SealCiphertextFactory.cpp:89-93
  * (secret key, public key, relinearisation key, the default Galois key set). Runs on the device. */
 abc_status abc_keygen(abc_ctx *ctx);
+/* same, with an explicit list of Galois elements instead of the default set (KeyGenerator::create_galois_keys(elts)):
+ * at N = 65536 with 31 primes one key-switching key is 975 MiB, so only the rotations a program needs are generated */
+abc_status abc_keygen_select(abc_ctx *ctx, const uint32_t *galois_elts, size_t n);
+/* GaloisTool::get_elt_from_step: 3^step mod 2N (step < 0: N/2 - |step|), 2N-1 for step 0; 0 if |step| >= N/2 */
+uint32_t abc_galois_elt_from_step(const abc_ctx *ctx, int step);
 enum { ABC_KEY_SECRET = 0, ABC_KEY_PUBLIC = 1, ABC_KEY_RELIN = 2, ABC_KEY_GALOIS = 3 };
 /* words: secret k*N, public 2*k*N, relin/galois L*2*k*N (layout [J][component][limb][N], NTT form) */
 size_t abc_key_words(const abc_ctx *ctx, int kind);

@@ -486,7 +486,7 @@ u32 obfv_elt_from_step(const obfv_ctx *c, int step) {
   return (u32)elt;
 }
 
-void obfv_keygen(obfv_ctx *c, u64 seed) {
+static void keygen_impl(obfv_ctx *c, u64 seed, const u32 *elts, size_t ne) {
   const size_t N = c->N, k = c->k, L = c->L;
   c->seed = seed;
   free(c->sk); free(c->pk); free(c->relin);
@@ -507,8 +507,7 @@ void obfv_keygen(obfv_ctx *c, u64 seed) {
     for (size_t j = 0; j < N; j++) nk[i * N + j] = mulmod(c->sk[i * N + j], c->sk[i * N + j], c->q[i]);
   c->relin = malloc(L * 2 * k * N * 8);
   gen_kswitch_key(c, nk, 0, c->relin);
-  /* Galois keys for the default element set (create_galois_keys) */
-  u32 elts[64]; size_t ne = obfv_galois_elts(c, elts, 64);
+  /* Galois keys (create_galois_keys): the default element set, or the caller's list */
   for (size_t e = 0; e < ne; e++) {
     u32 elt = elts[e], idx = (elt - 1) >> 1;
     if (c->galois[idx]) continue;
@@ -518,6 +517,11 @@ void obfv_keygen(obfv_ctx *c, u64 seed) {
   }
   free(nk);
 }
+void obfv_keygen(obfv_ctx *c, u64 seed) {
+  u32 elts[64]; size_t ne = obfv_galois_elts(c, elts, 64);
+  keygen_impl(c, seed, elts, ne);
+}
+void obfv_keygen_select(obfv_ctx *c, u64 seed, const u32 *elts, size_t ne) { keygen_impl(c, seed, elts, ne); }
 const u64 *obfv_secret_key(const obfv_ctx *c) { return c->sk; }
 const u64 *obfv_public_key(const obfv_ctx *c) { return c->pk; }
 const u64 *obfv_relin_key(const obfv_ctx *c) { return c->relin; }

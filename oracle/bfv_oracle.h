@@ -54,6 +54,7 @@ void obfv_ntt_inv(const obfv_ctx *c, size_t idx, uint64_t *limb);
 
 /* keys: deterministic from seed (our own counter-based sampler; see oracle/README.md). */
 void obfv_keygen(obfv_ctx *c, uint64_t seed);
+void obfv_keygen_select(obfv_ctx *c, uint64_t seed, const uint32_t *galois_elts, size_t n); /* explicit Galois set */
 const uint64_t *obfv_secret_key(const obfv_ctx *c);            /* [k][N] NTT form */
 const uint64_t *obfv_public_key(const obfv_ctx *c);            /* [2][k][N] NTT form */
 const uint64_t *obfv_relin_key(const obfv_ctx *c);             /* [L][2][k][N] NTT form */

@@ -42,6 +42,7 @@ def _load():
         "obfv_get_primes": (sz, [sz, i32, sz, u64p]),
         "obfv_ntt_fwd": (None, [vp, sz, u64p]), "obfv_ntt_inv": (None, [vp, sz, u64p]),
         "obfv_keygen": (None, [vp, u64]),
+        "obfv_keygen_select": (None, [vp, u64, u32p, sz]),
         "obfv_secret_key": (vp, [vp]), "obfv_public_key": (vp, [vp]), "obfv_relin_key": (vp, [vp]),
         "obfv_galois_key": (vp, [vp, u32]),
         "obfv_galois_elts": (sz, [vp, u32p, sz]),
@@ -89,7 +90,7 @@ class Oracle:
     """SEAL-3.6.5-restatement BFV context.  Mirrors what SealCiphertextFactory sets up
     (/root/reference/src/runtime/SealCiphertextFactory.cpp:72-100)."""
 
-    def __init__(self, N, primes=None, t=0, seed=None):
+    def __init__(self, N, primes=None, t=0, seed=None, galois_steps=None):
         L_ = lib()
         if primes is None:
             self._c = L_.obfv_create(N, None, 0, t)
@@ -106,7 +107,7 @@ class Oracle:
         self.ct_words = 2 * self.L * N
         self.seed = None
         if seed is not None:
-            self.keygen(seed)
+            self.keygen(seed, galois_steps)
 
     def __del__(self):
         if getattr(self, "_c", None):
@@ -137,9 +138,13 @@ class Oracle:
         return out
 
     # -- keys
-    def keygen(self, seed):
+    def keygen(self, seed, galois_steps=None):
         self.seed = seed
-        lib().obfv_keygen(self._c, seed)
+        if galois_steps is None:
+            lib().obfv_keygen(self._c, seed)
+        else:
+            elts = np.asarray([self.elt_from_step(s) for s in galois_steps], dtype=np.uint32)
+            lib().obfv_keygen_select(self._c, seed, elts, elts.size)
 
     def _view(self, ptr, shape):
         n = int(np.prod(shape))

@@ -125,3 +125,33 @@ def test_key_import_round_trip():
         assert np.array_equal(a.rotateRows(63).export()[0], o.rotate_rows(a_w, 63))
     finally:
         f.close()
+
+
+def test_n65536_k31_generic_limb_count():
+    """BASELINE.json configs[4] parameter set on one GPU: N = 65536, 30 x 55-bit + one 56-bit prime (SEAL has no default
+    above 32768), t = 786433; only the keys the deep chain needs (relin + rotate by 1).  Exercises the two-pass NTT with
+    A = 3 and the generic (L > 15) base-conversion kernels."""
+    from abc_b200 import CudaCiphertextFactory
+    from oracle.bfv_oracle import Oracle, get_primes
+    N = 65536
+    data = get_primes(N, 55, 30)
+    primes = data + get_primes(N, 56, 1)
+    o = Oracle(N, primes=primes, seed=SEED, galois_steps=[1])
+    f = CudaCiphertextFactory(N, primes=primes, seed=SEED, galois_steps=[1])
+    try:
+        assert f.k == 31 and f.t == o.t == 786433
+        rng = np.random.default_rng(65)
+        d = rng.integers(0, 4, N)
+        f.set_encrypt_nonce(1)
+        a = f.createCiphertext(d)
+        a_w = o.encrypt_slots(d, 1)
+        assert np.array_equal(a.export()[0], a_w), "encrypt"
+        sq_w = o.mul_relin(a_w, a_w)
+        sq = a.multiply(a)
+        assert np.array_equal(sq.export()[0], sq_w), "mul+relin"
+        rot = sq.rotateRows(1)
+        assert np.array_equal(rot.export()[0], o.rotate_rows(sq_w, 1)), "rotate"
+        want = np.concatenate([np.roll((d * d)[:N // 2], -1), np.roll((d * d)[N // 2:], -1)])
+        assert np.array_equal(f.decryptCiphertext(rot), want)
+    finally:
+        f.close()
