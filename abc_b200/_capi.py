@@ -64,6 +64,12 @@ SYMBOLS = {
     "abc_probe_ntt": (i32, [vp, i32, u32, vp, sz]),
     "abc_probe_multiply": (i32, [vp, vp, vp, vp, sz]),
     "abc_bench_ntt": (i32, [vp, i32, u32, sz, i32, f32p]),
+    "abc_comm_unique_id": (i32, [vp, vp]),
+    "abc_comm_init": (i32, [vp, i32, i32, vp]),
+    "abc_comm_rank": (i32, [vp]),
+    "abc_comm_world": (i32, [vp]),
+    "abc_owned_limbs": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
+    "abc_ct_allgather": (i32, [vp, vp]),
     "abc_timer_start": (i32, [vp]),
     "abc_timer_stop": (i32, [vp, f32p]),
     "abc_flush_l2": (i32, [vp, sz]),

@@ -112,6 +112,21 @@ class CudaCiphertextFactory:
     def has_galois_key(self, elt):
         return bool(self._lib.abc_has_galois_key(self._h, elt))
 
+    # -- limb sharding across GPUs (one process per GPU; include/abc_b200.h "limb sharding")
+    def comm_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        self._ck(self._lib.abc_comm_unique_id(self._h, buf))
+        return bytes(buf)
+
+    def comm_init(self, rank, world, unique_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self._lib.abc_comm_init(self._h, rank, world, buf))
+
+    def owned_limbs(self):
+        lo, hi = C.c_uint32(), C.c_uint32()
+        self._ck(self._lib.abc_owned_limbs(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def set_encrypt_nonce(self, nonce):
         self._ck(self._lib.abc_set_encrypt_nonce(self._h, nonce))
 
@@ -260,6 +275,12 @@ class CudaCiphertext:
         out = np.zeros((f.batch, 2, f.L, f.N), dtype=np.uint64)
         f._ck(f._lib.abc_ct_export(f._h, self._h, out.ctypes.data, out.size))
         return out
+
+    def allgather(self):
+        """Limb-sharded contexts: make every limb valid on every rank (NCCL all-gather)."""
+        f = self.factory
+        f._ck(f._lib.abc_ct_allgather(f._h, self._h))
+        return self
 
     def clone(self):
         f = self.factory

@@ -13,11 +13,12 @@
 template <int OP>  // 0 add, 1 sub, 2 negate
 __global__ void __launch_bounds__(256) k_addsub(u64 *__restrict__ dst, const u64 *__restrict__ a,
                                                 const u64 *__restrict__ b, const DevConst *__restrict__ C, int N,
-                                                int L, long long istride) {
+                                                int L, long long istride, int i0, int nrows) {
+  // grid.y = 2 * nrows: limbs i0 .. i0+nrows-1 of both polynomials (all L limbs unless the context is limb-sharded)
   const int e2 = blockIdx.x * 256 + threadIdx.x;
   if (e2 >= N / 2) return;
-  const int row = blockIdx.y;
-  const u64 q = C->q[row % L];
+  const int limb = i0 + (int)(blockIdx.y % nrows), row = (int)(blockIdx.y / nrows) * L + limb;
+  const u64 q = C->q[limb];
   const size_t off = (size_t)blockIdx.z * istride + (size_t)row * N;
   ulonglong2 x = reinterpret_cast<const ulonglong2 *>(a + off)[e2], r;
   if (OP == 2) {
@@ -145,10 +146,11 @@ __global__ void __launch_bounds__(128) k_behz_scale(const u64 *__restrict__ X, u
 template <int LT>
 __global__ void __launch_bounds__(256) k_ks_inner(const u64 *__restrict__ T, const u64 *__restrict__ key,
                                                   u64 *__restrict__ acc, const ModInfo *__restrict__ mods, int N, int k,
-                                                  int Lrt) {
+                                                  int Lrt, const int *__restrict__ imap) {
+  // grid.y indexes imap: the output moduli this rank computes (all k unless the context is limb-sharded)
   const int L = LT ? LT : Lrt;
   // two adjacent coefficients per thread (16-byte accesses), J loop unrolled
-  const int n2 = blockIdx.x * 256 + threadIdx.x, I = blockIdx.y, inst = blockIdx.z;
+  const int n2 = blockIdx.x * 256 + threadIdx.x, I = imap[blockIdx.y], inst = blockIdx.z;
   const ModInfo *Mp = mods + I;
   const u64 q = Mp->q, mh = Mp->mu_hi, ml = Mp->mu_lo;
   const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(T + ((size_t)(inst * k + I) * L) * N) + n2;
@@ -229,14 +231,14 @@ __device__ __forceinline__ u64 scaled_plain(u64 m, u64 fix, int i, const DevCons
 template <int SUB>
 __global__ void __launch_bounds__(256) k_plain_addsub(u64 *__restrict__ dst, const u64 *__restrict__ a,
                                                       const u64 *__restrict__ plain, long long plain_is,
-                                                      const DevConst *__restrict__ C, int N, int L) {
+                                                      const DevConst *__restrict__ C, int N, int L, int i0, int i1) {
   const int n = blockIdx.x * 256 + threadIdx.x, inst = blockIdx.z;
   const u64 m = plain[(size_t)inst * plain_is + n];
   u64 lo = C->t_half_up, hi = 0;
   mac128(lo, hi, m, C->q_mod_t);
   const u64 fix = div128_by(lo, hi, C->t, C->t_mu_hi, C->t_mu_lo);
   const size_t base = (size_t)inst * 2 * L * N + n;
-  for (int i = 0; i < L; ++i) {
+  for (int i = i0; i < i1; ++i) {  // limbs [i0, i1): all of them unless the context is limb-sharded
     const u64 q = C->q[i], s = scaled_plain(m, fix, i, C);
     const u64 x = a[base + (size_t)i * N];
     dst[base + (size_t)i * N] = SUB ? sub_mod(x, s, q) : add_mod(x, s, q);

@@ -3,6 +3,9 @@
 // plaintexts happens in the sm_100a kernels of kernels.cuh.  There is no CPU fallback.
 #include "../../include/abc_b200.h"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -47,6 +50,15 @@ struct abc_ctx {
   int *rs_c1 = nullptr;     // [L]   L + w
   int *rm_special = nullptr, *rd_special = nullptr;  // [2] special-prime rows of an accumulator block
   int *rs_accq = nullptr;   // [2L]  comp*k + i: data rows of an accumulator block
+  // limb sharding (multi-GPU, one process per GPU): this rank owns data limbs [own_lo, own_hi) of every ciphertext and
+  // computes the key-switch output moduli own U {special}; world == 1 owns everything.  Maps below follow the own set.
+  int rank = 0, world = 1, own_lo = 0, own_hi = 0;
+  ncclComm_t comm = nullptr;
+  int ks_nI = 0;                                    // |own| + 1
+  int *ks_I = nullptr;                              // [ks_nI] output moduli of the key switch (own..., special)
+  int *rm_modup_s = nullptr, *rd_modup_s = nullptr, *rs_modup_s = nullptr;   // [ks_nI * L]
+  int *rm_md = nullptr, *rd_md = nullptr, *rs_md = nullptr;                  // [2 * nown] ModDown rows
+  int *rm_own = nullptr, *rd_own = nullptr;                                  // [2 * nown] own rows of a ciphertext
   int *rs_zero = nullptr;   // [2k]  0
   u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;
   std::map<u32, u64 *> galois;
@@ -195,6 +207,8 @@ void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, s
   }
 }
 
+abc_status build_shard_maps(abc_ctx *c);
+
 abc_status build_tables(abc_ctx *c) {
   using hm::mulmod; using hm::invmod; using hm::shoup; using hm::prod_mod; using hm::barrett_ratio; using hm::bit_reverse; using hm::minimal_2nth_root; using hm::get_primes; using hm::bits_of; using hm::prod_bits;
   const int N = c->N, logN = c->logN, k = c->k, L = c->L;
@@ -327,6 +341,101 @@ abc_status build_tables(abc_ctx *c) {
   TRY(upload(c, &c->rd_special, v));
   v.resize(2 * L); for (int w = 0; w < 2 * L; ++w) v[w] = (w / L) * k + (w % L);
   TRY(upload(c, &c->rs_accq, v));
+  c->own_lo = 0; c->own_hi = L;
+  TRY(build_shard_maps(c));
+  return ABC_OK;
+}
+
+// maps that depend on the set of limbs this rank owns (rebuilt by abc_comm_init)
+abc_status build_shard_maps(abc_ctx *c) {
+  const int L = c->L, k = c->k, lo = c->own_lo, hi = c->own_hi, nown = hi - lo;
+  std::vector<int> I;
+  for (int i = lo; i < hi; ++i) I.push_back(i);
+  I.push_back(L);  // the special prime's accumulation is computed on every rank (ModDown needs it everywhere)
+  c->ks_nI = (int)I.size();
+  TRY(upload(c, &c->ks_I, I));
+  std::vector<int> m, d, sr;
+  for (int I_ : I) for (int J = 0; J < L; ++J) { m.push_back(I_); d.push_back(I_ * L + J); sr.push_back(J); }
+  TRY(upload(c, &c->rm_modup_s, m)); TRY(upload(c, &c->rd_modup_s, d)); TRY(upload(c, &c->rs_modup_s, sr));
+  m.clear(); d.clear(); sr.clear();
+  std::vector<int> od;
+  for (int comp = 0; comp < 2; ++comp) for (int i = lo; i < hi; ++i) {
+    m.push_back(i); d.push_back(comp * L + i); sr.push_back(comp * k + i); od.push_back(comp * L + i);
+  }
+  if (nown > 0) {
+    TRY(upload(c, &c->rm_md, m)); TRY(upload(c, &c->rd_md, d)); TRY(upload(c, &c->rs_md, sr));
+    TRY(upload(c, &c->rm_own, m)); TRY(upload(c, &c->rd_own, od));
+  }
+  return ABC_OK;
+}
+
+// ---- NCCL, loaded on first use so single-GPU users need no NCCL at all (in a torch process this resolves to the
+// libnccl.so.2 torch already loaded)
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi *nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+      api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+      api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
+      api.Broadcast = (decltype(api.Broadcast))dlsym(h, "ncclBroadcast");
+      api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+      if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Broadcast) api.h = h;
+    }
+  }
+  return api.h ? &api : nullptr;
+}
+#define NCK(call)                                                                                     \
+  do {                                                                                                \
+    ncclResult_t r_ = (call);                                                                         \
+    if (r_ != ncclSuccess) {                                                                          \
+      c->err = std::string(#call) + ": " + (nccl_api()->GetErrorString ? nccl_api()->GetErrorString(r_) : "NCCL error"); \
+      return ABC_ERR_CUDA;                                                                            \
+    }                                                                                                 \
+  } while (0)
+
+void limb_range(int L, int world, int rank, int *lo, int *hi) {
+  const int base = L / world, extra = L % world;
+  *lo = rank * base + std::min(rank, extra);
+  *hi = *lo + base + (rank < extra ? 1 : 0);
+}
+
+// all-gather of the limb-sharded polynomials `poly_mask` (bit 0: c0, bit 1: c1) of ciphertext block d, in place:
+// every rank broadcasts the limbs it owns (NCCL over NVLink; the exchange step of the limb-sharded key switch)
+abc_status allgather_limbs(abc_ctx *c, u64 *d, int poly_mask) {
+  if (c->world == 1) return ABC_OK;
+  NcclApi *n = nccl_api();
+  const size_t N = c->N, L = c->L;
+  c->launches++;
+  NCK(n->GroupStart());
+  for (int r = 0; r < c->world; ++r) {
+    int lo, hi;
+    limb_range(c->L, c->world, r, &lo, &hi);
+    if (hi == lo) continue;
+    for (int inst = 0; inst < c->B; ++inst)
+      for (int p = 0; p < 2; ++p) {
+        if (!(poly_mask & (1 << p))) continue;
+        u64 *ptr = d + ((size_t)inst * 2 + p) * L * N + (size_t)lo * N;
+        NCK(n->Broadcast(ptr, ptr, (size_t)(hi - lo) * N, ncclUint64, r, c->comm, c->stream));
+      }
+  }
+  NCK(n->GroupEnd());
   return ABC_OK;
 }
 
@@ -347,11 +456,11 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   TRY(scratch(c, SC_ACC, &acc, (size_t)B * 2 * k * N));
   LimbJob j = blank_job();
   j.dst = T; j.dst_is = (long long)k * L * N; j.src = target; j.src_is = target_is;
-  j.rowmod = c->rm_modup; j.rowsrc = c->rs_modup; j.galois_einv = einv;
-  TRY(launch_limb(c, einv ? LIMB_GALOIS_REDUCE_FWD : LIMB_REDUCE_FWD, c->ar_q, j, k * L, B, "ks_modup_ntt"));
+  j.rowmod = c->rm_modup_s; j.rowdst = c->rd_modup_s; j.rowsrc = c->rs_modup_s; j.galois_einv = einv;
+  TRY(launch_limb(c, einv ? LIMB_GALOIS_REDUCE_FWD : LIMB_REDUCE_FWD, c->ar_q, j, c->ks_nI * L, B, "ks_modup_ntt"));
   {
     Launch l(c, "ks_inner");
-    DISPATCH_L(c, (k_ks_inner<LL><<<dim3(N / 512, k, B), 256, 0, c->stream>>>(T, key, acc, c->d_mods, N, k, c->L)));
+    DISPATCH_L(c, (k_ks_inner<LL><<<dim3(N / 512, c->ks_nI, B), 256, 0, c->stream>>>(T, key, acc, c->d_mods, N, k, c->L, c->ks_I)));
     CK(cudaGetLastError());
   }
   j = blank_job();
@@ -359,11 +468,12 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   j.rowmod = c->rm_special; j.rowdst = c->rd_special;
   TRY(launch_limb(c, LIMB_INV, c->ar_q, j, 2, B, "ks_intt_special"));
   j = blank_job();
-  j.src = acc; j.src_is = (long long)2 * k * N; j.rowsrc = c->rs_accq; j.rowmod = c->rm_ct;
+  const int nown = c->own_hi - c->own_lo;
+  j.src = acc; j.src_is = (long long)2 * k * N; j.rowsrc = c->rs_md; j.rowdst = c->rd_md; j.rowmod = c->rm_md;
   j.dst = dst; j.dst_is = (long long)2 * L * N;
-  j.C = c->dC; j.tl = acc; j.tl_is = (long long)2 * k * N; j.L = L; j.k = k;
+  j.C = c->dC; j.tl = acc; j.tl_is = (long long)2 * k * N; j.L = L; j.k = k; j.i0 = c->own_lo; j.nrows = nown;
   j.base0 = base0; j.base0_is = base0_is; j.base1 = base1; j.base1_is = base1_is; j.base_einv = einv;
-  TRY(launch_limb(c, LIMB_INV_MODDOWN, c->ar_q, j, 2 * L, B, "ks_intt_moddown"));
+  if (nown > 0) TRY(launch_limb(c, LIMB_INV_MODDOWN, c->ar_q, j, 2 * nown, B, "ks_intt_moddown"));
   return ABC_OK;
 }
 
@@ -414,6 +524,7 @@ abc_status apply_galois(abc_ctx *c, const u64 *src, u64 *dst, u32 elt) {
   if (it == c->galois.end()) return fail(c, ABC_ERR_STATE, "Galois key not present");
   const long long LN = (long long)c->L * c->N;
   const u32 elt_inv = (u32)hm::invmod(elt, 2ull * c->N);
+  TRY(allgather_limbs(c, const_cast<u64 *>(src), 2));  // limb-sharded: ModUp needs every limb of c1 on every rank
   return keyswitch(c, src + LN, 2 * LN, it->second, src, 2 * LN, nullptr, 0, elt_inv, dst);
 }
 
@@ -514,16 +625,17 @@ abc_status mul_plain_device(abc_ctx *c, u64 *dst, const u64 *a, const u64 *plain
   j.src = plain; j.src_is = N; j.rowsrc = c->rs_zero; j.dst = P; j.dst_is = (long long)L * N; j.rowmod = c->rm_ct;
   TRY(launch_limb(c, LIMB_PLAINLIFT_FWD, c->ar_q, j, L, Bp, "plain_lift_ntt"));
   j = blank_job();
-  j.src = a; j.dst = dst; j.src_is = j.dst_is = (long long)2 * L * N; j.rowmod = c->rm_ct;
-  j.mul = P; j.mul_is = broadcast ? 0 : (long long)L * N; j.rowmul = c->rm_ct;
-  TRY(launch_limb(c, LIMB_FWD_MUL_INV, c->ar_q, j, 2 * L, B, "ct_mul_plain"));
+  const int nown = c->own_hi - c->own_lo;   // only the limbs this rank owns
+  j.src = a; j.dst = dst; j.src_is = j.dst_is = (long long)2 * L * N; j.rowmod = c->rm_own; j.rowdst = c->rd_own;
+  j.mul = P; j.mul_is = broadcast ? 0 : (long long)L * N; j.rowmul = c->rm_own;
+  if (nown > 0) TRY(launch_limb(c, LIMB_FWD_MUL_INV, c->ar_q, j, 2 * nown, B, "ct_mul_plain"));
   return ABC_OK;
 }
 
 template <int SUB> abc_status plain_addsub_device(abc_ctx *c, u64 *dst, const u64 *a, const u64 *plain, int broadcast) {
   Launch l(c, SUB ? "plain_sub" : "plain_add");
   k_plain_addsub<SUB><<<dim3(c->N / 256, 1, c->B), 256, 0, c->stream>>>(dst, a, plain, broadcast ? 0 : c->N, c->dC, c->N,
-                                                                      c->L);
+                                                                      c->L, c->own_lo, c->own_hi);
   CK(cudaGetLastError());
   return ABC_OK;
 }
@@ -633,6 +745,7 @@ void abc_ctx_destroy(abc_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
   for (auto &kv : c->galois) cudaFree(kv.second);
   cudaFree(c->d_sk); cudaFree(c->d_pk); cudaFree(c->d_relin);
   for (void *p : c->owned) cudaFree(p);
@@ -819,6 +932,7 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
   TRY(scratch(c, SC_DECX, &x, (size_t)B * L * N));
   TRY(scratch(c, SC_DECP, &plain, (size_t)B * N));
   CK(cudaMallocAsync((void **)&d_out, (size_t)B * N * sizeof(long long), c->stream));
+  TRY(allgather_limbs(c, ct->d, 3));  // limb-sharded: scale-and-round needs every limb
   LimbJob j = blank_job();
   j.src = ct->d; j.src_is = (long long)2 * L * N; j.rowsrc = c->rs_c1;
   j.mul = c->d_sk; j.mul_is = 0;
@@ -853,11 +967,13 @@ static abc_status addsub(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct 
     return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
   const int N = c->N, L = c->L;
   Launch l(c, op == 0 ? "add" : op == 1 ? "sub" : "negate");
-  dim3 grid((N / 2 + 255) / 256, 2 * L, c->B);
+  const int i0 = c->own_lo, nown = c->own_hi - c->own_lo;
+  if (nown == 0) return ABC_OK;
+  dim3 grid((N / 2 + 255) / 256, 2 * nown, c->B);
   const long long is = 2ll * L * N;
-  if (op == 0) k_addsub<0><<<grid, 256, 0, c->stream>>>(dst->d, a->d, b->d, c->dC, N, L, is);
-  else if (op == 1) k_addsub<1><<<grid, 256, 0, c->stream>>>(dst->d, a->d, b->d, c->dC, N, L, is);
-  else k_addsub<2><<<grid, 256, 0, c->stream>>>(dst->d, a->d, nullptr, c->dC, N, L, is);
+  if (op == 0) k_addsub<0><<<grid, 256, 0, c->stream>>>(dst->d, a->d, b->d, c->dC, N, L, is, i0, nown);
+  else if (op == 1) k_addsub<1><<<grid, 256, 0, c->stream>>>(dst->d, a->d, b->d, c->dC, N, L, is, i0, nown);
+  else k_addsub<2><<<grid, 256, 0, c->stream>>>(dst->d, a->d, nullptr, c->dC, N, L, is, i0, nown);
   CK(cudaGetLastError());
   return ABC_OK;
 }
@@ -871,6 +987,10 @@ abc_status abc_mul_relin(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct 
   const size_t LN = (size_t)c->L * c->N;
   u64 *out3 = nullptr;
   TRY(scratch(c, SC_OUT3, &out3, (size_t)c->B * 3 * LN));
+  // limb-sharded: BEHZ base conversion needs every limb of both operands; the product is computed on every rank
+  // (replicated), the relinearisation key switch only for the output moduli this rank owns
+  TRY(allgather_limbs(c, a->d, 3));
+  if (b != a) TRY(allgather_limbs(c, b->d, 3));
   TRY(behz_multiply(c, a->d, b->d, out3));
   TRY(keyswitch(c, out3 + 2 * LN, 3ll * LN, c->d_relin, out3, 3ll * LN, out3 + LN, 3ll * LN, 0, dst->d));
   return ABC_OK;
@@ -985,6 +1105,41 @@ abc_status abc_probe_multiply(abc_ctx *c, const abc_ct *a, const abc_ct *b, uint
   CK(cudaStreamSynchronize(c->stream));
   sfree(c, out3);
   return ABC_OK;
+}
+
+// ---- limb sharding across GPUs (one process per GPU)
+abc_status abc_comm_unique_id(abc_ctx *c, uint8_t *out128) {
+  NcclApi *n = nccl_api();
+  if (!n) return fail(c, ABC_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+  static_assert(sizeof(ncclUniqueId) == ABC_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  NCK(n->GetUniqueId(&id));
+  memcpy(out128, &id, sizeof id);
+  return ABC_OK;
+}
+abc_status abc_comm_init(abc_ctx *c, int rank, int world, const uint8_t *id128) {
+  NcclApi *n = nccl_api();
+  if (!n) return fail(c, ABC_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+  if (world < 1 || rank < 0 || rank >= world || world > c->L) return fail(c, ABC_ERR_PARAM, "need 1 <= world <= L and 0 <= rank < world");
+  if (c->comm) return fail(c, ABC_ERR_STATE, "communicator already initialised");
+  CK(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NCK(n->CommInitRank(&c->comm, world, id, rank));
+  c->rank = rank; c->world = world;
+  limb_range(c->L, world, rank, &c->own_lo, &c->own_hi);
+  CK(cudaStreamSynchronize(c->stream));
+  return build_shard_maps(c);
+}
+int abc_comm_rank(const abc_ctx *c) { return c->rank; }
+int abc_comm_world(const abc_ctx *c) { return c->world; }
+abc_status abc_owned_limbs(const abc_ctx *c, uint32_t *lo, uint32_t *hi) {
+  *lo = (uint32_t)c->own_lo; *hi = (uint32_t)c->own_hi;
+  return ABC_OK;
+}
+abc_status abc_ct_allgather(abc_ctx *c, abc_ct *ct) {
+  if (!valid_ct(c, ct)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+  return allgather_limbs(c, ct->d, 3);
 }
 
 // ---- timing / profiling

@@ -37,7 +37,8 @@ struct LimbJob {
   const u64 *tl; long long tl_is;               // accumulator block [2][k][N]; its rows (comp, L) hold INTT_p(acc_L)
   const u64 *base0, *base1; long long base0_is, base1_is;  // polynomial added into component 0 / 1 (nullptr = 0)
   u32 base_einv;                                // automorphism applied to base0/base1 while reading (0: none)
-  int L, k;
+  int L, k;                                     // data limbs / key-level primes of the context
+  int i0, nrows;                                // POST_MODDOWN rows: w = comp * nrows + (i - i0), limbs i0 .. i0+nrows-1
 };
 
 // combos of (PRE, FWD, MUL, INV, POST) the library uses
@@ -107,7 +108,7 @@ struct ModDownRow { u64 p, p_half, phm, ip, ips; const ulonglong2 *tl; const u64
 __device__ __forceinline__ ModDownRow moddown_row(const LimbJob &job, int n, int inst, int w) {
   // tail of switch_key_inplace for row (comp, i): dst = base + p^-1 * (acc_i - ([acc_L + p/2]_p mod q_i) + [p/2]_{q_i})
   const DevConst *C = job.C;
-  const int comp = w / job.L, i = w - comp * job.L;
+  const int comp = w / job.nrows, i = job.i0 + (w - comp * job.nrows);
   ModDownRow r;
   r.p = C->p; r.p_half = C->p_half; r.phm = C->p_half_mod_q[i]; r.ip = C->inv_p[i]; r.ips = C->inv_p_s[i];
   r.tl = reinterpret_cast<const ulonglong2 *>(job.tl + (size_t)inst * job.tl_is + (size_t)(comp * job.k + job.L) * n);

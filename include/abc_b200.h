@@ -126,6 +126,22 @@ abc_status abc_probe_multiply(abc_ctx *ctx, const abc_ct *a, const abc_ct *b, ui
 /* device-time of `iters` launches of the limb NTT kernel over n_rows resident rows (microbenchmark) */
 abc_status abc_bench_ntt(abc_ctx *ctx, int inverse, uint32_t mod_index, size_t n_rows, int iters, float *ms);
 
+/* --- limb sharding across the GPUs of one box (BASELINE.json configs[4]; one process + one context per GPU).
+ * After abc_comm_init every ciphertext is LIMB-SHARDED: rank r owns data limbs [lo_r, hi_r) (contiguous, sizes differ
+ * by at most one) of both polynomials of every instance; the other limbs of a handle's buffer are not maintained.
+ * add / sub / negate / plain ops touch owned limbs only (no communication).  rotate_rows all-gathers c1 (NCCL over
+ * NVLink) in front of the key-switch ModUp and computes only the output moduli it owns, plus the special prime,
+ * which every rank computes so that ModDown needs no second collective.  mul_relin all-gathers its operands, computes
+ * the BEHZ product on every rank and shards only the relinearisation.  decrypt_decode all-gathers first.  All ranks
+ * must issue the same ops in the same order with the same seed (same keys).  Results are bit-identical to world = 1. */
+#define ABC_COMM_ID_BYTES 128
+abc_status abc_comm_unique_id(abc_ctx *ctx, uint8_t *out128);   /* ncclGetUniqueId; call on one rank, share the bytes */
+abc_status abc_comm_init(abc_ctx *ctx, int rank, int world, const uint8_t *id128);   /* 1 <= world <= L */
+int abc_comm_rank(const abc_ctx *ctx);
+int abc_comm_world(const abc_ctx *ctx);
+abc_status abc_owned_limbs(const abc_ctx *ctx, uint32_t *lo, uint32_t *hi);
+abc_status abc_ct_allgather(abc_ctx *ctx, abc_ct *ct);          /* make every limb of ct valid on every rank */
+
 /* --- timing on the context's stream (CUDA events; torch.cuda.Event cannot see this stream) */
 abc_status abc_timer_start(abc_ctx *ctx);
 abc_status abc_timer_stop(abc_ctx *ctx, float *ms);            /* synchronises */
