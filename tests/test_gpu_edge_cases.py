@@ -155,3 +155,19 @@ def test_n65536_k31_generic_limb_count():
         assert np.array_equal(f.decryptCiphertext(rot), want)
     finally:
         f.close()
+
+
+def test_limb_sharded_key_switch_two_gpus():
+    """BASELINE.json configs[4] mechanism at test size: RNS limbs sharded over 2 GPUs, NCCL all-gather in front of the
+    key-switch ModUp, owned limbs bit-exact against the oracle (tools/shard_check.py).  Needs 2 visible GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run by hand: gpurun --gpus 2 -- torchrun ... tools/shard_check.py)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "shard_check.py"), "8192"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "shard_check ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
