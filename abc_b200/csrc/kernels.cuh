@@ -389,6 +389,33 @@ __global__ void __launch_bounds__(1024) k_peak_iadd(u32 *out, int iters) {
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
 }
+// pure-FP64 butterfly on exact integer-valued doubles (class 3 of the microbenchmark):
+//   Q = rint(y*w/q) (DFMA + DADD with the 1.5*2^52 magic), p = y*w as an error-free product (DMUL + DFMA),
+//   v = (p_hi - Q*q) + p_lo (DFMA exact because the result is < q, + DADD), x' = x + v, y' = x - v.
+__device__ __forceinline__ void bf_fwd_f64(double &x, double &y, double w, double winv, double q) {
+  const double Q = fma(y, winv, 6755399441055744.0) - 6755399441055744.0;
+  const double ph = y * w;
+  const double pl = fma(y, w, -ph);
+  const double v = fma(-Q, q, ph) + pl;
+  y = x - v;
+  x = x + v;
+}
+__global__ void __launch_bounds__(1024) k_peak_butterfly_f64(double *out, int iters, double q, double w, double winv) {
+  double x0 = threadIdx.x, y0 = blockIdx.x, x1 = x0 + 1, y1 = y0 + 2, x2 = x0 + 3, y2 = y0 + 4, x3 = x0 + 5, y3 = y0 + 6;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      bf_fwd_f64(x0, y0, w, winv, q); bf_fwd_f64(x1, y1, w, winv, q); bf_fwd_f64(x2, y2, w, winv, q); bf_fwd_f64(x3, y3, w, winv, q);
+    }
+    // range reset (8 ops per 32 butterflies), keeps the values exact integers below 2^44
+    x0 = fma(-floor(x0 * 5.6843418860808015e-14), 17592186044416.0, x0); y0 = fma(-floor(y0 * 5.6843418860808015e-14), 17592186044416.0, y0);
+    x1 = fma(-floor(x1 * 5.6843418860808015e-14), 17592186044416.0, x1); y1 = fma(-floor(y1 * 5.6843418860808015e-14), 17592186044416.0, y1);
+    x2 = fma(-floor(x2 * 5.6843418860808015e-14), 17592186044416.0, x2); y2 = fma(-floor(y2 * 5.6843418860808015e-14), 17592186044416.0, y2);
+    x3 = fma(-floor(x3 * 5.6843418860808015e-14), 17592186044416.0, x3); y3 = fma(-floor(y3 * 5.6843418860808015e-14), 17592186044416.0, y3);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + y0 + x1 + y1 + x2 + y2 + x3 + y3;
+}
+
 // register-resident NTT butterflies per second for one arithmetic class (the ceiling NTT kernels are quoted against)
 template <int AR>
 __global__ void __launch_bounds__(1024) k_peak_butterfly(u64 *out, int iters, u64 q, u64 w, u64 wc) {

@@ -59,6 +59,8 @@ struct abc_ctx {
   int *rm_modup_s = nullptr, *rd_modup_s = nullptr, *rs_modup_s = nullptr;   // [ks_nI * L]
   int *rm_md = nullptr, *rd_md = nullptr, *rs_md = nullptr;                  // [2 * nown] ModDown rows
   int *rm_own = nullptr, *rd_own = nullptr;                                  // [2 * nown] own rows of a ciphertext
+  int *rm_mdm = nullptr, *rd_mdm = nullptr, *rs_mdm = nullptr;               // [2 + 2 * nown] merged special + ModDown rows
+  u32 *ks_flags = nullptr; u32 ks_serial = 0;                                 // [B][2] ready flags of the merged launch
   int *rs_zero = nullptr;   // [2k]  0
   u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;
   std::map<u32, u64 *> galois;
@@ -171,7 +173,8 @@ LimbJob blank_job() { LimbJob j; memset(&j, 0, sizeof j); return j; }
 
 // ---- context construction --------------------------------------------------------------------
 void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, std::vector<ulonglong2> &itw,
-              std::vector<ulonglong2> &twf, std::vector<ulonglong2> &itwf) {
+              std::vector<ulonglong2> &twf, std::vector<ulonglong2> &itwf, std::vector<ulonglong2> &twd,
+              std::vector<ulonglong2> &itwd) {
   using hm::mulmod; using hm::invmod; using hm::shoup; using hm::prod_mod; using hm::barrett_ratio; using hm::bit_reverse; using hm::minimal_2nth_root; using hm::get_primes; using hm::bits_of; using hm::prod_bits;
   m.q = q;
   barrett_ratio(q, m.mu_hi, m.mu_lo);
@@ -193,7 +196,7 @@ void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, s
   // FP64-assisted class: companion = double(w/q) (correctly rounded: both operands are exact doubles)
   auto dbits = [q](u64 w) { double d = (double)w / (double)q; u64 b; memcpy(&b, &d, 8); return b; };
   m.ar_class = AR_SHOUP;
-  if ((q >> 49) == 0) m.ar_class = (q >> 45) == 0 ? AR_FP_LAZY : AR_FP;  // range plans in ntt.cuh
+  if ((q >> 49) == 0) m.ar_class = (q >> 45) == 0 ? AR_F64 : AR_FP;  // range plans in ntt.cuh (AR_FP_LAZY: ABC_FORCE_AR=2)
   twf.clear(); itwf.clear();
   m.ninv_f = m.wl_ninv_f = m.qinv_bits = 0;
   if (m.ar_class != AR_SHOUP) {
@@ -204,6 +207,17 @@ void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, s
     }
     m.ninv_f = dbits(m.ninv); m.wl_ninv_f = dbits(m.wl_ninv);
     double qi = 1.0 / (double)q; memcpy(&m.qinv_bits, &qi, 8);
+  }
+  twd.clear(); itwd.clear();
+  m.ninv_d = m.wl_ninv_d = 0;
+  if (m.ar_class == AR_F64) {
+    auto ibits = [](u64 w) { double d = (double)w; u64 b; memcpy(&b, &d, 8); return b; };  // exact: w < 2^45
+    twd.resize(N); itwd.resize(N);
+    for (int j = 0; j < N; ++j) {
+      twd[j] = make_ulonglong2(ibits(tw[j].x), dbits(tw[j].x));
+      itwd[j] = make_ulonglong2(ibits(itw[j].x), dbits(itw[j].x));
+    }
+    m.ninv_d = ibits(m.ninv); m.wl_ninv_d = ibits(m.wl_ninv);
   }
 }
 
@@ -228,11 +242,13 @@ abc_status build_tables(abc_ctx *c) {
   // ---- per-modulus tables
   const int nmods = k + c->nbsk + 1;
   std::vector<ModInfo> mods(nmods);
-  std::vector<ulonglong2> tw, itw, twf, itwf;
+  std::vector<ulonglong2> tw, itw, twf, itwf, twd, itwd;
   for (int i = 0; i < nmods; ++i) {
     const u64 q = i < k ? c->primes[i] : (i < k + c->nbsk ? c->bsk[i - k] : t);
-    fill_mod(mods[i], q, N, logN, tw, itw, twf, itwf);
-    ulonglong2 *d_tw = nullptr, *d_itw = nullptr, *d_twf = nullptr, *d_itwf = nullptr;
+    fill_mod(mods[i], q, N, logN, tw, itw, twf, itwf, twd, itwd);
+    ulonglong2 *d_tw = nullptr, *d_itw = nullptr, *d_twf = nullptr, *d_itwf = nullptr, *d_twd = nullptr, *d_itwd = nullptr;
+    if (!twd.empty()) { TRY(upload(c, &d_twd, twd)); TRY(upload(c, &d_itwd, itwd)); }
+    mods[i].twd = d_twd; mods[i].itwd = d_itwd;
     TRY(upload(c, &d_tw, tw));
     TRY(upload(c, &d_itw, itw));
     if (!twf.empty()) { TRY(upload(c, &d_twf, twf)); TRY(upload(c, &d_itwf, itwf)); }
@@ -240,7 +256,7 @@ abc_status build_tables(abc_ctx *c) {
   }
   TRY(upload(c, &c->d_mods, mods));
   c->hmods = mods;
-  c->ar_q = AR_FP_LAZY;
+  c->ar_q = AR_F64;
   for (int i = 0; i < k; ++i) c->ar_q = std::min(c->ar_q, mods[i].ar_class);
   c->ar_t = mods[c->idx_t].ar_class;
   if (const char *e = getenv("ABC_FORCE_AR")) c->force_ar = atoi(e);
@@ -365,6 +381,14 @@ abc_status build_shard_maps(abc_ctx *c) {
   if (nown > 0) {
     TRY(upload(c, &c->rm_md, m)); TRY(upload(c, &c->rd_md, d)); TRY(upload(c, &c->rs_md, sr));
     TRY(upload(c, &c->rm_own, m)); TRY(upload(c, &c->rd_own, od));
+    std::vector<int> mm = {L, L}, dm = {L, k + L}, sm_ = {L, k + L};
+    mm.insert(mm.end(), m.begin(), m.end()); dm.insert(dm.end(), d.begin(), d.end()); sm_.insert(sm_.end(), sr.begin(), sr.end());
+    TRY(upload(c, &c->rm_mdm, mm)); TRY(upload(c, &c->rd_mdm, dm)); TRY(upload(c, &c->rs_mdm, sm_));
+  }
+  if (!c->ks_flags) {
+    CK(cudaMalloc((void **)&c->ks_flags, (size_t)c->B * 2 * sizeof(u32)));
+    c->owned.push_back(c->ks_flags);
+    CK(cudaMemset(c->ks_flags, 0, (size_t)c->B * 2 * sizeof(u32)));
   }
   return ABC_OK;
 }
@@ -463,17 +487,26 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
     DISPATCH_L(c, (k_ks_inner<LL><<<dim3(N / 512, c->ks_nI, B), 256, 0, c->stream>>>(T, key, acc, c->d_mods, N, k, c->L, c->ks_I)));
     CK(cudaGetLastError());
   }
-  j = blank_job();
-  j.dst = acc; j.src = acc; j.dst_is = j.src_is = (long long)2 * k * N;
-  j.rowmod = c->rm_special; j.rowdst = c->rd_special;
-  TRY(launch_limb(c, LIMB_INV, c->ar_q, j, 2, B, "ks_intt_special"));
+  const bool merged = c->logN <= 14 && (c->own_hi - c->own_lo) > 0 && !getenv("ABC_KS_UNMERGED");
+  if (!merged) {
+    j = blank_job();
+    j.dst = acc; j.src = acc; j.dst_is = j.src_is = (long long)2 * k * N;
+    j.rowmod = c->rm_special; j.rowdst = c->rd_special;
+    TRY(launch_limb(c, LIMB_INV, c->ar_q, j, 2, B, "ks_intt_special"));
+  }
   j = blank_job();
   const int nown = c->own_hi - c->own_lo;
   j.src = acc; j.src_is = (long long)2 * k * N; j.rowsrc = c->rs_md; j.rowdst = c->rd_md; j.rowmod = c->rm_md;
   j.dst = dst; j.dst_is = (long long)2 * L * N;
   j.C = c->dC; j.tl = acc; j.tl_is = (long long)2 * k * N; j.L = L; j.k = k; j.i0 = c->own_lo; j.nrows = nown;
   j.base0 = base0; j.base0_is = base0_is; j.base1 = base1; j.base1_is = base1_is; j.base_einv = einv;
-  if (nown > 0) TRY(launch_limb(c, LIMB_INV_MODDOWN, c->ar_q, j, 2 * nown, B, "ks_intt_moddown"));
+  if (merged) {  // one launch: the two special-prime rows INTT and publish, the data rows INTT, wait, ModDown
+    j.rowsrc = c->rs_mdm; j.rowdst = c->rd_mdm; j.rowmod = c->rm_mdm;
+    j.flags = c->ks_flags; j.flag_serial = ++c->ks_serial;
+    TRY(launch_limb(c, LIMB_INV_MODDOWN, c->ar_q, j, 2 + 2 * nown, B, "ks_intt_moddown"));
+  } else if (nown > 0) {
+    TRY(launch_limb(c, LIMB_INV_MODDOWN, c->ar_q, j, 2 * nown, B, "ks_intt_moddown"));
+  }
   return ABC_OK;
 }
 
@@ -1237,6 +1270,7 @@ abc_status abc_measure_butterfly_peak(abc_ctx *c, int arith_class, double *butte
     CK(cudaEventRecord(c->ev0, c->stream));
     if (arith_class == AR_SHOUP) k_peak_butterfly<AR_SHOUP><<<grid, 1024, 0, c->stream>>>(out, iters, q, w, hm::shoup(w, q));
     else if (arith_class == AR_FP) k_peak_butterfly<AR_FP><<<grid, 1024, 0, c->stream>>>(out, iters, q, w, wc_fp);
+    else if (arith_class == 3) k_peak_butterfly_f64<<<grid, 1024, 0, c->stream>>>((double *)out, iters, (double)q, (double)w, wd);
     else k_peak_butterfly<AR_FP_LAZY><<<grid, 1024, 0, c->stream>>>(out, iters, q, w, wc_fp);
     CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaEventSynchronize(c->ev1));

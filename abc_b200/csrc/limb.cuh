@@ -39,6 +39,7 @@ struct LimbJob {
   u32 base_einv;                                // automorphism applied to base0/base1 while reading (0: none)
   int L, k;                                     // data limbs / key-level primes of the context
   int i0, nrows;                                // POST_MODDOWN rows: w = comp * nrows + (i - i0), limbs i0 .. i0+nrows-1
+  u32 *flags; u32 flag_serial;                  // merged special-row INTT + ModDown launch: flags[inst][comp] == serial when ready
 };
 
 // combos of (PRE, FWD, MUL, INV, POST) the library uses
@@ -121,7 +122,7 @@ __device__ __forceinline__ void limb_store_pair(const LimbJob &job, const ModInf
                                                 int drow, int arow, int e2, ulonglong2 v) {
   const u64 q = M.q;
   if (POST == POST_MODDOWN) {
-    const ulonglong2 t = md.tl[e2];
+    const ulonglong2 t = __ldcg(md.tl + e2);  // written by another CTA of this launch in the merged mode: L2, not L1
     const u64 rx = sub_mod(barrett64(add_mod(t.x, md.p_half, md.p), q, M.mu_hi), md.phm, q);
     const u64 ry = sub_mod(barrett64(add_mod(t.y, md.p_half, md.p), q, M.mu_hi), md.phm, q);
     v.x = mul_shoup(sub_mod(v.x, rx, q), md.ip, md.ips, q);
@@ -207,10 +208,39 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
     }
   } else {
     ModDownRow md;
-    if (POST == POST_MODDOWN) md = moddown_row(job, n, inst, w);
+    int wq = w;
+    if (POST == POST_MODDOWN && job.flags) {
+      // merged launch: rows 0,1 are the special-prime rows of components 0,1; every data row needs its component's
+      // INTT_p(acc_L) for the ModDown.  Rows are dispatched in blockIdx order (the two special rows of an instance
+      // first), so a data row only ever waits for CTAs that are already resident; it waits AFTER its own INTT.
+      if (w < 2) {
+        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(const_cast<u64 *>(job.tl) + (size_t)inst * job.tl_is +
+                                                       (size_t)(w * job.k + job.L) * n);
+        for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
+          ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
+          v.x = canon_inv<AR>(v.x, q, ar_aux<AR>(q)); v.y = canon_inv<AR>(v.y, q, ar_aux<AR>(q));
+          o[e2] = v;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicExch(job.flags + inst * 2 + w, job.flag_serial);
+        return;
+      }
+      wq = w - 2;
+      if (tid == 0) {
+        const u32 *fp = job.flags + inst * 2 + wq / job.nrows;
+        u32 seen;
+        do {
+          asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(fp) : "memory");
+          if (seen != job.flag_serial) __nanosleep(64);
+        } while (seen != job.flag_serial);
+      }
+      __syncthreads();
+    }
+    if (POST == POST_MODDOWN) md = moddown_row(job, n, inst, wq);
     for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
       ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
-      if (INV && !TAIL) { v.x = canon_inv<AR>(v.x, q); v.y = canon_inv<AR>(v.y, q); }  // a tail block stays in [0,2q) for the head pass
+      if (INV && !TAIL) { v.x = canon_inv<AR>(v.x, q, ar_aux<AR>(q)); v.y = canon_inv<AR>(v.y, q, ar_aux<AR>(q)); }  // a tail block stays in [0,2q) for the head pass
       limb_store_pair<POST>(job, M, md, n, inst, drow, mrow, eoff + e2, v);
     }
   }
@@ -348,6 +378,7 @@ int limb_dispatch(int combo, int ar, const LimbJob &job, const ModInfo *mods, in
     case AR_SHOUP: return limb_dispatch_ar<LOGN, AR_SHOUP>(combo, j, mods, W, B, stream);
     case AR_FP: return limb_dispatch_ar<LOGN, AR_FP>(combo, j, mods, W, B, stream);
     case AR_FP_LAZY: return limb_dispatch_ar<LOGN, AR_FP_LAZY>(combo, j, mods, W, B, stream);
+    case AR_F64: return limb_dispatch_ar<LOGN, AR_F64>(combo, j, mods, W, B, stream);
     default: return (int)cudaErrorInvalidValue;
   }
 }

@@ -20,6 +20,9 @@ struct ModInfo {
   const ulonglong2 *twf, *itwf;
   u64 ninv_f, wl_ninv_f;     // bits of double(ninv/q), double(wl_ninv/q)
   u64 qinv_bits;             // bits of double(1/q)
+  // pure-FP64 class (q < 2^45): twiddles {bits of double(w), bits of double(w/q)}
+  const ulonglong2 *twd, *itwd;
+  u64 ninv_d, wl_ninv_d;     // bits of double(ninv), double(wl_ninv)
   int ar_class;              // AR_SHOUP / AR_FP / AR_FP_LAZY: the fastest class this modulus allows
 };
 

@@ -247,7 +247,7 @@ def run_ours(args):
         bf_peak = f.measure_butterfly_peak()
         imad, iadd = f.measure_int_peak()
         logn = N_POLY.bit_length() - 1
-        ntt_rows = {"ks_modup_ntt": k * L, "ks_intt_special": 2, "ks_intt_moddown": 2 * L, "behz_ntt_q": 4 * L,
+        ntt_rows = {"ks_modup_ntt": k * L, "ks_intt_special": 2, "ks_intt_moddown": 2 * L + (0 if any(r["kernel"] == "ks_intt_special" for r in prof) else 2), "behz_ntt_q": 4 * L,
                     "behz_ntt_bsk": 4 * nb, "behz_intt_q": 3 * L, "behz_intt_bsk": 3 * nb}
         ntt_ms = sum(r["ms"] for r in prof if r["kernel"] in ntt_rows)
         ntt_bf = sum(r["launches"] * ntt_rows[r["kernel"]] for r in prof if r["kernel"] in ntt_rows) * B * (N_POLY // 2) * logn

@@ -6,8 +6,8 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 40
 f = CudaCiphertextFactory(N, keygen=False)
 logn = N.bit_length() - 1
-peaks = [f.measure_butterfly_peak(a) for a in (0, 1, 2)]
-print('butterfly microbench peaks (Shoup, FP, FP-lazy): %s G/s' % ['%.0f' % (p / 1e9) for p in peaks])
+peaks = [f.measure_butterfly_peak(a) for a in (0, 1, 2, 3)]
+print('butterfly microbench peaks (Shoup, FP, FP-lazy, pure-FP64): %s G/s' % ['%.0f' % (p / 1e9) for p in peaks])
 peak = peaks[0]
 for name, mi in (("q0", 0), ("bsk0", f.k)):
     for inv in (False, True):
