@@ -35,6 +35,7 @@ struct abc_ctx {
   DevConst *dC = nullptr;
   ModInfo *d_mods = nullptr;
   std::vector<ModInfo> hmods;
+  int prefetch_ahead = 0;   // CTAs resident at once (2 per SM): a CTA L2-prefetches the row of the CTA that replaces it
   int ar_q = 0, ar_t = 0, force_ar = -1;  // NTT arithmetic class of the key-level primes / of t (ntt.cuh)
   int idx_t = 0;
   std::vector<void *> owned;  // device allocations freed at destroy
@@ -137,12 +138,14 @@ template <typename T> abc_status upload(abc_ctx *c, T **dst, const std::vector<T
 // ---- limb-pipeline launcher (kernels live in limb_12/13/14.cu)
 abc_status launch_limb(abc_ctx *c, int combo, int ar, const LimbJob &job, int W, int B, const char *name) {
   if (c->force_ar >= 0 && c->force_ar < ar) ar = c->force_ar;
+  LimbJob jj = job;
+  jj.prefetch_ahead = c->prefetch_ahead;
   Launch l(c, name);
   int e;
   switch (c->logN) {
-    case 12: e = limb_dispatch<12>(combo, ar, job, c->d_mods, W, B, c->stream); break;
-    case 13: e = limb_dispatch<13>(combo, ar, job, c->d_mods, W, B, c->stream); break;
-    case 14: e = limb_dispatch<14>(combo, ar, job, c->d_mods, W, B, c->stream); break;
+    case 12: e = limb_dispatch<12>(combo, ar, jj, c->d_mods, W, B, c->stream); break;
+    case 13: e = limb_dispatch<13>(combo, ar, jj, c->d_mods, W, B, c->stream); break;
+    case 14: e = limb_dispatch<14>(combo, ar, jj, c->d_mods, W, B, c->stream); break;
     case 15: case 16: e = limb_dispatch_big(c->logN - 13, combo, job, c->d_mods, W, B, c->stream); break;
     default: return fail(c, ABC_ERR_UNSUPPORTED, "poly_degree not supported (4096 .. 65536)");
   }
@@ -260,6 +263,12 @@ abc_status build_tables(abc_ctx *c) {
   for (int i = 0; i < k; ++i) c->ar_q = std::min(c->ar_q, mods[i].ar_class);
   c->ar_t = mods[c->idx_t].ar_class;
   if (const char *e = getenv("ABC_FORCE_AR")) c->force_ar = atoi(e);
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    c->prefetch_ahead = 2 * sms;
+    if (const char *e = getenv("ABC_PREFETCH_AHEAD")) c->prefetch_ahead = atoi(e);
+  }
 
   // ---- constants
   DevConst &C = c->hC;

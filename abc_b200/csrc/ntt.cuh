@@ -184,18 +184,25 @@ __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restric
                                             int tid) {
   typedef NttDims<LOGN> D;
   constexpr int LG = LOGN - S0 - R;
+  // AR_F64 is bound by FP64 latency, not issue: its IT groups of 8 are loaded together and their butterflies
+  // interleaved (2x the independent chains); the integer classes keep one group live (register pressure).
+  constexpr int G = (AR == AR_F64) ? D::IT : 1;
 #pragma unroll
-  for (int it = 0; it < D::IT; ++it) {
-    const int vt = tid + it * D::T;
-    const int off = vt & ((1 << LG) - 1), blk = vt >> LG;
-    const int base = (blk << (LG + 3)) | off;
-    const int pbase = swz(base);
-    u64 x[8];
+  for (int it0 = 0; it0 < D::IT; it0 += G) {
+    int blk[G], base[G], pbase[G];
+    u64 x[G][8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) x[r] = sm[LG >= 7 ? pbase + (r << LG) : swz(base + (r << LG))];
-    if (S0 == 0) {  // first pass: canonical residues -> the class's representation
+    for (int g = 0; g < G; ++g) {
+      const int vt = tid + (it0 + g) * D::T;
+      blk[g] = vt >> LG;
+      base[g] = (blk[g] << (LG + 3)) | (vt & ((1 << LG) - 1));
+      pbase[g] = swz(base[g]);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) x[r] = ar_from_canon<AR>(x[r]);
+      for (int r = 0; r < 8; ++r) x[g][r] = sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))];
+      if (S0 == 0) {  // first pass: canonical residues -> the class's representation
+#pragma unroll
+        for (int r = 0; r < 8; ++r) x[g][r] = ar_from_canon<AR>(x[g][r]);
+      }
     }
 #pragma unroll
     for (int b = R - 1; b >= 0; --b) {
@@ -203,12 +210,17 @@ __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restric
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         if (r & (1 << b)) continue;
-        const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)((blk << 3) + r) >> (b + 1))]);
-        bf_fwd<AR>(x[r], x[r | (1 << b)], w, q, aux);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)((blk[g] << 3) + r) >> (b + 1))]);
+          bf_fwd<AR>(x[g][r], x[g][r | (1 << b)], w, q, aux);
+        }
       }
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) sm[LG >= 7 ? pbase + (r << LG) : swz(base + (r << LG))] = x[r];
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))] = x[g][r];
   }
 }
 
@@ -217,21 +229,26 @@ template <int LOGN, int S0, int R, bool FOLD, bool REDUCE, int AR>
 __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 aux, int tid) {
   typedef NttDims<LOGN> D;
   constexpr int LG = LOGN - S0 - R;
+  constexpr int G = (AR == AR_F64) ? D::IT : 1;
   const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.itw : (AR == AR_F64 ? M.itwd : M.itwf);
 #pragma unroll
-  for (int it = 0; it < D::IT; ++it) {
-    const int vt = tid + it * D::T;
-    const int off = vt & ((1 << LG) - 1), blk = vt >> LG;
-    const int base = (blk << (LG + 3)) | off;
-    const int pbase = swz(base);
-    u64 x[8];
+  for (int it0 = 0; it0 < D::IT; it0 += G) {
+    int blk[G], base[G], pbase[G];
+    u64 x[G][8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) x[r] = sm[LG >= 7 ? pbase + (r << LG) : swz(base + (r << LG))];
-    if ((AR == AR_FP_LAZY || AR == AR_F64) && REDUCE) {
-      const double qinv = f64_of(M.qinv_bits);
+    for (int g = 0; g < G; ++g) {
+      const int vt = tid + (it0 + g) * D::T;
+      blk[g] = vt >> LG;
+      base[g] = (blk[g] << (LG + 3)) | (vt & ((1 << LG) - 1));
+      pbase[g] = swz(base[g]);
 #pragma unroll
-      for (int r = 0; r < 8; ++r)
-        x[r] = AR == AR_F64 ? bits_of(reduce_f64(f64_of(x[r]), qinv, f64_of(aux))) : reduce_fp<true>(x[r], qinv, q, aux);
+      for (int r = 0; r < 8; ++r) x[g][r] = sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))];
+      if ((AR == AR_FP_LAZY || AR == AR_F64) && REDUCE) {
+        const double qinv = f64_of(M.qinv_bits);
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          x[g][r] = AR == AR_F64 ? bits_of(reduce_f64(f64_of(x[g][r]), qinv, f64_of(aux))) : reduce_fp<true>(x[g][r], qinv, q, aux);
+      }
     }
 #pragma unroll
     for (int b = 0; b < R; ++b) {
@@ -239,20 +256,25 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         if (r & (1 << b)) continue;
-        if (FOLD && s == 0) {
-          // last stage of the whole transform: fold N^-1 into both outputs
-          const u64 u = x[r], v = x[r | (1 << b)];
-          const u64 d = (AR == AR_FP_LAZY || AR == AR_F64) ? ar_sub<AR>(u, v) : u + aux - v;
-          x[r] = mul_tw<AR>(ar_add<AR>(u, v), AR == AR_F64 ? M.ninv_d : M.ninv, (AR == AR_SHOUP) ? M.ninv_s : M.ninv_f, q, aux);
-          x[r | (1 << b)] = mul_tw<AR>(d, AR == AR_F64 ? M.wl_ninv_d : M.wl_ninv, (AR == AR_SHOUP) ? M.wl_ninv_s : M.wl_ninv_f, q, aux);
-        } else {
-          const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)((blk << 3) + r) >> (b + 1))]);
-          bf_inv<AR>(x[r], x[r | (1 << b)], w, q, aux);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (FOLD && s == 0) {
+            // last stage of the whole transform: fold N^-1 into both outputs
+            const u64 u = x[g][r], v = x[g][r | (1 << b)];
+            const u64 d = (AR == AR_FP_LAZY || AR == AR_F64) ? ar_sub<AR>(u, v) : u + aux - v;
+            x[g][r] = mul_tw<AR>(ar_add<AR>(u, v), AR == AR_F64 ? M.ninv_d : M.ninv, (AR == AR_SHOUP) ? M.ninv_s : M.ninv_f, q, aux);
+            x[g][r | (1 << b)] = mul_tw<AR>(d, AR == AR_F64 ? M.wl_ninv_d : M.wl_ninv, (AR == AR_SHOUP) ? M.wl_ninv_s : M.wl_ninv_f, q, aux);
+          } else {
+            const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)((blk[g] << 3) + r) >> (b + 1))]);
+            bf_inv<AR>(x[g][r], x[g][r | (1 << b)], w, q, aux);
+          }
         }
       }
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) sm[LG >= 7 ? pbase + (r << LG) : swz(base + (r << LG))] = x[r];
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))] = x[g][r];
   }
 }
 
