@@ -37,6 +37,7 @@ struct abc_ctx {
   std::vector<ModInfo> hmods;
   int prefetch_ahead = 0;   // CTAs resident at once (2 per SM): a CTA L2-prefetches the row of the CTA that replaces it
   int ar_q = 0, ar_t = 0, force_ar = -1;  // NTT arithmetic class of the key-level primes / of t (ntt.cuh)
+  bool ks_unmerged = false, ks_unfused = false;  // ABC_KS_UNMERGED / ABC_KS_UNFUSED: A/B switches for the key-switch tail
   int idx_t = 0;
   std::vector<void *> owned;  // device allocations freed at destroy
   u32 *d_index_map = nullptr;
@@ -263,6 +264,8 @@ abc_status build_tables(abc_ctx *c) {
   for (int i = 0; i < k; ++i) c->ar_q = std::min(c->ar_q, mods[i].ar_class);
   c->ar_t = mods[c->idx_t].ar_class;
   if (const char *e = getenv("ABC_FORCE_AR")) c->force_ar = atoi(e);
+  c->ks_unmerged = getenv("ABC_KS_UNMERGED") != nullptr;
+  c->ks_unfused = getenv("ABC_KS_UNFUSED") != nullptr;
   {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -491,12 +494,14 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   j.dst = T; j.dst_is = (long long)k * L * N; j.src = target; j.src_is = target_is;
   j.rowmod = c->rm_modup_s; j.rowdst = c->rd_modup_s; j.rowsrc = c->rs_modup_s; j.galois_einv = einv;
   TRY(launch_limb(c, einv ? LIMB_GALOIS_REDUCE_FWD : LIMB_REDUCE_FWD, c->ar_q, j, c->ks_nI * L, B, "ks_modup_ntt"));
-  {
+  const bool merged = c->logN <= 14 && (c->own_hi - c->own_lo) > 0 && !c->ks_unmerged;
+  // exact-double class: the inner product runs in the load of the INTT + ModDown launch (no accumulator round trip)
+  const bool fused = merged && abc_ntt_arith_class(c) == AR_F64 && !c->ks_unfused;
+  if (!fused) {
     Launch l(c, "ks_inner");
     DISPATCH_L(c, (k_ks_inner<LL><<<dim3(N / 512, c->ks_nI, B), 256, 0, c->stream>>>(T, key, acc, c->d_mods, N, k, c->L, c->ks_I)));
     CK(cudaGetLastError());
   }
-  const bool merged = c->logN <= 14 && (c->own_hi - c->own_lo) > 0 && !getenv("ABC_KS_UNMERGED");
   if (!merged) {
     j = blank_job();
     j.dst = acc; j.src = acc; j.dst_is = j.src_is = (long long)2 * k * N;
@@ -512,7 +517,12 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   if (merged) {  // one launch: the two special-prime rows INTT and publish, the data rows INTT, wait, ModDown
     j.rowsrc = c->rs_mdm; j.rowdst = c->rd_mdm; j.rowmod = c->rm_mdm;
     j.flags = c->ks_flags; j.flag_serial = ++c->ks_serial;
-    TRY(launch_limb(c, LIMB_INV_MODDOWN, c->ar_q, j, 2 + 2 * nown, B, "ks_intt_moddown"));
+    if (fused) {
+      j.src = T; j.src_is = (long long)k * L * N; j.mul = key;
+      TRY(launch_limb(c, LIMB_KSINNER_INV_MODDOWN, c->ar_q, j, 2 + 2 * nown, B, "ks_inner_intt_moddown"));
+    } else {
+      TRY(launch_limb(c, LIMB_INV_MODDOWN, c->ar_q, j, 2 + 2 * nown, B, "ks_intt_moddown"));
+    }
   } else if (nown > 0) {
     TRY(launch_limb(c, LIMB_INV_MODDOWN, c->ar_q, j, 2 * nown, B, "ks_intt_moddown"));
   }

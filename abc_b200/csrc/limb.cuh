@@ -13,7 +13,8 @@
 #include "devconst.cuh"
 #include "ntt.cuh"
 
-enum { PRE_LOAD = 0, PRE_REDUCE = 1, PRE_PLAIN_LIFT = 2, PRE_TERNARY = 3, PRE_CBD = 4, PRE_ENCODE = 5, PRE_GALOIS_REDUCE = 6 };
+enum { PRE_LOAD = 0, PRE_REDUCE = 1, PRE_PLAIN_LIFT = 2, PRE_TERNARY = 3, PRE_CBD = 4, PRE_ENCODE = 5, PRE_GALOIS_REDUCE = 6,
+       PRE_KS_INNER = 7 };
 enum { POST_STORE = 0, POST_ADD = 1, POST_DECODE = 2, POST_MODDOWN = 3 };
 
 struct LimbJob {
@@ -58,7 +59,8 @@ enum {
   LIMB_MUL_INV = 10,       // * row, INTT                     (encrypt: pk * u)
   LIMB_GALOIS_REDUCE_FWD = 11,  // Galois gather + reduce mod q, NTT  (rotate: sigma(c1) ModUp)
   LIMB_INV_MODDOWN = 12,   // INTT, ModDown with rounding, + base (key-switch tail)
-  LIMB_NCOMBOS = 13
+  LIMB_KSINNER_INV_MODDOWN = 13,  // key-switch inner product over J in the load, INTT, ModDown (AR_F64 only)
+  LIMB_NCOMBOS = 14
 };
 
 __device__ __forceinline__ u64 small_to_mod(int v, u64 q) { return v < 0 ? q - (u64)(-v) : (u64)v; }
@@ -148,6 +150,55 @@ __device__ __forceinline__ void limb_store_pair(const LimbJob &job, const ModInf
   reinterpret_cast<ulonglong2 *>(job.dst + (size_t)inst * job.dst_is + (size_t)drow * n)[e2] = v;
 }
 
+// ---- bulk asynchronous copy of one row into shared memory (cp.async.bulk, completion on an mbarrier): one thread
+// issues it, no registers are staged, and the whole row is in flight from the first cycle of the CTA
+__device__ __forceinline__ void bulk_row_to_smem(u64 *sm, const u64 *src, u32 bytes, u64 *mbar, int tid) {
+  const u32 mb = (u32)__cvta_generic_to_shared(mbar), dst = (u32)__cvta_generic_to_shared(sm);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mb) : "memory");
+  }
+  __syncthreads();  // the barrier object is initialised before anyone polls it
+  u32 ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(mb) : "memory");
+  } while (!ok);
+}
+
+// ---- key-switch inner product in the load of the inverse transform (AR_F64: every prime < 2^45):
+// coefficients (2*e2, 2*e2+1) of  sum_J T[inst][I][J] * key[J][comp][I]  mod q_I, as centred doubles.
+// The low 64 bits of the sum come from the integer pipe (3 IMAD per term, no carries), the quotient from the FP64
+// pipe: Q = rint(fl(sum t*k) / q) is within 1 of the true quotient, so r = lo64(S) - lo64(Q*q) is S - Q*q exactly.
+__device__ __forceinline__ double ks_dot_f64(u64 lo, double s, double qinv, u64 q, double qd) {
+  const double t = fma(s, qinv, 4503599627370496.0);                       // 2^52 + rint(s/q), s >= 0
+  const u64 Q = bits_of(t) & 0x000FFFFFFFFFFFFFULL;
+  const u64 r = mad_lo64(Q, 0 - q, lo);                                    // signed, |r| < 2q
+  const double rd = __hiloint2double((int)((u32)(r >> 32) + 0x43380000u), (int)(u32)r) - 6755399441055744.0;
+  return reduce_f64(rd, qinv, qd);                                         // |.| <= 0.51q
+}
+__device__ __forceinline__ ulonglong2 ks_inner_pair(const ulonglong2 *__restrict__ t, const ulonglong2 *__restrict__ kp,
+                                                    int L, int rowv, int keyv2, const ModInfo &M) {
+  u64 lo0 = 0, lo1 = 0;
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+  for (int J = 0; J < L; ++J) {
+    const ulonglong2 tv = t[(size_t)J * rowv];
+    const ulonglong2 kv = __ldg(kp + (size_t)J * keyv2);
+    lo0 = mad_lo64(tv.x, kv.x, lo0); lo1 = mad_lo64(tv.y, kv.y, lo1);
+    s0 = fma(f64_of(ar_from_canon<AR_F64>(tv.x)), f64_of(ar_from_canon<AR_F64>(kv.x)), s0);
+    s1 = fma(f64_of(ar_from_canon<AR_F64>(tv.y)), f64_of(ar_from_canon<AR_F64>(kv.y)), s1);
+  }
+  const double qinv = f64_of(M.qinv_bits), qd = (double)M.q;
+  ulonglong2 v;
+  v.x = bits_of(ks_dot_f64(lo0, s0, qinv, M.q, qd));
+  v.y = bits_of(ks_dot_f64(lo1, s1, qinv, M.q, qd));
+  return v;
+}
+
 // ---- one limb (or, TAIL, one 2^LOGN-coefficient block of a larger limb) in shared memory
 template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST, int AR, bool TAIL>
 __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(LimbJob job,
@@ -179,8 +230,21 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
     }
   }
 
+  // AR_F64 ModUp: bulk-copy the source row as it lies, gather / negate / convert in the first pass, no Barrett
+  constexpr bool LINSRC = AR == AR_F64 && FWD && !TAIL && (PRE == PRE_REDUCE || PRE == PRE_GALOIS_REDUCE);
+
   // ---- load
-  if (PRE == PRE_ENCODE) {
+  if constexpr (LINSRC) {
+    __shared__ __align__(8) u64 mbar;
+    bulk_row_to_smem(sm, job.src + (size_t)inst * job.src_is + (size_t)srow * D::N, (u32)D::SMEM, &mbar, tid);
+  } else if (PRE == PRE_KS_INNER) {
+    // srow = comp * k + I: row of the accumulator block this CTA produces
+    const int comp = srow / job.k, I = srow - comp * job.k;
+    const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(job.src + (size_t)inst * job.src_is + (size_t)I * job.L * D::N);
+    const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(job.mul + (size_t)(comp * job.k + I) * D::N);
+    for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
+      *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = ks_inner_pair(t + e2, kp + e2, job.L, D::N / 2, job.k * D::N, M);
+  } else if (PRE == PRE_ENCODE) {
     // BatchEncoder::encode (SealCiphertextFactory.cpp:102-132): pad with the last value, scatter by the index map
     const long long *sl = job.slots_in + (size_t)inst * job.slots_is;
     for (int e = tid; e < D::N; e += D::T) {
@@ -192,9 +256,12 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
     for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
       *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = limb_load_pair<PRE>(job, M, mods, n, inst, srow, eoff + e2, h);
   }
-  __syncthreads();
+  if (!LINSRC) __syncthreads();
 
-  if (FWD) ntt_fwd_smem<LOGN, AR>(sm, M, twbase, tid);
+  if (FWD) {
+    if constexpr (LINSRC) ntt_fwd_smem<LOGN, AR, true>(sm, M, twbase, tid, mods[srow].q, PRE == PRE_GALOIS_REDUCE ? job.galois_einv : 0u);
+    else ntt_fwd_smem<LOGN, AR>(sm, M, twbase, tid);
+  }
 
   if (MUL) {
     const ulonglong2 *mp = reinterpret_cast<const ulonglong2 *>(job.mul + (size_t)inst * job.mul_is + (size_t)mrow * n) + eoff;
@@ -209,7 +276,7 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
     __syncthreads();
   }
 
-  if (INV) ntt_inv_smem<LOGN, !TAIL, AR>(sm, M, twbase, tid);
+  if (INV) ntt_inv_smem<LOGN, !TAIL, AR, PRE == PRE_KS_INNER>(sm, M, twbase, tid);
 
   // ---- store
   if (POST == POST_DECODE) {
@@ -381,6 +448,9 @@ static int limb_dispatch_ar(int combo, const LimbJob &j, const ModInfo *m, int W
     case LIMB_MUL_INV: return limb_launch<LOGN, PRE_LOAD, false, true, true, POST_STORE, AR, false>(j, m, W, B, s);
     case LIMB_GALOIS_REDUCE_FWD: return limb_launch<LOGN, PRE_GALOIS_REDUCE, true, false, false, POST_STORE, AR, false>(j, m, W, B, s);
     case LIMB_INV_MODDOWN: return limb_launch<LOGN, PRE_LOAD, false, false, true, POST_MODDOWN, AR, false>(j, m, W, B, s);
+    case LIMB_KSINNER_INV_MODDOWN:
+      if constexpr (AR == AR_F64) return limb_launch<LOGN, PRE_KS_INNER, false, false, true, POST_MODDOWN, AR, false>(j, m, W, B, s);
+      return (int)cudaErrorInvalidValue;
     default: return (int)cudaErrorInvalidValue;
   }
 }

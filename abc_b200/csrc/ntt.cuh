@@ -179,11 +179,17 @@ template <int AR> __device__ __forceinline__ void bf_inv(u64 &x, u64 &y, ulonglo
 
 // ---- strided pass: stages S0 .. S0+R-1 (stage s has 2^s groups, gap N >> (s+1)); twbase = 1 for a whole
 // transform, (2^a + block) when this limb is block `block` of the tail of a larger 2^(a+LOGN) transform.
-template <int LOGN, int S0, int R, int AR>
+// LINSRC (first pass of AR_F64 only): the limb sits in shared memory exactly as it lies in global memory (a bulk
+// copy, no swizzle) holding residues of the SOURCE prime qs; the pass reads coefficient e from
+// +-sm[e * einv mod 2N] (GaloisTool::apply_galois as a gather, einv = 0: identity), takes NO reduction modulo the
+// target prime (an exact-double transform accepts any |x| < 2^45 and canon_fwd reduces at the end), and, because
+// it is no longer in place, separates its loads from its stores with a barrier.
+template <int LOGN, int S0, int R, int AR, bool LINSRC = false>
 __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 aux,
-                                            int tid) {
+                                            int tid, u64 qs = 0, u32 einv = 0) {
   typedef NttDims<LOGN> D;
   constexpr int LG = LOGN - S0 - R;
+  static_assert(!LINSRC || (AR == AR_F64 && S0 == 0), "linear-source gather is the first pass of the exact-double class");
   // AR_F64 is bound by FP64 latency, not issue: its IT groups of 8 are loaded together and their butterflies
   // interleaved (2x the independent chains); the integer classes keep one group live (register pressure).
   constexpr int G = (AR == AR_F64) ? D::IT : 1;
@@ -197,12 +203,28 @@ __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restric
       blk[g] = vt >> LG;
       base[g] = (blk[g] << (LG + 3)) | (vt & ((1 << LG) - 1));
       pbase[g] = swz(base[g]);
+      if (LINSRC) {
+        constexpr u32 m2 = 2u * D::N - 1;
+        const u32 step = (einv << LG) & m2;
+        u32 r0 = einv ? ((u32)base[g] * einv) & m2 : (u32)base[g];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) x[g][r] = sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))];
-      if (S0 == 0) {  // first pass: canonical residues -> the class's representation
+        for (int r = 0; r < 8; ++r) {
+          const u64 v = sm[r0 & (D::N - 1)];
+          x[g][r] = ar_from_canon<AR>((r0 >= (u32)D::N && v) ? qs - v : v);
+          r0 = einv ? (r0 + step) & m2 : r0 + (1u << LG);
+        }
+      } else {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) x[g][r] = ar_from_canon<AR>(x[g][r]);
+        for (int r = 0; r < 8; ++r) x[g][r] = sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))];
+        if (S0 == 0) {  // first pass: canonical residues -> the class's representation
+#pragma unroll
+          for (int r = 0; r < 8; ++r) x[g][r] = ar_from_canon<AR>(x[g][r]);
+        }
       }
+    }
+    if (LINSRC) {
+      static_assert(!LINSRC || G == D::IT, "every group is in registers before the first store");
+      __syncthreads();
     }
 #pragma unroll
     for (int b = R - 1; b >= 0; --b) {
@@ -341,7 +363,8 @@ __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twba
   }
 }
 
-template <int LOGN, int AR>
+// REPIN: shared memory already holds the class's representation (the fused key-switch inner product stores doubles)
+template <int LOGN, int AR, bool REPIN = false>
 __device__ __forceinline__ void ntt_inv_first(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 aux, int tid) {
   typedef NttLast<LOGN> P;
   constexpr int E = P::E, H = E / 2;
@@ -353,7 +376,7 @@ __device__ __forceinline__ void ntt_inv_first(u64 *sm, const ModInfo &M, u32 twb
 #pragma unroll
     for (int i = 0; i < H; ++i) {
       ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(E * vt + 2 * i)]);
-      x[2 * i] = ar_from_canon<AR>(v.x); x[2 * i + 1] = ar_from_canon<AR>(v.y);
+      x[2 * i] = REPIN ? v.x : ar_from_canon<AR>(v.x); x[2 * i + 1] = REPIN ? v.y : ar_from_canon<AR>(v.y);
     }
 #pragma unroll
     for (int b = 0; b < P::LOGE; ++b) {
@@ -391,12 +414,12 @@ __device__ __forceinline__ void ntt_inv_first(u64 *sm, const ModInfo &M, u32 twb
 
 // ---- whole-limb transforms on a swizzled shared-memory limb.  Caller has filled sm[swz(e)] and synced.
 // Forward: input canonical (guarded classes accept < 4q), output canonical.  Returns after a barrier.
-template <int LOGN, int AR>
-__device__ __forceinline__ void ntt_fwd_smem(u64 *sm, const ModInfo &M, u32 twbase, int tid) {
+template <int LOGN, int AR, bool LINSRC = false>
+__device__ __forceinline__ void ntt_fwd_smem(u64 *sm, const ModInfo &M, u32 twbase, int tid, u64 qs = 0, u32 einv = 0) {
   typedef NttPlan<LOGN> P;
   const u64 q = M.q, aux = ar_aux<AR>(q);
   const ulonglong2 *tw = (AR == AR_SHOUP) ? M.tw : (AR == AR_F64 ? M.twd : M.twf);
-  ntt_fwd_mid<LOGN, 0, P::R0, AR>(sm, tw, twbase, q, aux, tid);
+  ntt_fwd_mid<LOGN, 0, P::R0, AR, LINSRC>(sm, tw, twbase, q, aux, tid, qs, einv);
   __syncthreads();
   ntt_fwd_mid<LOGN, P::R0, P::R1, AR>(sm, tw, twbase, q, aux, tid);
   __syncthreads();
@@ -413,12 +436,12 @@ __device__ __forceinline__ void ntt_fwd_smem(u64 *sm, const ModInfo &M, u32 twba
 // AR_FP_LAZY range plan (q*(log2(N)+2) < 2^51, q < 2^45): the sum chain doubles per stage, so it is reduced to
 // |x| <= 0.75q after the contiguous pass (4-5 stages) and again before the last strided pass (3 stages left):
 // no product ever sees an operand above 2^6 * 2 * 0.75q < 2^51.
-template <int LOGN, bool WHOLE, int AR>
+template <int LOGN, bool WHOLE, int AR, bool REPIN = false>
 __device__ __forceinline__ void ntt_inv_smem(u64 *sm, const ModInfo &M, u32 twbase, int tid) {
   typedef NttPlan<LOGN> P;
   static_assert(WHOLE || (AR != AR_FP_LAZY && AR != AR_F64), "tail blocks use a guarded class");
   const u64 q = M.q, aux = ar_aux<AR>(q);
-  ntt_inv_first<LOGN, AR>(sm, M, twbase, q, aux, tid);
+  ntt_inv_first<LOGN, AR, REPIN>(sm, M, twbase, q, aux, tid);
   __syncthreads();
   if constexpr (P::R2 > 0) {
     ntt_inv_mid<LOGN, P::R0 + P::R1, P::R2, false, true, AR>(sm, M, twbase, q, aux, tid);
