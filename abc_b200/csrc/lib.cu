@@ -37,6 +37,7 @@ struct abc_ctx {
   std::vector<ModInfo> hmods;
   int prefetch_ahead = 0;   // CTAs resident at once (2 per SM): a CTA L2-prefetches the row of the CTA that replaces it
   int ar_q = 0, ar_t = 0, force_ar = -1;  // NTT arithmetic class of the key-level primes / of t (ntt.cuh)
+  int ks_skew = 8;                               // ABC_KS_SKEW: special-prime rows run this many instances ahead
   bool ks_unmerged = false, ks_unfused = false;  // ABC_KS_UNMERGED / ABC_KS_UNFUSED: A/B switches for the key-switch tail
   int idx_t = 0;
   std::vector<void *> owned;  // device allocations freed at destroy
@@ -216,10 +217,18 @@ void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, s
   m.ninv_d = m.wl_ninv_d = 0;
   if (m.ar_class == AR_F64) {
     auto ibits = [](u64 w) { double d = (double)w; u64 b; memcpy(&b, &d, 8); return b; };  // exact: w < 2^45
-    twd.resize(N); itwd.resize(N);
-    for (int j = 0; j < N; ++j) {
-      twd[j] = make_ulonglong2(ibits(tw[j].x), dbits(tw[j].x));
-      itwd[j] = make_ulonglong2(ibits(itw[j].x), dbits(itw[j].x));
+    // 8-byte entries (two per ulonglong2 slot), the last two stages lane-contiguous for the contiguous pass (ntt.cuh tw_get)
+    twd.assign(N / 2, make_ulonglong2(0, 0)); itwd.assign(N / 2, make_ulonglong2(0, 0));
+    u64 *fw = reinterpret_cast<u64 *>(twd.data()), *iw = reinterpret_cast<u64 *>(itwd.data());
+    for (int j = 1; j < N; ++j) {
+      int s = 0;
+      while ((2 << s) <= j) ++s;                      // stage of index j: 2^s <= j < 2^(s+1)
+      int dst = j;
+      if (s >= logN - 2) {
+        const int per = 1 << (s - (logN - 3)), i = j - (1 << s);   // 2 or 4 twiddles per thread of the contiguous pass
+        dst = (1 << s) + (i % per) * (N / 8) + i / per;
+      }
+      fw[dst] = ibits(tw[j].x); iw[dst] = ibits(itw[j].x);
     }
     m.ninv_d = ibits(m.ninv); m.wl_ninv_d = ibits(m.wl_ninv);
   }
@@ -266,6 +275,7 @@ abc_status build_tables(abc_ctx *c) {
   if (const char *e = getenv("ABC_FORCE_AR")) c->force_ar = atoi(e);
   c->ks_unmerged = getenv("ABC_KS_UNMERGED") != nullptr;
   c->ks_unfused = getenv("ABC_KS_UNFUSED") != nullptr;
+  if (const char *e = getenv("ABC_KS_SKEW")) c->ks_skew = atoi(e) < 0 ? 0 : atoi(e);
   {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -516,7 +526,7 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   j.base0 = base0; j.base0_is = base0_is; j.base1 = base1; j.base1_is = base1_is; j.base_einv = einv;
   if (merged) {  // one launch: the two special-prime rows INTT and publish, the data rows INTT, wait, ModDown
     j.rowsrc = c->rs_mdm; j.rowdst = c->rd_mdm; j.rowmod = c->rm_mdm;
-    j.flags = c->ks_flags; j.flag_serial = ++c->ks_serial;
+    j.flags = c->ks_flags; j.flag_serial = ++c->ks_serial; j.skew = c->ks_skew;
     if (fused) {
       j.src = T; j.src_is = (long long)k * L * N; j.mul = key;
       TRY(launch_limb(c, LIMB_KSINNER_INV_MODDOWN, c->ar_q, j, 2 + 2 * nown, B, "ks_inner_intt_moddown"));

@@ -42,6 +42,7 @@ struct LimbJob {
   int L, k;                                     // data limbs / key-level primes of the context
   int i0, nrows;                                // POST_MODDOWN rows: w = comp * nrows + (i - i0), limbs i0 .. i0+nrows-1
   u32 *flags; u32 flag_serial;                  // merged special-row INTT + ModDown launch: flags[inst][comp] == serial when ready
+  int skew;                                     // ... special rows run this many instances ahead of their data rows
 };
 
 // combos of (PRE, FWD, MUL, INV, POST) the library uses
@@ -120,6 +121,28 @@ __device__ __forceinline__ ModDownRow moddown_row(const LimbJob &job, int n, int
   if (r.base) r.base += (size_t)inst * (comp == 0 ? job.base0_is : job.base1_is) + (size_t)i * n;
   return r;
 }
+// ModDown on the exact-double class: vd = INTT output as a centred double (|vd| < q), result canonical.
+// Same value as the integer formulation below: base + p^-1 * (v - ([t + p/2]_p mod q) + [p/2]_q) mod q.
+struct ModDownF64 { double pd, p_half, phm, ipd, ipc, qd, qinv; };
+__device__ __forceinline__ ModDownF64 moddown_f64(const ModDownRow &md, const ModInfo &M) {
+  ModDownF64 f;
+  f.pd = (double)md.p; f.p_half = (double)md.p_half; f.phm = (double)md.phm; f.ipd = (double)md.ip;
+  f.qd = (double)M.q; f.qinv = f64_of(M.qinv_bits); f.ipc = f.ipd * f.qinv;
+  return f;
+}
+__device__ __forceinline__ u64 moddown_one_f64(double vd, u64 t, bool has_base, u64 b, const ModDownF64 &f) {
+  double a = f64_of(ar_from_canon<AR_F64>(t)) + f.p_half;
+  a = a >= f.pd ? a - f.pd : a;                                   // [t + p/2]_p, exact
+  const double d = (vd - reduce_f64(a, f.qinv, f.qd)) + f.phm;    // |d| < 2.6q, exact integer
+  const double Q = fma(d, f.ipc, ABC_RINT_MAGIC) - ABC_RINT_MAGIC;
+  const double ph = d * f.ipd, pl = fma(d, f.ipd, -ph);
+  double r = fma(-Q, f.qd, ph) + pl;                              // d * p^-1 mod q, |r| <= 0.6q
+  if (has_base) r += f64_of(ar_from_canon<AR_F64>(b));
+  r = r < 0.0 ? r + f.qd : r;
+  r = r >= f.qd ? r - f.qd : r;
+  return bits_of(r + 4503599627370496.0) & 0x000FFFFFFFFFFFFFULL;
+}
+
 template <int POST>
 __device__ __forceinline__ void limb_store_pair(const LimbJob &job, const ModInfo &M, const ModDownRow &md, int n, int inst,
                                                 int drow, int arow, int e2, ulonglong2 v) {
@@ -205,8 +228,21 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
                                                                                const ModInfo *__restrict__ mods) {
   typedef NttDims<LOGN> D;
   extern __shared__ __align__(16) u64 sm[];
-  const int tid = threadIdx.x, inst = blockIdx.y;
-  const int w = TAIL ? (int)(blockIdx.x >> job.sub) : (int)blockIdx.x;
+  const int tid = threadIdx.x;
+  int inst = blockIdx.y, w = TAIL ? (int)(blockIdx.x >> job.sub) : (int)blockIdx.x;
+  if (POST == POST_MODDOWN && !TAIL && job.flags) {
+    // merged special-row + ModDown launch: CTAs are dispatched in linear block order, and the two special-prime rows
+    // of instance g + S are issued with the data rows of instance g, so they have published INTT_p(acc_L) long before
+    // their own data rows ask for it (a data row only ever waits for blocks with a smaller linear index: no deadlock)
+    const int W = gridDim.x, Bn = gridDim.y, nd = W - 2, S = job.skew < Bn ? job.skew : Bn;
+    const int b = blockIdx.y * W + blockIdx.x;
+    if (b < 2 * S) { inst = b >> 1; w = b & 1; }
+    else {
+      const int b1 = b - 2 * S, full = (Bn - S) * W;
+      if (b1 < full) { const int g = b1 / W, r = b1 - g * W; inst = r < 2 ? g + S : g; w = r; }
+      else { const int b2 = b1 - full, g = b2 / nd; inst = Bn - S + g; w = 2 + (b2 - g * nd); }
+    }
+  }
   const int blk = TAIL ? (int)(blockIdx.x & ((1u << job.sub) - 1)) : 0;
   const u32 twbase = TAIL ? ((1u << job.sub) + (u32)blk) : 1u;
   const int n = TAIL ? job.n : D::N;           // coefficients per limb
@@ -319,10 +355,33 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
       __syncthreads();
     }
     if (POST == POST_MODDOWN) md = moddown_row(job, n, inst, wq);
-    for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
-      ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
-      if (INV && !TAIL) { v.x = canon_inv<AR>(v.x, q, ar_aux<AR>(q)); v.y = canon_inv<AR>(v.y, q, ar_aux<AR>(q)); }  // a tail block stays in [0,2q) for the head pass
-      limb_store_pair<POST>(job, M, md, n, inst, drow, mrow, eoff + e2, v);
+    if constexpr (POST == POST_MODDOWN && AR == AR_F64 && !TAIL) {
+      const ModDownF64 f = moddown_f64(md, M);
+      const u32 einv = job.base_einv, m2 = 2u * D::N - 1;
+      ulonglong2 *out = reinterpret_cast<ulonglong2 *>(job.dst + (size_t)inst * job.dst_is + (size_t)drow * D::N);
+      for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
+        const ulonglong2 t = __ldcg(md.tl + e2);
+        ulonglong2 b = make_ulonglong2(0, 0);
+        if (md.base) {
+          if (einv) {
+            const u32 r0 = ((u32)(2 * e2) * einv) & m2, r1 = (r0 + einv) & m2;
+            b.x = md.base[r0 & (D::N - 1)]; b.y = md.base[r1 & (D::N - 1)];
+            if (r0 >= (u32)D::N) b.x = neg_mod(b.x, q);
+            if (r1 >= (u32)D::N) b.y = neg_mod(b.y, q);
+          } else {
+            b = reinterpret_cast<const ulonglong2 *>(md.base)[e2];
+          }
+        }
+        out[e2] = make_ulonglong2(moddown_one_f64(f64_of(v.x), t.x, md.base != nullptr, b.x, f),
+                                  moddown_one_f64(f64_of(v.y), t.y, md.base != nullptr, b.y, f));
+      }
+    } else {
+      for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
+        ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
+        if (INV && !TAIL) { v.x = canon_inv<AR>(v.x, q, ar_aux<AR>(q)); v.y = canon_inv<AR>(v.y, q, ar_aux<AR>(q)); }  // a tail block stays in [0,2q) for the head pass
+        limb_store_pair<POST>(job, M, md, n, inst, drow, mrow, eoff + e2, v);
+      }
     }
   }
 }

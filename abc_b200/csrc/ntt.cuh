@@ -28,7 +28,7 @@
 //   AR_F64     q < 2^45: the whole transform runs on the FP64 pipe, on exact integer-valued doubles.  A modular product
 //              is 6 FP64 instructions: Q = rint(y*(w/q)) (DFMA + DADD with the 1.5*2^52 magic), the error-free product
 //              y*w = ph + pl (DMUL + DFMA), v = (ph - Q*q) + pl (DFMA, exact because the result is an integer below
-//              2^53, + DADD); |v| <= 0.53q.  A butterfly is 8 FP64 instructions and no integer instruction, so the
+//              2^53, + DADD); |v| <= 0.53q with a correctly rounded w/q (0.9q at worst with the DMUL companion of tw_get: exactness never depends on it, only the range plan).  A butterfly is 8 FP64 instructions and no integer instruction, so the
 //              FP64 pipe (64 lanes/clk/SM on B200, otherwise idle) does the arithmetic while the integer pipes do
 //              the addressing: 2156 G butterflies/s register-resident vs 863 G (Shoup) and 1544 G (signed-lazy IMAD).
 #pragma once
@@ -86,6 +86,19 @@ template <int AR> __device__ __forceinline__ u64 ar_from_canon(u64 x) {
 }
 template <int AR> __device__ __forceinline__ u64 ar_add(u64 a, u64 b) { return AR == AR_F64 ? bits_of(f64_of(a) + f64_of(b)) : a + b; }
 template <int AR> __device__ __forceinline__ u64 ar_sub(u64 a, u64 b) { return AR == AR_F64 ? bits_of(f64_of(a) - f64_of(b)) : a - b; }
+
+// ---- twiddle fetch.  Integer classes: {w, companion} pairs, 16 bytes.  AR_F64: the table holds double(w) only
+// (8 bytes, half the L1 data-pipe wavefronts; ncu showed that pipe at 81 % with 16-byte twiddles) and the companion
+// w/q is one DMUL, w * (1/q): two roundings instead of one, so |product| <= 0.6q instead of 0.53q (range plan below).
+// In the AR_F64 table the last two stages are stored lane-contiguously for the contiguous pass: the twiddle thread vt
+// needs for its c-th butterfly group of stage s lives at 2^s + c * (N/8) + vt, so a warp's load is one 256-byte run.
+template <int AR> __device__ __forceinline__ ulonglong2 tw_get(const ulonglong2 *__restrict__ tw, u32 idx, double qinv) {
+  if (AR == AR_F64) {
+    const u64 w = __ldg(reinterpret_cast<const u64 *>(tw) + idx);
+    return make_ulonglong2(w, bits_of(f64_of(w) * qinv));
+  }
+  return __ldg(tw + idx);
+}
 
 // ---- modular product y*w with a precomputed companion c
 // AR_SHOUP   c = floor(w*2^64/q), any 64-bit y, result in [0,2q).
@@ -186,7 +199,7 @@ template <int AR> __device__ __forceinline__ void bf_inv(u64 &x, u64 &y, ulonglo
 // it is no longer in place, separates its loads from its stores with a barrier.
 template <int LOGN, int S0, int R, int AR, bool LINSRC = false>
 __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 aux,
-                                            int tid, u64 qs = 0, u32 einv = 0) {
+                                            int tid, double qinv, u64 qs = 0, u32 einv = 0) {
   typedef NttDims<LOGN> D;
   constexpr int LG = LOGN - S0 - R;
   static_assert(!LINSRC || (AR == AR_F64 && S0 == 0), "linear-source gather is the first pass of the exact-double class");
@@ -234,7 +247,7 @@ __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restric
         if (r & (1 << b)) continue;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)((blk[g] << 3) + r) >> (b + 1))]);
+          const ulonglong2 w = tw_get<AR>(tw, (twbase << s) + ((u32)((blk[g] << 3) + r) >> (b + 1)), qinv);
           bf_fwd<AR>(x[g][r], x[g][r | (1 << b)], w, q, aux);
         }
       }
@@ -253,6 +266,7 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
   constexpr int LG = LOGN - S0 - R;
   constexpr int G = (AR == AR_F64) ? D::IT : 1;
   const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.itw : (AR == AR_F64 ? M.itwd : M.itwf);
+  const double qinv = f64_of(M.qinv_bits);
 #pragma unroll
   for (int it0 = 0; it0 < D::IT; it0 += G) {
     int blk[G], base[G], pbase[G];
@@ -266,7 +280,6 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
 #pragma unroll
       for (int r = 0; r < 8; ++r) x[g][r] = sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))];
       if ((AR == AR_FP_LAZY || AR == AR_F64) && REDUCE) {
-        const double qinv = f64_of(M.qinv_bits);
 #pragma unroll
         for (int r = 0; r < 8; ++r)
           x[g][r] = AR == AR_F64 ? bits_of(reduce_f64(f64_of(x[g][r]), qinv, f64_of(aux))) : reduce_fp<true>(x[g][r], qinv, q, aux);
@@ -287,7 +300,7 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
             x[g][r] = mul_tw<AR>(ar_add<AR>(u, v), AR == AR_F64 ? M.ninv_d : M.ninv, (AR == AR_SHOUP) ? M.ninv_s : M.ninv_f, q, aux);
             x[g][r | (1 << b)] = mul_tw<AR>(d, AR == AR_F64 ? M.wl_ninv_d : M.wl_ninv, (AR == AR_SHOUP) ? M.wl_ninv_s : M.wl_ninv_f, q, aux);
           } else {
-            const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)((blk[g] << 3) + r) >> (b + 1))]);
+            const ulonglong2 w = tw_get<AR>(tw, (twbase << s) + ((u32)((blk[g] << 3) + r) >> (b + 1)), qinv);
             bf_inv<AR>(x[g][r], x[g][r | (1 << b)], w, q, aux);
           }
         }
@@ -309,15 +322,24 @@ template <int LOGN> struct NttLast {
   static constexpr int E = 8, LOGE = (E == 16) ? 4 : 3;
   static constexpr int GROUPS = 8 * NttDims<LOGN>::IT / E;
   static constexpr int NSH = LOGN - (NttPlan<LOGN>::R0 + NttPlan<LOGN>::R1 + NttPlan<LOGN>::R2) - LOGE;
-  static_assert(E == 8 || E == 16, "contiguous pass handles 8 or 16 coefficients per thread");
+  static_assert(E == 8, "contiguous pass handles 8 or 16 coefficients per thread");
   static_assert(NSH >= 0 && NSH <= 2, "stage plan does not add up");
 };
+
+// twiddle index of the in-register stage with partner distance 2^b of the contiguous pass (E = 8): natural order
+// 2^s + ((8*vt + r) >> (b+1)); AR_F64 stores the last two stages lane-contiguously (see tw_get)
+template <int LOGN, int AR>
+__device__ __forceinline__ u32 last_tw_index(u32 twbase, int s, int b, int vt, int r) {
+  if (AR == AR_F64 && b < 2) return (1u << s) + (u32)(r >> (b + 1)) * (u32)(NttDims<LOGN>::N / 8) + (u32)vt;
+  return (twbase << s) + ((u32)(8 * vt + r) >> (b + 1));
+}
 
 template <int LOGN, int AR>
 __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 aux, int tid) {
   typedef NttLast<LOGN> P;
   constexpr int E = P::E, H = E / 2;
   const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.tw : (AR == AR_F64 ? M.twd : M.twf);
+  const double qinv = f64_of(M.qinv_bits);
 #pragma unroll
   for (int g = 0; g < P::GROUPS; ++g) {
     const int vt = tid + g * NttDims<LOGN>::T;
@@ -330,7 +352,7 @@ __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twba
 #pragma unroll
     for (int j = P::NSH - 1; j >= 0; --j) {
       const int s = LOGN - 1 - P::LOGE - j;
-      const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)vt >> (1 + j))]);
+      const ulonglong2 w = tw_get<AR>(tw, (twbase << s) + ((u32)vt >> (1 + j)), qinv);
       const bool hi = (vt >> j) & 1;
 #pragma unroll
       for (int r = 0; r < H; ++r) {
@@ -349,7 +371,7 @@ __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twba
 #pragma unroll
       for (int r = 0; r < E; ++r) {
         if (r & (1 << b)) continue;
-        const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)(E * vt + r) >> (b + 1))]);
+        const ulonglong2 w = tw_get<AR>(tw, last_tw_index<LOGN, AR>(twbase, s, b, vt, r), qinv);
         bf_fwd<AR>(x[r], x[r | (1 << b)], w, q, aux);
       }
     }
@@ -369,6 +391,7 @@ __device__ __forceinline__ void ntt_inv_first(u64 *sm, const ModInfo &M, u32 twb
   typedef NttLast<LOGN> P;
   constexpr int E = P::E, H = E / 2;
   const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.itw : (AR == AR_F64 ? M.itwd : M.itwf);
+  const double qinv = f64_of(M.qinv_bits);
 #pragma unroll
   for (int g = 0; g < P::GROUPS; ++g) {
     const int vt = tid + g * NttDims<LOGN>::T;
@@ -384,14 +407,14 @@ __device__ __forceinline__ void ntt_inv_first(u64 *sm, const ModInfo &M, u32 twb
 #pragma unroll
       for (int r = 0; r < E; ++r) {
         if (r & (1 << b)) continue;
-        const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)(E * vt + r) >> (b + 1))]);
+        const ulonglong2 w = tw_get<AR>(tw, last_tw_index<LOGN, AR>(twbase, s, b, vt, r), qinv);
         bf_inv<AR>(x[r], x[r | (1 << b)], w, q, aux);
       }
     }
 #pragma unroll
     for (int j = 0; j < P::NSH; ++j) {
       const int s = LOGN - 1 - P::LOGE - j;
-      const ulonglong2 w = __ldg(&tw[(twbase << s) + ((u32)vt >> (1 + j))]);
+      const ulonglong2 w = tw_get<AR>(tw, (twbase << s) + ((u32)vt >> (1 + j)), qinv);
       const bool hi = (vt >> j) & 1;
 #pragma unroll
       for (int r = 0; r < H; ++r) {
@@ -419,12 +442,13 @@ __device__ __forceinline__ void ntt_fwd_smem(u64 *sm, const ModInfo &M, u32 twba
   typedef NttPlan<LOGN> P;
   const u64 q = M.q, aux = ar_aux<AR>(q);
   const ulonglong2 *tw = (AR == AR_SHOUP) ? M.tw : (AR == AR_F64 ? M.twd : M.twf);
-  ntt_fwd_mid<LOGN, 0, P::R0, AR, LINSRC>(sm, tw, twbase, q, aux, tid, qs, einv);
+  const double qinv = f64_of(M.qinv_bits);
+  ntt_fwd_mid<LOGN, 0, P::R0, AR, LINSRC>(sm, tw, twbase, q, aux, tid, qinv, qs, einv);
   __syncthreads();
-  ntt_fwd_mid<LOGN, P::R0, P::R1, AR>(sm, tw, twbase, q, aux, tid);
+  ntt_fwd_mid<LOGN, P::R0, P::R1, AR>(sm, tw, twbase, q, aux, tid, qinv);
   __syncthreads();
   if constexpr (P::R2 > 0) {
-    ntt_fwd_mid<LOGN, P::R0 + P::R1, P::R2, AR>(sm, tw, twbase, q, aux, tid);
+    ntt_fwd_mid<LOGN, P::R0 + P::R1, P::R2, AR>(sm, tw, twbase, q, aux, tid, qinv);
     __syncthreads();
   }
   ntt_fwd_last<LOGN, AR>(sm, M, twbase, q, aux, tid);
