@@ -52,6 +52,9 @@ SYMBOLS = {
     "abc_negate": (i32, [vp, vp, vp]),
     "abc_mul_relin": (i32, [vp, vp, vp, vp]),
     "abc_rotate_rows": (i32, [vp, vp, vp, i32]),
+    "abc_rotate_rows_add": (i32, [vp, vp, vp, i32, vp]),
+    "abc_ct_shared": (i32, [vp]),
+    "abc_ct_deferred": (i32, [vp]),
     "abc_add_plain": (i32, [vp, vp, vp, vp, sz, i32]),
     "abc_sub_plain": (i32, [vp, vp, vp, vp, sz, i32]),
     "abc_mul_plain": (i32, [vp, vp, vp, vp, sz, i32]),

@@ -326,6 +326,19 @@ class CudaCiphertext:
         f._ck(f._lib.abc_rotate_rows(f._h, dst._h, self._h, steps))
         return dst
 
+    def rotateRowsAdd(self, steps, addend):
+        """add(rotateRows(steps), addend) as one key switch (abc_rotate_rows_add).  The same fusion happens by itself
+        when a rotateRows result is added (the library defers the last key switch of a rotation)."""
+        f, dst = self.factory, self._new()
+        f._ck(f._lib.abc_rotate_rows_add(f._h, dst._h, self._h, steps, self._other(addend)._h))
+        return dst
+
+    def isDeferred(self):
+        return bool(self.factory._lib.abc_ct_deferred(self._h))
+
+    def sharedCount(self):
+        return int(self.factory._lib.abc_ct_shared(self._h))
+
     def rotateRowsInplace(self, steps):
         f = self.factory
         f._ck(f._lib.abc_rotate_rows(f._h, self._h, self._h, steps))

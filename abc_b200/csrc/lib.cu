@@ -38,6 +38,7 @@ struct abc_ctx {
   int prefetch_ahead = 0;   // CTAs resident at once (2 per SM): a CTA L2-prefetches the row of the CTA that replaces it
   int ar_q = 0, ar_t = 0, force_ar = -1;  // NTT arithmetic class of the key-level primes / of t (ntt.cuh)
   int ks_skew = 8;                               // ABC_KS_SKEW: special-prime rows run this many instances ahead
+  bool lazy_rotate = true;                       // ABC_EAGER_ROTATE: rotate_rows runs its last key switch immediately
   bool ks_unmerged = false, ks_unfused = false;  // ABC_KS_UNMERGED / ABC_KS_UNFUSED: A/B switches for the key-switch tail
   int idx_t = 0;
   std::vector<void *> owned;  // device allocations freed at destroy
@@ -81,7 +82,15 @@ struct abc_ctx {
   u64 *sc_ptr[12] = {nullptr};
   size_t sc_words[12] = {0};
 };
-struct abc_ct { abc_ctx *ctx; u64 *d; };
+// A ciphertext handle.  The device buffer is shared between clones (copy-on-write): RuntimeVisitor clones on every
+// variable read (RuntimeVisitor.cpp:436), so clone is O(1) and an op gives its destination a private buffer first.
+// A buffer may also be a DEFERRED rotation (d == nullptr): its value is the last Galois step of a rotate_rows applied
+// to `src`; an add consumes it fused (the addend is accumulated in that key switch's ModDown), anything else resolves it.
+struct CtBuf {
+  u64 *d = nullptr; int refs = 1;
+  CtBuf *src = nullptr; u32 elt = 0;
+};
+struct abc_ct { abc_ctx *ctx; CtBuf *b; };
 struct abc_pt { abc_ctx *ctx; u64 *d; int broadcast; };
 
 namespace {
@@ -275,6 +284,7 @@ abc_status build_tables(abc_ctx *c) {
   if (const char *e = getenv("ABC_FORCE_AR")) c->force_ar = atoi(e);
   c->ks_unmerged = getenv("ABC_KS_UNMERGED") != nullptr;
   c->ks_unfused = getenv("ABC_KS_UNFUSED") != nullptr;
+  c->lazy_rotate = getenv("ABC_EAGER_ROTATE") == nullptr;
   if (const char *e = getenv("ABC_KS_SKEW")) c->ks_skew = atoi(e) < 0 ? 0 : atoi(e);
   {
     int sms = 148;
@@ -495,7 +505,8 @@ size_t ct_words1(const abc_ctx *c) { return (size_t)2 * c->L * c->N; }
 //   3. INTT of the two special-prime rows                                                                    [limb pipeline]
 //   4. INTT of the 2L data rows fused with ModDown (rounded division by p) and the base accumulate            [limb pipeline]
 abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u64 *key, const u64 *base0,
-                     long long base0_is, const u64 *base1, long long base1_is, u32 einv, u64 *dst) {
+                     long long base0_is, const u64 *base1, long long base1_is, u32 einv, u64 *dst,
+                     const u64 *addend = nullptr, u64 *dst_plain = nullptr) {
   const int N = c->N, L = c->L, k = c->k, B = c->B;
   u64 *T = nullptr, *acc = nullptr;
   TRY(scratch(c, SC_T, &T, (size_t)B * k * L * N));
@@ -524,6 +535,8 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   j.dst = dst; j.dst_is = (long long)2 * L * N;
   j.C = c->dC; j.tl = acc; j.tl_is = (long long)2 * k * N; j.L = L; j.k = k; j.i0 = c->own_lo; j.nrows = nown;
   j.base0 = base0; j.base0_is = base0_is; j.base1 = base1; j.base1_is = base1_is; j.base_einv = einv;
+  j.add = addend; j.add_is = (long long)2 * L * N;  // a whole ciphertext accumulated into the result (rotate + add)
+  j.dst2 = dst_plain;                                // ... and the result without it (same layout as dst)
   if (merged) {  // one launch: the two special-prime rows INTT and publish, the data rows INTT, wait, ModDown
     j.rowsrc = c->rs_mdm; j.rowdst = c->rd_mdm; j.rowmod = c->rm_mdm;
     j.flags = c->ks_flags; j.flag_serial = ++c->ks_serial; j.skew = c->ks_skew;
@@ -581,13 +594,13 @@ abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
 
 // one Galois automorphism + key switch (Evaluator::apply_galois_inplace): dst = (sigma(c0), 0) + KeySwitch(sigma(c1)).
 // The coefficient permutation is never materialised: it is a gather in the ModUp load and in the ModDown base read.
-abc_status apply_galois(abc_ctx *c, const u64 *src, u64 *dst, u32 elt) {
+abc_status apply_galois(abc_ctx *c, const u64 *src, u64 *dst, u32 elt, const u64 *addend = nullptr, u64 *dst_plain = nullptr) {
   auto it = c->galois.find(elt);
   if (it == c->galois.end()) return fail(c, ABC_ERR_STATE, "Galois key not present");
   const long long LN = (long long)c->L * c->N;
   const u32 elt_inv = (u32)hm::invmod(elt, 2ull * c->N);
   TRY(allgather_limbs(c, const_cast<u64 *>(src), 2));  // limb-sharded: ModUp needs every limb of c1 on every rank
-  return keyswitch(c, src + LN, 2 * LN, it->second, src, 2 * LN, nullptr, 0, elt_inv, dst);
+  return keyswitch(c, src + LN, 2 * LN, it->second, src, 2 * LN, nullptr, 0, elt_inv, dst, addend, dst_plain);
 }
 
 u32 elt_from_step(const abc_ctx *c, int step) {
@@ -745,7 +758,7 @@ std::vector<u32> galois_elts_all(const abc_ctx *c) {
   return v;
 }
 
-bool valid_ct(const abc_ctx *c, const abc_ct *x) { return x && x->ctx == c && x->d; }
+bool valid_ct(const abc_ctx *c, const abc_ct *x) { return x && x->ctx == c && x->b; }
 
 }  // namespace
 
@@ -926,31 +939,74 @@ abc_status abc_ct_alloc(abc_ctx *c, abc_ct **out) {
   CK(cudaSetDevice(c->device));
   u64 *d = nullptr;
   TRY(salloc(c, &d, abc_ct_words(c)));
-  *out = new abc_ct{c, d};
+  CtBuf *b = new CtBuf; b->d = d;
+  *out = new abc_ct{c, b};
+  return ABC_OK;
+}
+// drop one reference to a buffer (stream-ordered free when it was the last one)
+static void buf_unref(abc_ctx *c, CtBuf *b) {
+  if (!b || --b->refs > 0) return;
+  if (b->d) sfree(c, b->d);
+  buf_unref(c, b->src);
+  delete b;
+}
+// point the handle at a buffer it alone owns
+static void ct_adopt(abc_ct *ct, u64 *d) {
+  buf_unref(ct->ctx, ct->b);
+  ct->b = new CtBuf; ct->b->d = d;
+}
+static void ct_share(abc_ct *dst, CtBuf *b) {
+  if (dst->b == b) return;
+  ++b->refs;
+  buf_unref(dst->ctx, dst->b);
+  dst->b = b;
+}
+// Materialise a deferred rotation: every clone sharing the buffer sees the result.
+static abc_status buf_resolve(abc_ctx *c, CtBuf *b) {
+  if (b->d) return ABC_OK;
+  u64 *d = nullptr;
+  TRY(salloc(c, &d, abc_ct_words(c)));
+  abc_status st = apply_galois(c, b->src->d, d, b->elt);
+  if (st != ABC_OK) { sfree(c, d); return st; }
+  b->d = d;
+  buf_unref(c, b->src); b->src = nullptr;
+  return ABC_OK;
+}
+static abc_status ct_resolve(abc_ctx *c, const abc_ct *ct) { return buf_resolve(c, ct->b); }
+// Copy-on-write: call after the operands' pointers are captured and before dst is written.  Every op overwrites the
+// whole of dst, so a shared (or deferred) buffer is simply swapped for a fresh one; the old one lives on in the clones.
+static abc_status ct_make_private(abc_ctx *c, abc_ct *dst) {
+  if (dst->b->refs == 1 && dst->b->d) return ABC_OK;
+  u64 *d = nullptr;
+  TRY(salloc(c, &d, abc_ct_words(c)));
+  ct_adopt(dst, d);
   return ABC_OK;
 }
 void abc_ct_free(abc_ct *ct) {
   if (!ct) return;
-  sfree(ct->ctx, ct->d);
+  buf_unref(ct->ctx, ct->b);
   delete ct;
 }
 size_t abc_ct_words(const abc_ctx *c) { return (size_t)c->B * ct_words1(c); }
 abc_status abc_ct_clone(abc_ctx *c, const abc_ct *src, abc_ct **out) {
   if (!valid_ct(c, src)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
-  TRY(abc_ct_alloc(c, out));
-  c->launches++;
-  CK(cudaMemcpyAsync((*out)->d, src->d, abc_ct_words(c) * 8, cudaMemcpyDeviceToDevice, c->stream));
+  ++src->b->refs;
+  *out = new abc_ct{c, src->b};
   return ABC_OK;
 }
+int abc_ct_shared(const abc_ct *ct) { return ct && ct->b ? ct->b->refs : 0; }
+int abc_ct_deferred(const abc_ct *ct) { return ct && ct->b && !ct->b->d ? 1 : 0; }
 abc_status abc_ct_export(abc_ctx *c, const abc_ct *ct, uint64_t *host, size_t words) {
   if (!valid_ct(c, ct) || words != abc_ct_words(c)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle or size");
-  CK(cudaMemcpyAsync(host, ct->d, words * 8, cudaMemcpyDeviceToHost, c->stream));
+  TRY(ct_resolve(c, ct));
+  CK(cudaMemcpyAsync(host, ct->b->d, words * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return ABC_OK;
 }
 abc_status abc_ct_import(abc_ctx *c, abc_ct *ct, const uint64_t *host, size_t words) {
   if (!valid_ct(c, ct) || words != abc_ct_words(c)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle or size");
-  CK(cudaMemcpyAsync(ct->d, host, words * 8, cudaMemcpyHostToDevice, c->stream));
+  TRY(ct_make_private(c, ct));
+  CK(cudaMemcpyAsync(ct->b->d, host, words * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return ABC_OK;
 }
@@ -971,7 +1027,7 @@ void abc_pt_free(abc_pt *pt) {
 abc_status abc_encrypt_pt(abc_ctx *c, const abc_pt *pt, abc_ct **out) {
   if (!pt || pt->ctx != c) return fail(c, ABC_ERR_PARAM, "invalid plaintext handle");
   TRY(abc_ct_alloc(c, out));
-  abc_status s = encrypt_device(c, pt->d, pt->broadcast, (*out)->d);
+  abc_status s = encrypt_device(c, pt->d, pt->broadcast, (*out)->b->d);
   if (s != ABC_OK) { abc_ct_free(*out); *out = nullptr; }
   return s;
 }
@@ -988,17 +1044,18 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
   if (!valid_ct(c, ct)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
   if (!c->d_sk) return fail(c, ABC_ERR_STATE, "secret key not present");
   CK(cudaSetDevice(c->device));
+  TRY(ct_resolve(c, ct));
   const int N = c->N, L = c->L, B = c->B;
   u64 *x = nullptr, *plain = nullptr;
   long long *d_out = nullptr;
   TRY(scratch(c, SC_DECX, &x, (size_t)B * L * N));
   TRY(scratch(c, SC_DECP, &plain, (size_t)B * N));
   CK(cudaMallocAsync((void **)&d_out, (size_t)B * N * sizeof(long long), c->stream));
-  TRY(allgather_limbs(c, ct->d, 3));  // limb-sharded: scale-and-round needs every limb
+  TRY(allgather_limbs(c, ct->b->d, 3));  // limb-sharded: scale-and-round needs every limb
   LimbJob j = blank_job();
-  j.src = ct->d; j.src_is = (long long)2 * L * N; j.rowsrc = c->rs_c1;
+  j.src = ct->b->d; j.src_is = (long long)2 * L * N; j.rowsrc = c->rs_c1;
   j.mul = c->d_sk; j.mul_is = 0;
-  j.add = ct->d; j.add_is = (long long)2 * L * N;
+  j.add = ct->b->d; j.add_is = (long long)2 * L * N;
   j.dst = x; j.dst_is = (long long)L * N; j.rowmod = c->rm_ct;
   TRY(launch_limb(c, LIMB_FWD_MUL_INV_ADD, c->ar_q, j, L, B, "dec_c1s_plus_c0"));
   {
@@ -1024,19 +1081,44 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
 }
 
 // ---- ciphertext ops
+static abc_status fused_rotate_add(abc_ctx *c, abc_ct *dst, const abc_ct *rot, const abc_ct *other);
 static abc_status addsub(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct *b, int op) {
   if (!valid_ct(c, dst) || !valid_ct(c, a) || (op != 2 && !valid_ct(c, b)))
     return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+  if (op == 0) {  // add with a deferred rotation: accumulate in its key switch
+    if (!a->b->d && !b->b->d) TRY(ct_resolve(c, a));
+    if (!b->b->d) return fused_rotate_add(c, dst, b, a);
+    if (!a->b->d) return fused_rotate_add(c, dst, a, b);
+  }
+  TRY(ct_resolve(c, a));
+  if (b) TRY(ct_resolve(c, b));
   const int N = c->N, L = c->L;
   Launch l(c, op == 0 ? "add" : op == 1 ? "sub" : "negate");
   const int i0 = c->own_lo, nown = c->own_hi - c->own_lo;
   if (nown == 0) return ABC_OK;
   dim3 grid((N / 2 + 255) / 256, 2 * nown, c->B);
   const long long is = 2ll * L * N;
-  if (op == 0) k_addsub<0><<<grid, 256, 0, c->stream>>>(dst->d, a->d, b->d, c->dC, N, L, is, i0, nown);
-  else if (op == 1) k_addsub<1><<<grid, 256, 0, c->stream>>>(dst->d, a->d, b->d, c->dC, N, L, is, i0, nown);
-  else k_addsub<2><<<grid, 256, 0, c->stream>>>(dst->d, a->d, nullptr, c->dC, N, L, is, i0, nown);
+  const u64 *pa = a->b->d, *pb = b ? b->b->d : nullptr;
+  TRY(ct_make_private(c, dst));
+  if (op == 0) k_addsub<0><<<grid, 256, 0, c->stream>>>(dst->b->d, pa, pb, c->dC, N, L, is, i0, nown);
+  else if (op == 1) k_addsub<1><<<grid, 256, 0, c->stream>>>(dst->b->d, pa, pb, c->dC, N, L, is, i0, nown);
+  else k_addsub<2><<<grid, 256, 0, c->stream>>>(dst->b->d, pa, nullptr, c->dC, N, L, is, i0, nown);
   CK(cudaGetLastError());
+  return ABC_OK;
+}
+// dst = rot + other where rot is a deferred rotation (other is resolved).  One key switch writes the sum; unless dst is
+// the only holder of rot it also writes the rotation itself (second ModDown output), which resolves rot for its other
+// holders at the cost of one extra store instead of a second key switch later.
+static abc_status fused_rotate_add(abc_ctx *c, abc_ct *dst, const abc_ct *rot, const abc_ct *other) {
+  CtBuf *rb = rot->b;
+  const bool dual = !(dst->b == rb && rb->refs == 1);
+  u64 *sum = nullptr, *plain = nullptr;
+  TRY(salloc(c, &sum, abc_ct_words(c)));
+  if (dual) TRY(salloc(c, &plain, abc_ct_words(c)));
+  abc_status st = apply_galois(c, rb->src->d, sum, rb->elt, other->b->d, plain);
+  if (st != ABC_OK) { sfree(c, sum); if (plain) sfree(c, plain); return st; }
+  if (dual) { rb->d = plain; buf_unref(c, rb->src); rb->src = nullptr; }
+  ct_adopt(dst, sum);
   return ABC_OK;
 }
 abc_status abc_add(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct *b) { return addsub(c, dst, a, b, 0); }
@@ -1051,54 +1133,84 @@ abc_status abc_mul_relin(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct 
   TRY(scratch(c, SC_OUT3, &out3, (size_t)c->B * 3 * LN));
   // limb-sharded: BEHZ base conversion needs every limb of both operands; the product is computed on every rank
   // (replicated), the relinearisation key switch only for the output moduli this rank owns
-  TRY(allgather_limbs(c, a->d, 3));
-  if (b != a) TRY(allgather_limbs(c, b->d, 3));
-  TRY(behz_multiply(c, a->d, b->d, out3));
-  TRY(keyswitch(c, out3 + 2 * LN, 3ll * LN, c->d_relin, out3, 3ll * LN, out3 + LN, 3ll * LN, 0, dst->d));
+  TRY(ct_resolve(c, a)); TRY(ct_resolve(c, b));
+  TRY(allgather_limbs(c, a->b->d, 3));
+  if (b->b != a->b) TRY(allgather_limbs(c, b->b->d, 3));
+  TRY(behz_multiply(c, a->b->d, b->b->d, out3));
+  TRY(ct_make_private(c, dst));  // the operands are consumed into out3 by now
+  TRY(keyswitch(c, out3 + 2 * LN, 3ll * LN, c->d_relin, out3, 3ll * LN, out3 + LN, 3ll * LN, 0, dst->b->d));
   return ABC_OK;
 }
 
-abc_status abc_rotate_rows(abc_ctx *c, abc_ct *dst, const abc_ct *a, int steps) {
-  if (!valid_ct(c, dst) || !valid_ct(c, a)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+// dst = rotate_rows(a, steps) [+ addend].  The addend is accumulated in the ModDown of the last key switch, which
+// gives exactly add(rotate_rows(a), addend): modular addition of canonical residues is associative.
+static abc_status rotate_impl(abc_ctx *c, abc_ct *dst, const abc_ct *a, int steps, const abc_ct *addend) {
+  if (!valid_ct(c, dst) || !valid_ct(c, a) || (addend && !valid_ct(c, addend)))
+    return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
   const int as = steps < 0 ? -steps : steps;
   if (as >= (c->N >> 1)) return fail(c, ABC_ERR_PARAM, "step count too large");
   std::vector<u32> plan;
   TRY(rotation_plan(c, steps, plan));
-  if (plan.empty()) {
-    if (dst != a) {
-      c->launches++;
-      CK(cudaMemcpyAsync(dst->d, a->d, abc_ct_words(c) * 8, cudaMemcpyDeviceToDevice, c->stream));
-    }
+  if (plan.empty()) {  // rotation by 0: dst becomes another clone of a
+    if (addend) return addsub(c, dst, a, addend, 0);
+    ct_share(dst, a->b);
     return ABC_OK;
   }
-  // each key switch writes a fresh buffer (its gathers read the previous one); the last one becomes dst's storage
-  const u64 *cur = a->d;
-  u64 *owned = nullptr;
-  for (u32 elt : plan) {
+  TRY(ct_resolve(c, a));
+  if (addend) TRY(ct_resolve(c, addend));
+  // The last Galois step is deferred (see CtBuf) unless an addend is given or the context is limb-sharded; the steps
+  // before it run now.  Each key switch writes a fresh buffer (its gathers read the previous one).
+  const bool defer = !addend && c->lazy_rotate && c->world == 1;
+  CtBuf *cur = a->b;
+  ++cur->refs;
+  for (size_t pi = 0; pi < plan.size(); ++pi) {
+    const bool last = pi + 1 == plan.size();
+    if (last && defer) {
+      CtBuf *nb = new CtBuf; nb->src = cur; nb->elt = plan[pi];  // takes over the reference held on cur
+      buf_unref(c, dst->b);
+      dst->b = nb;
+      return ABC_OK;
+    }
     u64 *out = nullptr;
-    TRY(salloc(c, &out, abc_ct_words(c)));
-    abc_status s = apply_galois(c, cur, out, elt);
-    if (owned) sfree(c, owned);
-    if (s != ABC_OK) { sfree(c, out); return s; }
-    cur = owned = out;
+    abc_status s = salloc(c, &out, abc_ct_words(c));
+    if (s == ABC_OK) {
+      s = apply_galois(c, cur->d, out, plan[pi], (addend && last) ? addend->b->d : nullptr);
+      if (s != ABC_OK) sfree(c, out);
+    }
+    buf_unref(c, cur);
+    if (s != ABC_OK) return s;
+    cur = new CtBuf; cur->d = out;
   }
-  sfree(c, dst->d);  // stream-ordered: after the kernels that read it
-  dst->d = owned;
+  buf_unref(c, dst->b);  // released stream-ordered: after the kernels that read it
+  dst->b = cur;
   return ABC_OK;
+}
+abc_status abc_rotate_rows(abc_ctx *c, abc_ct *dst, const abc_ct *a, int steps) { return rotate_impl(c, dst, a, steps, nullptr); }
+abc_status abc_rotate_rows_add(abc_ctx *c, abc_ct *dst, const abc_ct *a, int steps, const abc_ct *addend) {
+  return rotate_impl(c, dst, a, steps, addend);
 }
 
 // ---- plaintext operands
 abc_status abc_add_plain_pt(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_pt *pt) {
   if (!valid_ct(c, dst) || !valid_ct(c, a) || !pt || pt->ctx != c) return fail(c, ABC_ERR_PARAM, "invalid handle");
-  return plain_addsub_device<0>(c, dst->d, a->d, pt->d, pt->broadcast);
+  TRY(ct_resolve(c, a));
+  const u64 *pa = a->b->d;
+  TRY(ct_make_private(c, dst));
+  return plain_addsub_device<0>(c, dst->b->d, pa, pt->d, pt->broadcast);
 }
 abc_status abc_sub_plain_pt(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_pt *pt) {
   if (!valid_ct(c, dst) || !valid_ct(c, a) || !pt || pt->ctx != c) return fail(c, ABC_ERR_PARAM, "invalid handle");
-  return plain_addsub_device<1>(c, dst->d, a->d, pt->d, pt->broadcast);
+  TRY(ct_resolve(c, a));
+  const u64 *pa = a->b->d;
+  TRY(ct_make_private(c, dst));
+  return plain_addsub_device<1>(c, dst->b->d, pa, pt->d, pt->broadcast);
 }
 abc_status abc_mul_plain_pt(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_pt *pt) {
   if (!valid_ct(c, dst) || !valid_ct(c, a) || !pt || pt->ctx != c) return fail(c, ABC_ERR_PARAM, "invalid handle");
-  return mul_plain_device(c, dst->d, a->d, pt->d, pt->broadcast);
+  TRY(ct_resolve(c, a));
+  const u64 *pa = a->b->d;
+  TRY(ct_make_private(c, dst));
+  return mul_plain_device(c, dst->b->d, pa, pt->d, pt->broadcast);
 }
 #define PLAIN_OP(NAME, PTFN)                                                                                      \
   abc_status NAME(abc_ctx *c, abc_ct *dst, const abc_ct *a, const int64_t *slots, size_t n, int broadcast) {      \
@@ -1162,7 +1274,8 @@ abc_status abc_probe_multiply(abc_ctx *c, const abc_ct *a, const abc_ct *b, uint
   if (words != need) return fail(c, ABC_ERR_PARAM, "size mismatch");
   u64 *out3 = nullptr;
   TRY(salloc(c, &out3, need));
-  TRY(behz_multiply(c, a->d, b->d, out3));
+  TRY(ct_resolve(c, a)); TRY(ct_resolve(c, b));
+  TRY(behz_multiply(c, a->b->d, b->b->d, out3));
   CK(cudaMemcpyAsync(host_out3, out3, need * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   sfree(c, out3);
@@ -1201,7 +1314,8 @@ abc_status abc_owned_limbs(const abc_ctx *c, uint32_t *lo, uint32_t *hi) {
 }
 abc_status abc_ct_allgather(abc_ctx *c, abc_ct *ct) {
   if (!valid_ct(c, ct)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
-  return allgather_limbs(c, ct->d, 3);
+  TRY(ct_resolve(c, ct));
+  return allgather_limbs(c, ct->b->d, 3);
 }
 
 // ---- timing / profiling

@@ -19,6 +19,7 @@ enum { POST_STORE = 0, POST_ADD = 1, POST_DECODE = 2, POST_MODDOWN = 3 };
 
 struct LimbJob {
   u64 *dst; const u64 *src; const u64 *mul; const u64 *add;
+  u64 *dst2;                                  // POST_MODDOWN with `add`: also store the result WITHOUT the addend here (layout of dst)
   long long dst_is, src_is, mul_is, add_is;  // per-instance strides in words (0 = shared by all instances)
   const int *rowmod;                          // [W] modulus index of row w
   const int *rowdst;                          // [W] destination row, or nullptr = w
@@ -130,7 +131,7 @@ __device__ __forceinline__ ModDownF64 moddown_f64(const ModDownRow &md, const Mo
   f.qd = (double)M.q; f.qinv = f64_of(M.qinv_bits); f.ipc = f.ipd * f.qinv;
   return f;
 }
-__device__ __forceinline__ u64 moddown_one_f64(double vd, u64 t, bool has_base, u64 b, const ModDownF64 &f) {
+__device__ __forceinline__ double moddown_one_f64(double vd, u64 t, bool has_base, u64 b, const ModDownF64 &f) {
   double a = f64_of(ar_from_canon<AR_F64>(t)) + f.p_half;
   a = a >= f.pd ? a - f.pd : a;                                   // [t + p/2]_p, exact
   const double d = (vd - reduce_f64(a, f.qinv, f.qd)) + f.phm;    // |d| < 2.6q, exact integer
@@ -139,8 +140,12 @@ __device__ __forceinline__ u64 moddown_one_f64(double vd, u64 t, bool has_base, 
   double r = fma(-Q, f.qd, ph) + pl;                              // d * p^-1 mod q, |r| <= 0.6q
   if (has_base) r += f64_of(ar_from_canon<AR_F64>(b));
   r = r < 0.0 ? r + f.qd : r;
-  r = r >= f.qd ? r - f.qd : r;
-  return bits_of(r + 4503599627370496.0) & 0x000FFFFFFFFFFFFFULL;
+  return r >= f.qd ? r - f.qd : r;                                // canonical, as a double
+}
+__device__ __forceinline__ u64 f64_canon_bits(double r) { return bits_of(r + 4503599627370496.0) & 0x000FFFFFFFFFFFFFULL; }
+__device__ __forceinline__ double add_canon_f64(double r, u64 ad, double qd) {
+  r += f64_of(ar_from_canon<AR_F64>(ad));
+  return r >= qd ? r - qd : r;
 }
 
 template <int POST>
@@ -165,6 +170,11 @@ __device__ __forceinline__ void limb_store_pair(const LimbJob &job, const ModInf
         b = reinterpret_cast<const ulonglong2 *>(md.base)[e2];
       }
       v.x = add_mod(v.x, b.x, q); v.y = add_mod(v.y, b.y, q);
+    }
+    if (job.add) {  // rotate + add: a whole ciphertext accumulated into the result
+      if (job.dst2) reinterpret_cast<ulonglong2 *>(job.dst2 + (size_t)inst * job.dst_is + (size_t)drow * n)[e2] = v;
+      const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(job.add + (size_t)inst * job.add_is + (size_t)drow * n)[e2];
+      v.x = add_mod(v.x, a.x, q); v.y = add_mod(v.y, a.y, q);
     }
   } else if (POST == POST_ADD) {
     const ulonglong2 a = reinterpret_cast<const ulonglong2 *>(job.add + (size_t)inst * job.add_is + (size_t)arow * n)[e2];
@@ -359,6 +369,8 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
       const ModDownF64 f = moddown_f64(md, M);
       const u32 einv = job.base_einv, m2 = 2u * D::N - 1;
       ulonglong2 *out = reinterpret_cast<ulonglong2 *>(job.dst + (size_t)inst * job.dst_is + (size_t)drow * D::N);
+      ulonglong2 *out2 = job.dst2 ? reinterpret_cast<ulonglong2 *>(job.dst2 + (size_t)inst * job.dst_is + (size_t)drow * D::N) : nullptr;
+      const ulonglong2 *addp = job.add ? reinterpret_cast<const ulonglong2 *>(job.add + (size_t)inst * job.add_is + (size_t)drow * D::N) : nullptr;
       for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
         const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
         const ulonglong2 t = __ldcg(md.tl + e2);
@@ -373,8 +385,14 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
             b = reinterpret_cast<const ulonglong2 *>(md.base)[e2];
           }
         }
-        out[e2] = make_ulonglong2(moddown_one_f64(f64_of(v.x), t.x, md.base != nullptr, b.x, f),
-                                  moddown_one_f64(f64_of(v.y), t.y, md.base != nullptr, b.y, f));
+        double rx = moddown_one_f64(f64_of(v.x), t.x, md.base != nullptr, b.x, f);
+        double ry = moddown_one_f64(f64_of(v.y), t.y, md.base != nullptr, b.y, f);
+        if (addp) {
+          if (out2) out2[e2] = make_ulonglong2(f64_canon_bits(rx), f64_canon_bits(ry));
+          const ulonglong2 ad = addp[e2];
+          rx = add_canon_f64(rx, ad.x, f.qd); ry = add_canon_f64(ry, ad.y, f.qd);
+        }
+        out[e2] = make_ulonglong2(f64_canon_bits(rx), f64_canon_bits(ry));
       }
     } else {
       for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {

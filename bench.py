@@ -237,6 +237,8 @@ def run_ours(args):
         nb = L + 1
         alg = {"ks_modup_ntt": B * (L + k * L) * row, "ks_inner": B * (k * L + 2 * k) * row + 2 * k * L * row,
                "ks_intt_special": B * 4 * row, "ks_intt_moddown": B * (2 * L + 2 + 2 * L + 2 * L) * row,
+               # fused tail of a rotation's key switch: T rows in, sigma(c0) and the addend in, sum and plain rotation out, + key
+               "ks_inner_intt_moddown": B * (k * L + L + 2 * L + 2 * L + 2 * L) * row + 2 * k * L * row,
                "behz_ntt_q": B * 8 * L * row, "behz_ntt_bsk": B * 8 * nb * row,
                "behz_intt_q": B * 6 * L * row, "behz_intt_bsk": B * 6 * nb * row,
                "behz_lift": B * 4 * (L + 2 * L + 1) * row, "behz_tensor": B * 7 * (2 * L + 1) * row,
@@ -248,6 +250,7 @@ def run_ours(args):
         imad, iadd = f.measure_int_peak()
         logn = N_POLY.bit_length() - 1
         ntt_rows = {"ks_modup_ntt": k * L, "ks_intt_special": 2, "ks_intt_moddown": 2 * L + (0 if any(r["kernel"] == "ks_intt_special" for r in prof) else 2), "behz_ntt_q": 4 * L,
+                    "ks_inner_intt_moddown": 2 * L + 2,
                     "behz_ntt_bsk": 4 * nb, "behz_intt_q": 3 * L, "behz_intt_bsk": 3 * nb}
         ntt_ms = sum(r["ms"] for r in prof if r["kernel"] in ntt_rows)
         ntt_bf = sum(r["launches"] * ntt_rows[r["kernel"]] for r in prof if r["kernel"] in ntt_rows) * B * (N_POLY // 2) * logn
@@ -271,7 +274,7 @@ def run_ours(args):
                          "frac": ach / peaks["hbm_gbs"], "traffic": traffic_for(top["kernel"], B), "peak_source": how,
                          "algorithmic_bytes_per_launch": alg.get(top["kernel"], 0),
                          "share_of_step": top["ms"] / tot,
-                         "note": "this kernel family is INT-pipe-bound, see int_roofline"},
+                         "note": "this kernel family is bound by the FP64 / integer pipes, not HBM: see int_roofline"},
             "int_roofline": {"unit": "64-bit modular NTT butterflies/s (all limb-pipeline kernels of the step)",
                              "achieved": ntt_bf / (ntt_ms * 1e-3), "peak": bf_peak,
                              "frac": ntt_bf / (ntt_ms * 1e-3) / bf_peak, "ntt_share_of_step": ntt_ms / tot,

@@ -77,7 +77,9 @@ int abc_has_galois_key(const abc_ctx *ctx, uint32_t galois_elt);
 /* --- ciphertext handles (SealCiphertext ctor/copy/clone: src/runtime/SealCiphertext.cpp:10-34,71-78) */
 abc_status abc_ct_alloc(abc_ctx *ctx, abc_ct **out);            /* uninitialised size-2 ciphertexts */
 void abc_ct_free(abc_ct *ct);                                   /* stream-ordered; safe right after enqueue */
-abc_status abc_ct_clone(abc_ctx *ctx, const abc_ct *src, abc_ct **out);
+abc_status abc_ct_clone(abc_ctx *ctx, const abc_ct *src, abc_ct **out);   /* O(1): clones share the device buffer, copy-on-write */
+int abc_ct_shared(const abc_ct *ct);                            /* handles sharing this ciphertext's buffer (>= 1) */
+int abc_ct_deferred(const abc_ct *ct);                          /* 1 while the handle is a deferred rotation (see abc_rotate_rows) */
 size_t abc_ct_words(const abc_ctx *ctx);                        /* batch*2*L*N */
 abc_status abc_ct_export(abc_ctx *ctx, const abc_ct *ct, uint64_t *host, size_t words);
 abc_status abc_ct_import(abc_ctx *ctx, abc_ct *ct, const uint64_t *host, size_t words);
@@ -101,7 +103,15 @@ abc_status abc_add(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, const abc_ct *b);
 abc_status abc_sub(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, const abc_ct *b);
 abc_status abc_negate(abc_ctx *ctx, abc_ct *dst, const abc_ct *a);
 abc_status abc_mul_relin(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, const abc_ct *b);
+/* rotate_rows may DEFER its last key switch: the handle then stands for "Galois step e of buffer X" until something
+ * needs the data.  abc_add with a deferred operand runs that key switch with the other operand accumulated in its
+ * ModDown; every other consumer (and abc_sync does not count) materialises it first.  Results are bit-identical to
+ * the eager order.  ABC_EAGER_ROTATE=1 in the environment disables deferral; limb-sharded contexts never defer. */
 abc_status abc_rotate_rows(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, int steps);
+/* dst = add(rotate_rows(a, steps), addend) in one pass: the addend is accumulated in the ModDown of the last key
+ * switch (bit-identical to the two calls).  This is what `acc = acc +++ r` with `r = rotate(x, k)` costs when the
+ * wrappers defer the rotation (RuntimeVisitor.cpp:69,157).  dst may alias a and/or addend. */
+abc_status abc_rotate_rows_add(abc_ctx *ctx, abc_ct *dst, const abc_ct *a, int steps, const abc_ct *addend);
 
 /* --- ciphertext-plaintext ops (src/runtime/SealCiphertext.cpp:130-202). slots/n/broadcast as above.
  * The reference's all-(-1) negate fast path for multiplyPlain lives in the C++ wrapper. */

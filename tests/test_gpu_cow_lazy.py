@@ -1,0 +1,112 @@
+"""Copy-on-write clones and deferred rotations (include/abc_b200.h: abc_ct_clone, abc_rotate_rows,
+abc_rotate_rows_add) must be invisible in the results: every sequence below is compared bit for bit with the
+oracle's eager evaluation.  RuntimeVisitor clones on every variable read (src/runtime/RuntimeVisitor.cpp:436) and
+adds rotated variables (`acc = acc +++ r`), which is what these two mechanisms exist for."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SEED = 4673838
+
+
+@pytest.fixture(scope="module", params=["4096", "8192"])
+def pair(request, oracle4096, oracle8192):
+    from abc_b200 import CudaCiphertextFactory
+    n = int(request.param)
+    f = CudaCiphertextFactory(n, seed=SEED)
+    yield f, (oracle4096 if n == 4096 else oracle8192)
+    f.close()
+
+
+def fresh(f, o, rng, nonce):
+    d = rng.integers(0, 1025, size=f.N, dtype=np.int64)
+    f.set_encrypt_nonce(nonce)
+    return f.createCiphertext(d), o.encrypt_slots(d, nonce)
+
+
+def eq(ct, words):
+    return np.array_equal(ct.export()[0], words)
+
+
+def test_clone_is_shared_until_written(pair):
+    f, o = pair
+    rng = np.random.default_rng(5)
+    a, aw = fresh(f, o, rng, 31)
+    b, bw = fresh(f, o, rng, 32)
+    c = a.clone()
+    assert a.sharedCount() == 2 and c.sharedCount() == 2
+    c.addInplace(b)                       # writes c only
+    assert a.sharedCount() == 1 and c.sharedCount() == 1
+    assert eq(a, aw) and eq(c, o.add(aw, bw))
+    d = a.clone()
+    a.multiplyInplace(b)                  # writes a; the clone keeps the old value
+    assert eq(d, aw) and eq(a, o.mul_relin(aw, bw))
+    e = d.clone()
+    e.subtractPlainInplace([3, 4, 5])
+    assert eq(d, aw) and eq(e, o.sub_plain(aw, o.encode(o.expand([3, 4, 5]))))
+    g = d.clone()
+    g.rotateRowsInplace(3)
+    assert eq(d, aw) and eq(g, o.rotate_rows(aw, 3))
+    del c, d, e, g
+
+
+@pytest.mark.parametrize("steps", [1, -24, 63, 5])   # direct keys and NAF paths (63 = 64 - 1, 5 = 4 + 1)
+def test_deferred_rotation_then_add(pair, steps):
+    f, o = pair
+    rng = np.random.default_rng(6)
+    a, aw = fresh(f, o, rng, 41)
+    b, bw = fresh(f, o, rng, 42)
+    rw = o.rotate_rows(aw, steps)
+    r = a.rotateRows(steps)
+    assert r.isDeferred()
+    s1 = b.add(r)                         # fused; r keeps the plain rotation (second ModDown output)
+    assert eq(s1, o.add(bw, rw))
+    assert not r.isDeferred() and eq(r, rw)
+    r2 = a.rotateRows(steps)
+    s2 = r2.add(b)                        # deferred operand on the left
+    assert eq(s2, o.add(rw, bw)) and eq(r2, rw)
+    r3 = a.rotateRows(steps)
+    r3.addInplace(b)                      # the only holder is overwritten: single-output path
+    assert eq(r3, o.add(rw, bw))
+    assert eq(a, aw) and eq(b, bw)
+
+
+def test_deferred_rotation_other_consumers(pair):
+    f, o = pair
+    rng = np.random.default_rng(7)
+    a, aw = fresh(f, o, rng, 51)
+    b, bw = fresh(f, o, rng, 52)
+    rw = o.rotate_rows(aw, 2)
+    assert eq(a.rotateRows(2), rw)                                        # export resolves
+    assert np.array_equal(f.decryptCiphertext(a.rotateRows(2)), o.decrypt_slots(rw))
+    assert eq(a.rotateRows(2).multiply(b), o.mul_relin(rw, bw))
+    assert eq(b.subtract(a.rotateRows(2)), o.sub(bw, rw))
+    assert eq(a.rotateRows(2).rotateRows(-7), o.rotate_rows(rw, -7))      # rotation of a deferred rotation
+    assert eq(a.rotateRows(2).addPlain([9, 8, 7]), o.add_plain(rw, o.encode(o.expand([9, 8, 7]))))
+    r = a.rotateRows(2)
+    assert eq(r.add(r), o.add(rw, rw))                                    # both operands the same deferred buffer
+    r1, r2 = a.rotateRows(2), b.rotateRows(-1)
+    assert eq(r1.add(r2), o.add(rw, o.rotate_rows(bw, -1)))               # two deferred operands
+    c = a.rotateRows(2).clone()                                           # clone of a deferred handle
+    assert eq(c, rw)
+    z = a.rotateRows(0)
+    assert not z.isDeferred() and eq(z, aw)
+    a2 = a.clone()
+    a2.rotateRowsInplace(2)
+    a2.addInplace(a)                                                      # s = rot(s) + s, in place
+    assert eq(a2, o.add(rw, aw)) and eq(a, aw)
+
+
+def test_explicit_rotate_add_and_ladder(pair):
+    f, o = pair
+    rng = np.random.default_rng(8)
+    a, aw = fresh(f, o, rng, 61)
+    b, bw = fresh(f, o, rng, 62)
+    assert eq(a.rotateRowsAdd(-24, b), o.add(o.rotate_rows(aw, -24), bw))
+    assert eq(a.rotateRowsAdd(0, b), o.add(aw, bw))
+    s, sw = a, aw                                                         # the bench's rotate-and-sum ladder
+    for k in (8, 4, 2, 1):
+        s, sw = s.add(s.rotateRows(k)), o.add(sw, o.rotate_rows(sw, k))
+    assert eq(s, sw)
+    assert np.array_equal(f.decryptCiphertext(s), o.decrypt_slots(sw))
