@@ -435,6 +435,22 @@ __device__ __forceinline__ void ntt_inv_first(u64 *sm, const ModInfo &M, u32 twb
   }
 }
 
+// ---- scoped barriers between passes.  After a strided pass with gap 2^LG the transform splits into independent
+// blocks of 2^LG coefficients, and the next pass of such a block only reads what the 2^LG threads sharing tid >> LG
+// wrote (the second group of a thread, vt = tid + T, lands in a block owned by the same thread set).  So only the
+// first boundary needs the whole CTA; the later ones are a named barrier over 2^LG threads or a warp barrier, and the
+// rest of the CTA runs ahead instead of queueing up behind the slowest warp.
+template <int LG, int T> __device__ __forceinline__ void pass_sync(int tid) {
+  if constexpr ((1 << LG) >= T) {
+    __syncthreads();
+  } else if constexpr (LG <= 5) {
+    __syncwarp();
+  } else {
+    static_assert(T >> LG <= 15, "named barrier ids 1..15");
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (tid >> LG)), "n"(1 << LG) : "memory");
+  }
+}
+
 // ---- whole-limb transforms on a swizzled shared-memory limb.  Caller has filled sm[swz(e)] and synced.
 // Forward: input canonical (guarded classes accept < 4q), output canonical.  Returns after a barrier.
 template <int LOGN, int AR, bool LINSRC = false>
@@ -443,13 +459,14 @@ __device__ __forceinline__ void ntt_fwd_smem(u64 *sm, const ModInfo &M, u32 twba
   const u64 q = M.q, aux = ar_aux<AR>(q);
   const ulonglong2 *tw = (AR == AR_SHOUP) ? M.tw : (AR == AR_F64 ? M.twd : M.twf);
   const double qinv = f64_of(M.qinv_bits);
+  typedef NttDims<LOGN> D;
   ntt_fwd_mid<LOGN, 0, P::R0, AR, LINSRC>(sm, tw, twbase, q, aux, tid, qinv, qs, einv);
-  __syncthreads();
+  pass_sync<LOGN - P::R0, D::T>(tid);
   ntt_fwd_mid<LOGN, P::R0, P::R1, AR>(sm, tw, twbase, q, aux, tid, qinv);
-  __syncthreads();
+  pass_sync<LOGN - P::R0 - P::R1, D::T>(tid);
   if constexpr (P::R2 > 0) {
     ntt_fwd_mid<LOGN, P::R0 + P::R1, P::R2, AR>(sm, tw, twbase, q, aux, tid, qinv);
-    __syncthreads();
+    pass_sync<LOGN - P::R0 - P::R1 - P::R2, D::T>(tid);
   }
   ntt_fwd_last<LOGN, AR>(sm, M, twbase, q, aux, tid);
   __syncthreads();
@@ -465,14 +482,15 @@ __device__ __forceinline__ void ntt_inv_smem(u64 *sm, const ModInfo &M, u32 twba
   typedef NttPlan<LOGN> P;
   static_assert(WHOLE || (AR != AR_FP_LAZY && AR != AR_F64), "tail blocks use a guarded class");
   const u64 q = M.q, aux = ar_aux<AR>(q);
+  typedef NttDims<LOGN> D;
   ntt_inv_first<LOGN, AR, REPIN>(sm, M, twbase, q, aux, tid);
-  __syncthreads();
+  pass_sync<LOGN - P::R0 - P::R1 - P::R2, D::T>(tid);
   if constexpr (P::R2 > 0) {
     ntt_inv_mid<LOGN, P::R0 + P::R1, P::R2, false, true, AR>(sm, M, twbase, q, aux, tid);
-    __syncthreads();
+    pass_sync<LOGN - P::R0 - P::R1, D::T>(tid);
   }
   ntt_inv_mid<LOGN, P::R0, P::R1, false, P::R2 == 0, AR>(sm, M, twbase, q, aux, tid);
-  __syncthreads();
+  pass_sync<LOGN - P::R0, D::T>(tid);
   ntt_inv_mid<LOGN, 0, P::R0, WHOLE, true, AR>(sm, M, twbase, q, aux, tid);
   __syncthreads();
 }
