@@ -75,14 +75,15 @@ __global__ void __launch_bounds__(128) k_behz_lift(const u64 *__restrict__ a, co
 
 // BEHZ tensor product in q and Bsk (Evaluator::bfv_multiply "behz_ciphertext_product"), in place on X:
 // (X0,X1,X2,X3) = (a0,a1,b0,b1) -> (a0*b0, a0*b1+a1*b0, a1*b1).  grid: (N/256, W, B)
+// square != 0: both operands are the same ciphertext, only (X0,X1) were lifted: (a0*a0, a0*a1+a1*a0, a1*a1).
 __global__ void __launch_bounds__(256) k_behz_tensor(u64 *__restrict__ X, const ModInfo *__restrict__ mods,
-                                                     const int *__restrict__ rowmod, int N, int W) {
+                                                     const int *__restrict__ rowmod, int N, int W, int square) {
   const int n = blockIdx.x * 256 + threadIdx.x, w = blockIdx.y, inst = blockIdx.z;
   const ModInfo *Mp = mods + rowmod[w];
   const u64 q = Mp->q, mh = Mp->mu_hi, ml = Mp->mu_lo;
   u64 *p = X + ((size_t)inst * 4 * W + w) * N + n;
   const size_t ps = (size_t)W * N;
-  const u64 a0 = p[0], a1 = p[ps], b0 = p[2 * ps], b1 = p[3 * ps];
+  const u64 a0 = p[0], a1 = p[ps], b0 = square ? a0 : p[2 * ps], b1 = square ? a1 : p[3 * ps];
   p[0] = mul_mod(a0, b0, q, mh, ml);
   u64 lo = a0 * b1, hi = __umul64hi(a0, b1);
   mac128(lo, hi, a1, b0);

@@ -38,6 +38,7 @@ struct abc_ctx {
   int prefetch_ahead = 0;   // CTAs resident at once (2 per SM): a CTA L2-prefetches the row of the CTA that replaces it
   int ar_q = 0, ar_t = 0, force_ar = -1;  // NTT arithmetic class of the key-level primes / of t (ntt.cuh)
   int ks_skew = 8;                               // ABC_KS_SKEW: special-prime rows run this many instances ahead
+  bool no_square = false;                        // ABC_NO_SQUARE: multiply(x, x) takes the general path
   bool lazy_rotate = true;                       // ABC_EAGER_ROTATE: rotate_rows runs its last key switch immediately
   bool ks_unmerged = false, ks_unfused = false;  // ABC_KS_UNMERGED / ABC_KS_UNFUSED: A/B switches for the key-switch tail
   int idx_t = 0;
@@ -285,11 +286,12 @@ abc_status build_tables(abc_ctx *c) {
   c->ks_unmerged = getenv("ABC_KS_UNMERGED") != nullptr;
   c->ks_unfused = getenv("ABC_KS_UNFUSED") != nullptr;
   c->lazy_rotate = getenv("ABC_EAGER_ROTATE") == nullptr;
+  c->no_square = getenv("ABC_NO_SQUARE") != nullptr;
   if (const char *e = getenv("ABC_KS_SKEW")) c->ks_skew = atoi(e) < 0 ? 0 : atoi(e);
   {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    c->prefetch_ahead = 2 * sms;
+    c->prefetch_ahead = 0;  // > 0: a CTA also L2-prefetches the source row of the CTA this many blocks ahead (measured: no gain)
     if (const char *e = getenv("ABC_PREFETCH_AHEAD")) c->prefetch_ahead = atoi(e);
   }
 
@@ -557,9 +559,13 @@ abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
   const int N = c->N, L = c->L, B = c->B, W = c->W;
   u64 *X = nullptr;
   TRY(scratch(c, SC_X, &X, (size_t)B * 4 * W * N));
+  // multiply(x, x) (e.g. `d *** d` of the distance programs): the second operand's lift and forward transforms would
+  // repeat the first's, so only polys 0,1 are prepared; the products are the same modular expressions, bit for bit
+  const bool square = a == b && !c->no_square;
+  const int np = square ? 2 : 4;
   {
     Launch l(c, "behz_lift");
-    DISPATCH_L(c, (k_behz_lift<LL><<<dim3(N / 128, 4, B), 128, 0, c->stream>>>(a, b, X, c->dC, N, c->L)));
+    DISPATCH_L(c, (k_behz_lift<LL><<<dim3(N / 128, np, B), 128, 0, c->stream>>>(a, b, X, c->dC, N, c->L)));
     CK(cudaGetLastError());
   }
   LimbJob j = blank_job();
@@ -568,14 +574,14 @@ abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
   jq.rowmod = c->rm_behz_q; jq.rowdst = c->rd_behz_q;
   jb.rowmod = c->rm_behz_b; jb.rowdst = c->rd_behz_b;
   if (c->ar_q == AR_SHOUP) {
-    TRY(launch_limb(c, LIMB_FWD, AR_SHOUP, j, 4 * W, B, "behz_ntt"));
+    TRY(launch_limb(c, LIMB_FWD, AR_SHOUP, j, np * W, B, "behz_ntt"));
   } else {  // q rows on the FP64-assisted class, the 61-bit Bsk rows on the Shoup class
-    TRY(launch_limb(c, LIMB_FWD, c->ar_q, jq, 4 * L, B, "behz_ntt_q"));
-    TRY(launch_limb(c, LIMB_FWD, AR_SHOUP, jb, 4 * c->nbsk, B, "behz_ntt_bsk"));
+    TRY(launch_limb(c, LIMB_FWD, c->ar_q, jq, np * L, B, "behz_ntt_q"));
+    TRY(launch_limb(c, LIMB_FWD, AR_SHOUP, jb, np * c->nbsk, B, "behz_ntt_bsk"));
   }
   {
     Launch l(c, "behz_tensor");
-    k_behz_tensor<<<dim3(N / 256, W, B), 256, 0, c->stream>>>(X, c->d_mods, c->rm_behz, N, W);
+    k_behz_tensor<<<dim3(N / 256, W, B), 256, 0, c->stream>>>(X, c->d_mods, c->rm_behz, N, W, square ? 1 : 0);
     CK(cudaGetLastError());
   }
   if (c->ar_q == AR_SHOUP) {

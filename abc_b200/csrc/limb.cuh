@@ -288,6 +288,27 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
     const int comp = srow / job.k, I = srow - comp * job.k;
     const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(job.src + (size_t)inst * job.src_is + (size_t)I * job.L * D::N);
     const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(job.mul + (size_t)(comp * job.k + I) * D::N);
+    if (job.prefetch_ahead >= 0) {
+      // the L T rows are contiguous and come straight from DRAM (written by the ModUp launch, larger than L2 at
+      // bench batch sizes): pull them into L2 now so only the first loads of the loop below pay DRAM latency; same
+      // for the rows the ModDown epilogue reads tens of microseconds from now (addend, sigma(c0))
+      const char *p = reinterpret_cast<const char *>(t);
+      for (int line = tid; line < job.L * (int)(D::N * 8 / 128); line += D::T)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)line * 128));
+      if (POST == POST_MODDOWN && w >= 2) {
+        const int wq0 = w - 2, comp0 = wq0 / job.nrows, i0 = job.i0 + (wq0 - comp0 * job.nrows);
+        if (job.add) {
+          const char *pa = reinterpret_cast<const char *>(job.add + (size_t)inst * job.add_is + (size_t)drow * D::N);
+          for (int line = tid; line < (int)(D::N * 8 / 128); line += D::T)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + (size_t)line * 128));
+        }
+        if (comp0 == 0 && job.base0) {
+          const char *pb = reinterpret_cast<const char *>(job.base0 + (size_t)inst * job.base0_is + (size_t)i0 * D::N);
+          for (int line = tid; line < (int)(D::N * 8 / 128); line += D::T)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + (size_t)line * 128));
+        }
+      }
+    }
     for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
       *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = ks_inner_pair(t + e2, kp + e2, job.L, D::N / 2, job.k * D::N, M);
   } else if (PRE == PRE_ENCODE) {

@@ -110,3 +110,18 @@ def test_explicit_rotate_add_and_ladder(pair):
         s, sw = s.add(s.rotateRows(k)), o.add(sw, o.rotate_rows(sw, k))
     assert eq(s, sw)
     assert np.array_equal(f.decryptCiphertext(s), o.decrypt_slots(sw))
+
+
+def test_multiply_by_itself_takes_squaring_path(pair):
+    """multiply(x, x) lifts and transforms one operand only (lib.cu behz_multiply); same coefficients as the
+    general path, which the oracle always takes."""
+    f, o = pair
+    rng = np.random.default_rng(9)
+    a, aw = fresh(f, o, rng, 71)
+    want = o.mul_relin(aw, aw)
+    assert eq(a.multiply(a), want)
+    assert eq(a.multiply(a.clone()), want)          # clones share the buffer: also the squaring path
+    assert np.array_equal(f.probe_multiply(a, a)[0], o.multiply(aw, aw))   # the size-3 product before relinearisation
+    b = a.clone()
+    b.multiplyInplace(b)
+    assert eq(b, want) and eq(a, aw)
