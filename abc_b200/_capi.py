@@ -47,6 +47,7 @@ SYMBOLS = {
     "abc_encode_encrypt": (i32, [vp, vp, sz, i32, vpp]),
     "abc_decrypt_decode": (i32, [vp, vp, vp]),
     "abc_set_encrypt_nonce": (i32, [vp, u64]),
+    "abc_noise_budget": (i32, [vp, vp, vp]),
     "abc_add": (i32, [vp, vp, vp, vp]),
     "abc_sub": (i32, [vp, vp, vp, vp]),
     "abc_negate": (i32, [vp, vp, vp]),

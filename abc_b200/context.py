@@ -180,6 +180,12 @@ class CudaCiphertextFactory:
         self._ck(self._lib.abc_decrypt_decode(self._h, ct._h, out.ctypes.data))
         return out[0] if self.batch == 1 else out
 
+    def noiseBits(self, ct):
+        """SealCiphertext::noiseBits (SealCiphertext.cpp:80-83): invariant noise budget, int32 [batch] (int when batch == 1)."""
+        out = np.zeros(self.batch, dtype=np.int32)
+        self._ck(self._lib.abc_noise_budget(self._h, ct._h, out.ctypes.data))
+        return int(out[0]) if self.batch == 1 else out
+
     def getString(self, ct):
         vals = np.atleast_2d(self.decryptCiphertext(ct))[0]
         return "[" + ",".join(" %d" % v for v in vals) + " ]"
@@ -261,6 +267,9 @@ class CudaCiphertext:
 
     def getFactory(self):
         return self.factory
+
+    def noiseBits(self):
+        return self.factory.noiseBits(self)
 
     def _other(self, operand):
         if not isinstance(operand, CudaCiphertext) or operand.factory is not self.factory:

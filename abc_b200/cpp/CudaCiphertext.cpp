@@ -54,6 +54,14 @@ const CudaCiphertextFactory &CudaCiphertext::getFactory() const {
   throw std::runtime_error("Cast of AbstractFactory to CudaFactory failed. CudaCiphertext is probably invalid.");
 }
 
+int CudaCiphertext::noiseBits() const {
+  std::vector<int32_t> bits(abc_batch(getFactory().context()));
+  getFactory().check(abc_noise_budget(getFactory().context(), handle, bits.data()));
+  int m = bits[0];
+  for (int b : bits) m = b < m ? b : m;
+  return m;
+}
+
 std::unique_ptr<AbstractCiphertext> CudaCiphertext::clone() const { return std::make_unique<CudaCiphertext>(*this); }
 
 // ---- rotation (Evaluator::rotate_rows, SealCiphertext.cpp:52-61)

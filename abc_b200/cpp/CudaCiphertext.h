@@ -23,12 +23,16 @@ class CudaCiphertext : public AbstractCiphertext {
   CudaCiphertext(const std::reference_wrapper<const CudaCiphertextFactory> cudaFactory, abc_ct *owned);
   ~CudaCiphertext() override;
 
-  CudaCiphertext(const CudaCiphertext &other);                 // deep copy (device-to-device)
+  CudaCiphertext(const CudaCiphertext &other);                 // O(1): shares the device buffer, copy-on-write (abc_ct_clone)
   CudaCiphertext(CudaCiphertext &&other) noexcept;
   CudaCiphertext &operator=(const CudaCiphertext &other);
   CudaCiphertext &operator=(CudaCiphertext &&other);           // throws across factories (SealCiphertext.cpp:29-31)
 
   [[nodiscard]] abc_ct *getHandle() const { return handle; }
+
+  /// Invariant noise budget in bits (SealCiphertext::noiseBits, src/runtime/SealCiphertext.cpp:80-83); the minimum
+  /// over the instances of a batched factory.
+  [[nodiscard]] int noiseBits() const;
 
   [[nodiscard]] std::unique_ptr<AbstractCiphertext> multiply(const AbstractCiphertext &operand) const override;
   void multiplyInplace(const AbstractCiphertext &operand) override;

@@ -435,3 +435,53 @@ __global__ void __launch_bounds__(1024) k_peak_butterfly(u64 *out, int iters, u6
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ y0 ^ x1 ^ y1 ^ x2 ^ y2 ^ x3 ^ y3;
 }
+
+// Decryptor::invariant_noise_budget, the multi-precision part: x [B][L][N] = c0 + c1*s.  Per coefficient: CRT-compose
+// t*x (RNSBase::compose_array: sum_i [t x_i (Q/q_i)^-1]_{q_i} * (Q/q_i) mod Q), centre it
+// (poly_infty_norm_coeffmod), take its bit length; the block's maximum goes to bits[inst] (atomicMax).
+// tab: L rows of (Q/q_i), then Q, then (Q+1)/2, L little-endian words each.  grid: (N/128, B).  Diagnostic path.
+__global__ void __launch_bounds__(128) k_noise_bits(const u64 *__restrict__ x, const DevConst *__restrict__ C,
+                                                    const u64 *__restrict__ tab, int N, int L, int *__restrict__ bits) {
+  const int n = blockIdx.x * 128 + threadIdx.x, inst = blockIdx.y;
+  u64 acc[ABC_MAXL + 1];
+  for (int w = 0; w <= L; ++w) acc[w] = 0;
+  for (int i = 0; i < L; ++i) {
+    const u64 y = mul_shoup(x[((size_t)inst * L + i) * N + n], C->scale_c[i], C->scale_c_s[i], C->q[i]);
+    const u64 *P = tab + (size_t)i * L;
+    u64 carry = 0;
+    for (int w = 0; w < L; ++w) {
+      const u64 lo = y * P[w], hi = __umul64hi(y, P[w]);
+      const u64 s1 = acc[w] + lo, s2 = s1 + carry;
+      carry = hi + (s1 < lo) + (s2 < carry);
+      acc[w] = s2;
+    }
+    acc[L] += carry;
+  }
+  const u64 *Q = tab + (size_t)L * L, *H = Q + L;
+  auto ge = [&](const u64 *m) {  // acc >= m (m has L words)
+    if (acc[L]) return true;
+    for (int w = L - 1; w >= 0; --w) if (acc[w] != m[w]) return acc[w] > m[w];
+    return true;
+  };
+  while (ge(Q)) {
+    u64 borrow = 0;
+    for (int w = 0; w < L; ++w) {
+      const u64 a = acc[w], d = a - Q[w] - borrow;
+      borrow = (a < Q[w]) || (a == Q[w] && borrow);
+      acc[w] = d;
+    }
+    acc[L] -= borrow;
+  }
+  if (ge(H)) {  // centre: Q - acc
+    u64 borrow = 0;
+    for (int w = 0; w < L; ++w) {
+      const u64 a = Q[w], d = a - acc[w] - borrow;
+      borrow = (a < acc[w]) || (a == acc[w] && borrow);
+      acc[w] = d;
+    }
+  }
+  int b = 0;
+  for (int w = L - 1; w >= 0 && !b; --w) if (acc[w]) b = 64 * w + (64 - __clzll((long long)acc[w]));
+  b = __reduce_max_sync(0xffffffffu, b);
+  if ((threadIdx.x & 31) == 0) atomicMax(bits + inst, b);
+}

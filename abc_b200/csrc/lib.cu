@@ -68,6 +68,7 @@ struct abc_ctx {
   u32 *ks_flags = nullptr; u32 ks_serial = 0;                                 // [B][2] ready flags of the merged launch
   int *rs_zero = nullptr;   // [2k]  0
   u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;
+  u64 *d_noise_tab = nullptr; int q_bits = 0;   // abc_noise_budget: (Q/q_i), Q, (Q+1)/2 as L-word integers; bit_count(Q)
   std::map<u32, u64 *> galois;
   bool have_keys = false;
   std::string err;
@@ -1046,17 +1047,15 @@ abc_status abc_encode_encrypt(abc_ctx *c, const int64_t *slots, size_t n, int br
 }
 abc_status abc_set_encrypt_nonce(abc_ctx *c, uint64_t nonce) { c->enc_nonce = nonce; return ABC_OK; }
 
-abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) {
+// c0 + c1 * s mod q in coefficient form (Decryptor::dot_product_ct_sk_array), x [B][L][N] in the SC_DECX scratch slot
+static abc_status dot_ct_sk(abc_ctx *c, const abc_ct *ct, u64 **x_out) {
   if (!valid_ct(c, ct)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
   if (!c->d_sk) return fail(c, ABC_ERR_STATE, "secret key not present");
   CK(cudaSetDevice(c->device));
   TRY(ct_resolve(c, ct));
   const int N = c->N, L = c->L, B = c->B;
-  u64 *x = nullptr, *plain = nullptr;
-  long long *d_out = nullptr;
+  u64 *x = nullptr;
   TRY(scratch(c, SC_DECX, &x, (size_t)B * L * N));
-  TRY(scratch(c, SC_DECP, &plain, (size_t)B * N));
-  CK(cudaMallocAsync((void **)&d_out, (size_t)B * N * sizeof(long long), c->stream));
   TRY(allgather_limbs(c, ct->b->d, 3));  // limb-sharded: scale-and-round needs every limb
   LimbJob j = blank_job();
   j.src = ct->b->d; j.src_is = (long long)2 * L * N; j.rowsrc = c->rs_c1;
@@ -1064,6 +1063,57 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
   j.add = ct->b->d; j.add_is = (long long)2 * L * N;
   j.dst = x; j.dst_is = (long long)L * N; j.rowmod = c->rm_ct;
   TRY(launch_limb(c, LIMB_FWD_MUL_INV_ADD, c->ar_q, j, L, B, "dec_c1s_plus_c0"));
+  *x_out = x;
+  return ABC_OK;
+}
+
+// Decryptor::invariant_noise_budget (SealCiphertext::noiseBits, SealCiphertext.cpp:80-83), per instance:
+// bit_count(Q) - bit_count(|| t * (c0 + c1*s) mod Q ||_inf, centred) - 1, floored at 0.
+abc_status abc_noise_budget(abc_ctx *c, const abc_ct *ct, int32_t *out_bits) {
+  u64 *x = nullptr;
+  TRY(dot_ct_sk(c, ct, &x));
+  const int N = c->N, L = c->L, B = c->B;
+  if (!c->d_noise_tab) {  // multi-precision constants: (Q/q_i) for every i, Q, (Q+1)/2; L words each, little endian
+    std::vector<u64> tab((size_t)(L + 2) * L, 0);
+    auto mul_small = [&](u64 *w, u64 m) { u64 carry = 0; for (int i = 0; i < L; ++i) { unsigned __int128 t = (unsigned __int128)w[i] * m + carry; w[i] = (u64)t; carry = (u64)(t >> 64); } };
+    for (int i = 0; i <= L; ++i) {  // row L: the full product Q
+      u64 *w = &tab[(size_t)i * L];
+      w[0] = 1;
+      for (int j = 0; j < L; ++j) if (j != i) mul_small(w, c->primes[j]);
+    }
+    u64 *Q = &tab[(size_t)L * L], *H = Q + L;
+    u64 carry = 1;                                   // (Q + 1) / 2: Q is odd
+    for (int i = 0; i < L; ++i) { u64 v = Q[i] + carry; carry = v < carry ? 1 : 0; H[i] = v; }
+    for (int i = 0; i < L; ++i) H[i] = (H[i] >> 1) | (i + 1 < L ? H[i + 1] << 63 : carry << 63);
+    TRY(upload(c, &c->d_noise_tab, tab));
+    int qb = 0;
+    for (int i = L - 1; i >= 0 && !qb; --i) if (Q[i]) qb = 64 * i + hm::bits_of(Q[i]);
+    c->q_bits = qb;
+  }
+  int *d_bits = nullptr;
+  CK(cudaMallocAsync((void **)&d_bits, (size_t)B * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(d_bits, 0, (size_t)B * sizeof(int), c->stream));
+  {
+    Launch l(c, "noise_norm");
+    k_noise_bits<<<dim3(N / 128, B), 128, 0, c->stream>>>(x, c->dC, c->d_noise_tab, N, L, d_bits);
+    CK(cudaGetLastError());
+  }
+  std::vector<int> bits(B);
+  CK(cudaMemcpyAsync(bits.data(), d_bits, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  sfree(c, d_bits);
+  for (int i = 0; i < B; ++i) { const int d = c->q_bits - bits[i] - 1; out_bits[i] = d > 0 ? d : 0; }
+  return ABC_OK;
+}
+
+abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) {
+  u64 *x = nullptr, *plain = nullptr;
+  TRY(dot_ct_sk(c, ct, &x));
+  const int N = c->N, B = c->B;
+  long long *d_out = nullptr;
+  TRY(scratch(c, SC_DECP, &plain, (size_t)B * N));
+  CK(cudaMallocAsync((void **)&d_out, (size_t)B * N * sizeof(long long), c->stream));
+  LimbJob j = blank_job();
   {
     Launch l(c, "dec_scale_round");
     DISPATCH_L(c, (k_dec_finish<LL><<<dim3(N / 128, 1, B), 128, 0, c->stream>>>(x, plain, c->dC, N, c->L)));

@@ -92,6 +92,9 @@ abc_status abc_ct_import(abc_ctx *ctx, abc_ct *ct, const uint64_t *host, size_t 
 abc_status abc_encode_encrypt(abc_ctx *ctx, const int64_t *slots, size_t n, int broadcast, abc_ct **out);
 abc_status abc_decrypt_decode(abc_ctx *ctx, const abc_ct *ct, int64_t *out_slots /* batch*N */);
 /* encryption randomness counter: instance b of the next encryption uses nonce*batch + b */
+/* SealCiphertext::noiseBits = Decryptor::invariant_noise_budget (src/runtime/SealCiphertext.cpp:80-83): remaining
+ * noise budget in bits, one value per instance of the batch; 0 means decryption is no longer guaranteed. */
+abc_status abc_noise_budget(abc_ctx *ctx, const abc_ct *ct, int32_t *out_bits_per_instance);
 abc_status abc_set_encrypt_nonce(abc_ctx *ctx, uint64_t nonce);
 
 /* --- ciphertext-ciphertext ops.  dst may alias a (the *Inplace variants of the reference).

@@ -626,6 +626,70 @@ void obfv_decrypt(const obfv_ctx *c, const u64 *ct, size_t size, u64 *plain) {
   free(x); free(tmp); free(spow);
 }
 
+/* ------------------------------------------------------------------ noise budget (decryptor.cpp)
+ * Decryptor::invariant_noise_budget, reached from SealCiphertext::noiseBits (SealCiphertext.cpp:80-83):
+ * noise = dot_product_ct_sk_array(ct); noise *= t (mod q_i); CRT-compose (RNSBase::compose_array);
+ * norm = poly_infty_norm_coeffmod(noise, Q); budget = max(0, bit_count(Q) - bit_count(norm) - 1). */
+static int mp_bits(const u64 *w, size_t n) {
+  for (size_t i = n; i-- > 0;)
+    if (w[i]) { int b = 0; for (u64 v = w[i]; v; v >>= 1) b++; return (int)(64 * i) + b; }
+  return 0;
+}
+static int mp_ge(const u64 *a, const u64 *b, size_t n) {
+  for (size_t i = n; i-- > 0;) if (a[i] != b[i]) return a[i] > b[i];
+  return 1;
+}
+static void mp_sub(u64 *a, const u64 *b, size_t n) { /* a -= b */
+  u64 borrow = 0;
+  for (size_t i = 0; i < n; i++) { u128 d = (u128)a[i] - b[i] - borrow; a[i] = (u64)d; borrow = (u64)(d >> 64) & 1; }
+}
+int obfv_noise_budget(const obfv_ctx *c, const u64 *ct, size_t size) {
+  const size_t N = c->N, L = c->L;
+  u64 *x = malloc(L * N * 8), *tmp = malloc(N * 8), *spow = malloc(N * 8);
+  for (size_t i = 0; i < L; i++) {
+    const u64 q = c->q[i];
+    memset(x + i * N, 0, N * 8);
+    memcpy(spow, c->sk + i * N, N * 8);
+    for (size_t pidx = 1; pidx < size; pidx++) {
+      memcpy(tmp, ct + (pidx * L + i) * N, N * 8);
+      ntt_fwd(&c->nq[i], tmp, N);
+      for (size_t j = 0; j < N; j++) x[i * N + j] = addmod(x[i * N + j], bmul(tmp[j], spow[j], &c->bq[i]), q);
+      if (pidx + 1 < size) for (size_t j = 0; j < N; j++) spow[j] = bmul(spow[j], c->sk[i * N + j], &c->bq[i]);
+    }
+    ntt_inv(&c->nq[i], x + i * N, N);
+    for (size_t j = 0; j < N; j++) x[i * N + j] = bmul(addmod(x[i * N + j], ct[i * N + j], q), bred64(c->t, &c->bq[i]), &c->bq[i]);
+  }
+  /* multi-precision constants: punctured products Q/q_i, Q, (Q+1)/2 (L words, little endian) */
+  u64 P[MAXK][MAXK + 1], Q[MAXK + 1], H[MAXK + 1], acc[MAXK + 2];
+  for (size_t i = 0; i <= L; i++) {
+    u64 *w = i < L ? P[i] : Q;
+    memset(w, 0, (MAXK + 1) * 8); w[0] = 1;
+    for (size_t j = 0; j < L; j++) if (j != i) {
+      u64 carry = 0;
+      for (size_t a = 0; a < L; a++) { u128 t = (u128)w[a] * c->q[j] + carry; w[a] = (u64)t; carry = (u64)(t >> 64); }
+    }
+  }
+  { u128 cy = 1; for (size_t a = 0; a <= L; a++) { cy += Q[a]; H[a] = (u64)cy; cy >>= 64; }
+    for (size_t a = 0; a <= L; a++) H[a] = (H[a] >> 1) | (a < L ? H[a + 1] << 63 : 0); }
+  int maxbits = 0;
+  for (size_t j = 0; j < N; j++) {
+    memset(acc, 0, sizeof acc);
+    for (size_t i = 0; i < L; i++) {
+      const u64 y = bmul(x[i * N + j], c->inv_punct_q[i], &c->bq[i]);
+      u64 carry = 0;
+      for (size_t a = 0; a < L; a++) { u128 t = (u128)y * P[i][a] + acc[a] + carry; acc[a] = (u64)t; carry = (u64)(t >> 64); }
+      acc[L] += carry;
+    }
+    while (mp_ge(acc, Q, L + 1)) mp_sub(acc, Q, L + 1);
+    if (mp_ge(acc, H, L + 1)) { u64 r[MAXK + 1]; memcpy(r, Q, (L + 1) * 8); mp_sub(r, acc, L + 1); memcpy(acc, r, (L + 1) * 8); }
+    const int b = mp_bits(acc, L + 1);
+    if (b > maxbits) maxbits = b;
+  }
+  free(x); free(tmp); free(spow);
+  const int d = mp_bits(Q, L + 1) - maxbits - 1;
+  return d > 0 ? d : 0;
+}
+
 /* ------------------------------------------------------------------ add / sub / negate (evaluator.cpp)
  * reached from SealCiphertext.cpp:92,98,114,118,157,193 */
 void obfv_add(const obfv_ctx *c, const u64 *a, const u64 *b, u64 *out) {

@@ -69,6 +69,8 @@ void obfv_decode(const obfv_ctx *c, const uint64_t *plain, int64_t *slots);
 /* ciphertexts: [size][L][N] coefficient form, canonical residues. */
 void obfv_encrypt(const obfv_ctx *c, const uint64_t *plain, uint64_t nonce, uint64_t *ct2);
 void obfv_decrypt(const obfv_ctx *c, const uint64_t *ct, size_t size, uint64_t *plain);
+/* Decryptor::invariant_noise_budget (SealCiphertext::noiseBits, SealCiphertext.cpp:80-83) */
+int obfv_noise_budget(const obfv_ctx *c, const uint64_t *ct, size_t size);
 void obfv_add(const obfv_ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *out);
 void obfv_sub(const obfv_ctx *c, const uint64_t *a, const uint64_t *b, uint64_t *out);
 void obfv_negate(const obfv_ctx *c, const uint64_t *a, uint64_t *out);

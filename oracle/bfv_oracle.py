@@ -50,6 +50,7 @@ def _load():
         "obfv_encode": (None, [vp, i64p, u64p]), "obfv_decode": (None, [vp, u64p, i64p]),
         "obfv_encrypt": (None, [vp, u64p, u64, u64p]),
         "obfv_decrypt": (None, [vp, u64p, sz, u64p]),
+        "obfv_noise_budget": (C.c_int, [vp, u64p, sz]),
         "obfv_add": (None, [vp, u64p, u64p, u64p]), "obfv_sub": (None, [vp, u64p, u64p, u64p]),
         "obfv_negate": (None, [vp, u64p, u64p]),
         "obfv_add_plain": (None, [vp, u64p, u64p, u64p]), "obfv_sub_plain": (None, [vp, u64p, u64p, u64p]),
@@ -207,6 +208,11 @@ class Oracle:
         ct = np.ascontiguousarray(ct, dtype=np.uint64)
         lib().obfv_decrypt(self._c, ct, ct.shape[0], plain)
         return plain
+
+    def noise_budget(self, ct):
+        """Decryptor::invariant_noise_budget, SealCiphertext::noiseBits (SealCiphertext.cpp:80-83)."""
+        ct = np.ascontiguousarray(ct, dtype=np.uint64)
+        return int(lib().obfv_noise_budget(self._c, ct, ct.shape[0]))
 
     def decrypt_slots(self, ct):
         return self.decode(self.decrypt(ct))

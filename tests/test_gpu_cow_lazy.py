@@ -125,3 +125,20 @@ def test_multiply_by_itself_takes_squaring_path(pair):
     b = a.clone()
     b.multiplyInplace(b)
     assert eq(b, want) and eq(a, aw)
+
+
+def test_noise_budget_matches_oracle(pair):
+    """abc_noise_budget = Decryptor::invariant_noise_budget (SealCiphertext::noiseBits, SealCiphertext.cpp:80-83)."""
+    f, o = pair
+    rng = np.random.default_rng(10)
+    a, aw = fresh(f, o, rng, 81)
+    assert a.noiseBits() == o.noise_budget(aw) > 0
+    r = a.rotateRows(5)
+    assert r.noiseBits() == o.noise_budget(o.rotate_rows(aw, 5))
+    m, mw = a, aw
+    seen = []
+    for _ in range(5):
+        m, mw = m.multiply(m), o.mul_relin(mw, mw)
+        seen.append(m.noiseBits())
+        assert seen[-1] == o.noise_budget(mw)
+    assert seen[0] < a.noiseBits() and seen[-1] == 0

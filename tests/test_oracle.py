@@ -207,3 +207,24 @@ def test_sampler_distributions(oracle4096):
     e = o.ntt_inv(0, ((pk[0, 0].astype(object) + pk[1, 0].astype(object) * s) % q0).astype(np.uint64))
     ev = np.where(e > q0 // 2, e.astype(np.int64) - q0, e.astype(np.int64))
     assert np.abs(ev).max() <= 21 and 2.5 < ev.std() < 4.0
+
+
+def test_noise_budget_tracks_decryptability(oracle4096):
+    """invariant_noise_budget (SealCiphertext::noiseBits): positive while decryption is exact, shrinking with every
+    multiplication, 0 once the noise has overrun q/t (N=4096: 72-bit q, 20-bit t, two multiplications fit)."""
+    o = oracle4096
+    rng = np.random.default_rng(3)
+    d = rng.integers(0, 4, size=o.N, dtype=np.int64)
+    ct = o.encrypt_slots(d, 5)
+    fresh = o.noise_budget(ct)
+    assert 25 <= fresh <= 50
+    assert o.noise_budget(o.add(ct, ct)) in (fresh, fresh - 1, fresh - 2)
+    want, budgets = d.copy(), [fresh]
+    for _ in range(4):
+        ct = o.mul_relin(ct, ct)
+        want = (want * want) % o.t
+        budgets.append(o.noise_budget(ct))
+        ok = np.array_equal(o.decrypt_slots(ct) % o.t, want)
+        assert ok or budgets[-1] == 0, "a positive budget guarantees decryption"
+    assert budgets[1] < budgets[0] and budgets[-1] == 0
+    assert all(a >= b for a, b in zip(budgets, budgets[1:]))
