@@ -5,7 +5,7 @@ abc_b200/cpp (C++ CudaCiphertextFactory / CudaCiphertext behind ABC's AbstractCi
 and this Python binding of the C ABI.  There is no CPU fallback.
 """
 from .context import (AbcError, CudaCiphertext, CudaCiphertextFactory, CudaPlaintext, KEY_GALOIS, KEY_PUBLIC,
-                      KEY_RELIN, KEY_SECRET)
+                      KEY_RELIN, KEY_SECRET, seal_parameters_from_bytes)
 
 __all__ = ["AbcError", "CudaCiphertext", "CudaCiphertextFactory", "CudaPlaintext", "KEY_SECRET", "KEY_PUBLIC",
-           "KEY_RELIN", "KEY_GALOIS"]
+           "KEY_RELIN", "KEY_GALOIS", "seal_parameters_from_bytes"]

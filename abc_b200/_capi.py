@@ -83,6 +83,16 @@ SYMBOLS = {
     "abc_measure_int_peak": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "abc_measure_butterfly_peak": (i32, [vp, i32, C.POINTER(C.c_double)]),
     "abc_ntt_arith_class": (i32, [vp]),
+    "abc_seal_parms_id": (i32, [vp, i32, vp]),
+    "abc_seal_params_save": (i32, [vp, i32, vp, sz, C.POINTER(sz)]),
+    "abc_seal_params_parse": (i32, [vp, sz, C.POINTER(AbcParams), vp, sz]),
+    "abc_seal_ct_save": (i32, [vp, vp, u32, i32, vp, sz, C.POINTER(sz)]),
+    "abc_seal_ct_load": (i32, [vp, vp, u32, vp, sz]),
+    "abc_seal_key_save": (i32, [vp, i32, i32, vp, sz, C.POINTER(sz)]),
+    "abc_seal_key_load": (i32, [vp, i32, vp, sz]),
+    "abc_ct_export_instance": (i32, [vp, vp, u32, vp, sz]),
+    "abc_ct_import_instance": (i32, [vp, vp, u32, vp, sz]),
+    "abc_galois_elts": (i32, [vp, vp, sz, C.POINTER(sz)]),
 }
 
 _lib = None

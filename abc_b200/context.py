@@ -15,6 +15,17 @@ import numpy as np
 
 from . import _capi
 
+
+def seal_parameters_from_bytes(data):
+    """EncryptionParameters::load: -> dict(poly_degree, primes, plain_modulus) for CudaCiphertextFactory(...)."""
+    lib = _capi.load()
+    p = _capi.AbcParams()
+    primes = (C.c_uint64 * 64)()
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    if lib.abc_seal_params_parse(buf, len(data), C.byref(p), primes, 64) != 0:
+        raise AbcError(lib.abc_last_error(None).decode())
+    return dict(poly_degree=p.poly_degree, primes=[int(primes[i]) for i in range(p.n_primes)], plain_modulus=int(p.plain_modulus))
+
 KEY_SECRET, KEY_PUBLIC, KEY_RELIN, KEY_GALOIS = 0, 1, 2, 3
 
 
@@ -189,6 +200,47 @@ class CudaCiphertextFactory:
     def getString(self, ct):
         vals = np.atleast_2d(self.decryptCiphertext(ct))[0]
         return "[" + ",".join(" %d" % v for v in vals) + " ]"
+
+    # -- Microsoft SEAL 3.6 binary streams (include/abc_b200.h "SEAL 3.6 binary streams"; csrc/sealio.cu)
+    def _save(self, call):
+        n = C.c_size_t()
+        call(None, 0, C.byref(n))                      # size query (fails with "buffer too small", fills n)
+        buf = (C.c_uint8 * n.value)()
+        self._ck(call(buf, n.value, C.byref(n)))
+        return bytes(buf[:n.value])
+
+    def sealParmsId(self, key_level=False):
+        out = (C.c_uint64 * 4)()
+        self._ck(self._lib.abc_seal_parms_id(self._h, int(key_level), out))
+        return bytes(out)
+
+    def saveSealParameters(self, compr=0):
+        return self._save(lambda b, cap, n: self._lib.abc_seal_params_save(self._h, compr, b, cap, n))
+
+    def saveSealCiphertext(self, ct, instance=0, compr=0):
+        """seal::Ciphertext::save of one instance of the batch."""
+        return self._save(lambda b, cap, n: self._lib.abc_seal_ct_save(self._h, ct._h, instance, compr, b, cap, n))
+
+    def loadSealCiphertext(self, data, instance=0, into=None):
+        """seal::Ciphertext::load into one instance of `into` (a new handle when omitted)."""
+        ct = into if into is not None else self.allocCiphertext()
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        self._ck(self._lib.abc_seal_ct_load(self._h, ct._h, instance, buf, len(data)))
+        return ct
+
+    def saveSealKey(self, kind, compr=0):
+        return self._save(lambda b, cap, n: self._lib.abc_seal_key_save(self._h, kind, compr, b, cap, n))
+
+    def loadSealKey(self, kind, data):
+        buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+        self._ck(self._lib.abc_seal_key_load(self._h, kind, buf, len(data)))
+
+    def galois_elts(self):
+        n = C.c_size_t()
+        self._ck(self._lib.abc_galois_elts(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint32)
+        self._ck(self._lib.abc_galois_elts(self._h, out.ctypes.data, out.size, C.byref(n)))
+        return [int(e) for e in out]
 
     # -- probes / measurement
     def probe_ntt(self, mod_index, rows, inverse=False):

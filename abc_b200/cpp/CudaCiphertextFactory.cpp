@@ -41,6 +41,35 @@ CudaCiphertextFactory::CudaCiphertextFactory(unsigned int numElementsPerCipherte
 
 CudaCiphertextFactory::~CudaCiphertextFactory() { abc_ctx_destroy(ctx); }
 
+std::unique_ptr<AbstractCiphertext> CudaCiphertextFactory::loadCiphertext(const std::vector<uint8_t> &sealStream,
+                                                                          unsigned int instance) const {
+  auto result = std::make_unique<CudaCiphertext>(*this);
+  check(abc_seal_ct_load(ctx, result->getHandle(), instance, sealStream.data(), sealStream.size()));
+  return result;
+}
+std::vector<uint8_t> CudaCiphertextFactory::saveCiphertext(const AbstractCiphertext &abstractCiphertext,
+                                                           unsigned int instance, int compr) const {
+  auto c = dynamic_cast<const CudaCiphertext *>(&abstractCiphertext);
+  if (!c) throw std::runtime_error("Cast of AbstractCiphertext to CudaCiphertext failed!");
+  size_t len = 0;
+  abc_seal_ct_save(ctx, c->getHandle(), instance, compr, nullptr, 0, &len);  // size query
+  std::vector<uint8_t> out(len);
+  check(abc_seal_ct_save(ctx, c->getHandle(), instance, compr, out.data(), out.size(), &len));
+  out.resize(len);
+  return out;
+}
+void CudaCiphertextFactory::loadKey(int kind, const std::vector<uint8_t> &sealStream) const {
+  check(abc_seal_key_load(ctx, kind, sealStream.data(), sealStream.size()));
+}
+std::vector<uint8_t> CudaCiphertextFactory::saveKey(int kind, int compr) const {
+  size_t len = 0;
+  abc_seal_key_save(ctx, kind, compr, nullptr, 0, &len);
+  std::vector<uint8_t> out(len);
+  check(abc_seal_key_save(ctx, kind, compr, out.data(), out.size(), &len));
+  out.resize(len);
+  return out;
+}
+
 unsigned int CudaCiphertextFactory::getCiphertextSlotSize() const { return ciphertextSlotSize; }
 unsigned int CudaCiphertextFactory::getBatchSize() const { return abc_batch(ctx); }
 void CudaCiphertextFactory::synchronize() const { check(abc_sync(ctx)); }

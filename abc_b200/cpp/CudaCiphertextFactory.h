@@ -56,6 +56,13 @@ class CudaCiphertextFactory : public AbstractCiphertextFactory {
   void decryptCiphertextBatch(AbstractCiphertext &abstractCiphertext, std::vector<int64_t> &out) const;
   /// Raw coefficients [batch][2][L][N] of a ciphertext (the bit-exactness probe).
   std::vector<uint64_t> exportCoefficients(const AbstractCiphertext &abstractCiphertext) const;
+  /// Microsoft SEAL 3.6 binary streams (seal::Ciphertext::save/load, SecretKey/PublicKey/RelinKeys/GaloisKeys::save/load):
+  /// the way artefacts of a SEAL-backed SealCiphertextFactory move to this backend and back.  compr: 0 none, 1 zlib,
+  /// 2 zstd.  `instance` selects one ciphertext of a batched handle.  kind: ABC_KEY_SECRET .. ABC_KEY_GALOIS.
+  std::unique_ptr<AbstractCiphertext> loadCiphertext(const std::vector<uint8_t> &sealStream, unsigned int instance = 0) const;
+  std::vector<uint8_t> saveCiphertext(const AbstractCiphertext &abstractCiphertext, unsigned int instance = 0, int compr = 0) const;
+  void loadKey(int kind, const std::vector<uint8_t> &sealStream) const;
+  std::vector<uint8_t> saveKey(int kind, int compr = 0) const;
   /// Blocks until all enqueued work of this factory has finished.
   void synchronize() const;
   /// Kernels launched so far.

@@ -940,6 +940,17 @@ abc_status abc_key_import(abc_ctx *c, int kind, uint32_t elt, const uint64_t *ho
   return ABC_OK;
 }
 int abc_has_galois_key(const abc_ctx *c, uint32_t elt) { return c->galois.count(elt) ? 1 : 0; }
+abc_status abc_galois_elts(const abc_ctx *c, uint32_t *out, size_t cap, size_t *n) {
+  if (n) *n = c->galois.size();
+  if (!out) return ABC_OK;
+  if (cap < c->galois.size()) return ABC_ERR_PARAM;
+  size_t i = 0;
+  for (auto &kv : c->galois) out[i++] = kv.first;
+  return ABC_OK;
+}
+void abc_set_error(abc_ctx *c, const char *msg) {  // for the other translation units of the library (sealio.cu)
+  if (c) c->err = msg; else g_create_error = msg;
+}
 
 // ---- handles
 abc_status abc_ct_alloc(abc_ctx *c, abc_ct **out) {
@@ -1007,6 +1018,29 @@ abc_status abc_ct_export(abc_ctx *c, const abc_ct *ct, uint64_t *host, size_t wo
   if (!valid_ct(c, ct) || words != abc_ct_words(c)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle or size");
   TRY(ct_resolve(c, ct));
   CK(cudaMemcpyAsync(host, ct->b->d, words * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ABC_OK;
+}
+// one instance of the batch (the unit of a SEAL stream); the other instances of the handle keep their content
+abc_status abc_ct_export_instance(abc_ctx *c, const abc_ct *ct, uint32_t inst, uint64_t *host, size_t words) {
+  if (!valid_ct(c, ct) || words != ct_words1(c) || inst >= (uint32_t)c->B)
+    return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle, instance or size");
+  TRY(ct_resolve(c, ct));
+  CK(cudaMemcpyAsync(host, ct->b->d + (size_t)inst * words, words * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ABC_OK;
+}
+abc_status abc_ct_import_instance(abc_ctx *c, abc_ct *ct, uint32_t inst, const uint64_t *host, size_t words) {
+  if (!valid_ct(c, ct) || words != ct_words1(c) || inst >= (uint32_t)c->B)
+    return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle, instance or size");
+  TRY(ct_resolve(c, ct));
+  if (ct->b->refs > 1) {  // copy-on-write with content: only one instance is overwritten
+    u64 *d = nullptr;
+    TRY(salloc(c, &d, abc_ct_words(c)));
+    CK(cudaMemcpyAsync(d, ct->b->d, abc_ct_words(c) * 8, cudaMemcpyDeviceToDevice, c->stream));
+    ct_adopt(ct, d);
+  }
+  CK(cudaMemcpyAsync(ct->b->d + (size_t)inst * words, host, words * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return ABC_OK;
 }

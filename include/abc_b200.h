@@ -174,6 +174,28 @@ abc_status abc_measure_butterfly_peak(abc_ctx *ctx, int arith_class, double *but
 /* arithmetic class the context uses for its key-level primes */
 int abc_ntt_arith_class(const abc_ctx *ctx);
 
+/* --- Microsoft SEAL 3.6 binary streams (seal::Serialization::Save/Load; SEAL is the un-vendored dependency behind
+ * src/runtime/SealCiphertext*.cpp, pinned at 3.6.5 by Docker/Dockerfile:9).  This is how "the same SEAL-serialised
+ * input ciphertexts and keys" reach the device: seal::Ciphertext (one per batch instance), SecretKey, PublicKey,
+ * RelinKeys, GaloisKeys, EncryptionParameters.  compr_mode none / zlib / zstd on load and save (zstd through
+ * libzstd.so.1 when it can be dlopen'ed).  Loads validate magic, version, parms_id (BLAKE2b of the parameters), sizes,
+ * NTT-form flag and coefficient ranges, like seal::is_valid_for.  Seeded (symmetric) ciphertexts are rejected.
+ * save: *len receives the stream size; with buf == NULL or cap too small the call fails and only reports the size. */
+enum { ABC_SEAL_COMPR_NONE = 0, ABC_SEAL_COMPR_ZLIB = 1, ABC_SEAL_COMPR_ZSTD = 2 };
+abc_status abc_seal_parms_id(abc_ctx *ctx, int key_level, uint64_t out[4]);  /* EncryptionParameters::parms_id */
+abc_status abc_seal_params_save(abc_ctx *ctx, int compr, uint8_t *buf, size_t cap, size_t *len);
+/* EncryptionParameters stream -> abc_params (poly_degree, primes, plain_modulus; device/batch/seed untouched) */
+abc_status abc_seal_params_parse(const uint8_t *bytes, size_t len, abc_params *out, uint64_t *primes_out, size_t primes_cap);
+abc_status abc_seal_ct_save(abc_ctx *ctx, const abc_ct *ct, uint32_t instance, int compr, uint8_t *buf, size_t cap, size_t *len);
+abc_status abc_seal_ct_load(abc_ctx *ctx, abc_ct *ct, uint32_t instance, const uint8_t *bytes, size_t len);
+abc_status abc_seal_key_save(abc_ctx *ctx, int kind, int compr, uint8_t *buf, size_t cap, size_t *len);
+abc_status abc_seal_key_load(abc_ctx *ctx, int kind, const uint8_t *bytes, size_t len);  /* GALOIS: every key in the stream */
+/* raw coefficients of ONE instance, [2][L][N] (what a seal::Ciphertext's DynArray holds) */
+abc_status abc_ct_export_instance(abc_ctx *ctx, const abc_ct *ct, uint32_t instance, uint64_t *host, size_t words);
+abc_status abc_ct_import_instance(abc_ctx *ctx, abc_ct *ct, uint32_t instance, const uint64_t *host, size_t words);
+/* Galois elements with a key on the device: *n receives the count; out may be NULL to query it */
+abc_status abc_galois_elts(const abc_ctx *ctx, uint32_t *out, size_t cap, size_t *n);
+
 #ifdef __cplusplus
 }
 #endif
