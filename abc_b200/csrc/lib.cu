@@ -88,9 +88,13 @@ struct abc_ctx {
 // variable read (RuntimeVisitor.cpp:436), so clone is O(1) and an op gives its destination a private buffer first.
 // A buffer may also be a DEFERRED rotation (d == nullptr): its value is the last Galois step of a rotate_rows applied
 // to `src`; an add consumes it fused (the addend is accumulated in that key switch's ModDown), anything else resolves it.
+// After a fused add the rotation itself was never stored; a handle that still stands for it becomes the DIFFERENCE
+// sum - other of two live buffers (exact: canonical modular subtraction undoes the addition), one HBM-bound kernel if
+// anybody ever asks, nothing if the handle is simply dropped (the usual fate of `r` in `acc = acc +++ r`).
 struct CtBuf {
   u64 *d = nullptr; int refs = 1;
-  CtBuf *src = nullptr; u32 elt = 0;
+  CtBuf *src = nullptr; u32 elt = 0;       // deferred rotation: value = Galois step `elt` of src
+  CtBuf *sum = nullptr, *other = nullptr;  // deferred difference: value = sum - other
 };
 struct abc_ct { abc_ctx *ctx; CtBuf *b; };
 struct abc_pt { abc_ctx *ctx; u64 *d; int broadcast; };
@@ -965,7 +969,7 @@ abc_status abc_ct_alloc(abc_ctx *c, abc_ct **out) {
 static void buf_unref(abc_ctx *c, CtBuf *b) {
   if (!b || --b->refs > 0) return;
   if (b->d) sfree(c, b->d);
-  buf_unref(c, b->src);
+  buf_unref(c, b->src); buf_unref(c, b->sum); buf_unref(c, b->other);
   delete b;
 }
 // point the handle at a buffer it alone owns
@@ -984,6 +988,16 @@ static abc_status buf_resolve(abc_ctx *c, CtBuf *b) {
   if (b->d) return ABC_OK;
   u64 *d = nullptr;
   TRY(salloc(c, &d, abc_ct_words(c)));
+  if (b->sum) {
+    Launch l(c, "sub");
+    const int nown = c->own_hi - c->own_lo;
+    k_addsub<1><<<dim3((c->N / 2 + 255) / 256, 2 * nown, c->B), 256, 0, c->stream>>>(d, b->sum->d, b->other->d, c->dC, c->N, c->L,
+                                                                                      2ll * c->L * c->N, c->own_lo, nown);
+    if (cudaGetLastError() != cudaSuccess) { sfree(c, d); return fail(c, ABC_ERR_CUDA, "sub launch failed"); }
+    b->d = d;
+    buf_unref(c, b->sum); buf_unref(c, b->other); b->sum = b->other = nullptr;
+    return ABC_OK;
+  }
   abc_status st = apply_galois(c, b->src->d, d, b->elt);
   if (st != ABC_OK) { sfree(c, d); return st; }
   b->d = d;
@@ -1196,19 +1210,24 @@ static abc_status addsub(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct 
   CK(cudaGetLastError());
   return ABC_OK;
 }
-// dst = rot + other where rot is a deferred rotation (other is resolved).  One key switch writes the sum; unless dst is
-// the only holder of rot it also writes the rotation itself (second ModDown output), which resolves rot for its other
-// holders at the cost of one extra store instead of a second key switch later.
+// dst = rot + other where rot is a deferred rotation (other is resolved).  One key switch writes the sum.  If rot has
+// holders besides dst it turns into the deferred difference sum - other (see CtBuf): never a second key switch.
 static abc_status fused_rotate_add(abc_ctx *c, abc_ct *dst, const abc_ct *rot, const abc_ct *other) {
-  CtBuf *rb = rot->b;
-  const bool dual = !(dst->b == rb && rb->refs == 1);
-  u64 *sum = nullptr, *plain = nullptr;
+  CtBuf *rb = rot->b, *ob = other->b;
+  if (rb->sum) { TRY(buf_resolve(c, rb)); return addsub(c, dst, rot, other, 0); }  // already a difference: plain add
+  const bool keep = !(dst->b == rb && rb->refs == 1);
+  u64 *sum = nullptr;
   TRY(salloc(c, &sum, abc_ct_words(c)));
-  if (dual) TRY(salloc(c, &plain, abc_ct_words(c)));
-  abc_status st = apply_galois(c, rb->src->d, sum, rb->elt, other->b->d, plain);
-  if (st != ABC_OK) { sfree(c, sum); if (plain) sfree(c, plain); return st; }
-  if (dual) { rb->d = plain; buf_unref(c, rb->src); rb->src = nullptr; }
-  ct_adopt(dst, sum);
+  abc_status st = apply_galois(c, rb->src->d, sum, rb->elt, ob->d, nullptr);
+  if (st != ABC_OK) { sfree(c, sum); return st; }
+  CtBuf *sb = new CtBuf; sb->d = sum;
+  if (keep) {
+    buf_unref(c, rb->src); rb->src = nullptr;
+    rb->sum = sb; ++sb->refs;
+    rb->other = ob; ++ob->refs;
+  }
+  buf_unref(c, dst->b);
+  dst->b = sb;
   return ABC_OK;
 }
 abc_status abc_add(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct *b) { return addsub(c, dst, a, b, 0); }

@@ -237,8 +237,8 @@ def run_ours(args):
         nb = L + 1
         alg = {"ks_modup_ntt": B * (L + k * L) * row, "ks_inner": B * (k * L + 2 * k) * row + 2 * k * L * row,
                "ks_intt_special": B * 4 * row, "ks_intt_moddown": B * (2 * L + 2 + 2 * L + 2 * L) * row,
-               # fused tail of a rotation's key switch: T rows in, sigma(c0) and the addend in, sum and plain rotation out, + key
-               "ks_inner_intt_moddown": B * (k * L + L + 2 * L + 2 * L + 2 * L) * row + 2 * k * L * row,
+               # fused tail of a rotation's key switch: T rows in, sigma(c0) and the addend in, sum out, + key
+               "ks_inner_intt_moddown": B * (k * L + L + 2 * L + 2 * L) * row + 2 * k * L * row,
                "behz_ntt_q": B * 8 * L * row, "behz_ntt_bsk": B * 8 * nb * row,
                "behz_intt_q": B * 6 * L * row, "behz_intt_bsk": B * 6 * nb * row,
                "behz_lift": B * 4 * (L + 2 * L + 1) * row, "behz_tensor": B * 7 * (2 * L + 1) * row,

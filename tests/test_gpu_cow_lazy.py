@@ -60,12 +60,22 @@ def test_deferred_rotation_then_add(pair, steps):
     rw = o.rotate_rows(aw, steps)
     r = a.rotateRows(steps)
     assert r.isDeferred()
-    s1 = b.add(r)                         # fused; r keeps the plain rotation (second ModDown output)
+    s1 = b.add(r)                         # fused; r now stands for the difference s1 - b, still nothing stored
     assert eq(s1, o.add(bw, rw))
-    assert not r.isDeferred() and eq(r, rw)
+    assert r.isDeferred()
+    n0 = f.launch_count()
+    assert eq(r, rw) and not r.isDeferred()
+    assert f.launch_count() - n0 == 1     # one subtraction, not a second key switch
+    assert eq(b.add(r), o.add(bw, rw))    # and r is an ordinary ciphertext from here on
     r2 = a.rotateRows(steps)
     s2 = r2.add(b)                        # deferred operand on the left
-    assert eq(s2, o.add(rw, bw)) and eq(r2, rw)
+    s3 = r2.add(a)                        # the difference node used in another add
+    assert eq(s2, o.add(rw, bw)) and eq(s3, o.add(rw, aw)) and eq(r2, rw)
+    acc = b.clone()
+    r4 = a.rotateRows(steps)
+    acc.addInplace(r4)                    # RuntimeVisitor's `acc = acc +++ r`: the addend is also the destination
+    acc.addInplace(a)                     # the sum buffer is still referenced by r4: copy-on-write keeps r4 intact
+    assert eq(acc, o.add(o.add(bw, rw), aw)) and eq(r4, rw) and eq(b, bw)
     r3 = a.rotateRows(steps)
     r3.addInplace(b)                      # the only holder is overwritten: single-output path
     assert eq(r3, o.add(rw, bw))

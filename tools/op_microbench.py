@@ -14,6 +14,7 @@ import sys
 
 import numpy as np
 
+os.environ["ABC_EAGER_ROTATE"] = "1"   # time rotate_rows itself: by default its last key switch is deferred to the consumer
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from abc_b200 import CudaCiphertextFactory  # noqa: E402
 
@@ -96,6 +97,9 @@ def main():
                 nks = 1 if k in (1, 4) else 2
                 ops["rotate(%d)" % k] = ((lambda k=k: f._ck(lib.abc_rotate_rows(f._h, out._h, a._h, k))),
                                          16 * L * N * (L + 3) * nks, nks)
+            # add(rotate_rows(a, 1), b) as one key switch (what a rotate-and-sum ladder step costs)
+            ops["rotate(1)+add"] = ((lambda: f._ck(lib.abc_rotate_rows_add(f._h, out._h, a._h, 1, b._h))),
+                                    16 * L * N * (L + 3) + 16 * L * N, 1)
             for name, (fn, alg_bytes, nks) in ops.items():
                 ms = time_op(f, fn, args.reps, flush)
                 # keys are shared by the batch: amortise the key term
