@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libabc_b200.so")
+LIB_PATH = os.environ.get("ABC_B200_LIB") or os.path.join(_HERE, "lib", "libabc_b200.so")  # override: A/B builds of the same ABI
 
 # every symbol include/abc_b200.h declares: name -> (restype, argtypes)
 vp, sz, u64, u32, i32, f32p = C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_float)

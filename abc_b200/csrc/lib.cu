@@ -16,6 +16,7 @@
 
 #include "hostmath.hpp"
 #include "kernels.cuh"
+#include "ksfused.cuh"
 
 namespace {
 thread_local std::string g_create_error;
@@ -41,6 +42,9 @@ struct abc_ctx {
   bool no_square = false;                        // ABC_NO_SQUARE: multiply(x, x) takes the general path
   bool lazy_rotate = true;                       // ABC_EAGER_ROTATE: rotate_rows runs its last key switch immediately
   bool ks_unmerged = false, ks_unfused = false;  // ABC_KS_UNMERGED / ABC_KS_UNFUSED: A/B switches for the key-switch tail
+  int ks_one_launch = -1;                        // ABC_KS_ONE_LAUNCH=0/1: force the single-launch key switch off / on (-1: by size)
+  int ks1_threads = 1024;                        // ABC_KS1_THREADS: CTA size of the single-launch key switch at N = 8192
+  int ks1_skew = 40;                             // ABC_KS1_SKEW: single-launch key switch, special units run this far ahead
   int idx_t = 0;
   std::vector<void *> owned;  // device allocations freed at destroy
   u32 *d_index_map = nullptr;
@@ -70,6 +74,7 @@ struct abc_ctx {
   u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;
   u64 *d_noise_tab = nullptr; int q_bits = 0;   // abc_noise_budget: (Q/q_i), Q, (Q+1)/2 as L-word integers; bit_count(Q)
   std::map<u32, u64 *> galois;
+  std::map<const u64 *, double *> key_f64;  // exact-double copies of key-switch keys (single-launch key switch), made on first use
   bool have_keys = false;
   std::string err;
   uint64_t launches = 0;
@@ -194,7 +199,7 @@ LimbJob blank_job() { LimbJob j; memset(&j, 0, sizeof j); return j; }
 // ---- context construction --------------------------------------------------------------------
 void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, std::vector<ulonglong2> &itw,
               std::vector<ulonglong2> &twf, std::vector<ulonglong2> &itwf, std::vector<ulonglong2> &twd,
-              std::vector<ulonglong2> &itwd) {
+              std::vector<ulonglong2> &itwd, std::vector<ulonglong2> &twp, std::vector<ulonglong2> &itwp) {
   using hm::mulmod; using hm::invmod; using hm::shoup; using hm::prod_mod; using hm::barrett_ratio; using hm::bit_reverse; using hm::minimal_2nth_root; using hm::get_primes; using hm::bits_of; using hm::prod_bits;
   m.q = q;
   barrett_ratio(q, m.mu_hi, m.mu_lo);
@@ -228,10 +233,16 @@ void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, s
     m.ninv_f = dbits(m.ninv); m.wl_ninv_f = dbits(m.wl_ninv);
     double qi = 1.0 / (double)q; memcpy(&m.qinv_bits, &qi, 8);
   }
-  twd.clear(); itwd.clear();
+  twd.clear(); itwd.clear(); twp.clear(); itwp.clear();
   m.ninv_d = m.wl_ninv_d = 0;
   if (m.ar_class == AR_F64) {
     auto ibits = [](u64 w) { double d = (double)w; u64 b; memcpy(&b, &d, 8); return b; };  // exact: w < 2^45
+    const int np = N < 1024 ? N : 1024;               // strided passes cover stages 0..8 at most
+    twp.resize(np); itwp.resize(np);
+    for (int j = 0; j < np; ++j) {
+      twp[j] = make_ulonglong2(ibits(tw[j].x), dbits(tw[j].x));
+      itwp[j] = make_ulonglong2(ibits(itw[j].x), dbits(itw[j].x));
+    }
     // 8-byte entries (two per ulonglong2 slot), the last two stages lane-contiguous for the contiguous pass (ntt.cuh tw_get)
     twd.assign(N / 2, make_ulonglong2(0, 0)); itwd.assign(N / 2, make_ulonglong2(0, 0));
     u64 *fw = reinterpret_cast<u64 *>(twd.data()), *iw = reinterpret_cast<u64 *>(itwd.data());
@@ -270,13 +281,14 @@ abc_status build_tables(abc_ctx *c) {
   // ---- per-modulus tables
   const int nmods = k + c->nbsk + 1;
   std::vector<ModInfo> mods(nmods);
-  std::vector<ulonglong2> tw, itw, twf, itwf, twd, itwd;
+  std::vector<ulonglong2> tw, itw, twf, itwf, twd, itwd, twp, itwp;
   for (int i = 0; i < nmods; ++i) {
     const u64 q = i < k ? c->primes[i] : (i < k + c->nbsk ? c->bsk[i - k] : t);
-    fill_mod(mods[i], q, N, logN, tw, itw, twf, itwf, twd, itwd);
+    fill_mod(mods[i], q, N, logN, tw, itw, twf, itwf, twd, itwd, twp, itwp);
     ulonglong2 *d_tw = nullptr, *d_itw = nullptr, *d_twf = nullptr, *d_itwf = nullptr, *d_twd = nullptr, *d_itwd = nullptr;
-    if (!twd.empty()) { TRY(upload(c, &d_twd, twd)); TRY(upload(c, &d_itwd, itwd)); }
-    mods[i].twd = d_twd; mods[i].itwd = d_itwd;
+    ulonglong2 *d_twp = nullptr, *d_itwp = nullptr;
+    if (!twd.empty()) { TRY(upload(c, &d_twd, twd)); TRY(upload(c, &d_itwd, itwd)); TRY(upload(c, &d_twp, twp)); TRY(upload(c, &d_itwp, itwp)); }
+    mods[i].twd = d_twd; mods[i].itwd = d_itwd; mods[i].twp = d_twp; mods[i].itwp = d_itwp;
     TRY(upload(c, &d_tw, tw));
     TRY(upload(c, &d_itw, itw));
     if (!twf.empty()) { TRY(upload(c, &d_twf, twf)); TRY(upload(c, &d_itwf, itwf)); }
@@ -290,6 +302,10 @@ abc_status build_tables(abc_ctx *c) {
   if (const char *e = getenv("ABC_FORCE_AR")) c->force_ar = atoi(e);
   c->ks_unmerged = getenv("ABC_KS_UNMERGED") != nullptr;
   c->ks_unfused = getenv("ABC_KS_UNFUSED") != nullptr;
+  if (const char *e = getenv("ABC_KS_ONE_LAUNCH")) c->ks_one_launch = atoi(e) ? 1 : 0;
+  if (getenv("ABC_KS_TWO_LAUNCH")) c->ks_one_launch = 0;
+  if (const char *e = getenv("ABC_KS1_THREADS")) c->ks1_threads = atoi(e);
+  if (const char *e = getenv("ABC_KS1_SKEW")) c->ks1_skew = atoi(e) < 0 ? 0 : atoi(e);
   c->lazy_rotate = getenv("ABC_EAGER_ROTATE") == nullptr;
   c->no_square = getenv("ABC_NO_SQUARE") != nullptr;
   if (const char *e = getenv("ABC_KS_SKEW")) c->ks_skew = atoi(e) < 0 ? 0 : atoi(e);
@@ -503,6 +519,31 @@ abc_status allgather_limbs(abc_ctx *c, u64 *d, int poly_mask) {
 }
 
 // ---- op building blocks ------------------------------------------------------------------------
+__global__ void k_key_to_f64(const u64 *__restrict__ in, double *__restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+void drop_key_f64(abc_ctx *c) {
+  if (c->key_f64.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (auto &kv : c->key_f64) cudaFree(kv.second);
+  c->key_f64.clear();
+}
+// the key as exact doubles (every residue < 2^45), same layout; converted once per key, dropped when keys change
+abc_status key_as_f64(abc_ctx *c, const u64 *key, const double **out) {
+  auto it = c->key_f64.find(key);
+  if (it == c->key_f64.end()) {
+    const size_t n = (size_t)c->L * 2 * c->k * c->N;
+    double *d = nullptr;
+    CK(cudaMalloc((void **)&d, n * 8));
+    Launch l(c, "key_to_f64");
+    k_key_to_f64<<<592, 256, 0, c->stream>>>(key, d, n);
+    CK(cudaGetLastError());
+    it = c->key_f64.emplace(key, d).first;
+  }
+  *out = it->second;
+  return ABC_OK;
+}
+
 size_t ct_words1(const abc_ctx *c) { return (size_t)2 * c->L * c->N; }
 
 // Evaluator::switch_key_inplace: dst[inst][2][L][N] = sigma(base0, base1) + KeySwitch(sigma(target)), where sigma is the
@@ -516,6 +557,29 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
                      const u64 *addend = nullptr, u64 *dst_plain = nullptr) {
   const int N = c->N, L = c->L, k = c->k, B = c->B;
   u64 *T = nullptr, *acc = nullptr;
+  // exact-double class: the whole key switch can be one launch (ksfused.cu), nothing but INTT_p(acc_L) goes through HBM.
+  // N = 4096: two CTAs per SM, 20 % faster than ModUp launch + tail launch (measured, op_microbench).  N = 8192: its
+  // accumulators leave room for one CTA per SM only, which makes it a tie (-1 .. +4 % depending on the batch) at a
+  // third of the HBM traffic; the two-launch sequence stays the default there, ABC_KS_ONE_LAUNCH=1 selects this one.
+  const bool one_launch = c->ks_one_launch >= 0 ? c->ks_one_launch == 1 : c->logN <= 12;
+  if (one_launch && c->logN <= 13 && (c->own_hi - c->own_lo) > 0 && abc_ntt_arith_class(c) == AR_F64 && !c->ks_unmerged &&
+      !c->ks_unfused) {
+    TRY(scratch(c, SC_ACC, &acc, (size_t)B * 2 * N));
+    KsJob kj;
+    memset(&kj, 0, sizeof kj);
+    const double *keyd = nullptr;
+    TRY(key_as_f64(c, key, &keyd));
+    kj.target = target; kj.target_is = target_is; kj.key = keyd;
+    kj.dst = dst; kj.dst_is = (long long)2 * L * N; kj.dst2 = dst_plain; kj.add = addend; kj.add_is = (long long)2 * L * N;
+    kj.base0 = base0; kj.base0_is = base0_is; kj.base1 = base1; kj.base1_is = base1_is; kj.einv = einv;
+    kj.tl = acc; kj.tl_is = (long long)2 * N;
+    kj.flags = c->ks_flags; kj.serial = ++c->ks_serial; kj.skew = c->ks1_skew;
+    kj.C = c->dC; kj.Iset = c->ks_I; kj.nI = c->ks_nI; kj.L = L; kj.k = k; kj.B = B; kj.threads = c->ks1_threads;
+    Launch l(c, "ks_fused");
+    const int e = ks_fused_launch(c->logN, kj, c->d_mods, c->stream);
+    if (e != 0) { c->err = std::string("ks_fused: ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
+    return ABC_OK;
+  }
   TRY(scratch(c, SC_T, &T, (size_t)B * k * L * N));
   TRY(scratch(c, SC_ACC, &acc, (size_t)B * 2 * k * N));
   LimbJob j = blank_job();
@@ -833,6 +897,7 @@ void abc_ctx_destroy(abc_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
   for (auto &kv : c->galois) cudaFree(kv.second);
+  for (auto &kv : c->key_f64) cudaFree(kv.second);
   cudaFree(c->d_sk); cudaFree(c->d_pk); cudaFree(c->d_relin);
   for (void *p : c->owned) cudaFree(p);
   if (c->flush_buf) cudaFree(c->flush_buf);
@@ -867,6 +932,7 @@ static abc_status keygen_impl(abc_ctx *c, const std::vector<u32> &elts) {
   const int N = c->N, k = c->k, L = c->L;
   CK(cudaSetDevice(c->device));
   const size_t kw = (size_t)L * 2 * k * N;
+  drop_key_f64(c);
   if (!c->d_sk) CK(cudaMalloc((void **)&c->d_sk, (size_t)k * N * 8));
   if (!c->d_pk) CK(cudaMalloc((void **)&c->d_pk, (size_t)2 * k * N * 8));
   if (!c->d_relin) CK(cudaMalloc((void **)&c->d_relin, kw * 8));
@@ -937,6 +1003,7 @@ abc_status abc_key_import(abc_ctx *c, int kind, uint32_t elt, const uint64_t *ho
   u64 **slot = key_slot(c, kind, elt, true);
   if (!slot) return fail(c, ABC_ERR_PARAM, "invalid key kind / Galois element");
   if (words != abc_key_words(c, kind)) return fail(c, ABC_ERR_PARAM, "key size mismatch");
+  drop_key_f64(c);
   if (!*slot) CK(cudaMalloc((void **)slot, words * 8));
   CK(cudaMemcpyAsync(*slot, host, words * 8, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));

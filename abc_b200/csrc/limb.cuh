@@ -148,6 +148,54 @@ __device__ __forceinline__ double add_canon_f64(double r, u64 ad, double qd) {
   return r >= qd ? r - qd : r;
 }
 
+// ---- ModDown epilogue of one data row on the exact-double class: sm holds the INTT output as centred doubles
+// (swizzled); out = base (through the automorphism einv) + p^-1 * (v - [t + p/2]_p + [p/2]) mod q, + addp if given
+// (out2 then receives the result without it)
+template <int LOGN, int T>
+__device__ __forceinline__ void moddown_store_f64(const u64 *sm, const ModInfo &M, const ModDownRow &md, u32 einv,
+                                                  ulonglong2 *__restrict__ out, ulonglong2 *__restrict__ out2,
+                                                  const ulonglong2 *__restrict__ addp, int tid) {
+  constexpr int N = 1 << LOGN, IT = N / 2 / T, CH = IT < 4 ? IT : 4;
+  static_assert(IT % CH == 0, "whole chunks");
+  const u64 q = M.q;
+  const ModDownF64 f = moddown_f64(md, M);
+  const u32 m2 = 2u * N - 1;
+#pragma unroll 1
+  for (int i0 = 0; i0 < IT; i0 += CH) {
+    // everything this chunk reads from global memory is requested before the first dependent instruction
+    ulonglong2 t[CH], ad[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int e2 = tid + (i0 + i) * T;
+      t[i] = __ldcg(md.tl + e2);
+      if (addp) ad[i] = addp[e2];
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      const int e2 = tid + (i0 + i) * T;
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
+      ulonglong2 b = make_ulonglong2(0, 0);
+      if (md.base) {
+        if (einv) {
+          const u32 r0 = ((u32)(2 * e2) * einv) & m2, r1 = (r0 + einv) & m2;
+          b.x = md.base[r0 & (N - 1)]; b.y = md.base[r1 & (N - 1)];
+          if (r0 >= (u32)N) b.x = neg_mod(b.x, q);
+          if (r1 >= (u32)N) b.y = neg_mod(b.y, q);
+        } else {
+          b = reinterpret_cast<const ulonglong2 *>(md.base)[e2];
+        }
+      }
+      double rx = moddown_one_f64(f64_of(v.x), t[i].x, md.base != nullptr, b.x, f);
+      double ry = moddown_one_f64(f64_of(v.y), t[i].y, md.base != nullptr, b.y, f);
+      if (addp) {
+        if (out2) out2[e2] = make_ulonglong2(f64_canon_bits(rx), f64_canon_bits(ry));
+        rx = add_canon_f64(rx, ad[i].x, f.qd); ry = add_canon_f64(ry, ad[i].y, f.qd);
+      }
+      out[e2] = make_ulonglong2(f64_canon_bits(rx), f64_canon_bits(ry));
+    }
+  }
+}
+
 template <int POST>
 __device__ __forceinline__ void limb_store_pair(const LimbJob &job, const ModInfo &M, const ModDownRow &md, int n, int inst,
                                                 int drow, int arow, int e2, ulonglong2 v) {
@@ -387,34 +435,10 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
     }
     if (POST == POST_MODDOWN) md = moddown_row(job, n, inst, wq);
     if constexpr (POST == POST_MODDOWN && AR == AR_F64 && !TAIL) {
-      const ModDownF64 f = moddown_f64(md, M);
-      const u32 einv = job.base_einv, m2 = 2u * D::N - 1;
-      ulonglong2 *out = reinterpret_cast<ulonglong2 *>(job.dst + (size_t)inst * job.dst_is + (size_t)drow * D::N);
-      ulonglong2 *out2 = job.dst2 ? reinterpret_cast<ulonglong2 *>(job.dst2 + (size_t)inst * job.dst_is + (size_t)drow * D::N) : nullptr;
-      const ulonglong2 *addp = job.add ? reinterpret_cast<const ulonglong2 *>(job.add + (size_t)inst * job.add_is + (size_t)drow * D::N) : nullptr;
-      for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
-        const ulonglong2 t = __ldcg(md.tl + e2);
-        ulonglong2 b = make_ulonglong2(0, 0);
-        if (md.base) {
-          if (einv) {
-            const u32 r0 = ((u32)(2 * e2) * einv) & m2, r1 = (r0 + einv) & m2;
-            b.x = md.base[r0 & (D::N - 1)]; b.y = md.base[r1 & (D::N - 1)];
-            if (r0 >= (u32)D::N) b.x = neg_mod(b.x, q);
-            if (r1 >= (u32)D::N) b.y = neg_mod(b.y, q);
-          } else {
-            b = reinterpret_cast<const ulonglong2 *>(md.base)[e2];
-          }
-        }
-        double rx = moddown_one_f64(f64_of(v.x), t.x, md.base != nullptr, b.x, f);
-        double ry = moddown_one_f64(f64_of(v.y), t.y, md.base != nullptr, b.y, f);
-        if (addp) {
-          if (out2) out2[e2] = make_ulonglong2(f64_canon_bits(rx), f64_canon_bits(ry));
-          const ulonglong2 ad = addp[e2];
-          rx = add_canon_f64(rx, ad.x, f.qd); ry = add_canon_f64(ry, ad.y, f.qd);
-        }
-        out[e2] = make_ulonglong2(f64_canon_bits(rx), f64_canon_bits(ry));
-      }
+      moddown_store_f64<LOGN, D::T>(
+          sm, M, md, job.base_einv, reinterpret_cast<ulonglong2 *>(job.dst + (size_t)inst * job.dst_is + (size_t)drow * D::N),
+          job.dst2 ? reinterpret_cast<ulonglong2 *>(job.dst2 + (size_t)inst * job.dst_is + (size_t)drow * D::N) : nullptr,
+          job.add ? reinterpret_cast<const ulonglong2 *>(job.add + (size_t)inst * job.add_is + (size_t)drow * D::N) : nullptr, tid);
     } else {
       for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
         ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);

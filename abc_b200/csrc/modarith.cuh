@@ -22,6 +22,7 @@ struct ModInfo {
   u64 qinv_bits;             // bits of double(1/q)
   // pure-FP64 class (q < 2^45): twiddles {bits of double(w), bits of double(w/q)}
   const ulonglong2 *twd, *itwd;
+  const ulonglong2 *twp, *itwp;  // ... and {double(w), double(w/q)} pairs for the strided passes (indices < 1024)
   u64 ninv_d, wl_ninv_d;     // bits of double(ninv), double(wl_ninv)
   int ar_class;              // AR_SHOUP / AR_FP / AR_FP_LAZY: the fastest class this modulus allows
 };

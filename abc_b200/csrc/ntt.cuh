@@ -37,6 +37,9 @@
 #ifndef ABC_MINB
 #define ABC_MINB 2
 #endif
+#ifndef ABC_F64_TW_PAIRS
+#define ABC_F64_TW_PAIRS 0  /* exact-double class, strided passes: 16-byte {w, w/q} twiddles (0: 8-byte w + one DMUL) */
+#endif
 enum { AR_SHOUP = 0, AR_FP = 1, AR_FP_LAZY = 2, AR_F64 = 3 };
 #define ABC_RINT_MAGIC 6755399441055744.0 /* 1.5 * 2^52: x + MAGIC - MAGIC = rint(x) for |x| < 2^51 */
 __device__ __forceinline__ double f64_of(u64 bits) { return __longlong_as_double((long long)bits); }
@@ -51,10 +54,12 @@ template <> struct NttPlan<12> { static constexpr int R0 = 3, R1 = 3, R2 = 2; };
 template <> struct NttPlan<13> { static constexpr int R0 = 3, R1 = 3, R2 = 3; };   // + 1 shuffle + 3 in-register
 template <> struct NttPlan<14> { static constexpr int R0 = 3, R1 = 3, R2 = 3; };   // + 2 shuffle + 3 in-register
 
-template <int LOGN> struct NttDims {
+// TT != 0 overrides the CTA size (the fused key switch runs N = 8192 as ONE 1024-thread CTA per SM: its accumulators
+// take the shared memory a second CTA would need)
+template <int LOGN, int TT = 0> struct NttDims {
   static constexpr int N = 1 << LOGN;
-  static constexpr int T = (LOGN >= 14) ? 1024 : ((N / 8 < 512) ? N / 8 : 512);
-  static constexpr int MINB = (LOGN >= 14) ? 1 : ABC_MINB;
+  static constexpr int T = TT ? TT : ((LOGN >= 14) ? 1024 : ((N / 8 < 512) ? N / 8 : 512));
+  static constexpr int MINB = (TT || LOGN >= 14) ? 1 : ABC_MINB;
   static constexpr int IT = N / 8 / T;
   static constexpr size_t SMEM = (size_t)N * 8;
 };
@@ -87,7 +92,9 @@ template <int AR> __device__ __forceinline__ u64 ar_from_canon(u64 x) {
 template <int AR> __device__ __forceinline__ u64 ar_add(u64 a, u64 b) { return AR == AR_F64 ? bits_of(f64_of(a) + f64_of(b)) : a + b; }
 template <int AR> __device__ __forceinline__ u64 ar_sub(u64 a, u64 b) { return AR == AR_F64 ? bits_of(f64_of(a) - f64_of(b)) : a - b; }
 
-// ---- twiddle fetch.  Integer classes: {w, companion} pairs, 16 bytes.  AR_F64: the table holds double(w) only
+// ---- twiddle fetch.  Integer classes: {w, companion} pairs, 16 bytes.  AR_F64, strided passes: the same, from the
+// small table twp (stages 0 .. R0+R1+R2-1: at most 512 entries, a warp reads one or two of them per load, L1-resident).
+// AR_F64, contiguous pass (every lane its own twiddles): the table twd holds double(w) only
 // (8 bytes, half the L1 data-pipe wavefronts; ncu showed that pipe at 81 % with 16-byte twiddles) and the companion
 // w/q is one DMUL, w * (1/q): two roundings instead of one, so |product| <= 0.6q instead of 0.53q (range plan below).
 // In the AR_F64 table the last two stages are stored lane-contiguously for the contiguous pass: the twiddle thread vt
@@ -97,6 +104,12 @@ template <int AR> __device__ __forceinline__ ulonglong2 tw_get(const ulonglong2 
     const u64 w = __ldg(reinterpret_cast<const u64 *>(tw) + idx);
     return make_ulonglong2(w, bits_of(f64_of(w) * qinv));
   }
+  return __ldg(tw + idx);
+}
+
+// twiddle of a strided pass
+template <int AR> __device__ __forceinline__ ulonglong2 mid_tw(const ulonglong2 *__restrict__ tw, u32 idx, double qinv) {
+  if (AR == AR_F64 && !ABC_F64_TW_PAIRS) return tw_get<AR>(tw, idx, qinv);
   return __ldg(tw + idx);
 }
 
@@ -197,10 +210,10 @@ template <int AR> __device__ __forceinline__ void bf_inv(u64 &x, u64 &y, ulonglo
 // +-sm[e * einv mod 2N] (GaloisTool::apply_galois as a gather, einv = 0: identity), takes NO reduction modulo the
 // target prime (an exact-double transform accepts any |x| < 2^45 and canon_fwd reduces at the end), and, because
 // it is no longer in place, separates its loads from its stores with a barrier.
-template <int LOGN, int S0, int R, int AR, bool LINSRC = false>
+template <int LOGN, int S0, int R, int AR, bool LINSRC = false, int TT = 0>
 __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 aux,
                                             int tid, double qinv, u64 qs = 0, u32 einv = 0) {
-  typedef NttDims<LOGN> D;
+  typedef NttDims<LOGN, TT> D;
   constexpr int LG = LOGN - S0 - R;
   static_assert(!LINSRC || (AR == AR_F64 && S0 == 0), "linear-source gather is the first pass of the exact-double class");
   // AR_F64 is bound by FP64 latency, not issue: its IT groups of 8 are loaded together and their butterflies
@@ -247,7 +260,7 @@ __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restric
         if (r & (1 << b)) continue;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-          const ulonglong2 w = tw_get<AR>(tw, (twbase << s) + ((u32)((blk[g] << 3) + r) >> (b + 1)), qinv);
+          const ulonglong2 w = mid_tw<AR>(tw, (twbase << s) + ((u32)((blk[g] << 3) + r) >> (b + 1)), qinv);
           bf_fwd<AR>(x[g][r], x[g][r | (1 << b)], w, q, aux);
         }
       }
@@ -260,12 +273,18 @@ __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restric
 }
 
 // REDUCE (AR_FP_LAZY only): bring the loaded values back to |x| <= 0.75q before this pass's stages
-template <int LOGN, int S0, int R, bool FOLD, bool REDUCE, int AR>
-__device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 aux, int tid) {
-  typedef NttDims<LOGN> D;
+// EPI: what happens to the pass's results.  StoreSmem (default) writes them back in place; any other type is called as
+// epi(e, bits) with the coefficient index e and the value in the class's representation, and nothing is stored (the
+// last pass of a transform handing its outputs straight to an epilogue, e.g. the key switch's ModDown).
+struct StoreSmem {};
+template <class A, class B> struct SameType { static constexpr bool value = false; };
+template <class A> struct SameType<A, A> { static constexpr bool value = true; };
+template <int LOGN, int S0, int R, bool FOLD, bool REDUCE, int AR, int TT = 0, class EPI = StoreSmem>
+__device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 aux, int tid, EPI epi = EPI()) {
+  typedef NttDims<LOGN, TT> D;
   constexpr int LG = LOGN - S0 - R;
   constexpr int G = (AR == AR_F64) ? D::IT : 1;
-  const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.itw : (AR == AR_F64 ? M.itwd : M.itwf);
+  const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.itw : (AR == AR_F64 ? (ABC_F64_TW_PAIRS ? M.itwp : M.itwd) : M.itwf);
   const double qinv = f64_of(M.qinv_bits);
 #pragma unroll
   for (int it0 = 0; it0 < D::IT; it0 += G) {
@@ -300,27 +319,34 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
             x[g][r] = mul_tw<AR>(ar_add<AR>(u, v), AR == AR_F64 ? M.ninv_d : M.ninv, (AR == AR_SHOUP) ? M.ninv_s : M.ninv_f, q, aux);
             x[g][r | (1 << b)] = mul_tw<AR>(d, AR == AR_F64 ? M.wl_ninv_d : M.wl_ninv, (AR == AR_SHOUP) ? M.wl_ninv_s : M.wl_ninv_f, q, aux);
           } else {
-            const ulonglong2 w = tw_get<AR>(tw, (twbase << s) + ((u32)((blk[g] << 3) + r) >> (b + 1)), qinv);
+            const ulonglong2 w = mid_tw<AR>(tw, (twbase << s) + ((u32)((blk[g] << 3) + r) >> (b + 1)), qinv);
             bf_inv<AR>(x[g][r], x[g][r | (1 << b)], w, q, aux);
           }
         }
       }
     }
+    if constexpr (SameType<EPI, StoreSmem>::value) {
 #pragma unroll
-    for (int g = 0; g < G; ++g)
+      for (int g = 0; g < G; ++g)
 #pragma unroll
-      for (int r = 0; r < 8; ++r) sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))] = x[g][r];
+        for (int r = 0; r < 8; ++r) sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))] = x[g][r];
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) epi(base[g] + (r << LG), x[g][r]);
+    }
   }
 }
 
 // ---- contiguous pass: every thread owns E = 8 CONSECUTIVE coefficients per group: gaps 4,2,1 are in-register, the
 // NSH stages above them (gaps 8, 16) are warp-shuffle butterflies between lane pairs, each lane computing half of the
 // pair's butterflies.
-template <int LOGN> struct NttLast {
+template <int LOGN, int TT = 0> struct NttLast {
   // E = 16 (no shuffle stage at N = 8192) was measured slower than two groups of 8 with one shuffle stage
   // (13.7 vs 15.0 Mrows/s forward): the 32 live data registers cost more than the shuffles save.
   static constexpr int E = 8, LOGE = (E == 16) ? 4 : 3;
-  static constexpr int GROUPS = 8 * NttDims<LOGN>::IT / E;
+  static constexpr int GROUPS = 8 * NttDims<LOGN, TT>::IT / E;
   static constexpr int NSH = LOGN - (NttPlan<LOGN>::R0 + NttPlan<LOGN>::R1 + NttPlan<LOGN>::R2) - LOGE;
   static_assert(E == 8, "contiguous pass handles 8 or 16 coefficients per thread");
   static_assert(NSH >= 0 && NSH <= 2, "stage plan does not add up");
@@ -334,47 +360,55 @@ __device__ __forceinline__ u32 last_tw_index(u32 twbase, int s, int b, int vt, i
   return (twbase << s) + ((u32)(8 * vt + r) >> (b + 1));
 }
 
-template <int LOGN, int AR>
+// the butterflies of the contiguous forward pass on one thread's 8 consecutive coefficients (vt = first / 8)
+template <int LOGN, int AR, int TT = 0>
+__device__ __forceinline__ void ntt_fwd_last_math(u64 (&x)[8], const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 aux,
+                                                  int vt, double qinv) {
+  typedef NttLast<LOGN, TT> P;
+  constexpr int E = P::E, H = E / 2;
+#pragma unroll
+  for (int j = P::NSH - 1; j >= 0; --j) {
+    const int s = LOGN - 1 - P::LOGE - j;
+    const ulonglong2 w = tw_get<AR>(tw, (twbase << s) + ((u32)vt >> (1 + j)), qinv);
+    const bool hi = (vt >> j) & 1;
+#pragma unroll
+    for (int r = 0; r < H; ++r) {
+      u64 recv = __shfl_xor_sync(0xffffffffu, hi ? x[r] : x[H + r], 1 << j);
+      u64 a = hi ? recv : x[r];
+      u64 b = hi ? x[H + r] : recv;
+      bf_fwd<AR>(a, b, w, q, aux);
+      u64 got = __shfl_xor_sync(0xffffffffu, hi ? a : b, 1 << j);
+      x[r] = hi ? got : a;
+      x[H + r] = hi ? b : got;
+    }
+  }
+#pragma unroll
+  for (int b = P::LOGE - 1; b >= 0; --b) {
+    const int s = LOGN - 1 - b;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      if (r & (1 << b)) continue;
+      const ulonglong2 w = tw_get<AR>(tw, last_tw_index<LOGN, AR>(twbase, s, b, vt, r), qinv);
+      bf_fwd<AR>(x[r], x[r | (1 << b)], w, q, aux);
+    }
+  }
+}
+template <int LOGN, int AR, int TT = 0>
 __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 aux, int tid) {
-  typedef NttLast<LOGN> P;
+  typedef NttLast<LOGN, TT> P;
   constexpr int E = P::E, H = E / 2;
   const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.tw : (AR == AR_F64 ? M.twd : M.twf);
   const double qinv = f64_of(M.qinv_bits);
 #pragma unroll
   for (int g = 0; g < P::GROUPS; ++g) {
-    const int vt = tid + g * NttDims<LOGN>::T;
+    const int vt = tid + g * NttDims<LOGN, TT>::T;
     u64 x[E];
 #pragma unroll
     for (int i = 0; i < H; ++i) {
       ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(E * vt + 2 * i)]);
       x[2 * i] = v.x; x[2 * i + 1] = v.y;
     }
-#pragma unroll
-    for (int j = P::NSH - 1; j >= 0; --j) {
-      const int s = LOGN - 1 - P::LOGE - j;
-      const ulonglong2 w = tw_get<AR>(tw, (twbase << s) + ((u32)vt >> (1 + j)), qinv);
-      const bool hi = (vt >> j) & 1;
-#pragma unroll
-      for (int r = 0; r < H; ++r) {
-        u64 recv = __shfl_xor_sync(0xffffffffu, hi ? x[r] : x[H + r], 1 << j);
-        u64 a = hi ? recv : x[r];
-        u64 b = hi ? x[H + r] : recv;
-        bf_fwd<AR>(a, b, w, q, aux);
-        u64 got = __shfl_xor_sync(0xffffffffu, hi ? a : b, 1 << j);
-        x[r] = hi ? got : a;
-        x[H + r] = hi ? b : got;
-      }
-    }
-#pragma unroll
-    for (int b = P::LOGE - 1; b >= 0; --b) {
-      const int s = LOGN - 1 - b;
-#pragma unroll
-      for (int r = 0; r < E; ++r) {
-        if (r & (1 << b)) continue;
-        const ulonglong2 w = tw_get<AR>(tw, last_tw_index<LOGN, AR>(twbase, s, b, vt, r), qinv);
-        bf_fwd<AR>(x[r], x[r | (1 << b)], w, q, aux);
-      }
-    }
+    ntt_fwd_last_math<LOGN, AR, TT>(x, tw, twbase, q, aux, vt, qinv);
 #pragma unroll
     for (int i = 0; i < H; ++i) {
       ulonglong2 v;
@@ -386,47 +420,55 @@ __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twba
 }
 
 // REPIN: shared memory already holds the class's representation (the fused key-switch inner product stores doubles)
-template <int LOGN, int AR, bool REPIN = false>
+// the butterflies of the contiguous inverse pass on one thread's 8 consecutive coefficients (class representation in x)
+template <int LOGN, int AR, int TT = 0>
+__device__ __forceinline__ void ntt_inv_first_math(u64 (&x)[8], const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 aux,
+                                                   int vt, double qinv) {
+  typedef NttLast<LOGN, TT> P;
+  constexpr int E = P::E, H = E / 2;
+#pragma unroll
+  for (int b = 0; b < P::LOGE; ++b) {
+    const int s = LOGN - 1 - b;
+#pragma unroll
+    for (int r = 0; r < E; ++r) {
+      if (r & (1 << b)) continue;
+      const ulonglong2 w = tw_get<AR>(tw, last_tw_index<LOGN, AR>(twbase, s, b, vt, r), qinv);
+      bf_inv<AR>(x[r], x[r | (1 << b)], w, q, aux);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < P::NSH; ++j) {
+    const int s = LOGN - 1 - P::LOGE - j;
+    const ulonglong2 w = tw_get<AR>(tw, (twbase << s) + ((u32)vt >> (1 + j)), qinv);
+    const bool hi = (vt >> j) & 1;
+#pragma unroll
+    for (int r = 0; r < H; ++r) {
+      u64 recv = __shfl_xor_sync(0xffffffffu, hi ? x[r] : x[H + r], 1 << j);
+      u64 a = hi ? recv : x[r];
+      u64 b = hi ? x[H + r] : recv;
+      bf_inv<AR>(a, b, w, q, aux);
+      u64 got = __shfl_xor_sync(0xffffffffu, hi ? a : b, 1 << j);
+      x[r] = hi ? got : a;
+      x[H + r] = hi ? b : got;
+    }
+  }
+}
+template <int LOGN, int AR, bool REPIN = false, int TT = 0>
 __device__ __forceinline__ void ntt_inv_first(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 aux, int tid) {
-  typedef NttLast<LOGN> P;
+  typedef NttLast<LOGN, TT> P;
   constexpr int E = P::E, H = E / 2;
   const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.itw : (AR == AR_F64 ? M.itwd : M.itwf);
   const double qinv = f64_of(M.qinv_bits);
 #pragma unroll
   for (int g = 0; g < P::GROUPS; ++g) {
-    const int vt = tid + g * NttDims<LOGN>::T;
+    const int vt = tid + g * NttDims<LOGN, TT>::T;
     u64 x[E];
 #pragma unroll
     for (int i = 0; i < H; ++i) {
       ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(E * vt + 2 * i)]);
       x[2 * i] = REPIN ? v.x : ar_from_canon<AR>(v.x); x[2 * i + 1] = REPIN ? v.y : ar_from_canon<AR>(v.y);
     }
-#pragma unroll
-    for (int b = 0; b < P::LOGE; ++b) {
-      const int s = LOGN - 1 - b;
-#pragma unroll
-      for (int r = 0; r < E; ++r) {
-        if (r & (1 << b)) continue;
-        const ulonglong2 w = tw_get<AR>(tw, last_tw_index<LOGN, AR>(twbase, s, b, vt, r), qinv);
-        bf_inv<AR>(x[r], x[r | (1 << b)], w, q, aux);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < P::NSH; ++j) {
-      const int s = LOGN - 1 - P::LOGE - j;
-      const ulonglong2 w = tw_get<AR>(tw, (twbase << s) + ((u32)vt >> (1 + j)), qinv);
-      const bool hi = (vt >> j) & 1;
-#pragma unroll
-      for (int r = 0; r < H; ++r) {
-        u64 recv = __shfl_xor_sync(0xffffffffu, hi ? x[r] : x[H + r], 1 << j);
-        u64 a = hi ? recv : x[r];
-        u64 b = hi ? x[H + r] : recv;
-        bf_inv<AR>(a, b, w, q, aux);
-        u64 got = __shfl_xor_sync(0xffffffffu, hi ? a : b, 1 << j);
-        x[r] = hi ? got : a;
-        x[H + r] = hi ? b : got;
-      }
-    }
+    ntt_inv_first_math<LOGN, AR, TT>(x, tw, twbase, q, aux, vt, qinv);
 #pragma unroll
     for (int i = 0; i < H; ++i) {
       ulonglong2 v; v.x = x[2 * i]; v.y = x[2 * i + 1];
@@ -453,22 +495,27 @@ template <int LG, int T> __device__ __forceinline__ void pass_sync(int tid) {
 
 // ---- whole-limb transforms on a swizzled shared-memory limb.  Caller has filled sm[swz(e)] and synced.
 // Forward: input canonical (guarded classes accept < 4q), output canonical.  Returns after a barrier.
-template <int LOGN, int AR, bool LINSRC = false>
-__device__ __forceinline__ void ntt_fwd_smem(u64 *sm, const ModInfo &M, u32 twbase, int tid, u64 qs = 0, u32 einv = 0) {
+// the strided passes of the forward transform; returns after the barrier in front of the contiguous pass
+template <int LOGN, int AR, bool LINSRC = false, int TT = 0>
+__device__ __forceinline__ void ntt_fwd_smem_mids(u64 *sm, const ModInfo &M, u32 twbase, int tid, u64 qs = 0, u32 einv = 0) {
   typedef NttPlan<LOGN> P;
   const u64 q = M.q, aux = ar_aux<AR>(q);
-  const ulonglong2 *tw = (AR == AR_SHOUP) ? M.tw : (AR == AR_F64 ? M.twd : M.twf);
+  const ulonglong2 *tw = (AR == AR_SHOUP) ? M.tw : (AR == AR_F64 ? (ABC_F64_TW_PAIRS ? M.twp : M.twd) : M.twf);
   const double qinv = f64_of(M.qinv_bits);
-  typedef NttDims<LOGN> D;
-  ntt_fwd_mid<LOGN, 0, P::R0, AR, LINSRC>(sm, tw, twbase, q, aux, tid, qinv, qs, einv);
+  typedef NttDims<LOGN, TT> D;
+  ntt_fwd_mid<LOGN, 0, P::R0, AR, LINSRC, TT>(sm, tw, twbase, q, aux, tid, qinv, qs, einv);
   pass_sync<LOGN - P::R0, D::T>(tid);
-  ntt_fwd_mid<LOGN, P::R0, P::R1, AR>(sm, tw, twbase, q, aux, tid, qinv);
+  ntt_fwd_mid<LOGN, P::R0, P::R1, AR, false, TT>(sm, tw, twbase, q, aux, tid, qinv);
   pass_sync<LOGN - P::R0 - P::R1, D::T>(tid);
   if constexpr (P::R2 > 0) {
-    ntt_fwd_mid<LOGN, P::R0 + P::R1, P::R2, AR>(sm, tw, twbase, q, aux, tid, qinv);
+    ntt_fwd_mid<LOGN, P::R0 + P::R1, P::R2, AR, false, TT>(sm, tw, twbase, q, aux, tid, qinv);
     pass_sync<LOGN - P::R0 - P::R1 - P::R2, D::T>(tid);
   }
-  ntt_fwd_last<LOGN, AR>(sm, M, twbase, q, aux, tid);
+}
+template <int LOGN, int AR, bool LINSRC = false, int TT = 0>
+__device__ __forceinline__ void ntt_fwd_smem(u64 *sm, const ModInfo &M, u32 twbase, int tid, u64 qs = 0, u32 einv = 0) {
+  ntt_fwd_smem_mids<LOGN, AR, LINSRC, TT>(sm, M, twbase, tid, qs, einv);
+  ntt_fwd_last<LOGN, AR, TT>(sm, M, twbase, M.q, ar_aux<AR>(M.q), tid);
   __syncthreads();
 }
 // Inverse: input canonical; output needs canon_inv<AR> (the caller's copy-out applies it).
@@ -477,20 +524,25 @@ __device__ __forceinline__ void ntt_fwd_smem(u64 *sm, const ModInfo &M, u32 twba
 // AR_FP_LAZY range plan (q*(log2(N)+2) < 2^51, q < 2^45): the sum chain doubles per stage, so it is reduced to
 // |x| <= 0.75q after the contiguous pass (4-5 stages) and again before the last strided pass (3 stages left):
 // no product ever sees an operand above 2^6 * 2 * 0.75q < 2^51.
-template <int LOGN, bool WHOLE, int AR, bool REPIN = false>
-__device__ __forceinline__ void ntt_inv_smem(u64 *sm, const ModInfo &M, u32 twbase, int tid) {
+// the strided passes of the inverse transform (everything after the contiguous pass); returns after a barrier
+template <int LOGN, bool WHOLE, int AR, int TT = 0>
+__device__ __forceinline__ void ntt_inv_smem_mids(u64 *sm, const ModInfo &M, u32 twbase, int tid) {
   typedef NttPlan<LOGN> P;
-  static_assert(WHOLE || (AR != AR_FP_LAZY && AR != AR_F64), "tail blocks use a guarded class");
   const u64 q = M.q, aux = ar_aux<AR>(q);
-  typedef NttDims<LOGN> D;
-  ntt_inv_first<LOGN, AR, REPIN>(sm, M, twbase, q, aux, tid);
+  typedef NttDims<LOGN, TT> D;
   pass_sync<LOGN - P::R0 - P::R1 - P::R2, D::T>(tid);
   if constexpr (P::R2 > 0) {
-    ntt_inv_mid<LOGN, P::R0 + P::R1, P::R2, false, true, AR>(sm, M, twbase, q, aux, tid);
+    ntt_inv_mid<LOGN, P::R0 + P::R1, P::R2, false, true, AR, TT>(sm, M, twbase, q, aux, tid);
     pass_sync<LOGN - P::R0 - P::R1, D::T>(tid);
   }
-  ntt_inv_mid<LOGN, P::R0, P::R1, false, P::R2 == 0, AR>(sm, M, twbase, q, aux, tid);
+  ntt_inv_mid<LOGN, P::R0, P::R1, false, P::R2 == 0, AR, TT>(sm, M, twbase, q, aux, tid);
   pass_sync<LOGN - P::R0, D::T>(tid);
-  ntt_inv_mid<LOGN, 0, P::R0, WHOLE, true, AR>(sm, M, twbase, q, aux, tid);
+  ntt_inv_mid<LOGN, 0, P::R0, WHOLE, true, AR, TT>(sm, M, twbase, q, aux, tid);
   __syncthreads();
+}
+template <int LOGN, bool WHOLE, int AR, bool REPIN = false, int TT = 0>
+__device__ __forceinline__ void ntt_inv_smem(u64 *sm, const ModInfo &M, u32 twbase, int tid) {
+  static_assert(WHOLE || (AR != AR_FP_LAZY && AR != AR_F64), "tail blocks use a guarded class");
+  ntt_inv_first<LOGN, AR, REPIN, TT>(sm, M, twbase, M.q, ar_aux<AR>(M.q), tid);
+  ntt_inv_smem_mids<LOGN, WHOLE, AR, TT>(sm, M, twbase, tid);
 }

@@ -171,3 +171,34 @@ def test_limb_sharded_key_switch_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "shard_check.py"), "8192"],
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "shard_check ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("N", [4096, 8192])
+@pytest.mark.parametrize("one_launch", ["0", "1"])
+def test_key_switch_single_launch_and_two_launch_agree(N, one_launch, monkeypatch):
+    """The exact-double key switch exists as ONE launch (csrc/ksfused.cu: accumulators in shared memory, no ModUp block
+    in HBM) and as ModUp launch + tail launch; the default is picked by size.  Both are forced here and must give the
+    oracle's coefficients for relinearisation, single and NAF rotations, the fused rotate+add and a batch of 3."""
+    from abc_b200 import CudaCiphertextFactory
+    from oracle.bfv_oracle import Oracle
+    monkeypatch.setenv("ABC_KS_ONE_LAUNCH", one_launch)
+    o = Oracle(N, seed=SEED)
+    f = CudaCiphertextFactory(N, seed=SEED, batch=3)
+    try:
+        rng = np.random.default_rng(N + int(one_launch))
+        da, db = rng.integers(0, 1025, (3, N)), rng.integers(0, 1025, (3, N))
+        a_w = np.stack([o.encrypt_slots(da[i], 10 + i) for i in range(3)])
+        b_w = np.stack([o.encrypt_slots(db[i], 20 + i) for i in range(3)])
+        a, b = f.importCiphertext(a_w), f.importCiphertext(b_w)
+        prod = a.multiply(b).export()
+        for i in range(3):
+            assert np.array_equal(prod[i], o.mul_relin(a_w[i], b_w[i])), "mul+relin inst %d" % i
+        for steps in (1, -24, 63):
+            rot = a.rotateRows(steps).export()
+            for i in range(3):
+                assert np.array_equal(rot[i], o.rotate_rows(a_w[i], steps)), "rotate %d inst %d" % (steps, i)
+        s = b.add(a.rotateRows(4)).export()          # deferred rotation consumed by the add: addend in the ModDown
+        for i in range(3):
+            assert np.array_equal(s[i], o.add(b_w[i], o.rotate_rows(a_w[i], 4))), "rotate+add inst %d" % i
+    finally:
+        f.close()
