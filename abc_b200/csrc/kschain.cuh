@@ -1,0 +1,13 @@
+// kschain.cuh — descriptor + launcher of the chained key switch (kschain.cu)
+#pragma once
+#include "limb.cuh"
+
+struct KsChain {
+  LimbJob up;          // ModUp + NTT rows (t_image = 1, done = counters)
+  LimbJob tail;        // inner product + INTT + ModDown rows (flags / done set)
+  const u32 *sched;    // [n_blocks] role << 30 | inst << 8 | row, in dependency order
+  int n_blocks;
+};
+
+// returns a cudaError_t as int; logN in {12, 13}, every key-level prime < 2^45
+int ks_chain_launch(int logN, const KsChain &ch, const ModInfo *mods, cudaStream_t stream);

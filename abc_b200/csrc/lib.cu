@@ -17,6 +17,7 @@
 #include "hostmath.hpp"
 #include "kernels.cuh"
 #include "ksfused.cuh"
+#include "kschain.cuh"
 
 namespace {
 thread_local std::string g_create_error;
@@ -42,6 +43,7 @@ struct abc_ctx {
   bool no_square = false;                        // ABC_NO_SQUARE: multiply(x, x) takes the general path
   bool lazy_rotate = true;                       // ABC_EAGER_ROTATE: rotate_rows runs its last key switch immediately
   bool ks_unmerged = false, ks_unfused = false;  // ABC_KS_UNMERGED / ABC_KS_UNFUSED: A/B switches for the key-switch tail
+  bool ks_no_image = false;                      // ABC_KS_NO_IMAGE: ModUp rows stored element by element instead of as bulk-copied images
   int ks_one_launch = -1;                        // ABC_KS_ONE_LAUNCH=0/1: force the single-launch key switch off / on (-1: by size)
   int ks1_threads = 1024;                        // ABC_KS1_THREADS: CTA size of the single-launch key switch at N = 8192
   int ks1_skew = 40;                             // ABC_KS1_SKEW: single-launch key switch, special units run this far ahead
@@ -69,6 +71,9 @@ struct abc_ctx {
   int *rm_md = nullptr, *rd_md = nullptr, *rs_md = nullptr;                  // [2 * nown] ModDown rows
   int *rm_own = nullptr, *rd_own = nullptr;                                  // [2 * nown] own rows of a ciphertext
   int *rm_mdm = nullptr, *rd_mdm = nullptr, *rs_mdm = nullptr;               // [2 + 2 * nown] merged special + ModDown rows
+  u32 *ks_sched = nullptr; int ks_sched_n = 0;                                // chained key switch: block schedule (kschain.cu)
+  u32 *ks_done = nullptr; u32 ks_chain_serial = 0;                            // ... [B][k] ModUp rows stored so far (L per launch)
+  int ks_chain = 0, ks_chain_skew = 16;                                       // ABC_KS_CHAIN=0/1, ABC_KS_CHAIN_SKEW
   u32 *ks_flags = nullptr; u32 ks_serial = 0;                                 // [B][2] ready flags of the merged launch
   int *rs_zero = nullptr;   // [2k]  0
   u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;
@@ -304,6 +309,9 @@ abc_status build_tables(abc_ctx *c) {
   c->ks_unfused = getenv("ABC_KS_UNFUSED") != nullptr;
   if (const char *e = getenv("ABC_KS_ONE_LAUNCH")) c->ks_one_launch = atoi(e) ? 1 : 0;
   if (getenv("ABC_KS_TWO_LAUNCH")) c->ks_one_launch = 0;
+  c->ks_no_image = getenv("ABC_KS_NO_IMAGE") != nullptr;
+  if (const char *e = getenv("ABC_KS_CHAIN")) c->ks_chain = atoi(e);
+  if (const char *e = getenv("ABC_KS_CHAIN_SKEW")) c->ks_chain_skew = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("ABC_KS1_THREADS")) c->ks1_threads = atoi(e);
   if (const char *e = getenv("ABC_KS1_SKEW")) c->ks1_skew = atoi(e) < 0 ? 0 : atoi(e);
   c->lazy_rotate = getenv("ABC_EAGER_ROTATE") == nullptr;
@@ -439,6 +447,24 @@ abc_status build_shard_maps(abc_ctx *c) {
     std::vector<int> mm = {L, L}, dm = {L, k + L}, sm_ = {L, k + L};
     mm.insert(mm.end(), m.begin(), m.end()); dm.insert(dm.end(), d.begin(), d.end()); sm_.insert(sm_.end(), sr.begin(), sr.end());
     TRY(upload(c, &c->rm_mdm, mm)); TRY(upload(c, &c->rd_mdm, dm)); TRY(upload(c, &c->rs_mdm, sm_));
+  }
+  if (nown > 0 && c->B < (1 << 22) && c->ks_nI * L < 256 && 2 + 2 * nown < 256) {
+    // chained key switch: ModUp rows of instance g, the two special-prime tail rows of instance g - (S1 - S2) and the
+    // data tail rows of instance g - S1, for g = 0 .. B + S1 - 1 (every wait points at an earlier block)
+    const int Bn = c->B, S1 = c->ks_chain_skew, S2 = std::min(c->ks_skew, S1 - 1) < 0 ? 0 : std::min(c->ks_skew, S1 - 1);
+    std::vector<u32> sch;
+    for (int g = 0; g < Bn + S1; ++g) {
+      if (g < Bn) for (int w = 0; w < c->ks_nI * L; ++w) sch.push_back((u32)g << 8 | (u32)w);
+      const int gs = g - (S1 - S2), gd = g - S1;
+      if (gs >= 0 && gs < Bn) for (int w = 0; w < 2; ++w) sch.push_back(1u << 30 | (u32)gs << 8 | (u32)w);
+      if (gd >= 0 && gd < Bn) for (int w = 2; w < 2 + 2 * nown; ++w) sch.push_back(1u << 30 | (u32)gd << 8 | (u32)w);
+    }
+    TRY(upload(c, &c->ks_sched, sch));
+    c->ks_sched_n = (int)sch.size();
+    CK(cudaMalloc((void **)&c->ks_done, (size_t)c->B * c->k * sizeof(u32)));
+    c->owned.push_back(c->ks_done);
+    CK(cudaMemset(c->ks_done, 0, (size_t)c->B * c->k * sizeof(u32)));
+    c->ks_chain_serial = 0;
   }
   if (!c->ks_flags) {
     CK(cudaMalloc((void **)&c->ks_flags, (size_t)c->B * 2 * sizeof(u32)));
@@ -585,10 +611,14 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   LimbJob j = blank_job();
   j.dst = T; j.dst_is = (long long)k * L * N; j.src = target; j.src_is = target_is;
   j.rowmod = c->rm_modup_s; j.rowdst = c->rd_modup_s; j.rowsrc = c->rs_modup_s; j.galois_einv = einv;
-  TRY(launch_limb(c, einv ? LIMB_GALOIS_REDUCE_FWD : LIMB_REDUCE_FWD, c->ar_q, j, c->ks_nI * L, B, "ks_modup_ntt"));
   const bool merged = c->logN <= 14 && (c->own_hi - c->own_lo) > 0 && !c->ks_unmerged;
   // exact-double class: the inner product runs in the load of the INTT + ModDown launch (no accumulator round trip)
   const bool fused = merged && abc_ntt_arith_class(c) == AR_F64 && !c->ks_unfused;
+  const int t_image = fused && c->logN <= 14 && !c->ks_no_image ? 1 : 0;  // T rows as bulk-stored images of the swizzled limb
+  j.t_image = t_image;
+  const bool chain = t_image && c->ks_chain && c->ks_sched && c->logN <= 13 && c->force_ar < 0;
+  LimbJob jup = j;
+  if (!chain) TRY(launch_limb(c, einv ? LIMB_GALOIS_REDUCE_FWD : LIMB_REDUCE_FWD, c->ar_q, j, c->ks_nI * L, B, "ks_modup_ntt"));
   if (!fused) {
     Launch l(c, "ks_inner");
     DISPATCH_L(c, (k_ks_inner<LL><<<dim3(N / 512, c->ks_nI, B), 256, 0, c->stream>>>(T, key, acc, c->d_mods, N, k, c->L, c->ks_I)));
@@ -612,7 +642,24 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
     j.rowsrc = c->rs_mdm; j.rowdst = c->rd_mdm; j.rowmod = c->rm_mdm;
     j.flags = c->ks_flags; j.flag_serial = ++c->ks_serial; j.skew = c->ks_skew;
     if (fused) {
-      j.src = T; j.src_is = (long long)k * L * N; j.mul = key;
+      j.src = T; j.src_is = (long long)k * L * N; j.mul = key; j.t_image = t_image;
+      if (t_image) {  // raw-double T rows are multiplied with the exact-double copy of the key
+        const double *keyd = nullptr;
+        TRY(key_as_f64(c, key, &keyd));
+        j.mul = reinterpret_cast<const u64 *>(keyd);
+      }
+      if (chain) {
+        KsChain ch;
+        ch.up = jup; ch.tail = j; ch.sched = c->ks_sched; ch.n_blocks = c->ks_sched_n;
+        ch.up.n = ch.tail.n = N; ch.up.sub = ch.tail.sub = 0; ch.up.prefetch_ahead = 0; ch.tail.prefetch_ahead = c->prefetch_ahead;
+        ch.up.k = k; ch.up.L = L;
+        ch.up.done = ch.tail.done = c->ks_done;
+        ch.tail.done_target = ch.up.done_target = (u32)L * ++c->ks_chain_serial;
+        Launch l(c, "ks_chain");
+        const int e = ks_chain_launch(c->logN, ch, c->d_mods, c->stream);
+        if (e != 0) { c->err = std::string("ks_chain: ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
+        return ABC_OK;
+      }
       TRY(launch_limb(c, LIMB_KSINNER_INV_MODDOWN, c->ar_q, j, 2 + 2 * nown, B, "ks_inner_intt_moddown"));
     } else {
       TRY(launch_limb(c, LIMB_INV_MODDOWN, c->ar_q, j, 2 + 2 * nown, B, "ks_intt_moddown"));

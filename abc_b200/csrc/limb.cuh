@@ -44,7 +44,15 @@ struct LimbJob {
   int i0, nrows;                                // POST_MODDOWN rows: w = comp * nrows + (i - i0), limbs i0 .. i0+nrows-1
   u32 *flags; u32 flag_serial;                  // merged special-row INTT + ModDown launch: flags[inst][comp] == serial when ready
   int skew;                                     // ... special rows run this many instances ahead of their data rows
+  // key-switch ModUp block T as the IMAGE of the swizzled shared-memory limb: the forward launch writes each row with one
+  // bulk copy (no LDS + STG loop), the tail launch reads pair e2 at t[swz2(e2)] (a permutation inside 128-byte lines, so
+  // the loads stay coalesced).  T is private to the key switch, so its element order is ours to choose.
+  int t_image;
+  // chained ModUp + tail launch (kschain.cu): done[inst][modulus] counts the ModUp rows stored so far (L per key switch)
+  u32 *done; u32 done_target;
 };
+// physical 16-byte index of element pair e2 in the swizzled image of a limb (swz(2 * e2) / 2)
+__device__ __forceinline__ int swz2(int e2) { return e2 ^ ((e2 >> 3) & 7); }
 
 // combos of (PRE, FWD, MUL, INV, POST) the library uses
 enum {
@@ -267,7 +275,7 @@ __device__ __forceinline__ ulonglong2 ks_inner_pair(const ulonglong2 *__restrict
   double s0 = 0.0, s1 = 0.0;
 #pragma unroll 4
   for (int J = 0; J < L; ++J) {
-    const ulonglong2 tv = t[(size_t)J * rowv];
+    const ulonglong2 tv = __ldcg(t + (size_t)J * rowv);  // streamed once, possibly written by this very launch: L2
     const ulonglong2 kv = __ldg(kp + (size_t)J * keyv2);
     lo0 = mad_lo64(tv.x, kv.x, lo0); lo1 = mad_lo64(tv.y, kv.y, lo1);
     s0 = fma(f64_of(ar_from_canon<AR_F64>(tv.x)), f64_of(ar_from_canon<AR_F64>(kv.x)), s0);
@@ -280,27 +288,29 @@ __device__ __forceinline__ ulonglong2 ks_inner_pair(const ulonglong2 *__restrict
   return v;
 }
 
-// ---- one limb (or, TAIL, one 2^LOGN-coefficient block of a larger limb) in shared memory
+// The same inner product when T is the raw-double image the ModUp launch leaves (t_image) and the key is its exact-double
+// copy: every term is reduced on the FP64 pipe (mul_tw, |term| <= 0.6q), no conversions and no integer multiplies.
+__device__ __forceinline__ ulonglong2 ks_inner_pair_f64(const double2 *__restrict__ t, const double2 *__restrict__ kp, int L,
+                                                        int rowv, int keyv2, const ModInfo &M) {
+  const double qinv = f64_of(M.qinv_bits), qd = (double)M.q;
+  const u64 qb = bits_of(qd);
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+  for (int J = 0; J < L; ++J) {
+    const double2 tv = __ldcg(t + (size_t)J * rowv);
+    const double2 kv = __ldg(kp + (size_t)J * keyv2);
+    s0 += f64_of(mul_tw<AR_F64>(bits_of(tv.x), bits_of(kv.x), bits_of(kv.x * qinv), M.q, qb));
+    s1 += f64_of(mul_tw<AR_F64>(bits_of(tv.y), bits_of(kv.y), bits_of(kv.y * qinv), M.q, qb));
+  }
+  return make_ulonglong2(bits_of(reduce_f64(s0, qinv, qd)), bits_of(reduce_f64(s1, qinv, qd)));
+}
+
+// ---- one limb (or, TAIL, one 2^LOGN-coefficient block of a larger limb) in shared memory: row w of instance inst
 template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST, int AR, bool TAIL>
-__global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(LimbJob job,
-                                                                               const ModInfo *__restrict__ mods) {
+__device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__restrict__ mods, int inst, int w) {
   typedef NttDims<LOGN> D;
   extern __shared__ __align__(16) u64 sm[];
   const int tid = threadIdx.x;
-  int inst = blockIdx.y, w = TAIL ? (int)(blockIdx.x >> job.sub) : (int)blockIdx.x;
-  if (POST == POST_MODDOWN && !TAIL && job.flags) {
-    // merged special-row + ModDown launch: CTAs are dispatched in linear block order, and the two special-prime rows
-    // of instance g + S are issued with the data rows of instance g, so they have published INTT_p(acc_L) long before
-    // their own data rows ask for it (a data row only ever waits for blocks with a smaller linear index: no deadlock)
-    const int W = gridDim.x, Bn = gridDim.y, nd = W - 2, S = job.skew < Bn ? job.skew : Bn;
-    const int b = blockIdx.y * W + blockIdx.x;
-    if (b < 2 * S) { inst = b >> 1; w = b & 1; }
-    else {
-      const int b1 = b - 2 * S, full = (Bn - S) * W;
-      if (b1 < full) { const int g = b1 / W, r = b1 - g * W; inst = r < 2 ? g + S : g; w = r; }
-      else { const int b2 = b1 - full, g = b2 / nd; inst = Bn - S + g; w = 2 + (b2 - g * nd); }
-    }
-  }
   const int blk = TAIL ? (int)(blockIdx.x & ((1u << job.sub) - 1)) : 0;
   const u32 twbase = TAIL ? ((1u << job.sub) + (u32)blk) : 1u;
   const int n = TAIL ? job.n : D::N;           // coefficients per limb
@@ -336,7 +346,18 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
     const int comp = srow / job.k, I = srow - comp * job.k;
     const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(job.src + (size_t)inst * job.src_is + (size_t)I * job.L * D::N);
     const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(job.mul + (size_t)(comp * job.k + I) * D::N);
-    if (job.prefetch_ahead >= 0) {
+    if (job.done) {  // chained launch: T[inst][I][0..L) comes from blocks earlier in this grid
+      if (tid == 0) {
+        const u32 *dp = job.done + inst * job.k + I;
+        u32 seen;
+        do {
+          asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(dp) : "memory");
+          if ((int)(seen - job.done_target) < 0) __nanosleep(64);
+        } while ((int)(seen - job.done_target) < 0);
+      }
+      __syncthreads();
+    }
+    if (job.prefetch_ahead >= 0 && !job.done) {
       // the L T rows are contiguous and come straight from DRAM (written by the ModUp launch, larger than L2 at
       // bench batch sizes): pull them into L2 now so only the first loads of the loop below pay DRAM latency; same
       // for the rows the ModDown epilogue reads tens of microseconds from now (addend, sigma(c0))
@@ -357,8 +378,15 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
         }
       }
     }
-    for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
-      *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = ks_inner_pair(t + e2, kp + e2, job.L, D::N / 2, job.k * D::N, M);
+    if (job.t_image) {
+      for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
+        *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) =
+            ks_inner_pair_f64(reinterpret_cast<const double2 *>(t) + swz2(e2), reinterpret_cast<const double2 *>(kp) + e2, job.L,
+                              D::N / 2, job.k * D::N, M);
+    } else {
+      for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
+        *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = ks_inner_pair(t + e2, kp + e2, job.L, D::N / 2, job.k * D::N, M);
+    }
   } else if (PRE == PRE_ENCODE) {
     // BatchEncoder::encode (SealCiphertextFactory.cpp:102-132): pad with the last value, scatter by the index map
     const long long *sl = job.slots_in + (size_t)inst * job.slots_is;
@@ -374,8 +402,31 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
   if (!LINSRC) __syncthreads();
 
   if (FWD) {
-    if constexpr (LINSRC) ntt_fwd_smem<LOGN, AR, true>(sm, M, twbase, tid, mods[srow].q, PRE == PRE_GALOIS_REDUCE ? job.galois_einv : 0u);
-    else ntt_fwd_smem<LOGN, AR>(sm, M, twbase, tid);
+    if constexpr (LINSRC) {
+      if (job.t_image) {  // (uniform) the row leaves as the image of the swizzled limb: one bulk copy, issued by one thread
+        ntt_fwd_smem_mids<LOGN, AR, true>(sm, M, twbase, tid, mods[srow].q, PRE == PRE_GALOIS_REDUCE ? job.galois_einv : 0u);
+        ntt_fwd_last<LOGN, AR, 0, true>(sm, M, twbase, q, ar_aux<AR>(q), tid);  // raw doubles: the tail multiplies them as they are
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
+        __syncthreads();
+        if (tid == 0) {
+          u64 *g = job.dst + (size_t)inst * job.dst_is + (size_t)drow * D::N;
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       ::"l"(g), "r"((u32)__cvta_generic_to_shared(sm)), "r"((u32)D::SMEM) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (job.done) {  // chained launch: the tail rows of this instance wait for the L rows of their modulus
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __threadfence();
+            atomicAdd(job.done + inst * job.k + job.rowmod[w], 1u);
+          } else {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory is read out before the CTA retires
+          }
+        }
+        return;
+      }
+      ntt_fwd_smem<LOGN, AR, true>(sm, M, twbase, tid, mods[srow].q, PRE == PRE_GALOIS_REDUCE ? job.galois_einv : 0u);
+    } else {
+      ntt_fwd_smem<LOGN, AR>(sm, M, twbase, tid);
+    }
   }
 
   if (MUL) {
@@ -447,6 +498,26 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
       }
     }
   }
+}
+
+template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST, int AR, bool TAIL>
+__global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(LimbJob job,
+                                                                               const ModInfo *__restrict__ mods) {
+  int inst = blockIdx.y, w = TAIL ? (int)(blockIdx.x >> job.sub) : (int)blockIdx.x;
+  if (POST == POST_MODDOWN && !TAIL && job.flags) {
+    // merged special-row + ModDown launch: CTAs are dispatched in linear block order, and the two special-prime rows
+    // of instance g + S are issued with the data rows of instance g, so they have published INTT_p(acc_L) long before
+    // their own data rows ask for it (a data row only ever waits for blocks with a smaller linear index: no deadlock)
+    const int W = gridDim.x, Bn = gridDim.y, nd = W - 2, S = job.skew < Bn ? job.skew : Bn;
+    const int b = blockIdx.y * W + blockIdx.x;
+    if (b < 2 * S) { inst = b >> 1; w = b & 1; }
+    else {
+      const int b1 = b - 2 * S, full = (Bn - S) * W;
+      if (b1 < full) { const int g = b1 / W, r = b1 - g * W; inst = r < 2 ? g + S : g; w = r; }
+      else { const int b2 = b1 - full, g = b2 / nd; inst = Bn - S + g; w = 2 + (b2 - g * nd); }
+    }
+  }
+  limb_body<LOGN, PRE, FWD, MUL, INV, POST, AR, TAIL>(job, mods, inst, w);
 }
 
 // ---- head passes of the two-pass transform (N >= 32768): 2^A coefficients per thread at stride N >> A,

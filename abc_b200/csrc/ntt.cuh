@@ -393,7 +393,9 @@ __device__ __forceinline__ void ntt_fwd_last_math(u64 (&x)[8], const ulonglong2 
     }
   }
 }
-template <int LOGN, int AR, int TT = 0>
+// RAW (exact-double class): leave the outputs as the lazy doubles they are (|x| < (log2(N) + 2) q) instead of canonical
+// residues — for consumers that multiply them in the same arithmetic (the key switch's ModUp block)
+template <int LOGN, int AR, int TT = 0, bool RAW = false>
 __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 aux, int tid) {
   typedef NttLast<LOGN, TT> P;
   constexpr int E = P::E, H = E / 2;
@@ -412,8 +414,8 @@ __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twba
 #pragma unroll
     for (int i = 0; i < H; ++i) {
       ulonglong2 v;
-      v.x = canon_fwd<AR>(x[2 * i], M, q, aux);
-      v.y = canon_fwd<AR>(x[2 * i + 1], M, q, aux);
+      v.x = RAW ? x[2 * i] : canon_fwd<AR>(x[2 * i], M, q, aux);
+      v.y = RAW ? x[2 * i + 1] : canon_fwd<AR>(x[2 * i + 1], M, q, aux);
       *reinterpret_cast<ulonglong2 *>(&sm[swz(E * vt + 2 * i)]) = v;
     }
   }
