@@ -73,7 +73,7 @@ struct abc_ctx {
   int *rm_mdm = nullptr, *rd_mdm = nullptr, *rs_mdm = nullptr;               // [2 + 2 * nown] merged special + ModDown rows
   u32 *ks_sched = nullptr; int ks_sched_n = 0;                                // chained key switch: block schedule (kschain.cu)
   u32 *ks_done = nullptr; u32 ks_chain_serial = 0;                            // ... [B][k] ModUp rows stored so far (L per launch)
-  int ks_chain = 0, ks_chain_skew = 16;                                       // ABC_KS_CHAIN=0/1, ABC_KS_CHAIN_SKEW
+  int ks_chain = 1, ks_chain_skew = 16;                                       // ABC_KS_CHAIN=0/1, ABC_KS_CHAIN_SKEW
   u32 *ks_flags = nullptr; u32 ks_serial = 0;                                 // [B][2] ready flags of the merged launch
   int *rs_zero = nullptr;   // [2k]  0
   u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;

@@ -122,7 +122,7 @@ struct ModDownRow { u64 p, p_half, phm, ip, ips; const ulonglong2 *tl; const u64
 __device__ __forceinline__ ModDownRow moddown_row(const LimbJob &job, int n, int inst, int w) {
   // tail of switch_key_inplace for row (comp, i): dst = base + p^-1 * (acc_i - ([acc_L + p/2]_p mod q_i) + [p/2]_{q_i})
   const DevConst *C = job.C;
-  const int comp = w / job.nrows, i = job.i0 + (w - comp * job.nrows);
+  const int comp = w >= job.nrows ? 1 : 0, i = job.i0 + (w - comp * job.nrows);  // w < 2 * nrows
   ModDownRow r;
   r.p = C->p; r.p_half = C->p_half; r.phm = C->p_half_mod_q[i]; r.ip = C->inv_p[i]; r.ips = C->inv_p_s[i];
   r.tl = reinterpret_cast<const ulonglong2 *>(job.tl + (size_t)inst * job.tl_is + (size_t)(comp * job.k + job.L) * n);
@@ -343,7 +343,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
     bulk_row_to_smem(sm, job.src + (size_t)inst * job.src_is + (size_t)srow * D::N, (u32)D::SMEM, &mbar, tid);
   } else if (PRE == PRE_KS_INNER) {
     // srow = comp * k + I: row of the accumulator block this CTA produces
-    const int comp = srow / job.k, I = srow - comp * job.k;
+    const int comp = srow >= job.k ? 1 : 0, I = srow - comp * job.k;  // srow < 2k
     const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(job.src + (size_t)inst * job.src_is + (size_t)I * job.L * D::N);
     const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(job.mul + (size_t)(comp * job.k + I) * D::N);
     if (job.done) {  // chained launch: T[inst][I][0..L) comes from blocks earlier in this grid
@@ -365,7 +365,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
       for (int line = tid; line < job.L * (int)(D::N * 8 / 128); line += D::T)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)line * 128));
       if (POST == POST_MODDOWN && w >= 2) {
-        const int wq0 = w - 2, comp0 = wq0 / job.nrows, i0 = job.i0 + (wq0 - comp0 * job.nrows);
+        const int wq0 = w - 2, comp0 = wq0 >= job.nrows ? 1 : 0, i0 = job.i0 + (wq0 - comp0 * job.nrows);
         if (job.add) {
           const char *pa = reinterpret_cast<const char *>(job.add + (size_t)inst * job.add_is + (size_t)drow * D::N);
           for (int line = tid; line < (int)(D::N * 8 / 128); line += D::T)
@@ -475,7 +475,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
       }
       wq = w - 2;
       if (tid == 0) {
-        const u32 *fp = job.flags + inst * 2 + wq / job.nrows;
+        const u32 *fp = job.flags + inst * 2 + (wq >= job.nrows ? 1 : 0);
         u32 seen;
         do {
           asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(fp) : "memory");

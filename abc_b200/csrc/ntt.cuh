@@ -230,14 +230,16 @@ __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restric
       base[g] = (blk[g] << (LG + 3)) | (vt & ((1 << LG) - 1));
       pbase[g] = swz(base[g]);
       if (LINSRC) {
-        constexpr u32 m2 = 2u * D::N - 1;
-        const u32 step = (einv << LG) & m2;
-        u32 r0 = einv ? ((u32)base[g] * einv) & m2 : (u32)base[g];
+        // index e * einv mod 2N: the low log2(N) bits address the source, bit log2(N) is the sign; r0 is left to wrap
+        // (2N divides 2^32), and the identity is just einv = 1 (no sign bit ever set: e < N)
+        const u32 e1 = einv ? einv : 1u, step = e1 << LG;
+        u32 r0 = (u32)base[g] * e1;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const u64 v = sm[r0 & (D::N - 1)];
-          x[g][r] = ar_from_canon<AR>((r0 >= (u32)D::N && v) ? qs - v : v);
-          r0 = einv ? (r0 + step) & m2 : r0 + (1u << LG);
+          u64 v = sm[r0 & (D::N - 1)];
+          if ((r0 & (u32)D::N) && v) v = qs - v;
+          x[g][r] = ar_from_canon<AR>(v);
+          r0 += step;
         }
       } else {
 #pragma unroll

@@ -241,6 +241,10 @@ def run_ours(args):
                "ks_intt_special": B * 4 * row, "ks_intt_moddown": B * (2 * L + 2 + 2 * L + 2 * L) * row,
                # fused tail of a rotation's key switch: T rows in, sigma(c0) and the addend in, sum out, + key
                "ks_inner_intt_moddown": B * (k * L + L + 2 * L + 2 * L) * row + 2 * k * L * row,
+               # whole key switch of a rotation in one grid (chained ModUp + tail rows, or the single-launch kernel): c1 and
+               # sigma(c0) in, the addend ciphertext in, the sum out, + key; the ModUp block T is not algorithmic traffic
+               "ks_chain": B * (L + L + 2 * L + 2 * L) * row + 2 * k * L * row,
+               "ks_fused": B * (L + L + 2 * L + 2 * L) * row + 2 * k * L * row,
                "behz_ntt_q": B * 4 * L * row, "behz_ntt_bsk": B * 4 * nb * row,      # d *** d: squaring path, 2 of 4 polys
                "behz_intt_q": B * 6 * L * row, "behz_intt_bsk": B * 6 * nb * row,
                "behz_lift": B * 2 * (L + 2 * L + 1) * row, "behz_tensor": B * 7 * (2 * L + 1) * row,
@@ -256,7 +260,8 @@ def run_ours(args):
         arq = f.ntt_arith_class()
         ntt_rows = {"ks_modup_ntt": (k * L, arq), "ks_intt_special": (2, arq),
                     "ks_intt_moddown": (2 * L + (0 if any(r["kernel"] == "ks_intt_special" for r in prof) else 2), arq),
-                    "ks_inner_intt_moddown": (2 * L + 2, arq), "behz_ntt_q": (2 * L, arq), "behz_ntt_bsk": (2 * nb, 0),
+                    "ks_inner_intt_moddown": (2 * L + 2, arq), "ks_chain": (k * L + 2 * L + 2, arq),
+                    "ks_fused": (k * L + 2 * L + 2, arq), "behz_ntt_q": (2 * L, arq), "behz_ntt_bsk": (2 * nb, 0),
                     "behz_intt_q": (3 * L, arq), "behz_intt_bsk": (3 * nb, 0)}
         bf_peaks = {arq: bf_peak, 0: f.measure_butterfly_peak(0)}
         ntt_ms = sum(r["ms"] for r in prof if r["kernel"] in ntt_rows)

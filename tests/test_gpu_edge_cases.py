@@ -173,19 +173,29 @@ def test_limb_sharded_key_switch_two_gpus():
     assert p.returncode == 0 and "shard_check ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
 
 
+KS_VARIANTS = {
+    "one_launch": {"ABC_KS_ONE_LAUNCH": "1"},                                   # ksfused.cu: accumulators in shared memory
+    "chained": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAIN": "1"},                 # kschain.cu: ModUp + tail rows in one grid
+    "two_launch": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAIN": "0"},              # ModUp launch, tail launch (T as images)
+    "two_launch_canonical_T": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAIN": "0", "ABC_KS_NO_IMAGE": "1"},
+    "unfused_tail": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_UNFUSED": "1"},          # separate inner-product kernel
+}
+
+
 @pytest.mark.parametrize("N", [4096, 8192])
-@pytest.mark.parametrize("one_launch", ["0", "1"])
-def test_key_switch_single_launch_and_two_launch_agree(N, one_launch, monkeypatch):
-    """The exact-double key switch exists as ONE launch (csrc/ksfused.cu: accumulators in shared memory, no ModUp block
-    in HBM) and as ModUp launch + tail launch; the default is picked by size.  Both are forced here and must give the
-    oracle's coefficients for relinearisation, single and NAF rotations, the fused rotate+add and a batch of 3."""
+@pytest.mark.parametrize("variant", sorted(KS_VARIANTS))
+def test_key_switch_variants_agree(N, variant, monkeypatch):
+    """The exact-double key switch exists in several launch structures (the default is picked by size); each is forced
+    here and must give the oracle's coefficients for relinearisation, single and NAF rotations, the fused rotate+add
+    and a batch of 3 (more instances than the chained schedule's skew would be covered by the bench's result check)."""
     from abc_b200 import CudaCiphertextFactory
     from oracle.bfv_oracle import Oracle
-    monkeypatch.setenv("ABC_KS_ONE_LAUNCH", one_launch)
+    for kk, vv in KS_VARIANTS[variant].items():
+        monkeypatch.setenv(kk, vv)
     o = Oracle(N, seed=SEED)
     f = CudaCiphertextFactory(N, seed=SEED, batch=3)
     try:
-        rng = np.random.default_rng(N + int(one_launch))
+        rng = np.random.default_rng(N + len(variant))
         da, db = rng.integers(0, 1025, (3, N)), rng.integers(0, 1025, (3, N))
         a_w = np.stack([o.encrypt_slots(da[i], 10 + i) for i in range(3)])
         b_w = np.stack([o.encrypt_slots(db[i], 20 + i) for i in range(3)])
@@ -202,3 +212,31 @@ def test_key_switch_single_launch_and_two_launch_agree(N, one_launch, monkeypatc
             assert np.array_equal(s[i], o.add(b_w[i], o.rotate_rows(a_w[i], 4))), "rotate+add inst %d" % i
     finally:
         f.close()
+
+
+def test_chained_key_switch_large_batch_matches_two_launch(monkeypatch):
+    """48 instances (3x the chained schedule's skew, so ModUp rows of later instances are in flight while earlier ones
+    finish): rotate, rotate+add and mul+relin coefficients of the chained grid equal the two-launch sequence's, and
+    instance 0 / 47 equal the oracle's."""
+    from abc_b200 import CudaCiphertextFactory
+    from oracle.bfv_oracle import Oracle
+    N, B = 8192, 48
+    rng = np.random.default_rng(7)
+    da, db = rng.integers(0, 1025, (B, N)), rng.integers(0, 1025, (B, N))
+    outs = {}
+    for variant in ("chained", "two_launch"):
+        for kk, vv in KS_VARIANTS[variant].items():
+            monkeypatch.setenv(kk, vv)
+        f = CudaCiphertextFactory(N, seed=SEED, batch=B)
+        try:
+            f.set_encrypt_nonce(5)
+            a, b = f.createCiphertext(da), f.createCiphertext(db)
+            outs[variant] = (a.export(), a.rotateRows(-24).export(), b.add(a.rotateRows(1)).export(), a.multiply(b).export())
+        finally:
+            f.close()
+    for x, y in zip(outs["chained"], outs["two_launch"]):
+        assert np.array_equal(x, y)
+    o = Oracle(N, seed=SEED)
+    a_in, rot = outs["chained"][0], outs["chained"][1]
+    for i in (0, B - 1):
+        assert np.array_equal(rot[i], o.rotate_rows(a_in[i], -24))
