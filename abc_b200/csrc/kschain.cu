@@ -7,7 +7,7 @@
 // S1 instances' worth of T is alive at any time (L2-resident), and an SM holds a transform-bound ModUp CTA next to a
 // load-bound tail CTA instead of two of the same kind.  A tail row waits (acquire on a counter its L ModUp rows bump
 // after their bulk stores complete) only for blocks with a smaller linear index, so the grid cannot deadlock.
-// Schedule (host-built, abc_ctx::ks_sched): entry = role << 30 | inst << 8 | row.
+// Schedule (host-built, abc_ctx::ks_sched): entry.x = role << 31 | inst, entry.y = row | modulus << 8 | drow << 16 | srow << 24.
 #define ABC_LIMB_IMPL
 #include "kschain.cuh"
 
@@ -15,12 +15,14 @@ namespace {
 
 template <int LOGN, bool GAL>
 __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_ks_chain(KsChain ch, const ModInfo *__restrict__ mods) {
-  const u32 s = ch.sched[blockIdx.x];
-  const int inst = (int)((s >> 8) & 0x3fffff), w = (int)(s & 0xff);
-  if ((s >> 30) == 0)
-    limb_body<LOGN, GAL ? PRE_GALOIS_REDUCE : PRE_REDUCE, true, false, false, POST_STORE, AR_F64, false>(ch.up, mods, inst, w);
+  // schedule entry: x = role << 31 | inst, y = w | modulus << 8 | drow << 16 | srow << 24
+  const uint2 s = __ldg(ch.sched + blockIdx.x);
+  const int inst = (int)(s.x & 0x7fffffffu), w = (int)(s.y & 0xff);
+  const RowIds ids{(int)((s.y >> 8) & 0xff), (int)((s.y >> 16) & 0xff), (int)(s.y >> 24)};
+  if ((s.x >> 31) == 0)
+    limb_body<LOGN, GAL ? PRE_GALOIS_REDUCE : PRE_REDUCE, true, false, false, POST_STORE, AR_F64, false>(ch.up, mods, inst, w, ids);
   else
-    limb_body<LOGN, PRE_KS_INNER, false, false, true, POST_MODDOWN, AR_F64, false>(ch.tail, mods, inst, w);
+    limb_body<LOGN, PRE_KS_INNER, false, false, true, POST_MODDOWN, AR_F64, false>(ch.tail, mods, inst, w, ids);
 }
 
 template <int LOGN, bool GAL>

@@ -5,7 +5,7 @@
 struct KsChain {
   LimbJob up;          // ModUp + NTT rows (t_image = 1, done = counters)
   LimbJob tail;        // inner product + INTT + ModDown rows (flags / done set)
-  const u32 *sched;    // [n_blocks] role << 30 | inst << 8 | row, in dependency order
+  const uint2 *sched;  // [n_blocks] in dependency order: x = role << 31 | inst, y = row | modulus << 8 | drow << 16 | srow << 24
   int n_blocks;
 };
 

@@ -71,7 +71,7 @@ struct abc_ctx {
   int *rm_md = nullptr, *rd_md = nullptr, *rs_md = nullptr;                  // [2 * nown] ModDown rows
   int *rm_own = nullptr, *rd_own = nullptr;                                  // [2 * nown] own rows of a ciphertext
   int *rm_mdm = nullptr, *rd_mdm = nullptr, *rs_mdm = nullptr;               // [2 + 2 * nown] merged special + ModDown rows
-  u32 *ks_sched = nullptr; int ks_sched_n = 0;                                // chained key switch: block schedule (kschain.cu)
+  uint2 *ks_sched = nullptr; int ks_sched_n = 0;                                // chained key switch: block schedule (kschain.cu)
   u32 *ks_done = nullptr; u32 ks_chain_serial = 0;                            // ... [B][k] ModUp rows stored so far (L per launch)
   int ks_chain = 1, ks_chain_skew = 16;                                       // ABC_KS_CHAIN=0/1, ABC_KS_CHAIN_SKEW
   u32 *ks_flags = nullptr; u32 ks_serial = 0;                                 // [B][2] ready flags of the merged launch
@@ -448,16 +448,26 @@ abc_status build_shard_maps(abc_ctx *c) {
     mm.insert(mm.end(), m.begin(), m.end()); dm.insert(dm.end(), d.begin(), d.end()); sm_.insert(sm_.end(), sr.begin(), sr.end());
     TRY(upload(c, &c->rm_mdm, mm)); TRY(upload(c, &c->rd_mdm, dm)); TRY(upload(c, &c->rs_mdm, sm_));
   }
-  if (nown > 0 && c->B < (1 << 22) && c->ks_nI * L < 256 && 2 + 2 * nown < 256) {
+  if (nown > 0 && c->ks_nI * L < 256 && 2 * k < 256 && k * L < 256) {
     // chained key switch: ModUp rows of instance g, the two special-prime tail rows of instance g - (S1 - S2) and the
-    // data tail rows of instance g - S1, for g = 0 .. B + S1 - 1 (every wait points at an earlier block)
+    // data tail rows of instance g - S1, for g = 0 .. B + S1 - 1 (every wait points at an earlier block).  Every entry
+    // carries its row's modulus, destination row and source row (the row maps of the two-launch sequence, resolved here)
     const int Bn = c->B, S1 = c->ks_chain_skew, S2 = std::min(c->ks_skew, S1 - 1) < 0 ? 0 : std::min(c->ks_skew, S1 - 1);
-    std::vector<u32> sch;
+    std::vector<uint2> sch;
+    auto up_row = [&](int g, int w) {      // w = idx(I) * L + J: T row I * L + J from target limb J, modulus I
+      const int Iv = I[w / L], J = w % L;
+      sch.push_back(make_uint2((u32)g, (u32)w | (u32)Iv << 8 | (u32)(Iv * L + J) << 16 | (u32)J << 24));
+    };
+    auto tail_row = [&](int g, int w) {    // w < 2: special-prime row of component w; else data row (comp, i)
+      const int comp = w < 2 ? w : (w - 2) / nown, Iv = w < 2 ? L : lo + (w - 2) % nown;
+      const int drow = w < 2 ? (w == 0 ? L : k + L) : comp * L + Iv;
+      sch.push_back(make_uint2(1u << 31 | (u32)g, (u32)w | (u32)Iv << 8 | (u32)drow << 16 | (u32)(comp * k + Iv) << 24));
+    };
     for (int g = 0; g < Bn + S1; ++g) {
-      if (g < Bn) for (int w = 0; w < c->ks_nI * L; ++w) sch.push_back((u32)g << 8 | (u32)w);
+      if (g < Bn) for (int w = 0; w < c->ks_nI * L; ++w) up_row(g, w);
       const int gs = g - (S1 - S2), gd = g - S1;
-      if (gs >= 0 && gs < Bn) for (int w = 0; w < 2; ++w) sch.push_back(1u << 30 | (u32)gs << 8 | (u32)w);
-      if (gd >= 0 && gd < Bn) for (int w = 2; w < 2 + 2 * nown; ++w) sch.push_back(1u << 30 | (u32)gd << 8 | (u32)w);
+      if (gs >= 0 && gs < Bn) for (int w = 0; w < 2; ++w) tail_row(gs, w);
+      if (gd >= 0 && gd < Bn) for (int w = 2; w < 2 + 2 * nown; ++w) tail_row(gd, w);
     }
     TRY(upload(c, &c->ks_sched, sch));
     c->ks_sched_n = (int)sch.size();

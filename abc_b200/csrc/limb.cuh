@@ -306,8 +306,12 @@ __device__ __forceinline__ ulonglong2 ks_inner_pair_f64(const double2 *__restric
 }
 
 // ---- one limb (or, TAIL, one 2^LOGN-coefficient block of a larger limb) in shared memory: row w of instance inst
+// RowIds: the caller already knows modulus / destination row / source row of row w (the chained key switch packs them
+// into its schedule: no dependent loads from the row maps in front of the first copy); modidx < 0 = look them up
+struct RowIds { int modidx, drow, srow; };
 template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST, int AR, bool TAIL>
-__device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__restrict__ mods, int inst, int w) {
+__device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__restrict__ mods, int inst, int w,
+                                          RowIds ids = RowIds{-1, 0, 0}) {
   typedef NttDims<LOGN> D;
   extern __shared__ __align__(16) u64 sm[];
   const int tid = threadIdx.x;
@@ -315,10 +319,11 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
   const u32 twbase = TAIL ? ((1u << job.sub) + (u32)blk) : 1u;
   const int n = TAIL ? job.n : D::N;           // coefficients per limb
   const int eoff = blk * (D::N / 2);           // this block's offset in 16-byte units
-  const ModInfo M = mods[job.rowmod[w]];
+  const int modidx = ids.modidx >= 0 ? ids.modidx : job.rowmod[w];
+  const ModInfo M = mods[modidx];
   const u64 q = M.q;
-  const int drow = job.rowdst ? job.rowdst[w] : w;
-  const int srow = job.rowsrc ? job.rowsrc[w] : drow;
+  const int drow = ids.modidx >= 0 ? ids.drow : (job.rowdst ? job.rowdst[w] : w);
+  const int srow = ids.modidx >= 0 ? ids.srow : (job.rowsrc ? job.rowsrc[w] : drow);
   const int mrow = job.rowmul ? job.rowmul[w] : w;
 
   // ---- L2 prefetch of the row a later CTA of this launch will load (ncu: 35 % of this kernel's stall samples sat on
@@ -416,7 +421,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
           if (job.done) {  // chained launch: the tail rows of this instance wait for the L rows of their modulus
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             __threadfence();
-            atomicAdd(job.done + inst * job.k + job.rowmod[w], 1u);
+            atomicAdd(job.done + inst * job.k + modidx, 1u);
           } else {
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory is read out before the CTA retires
           }

@@ -237,7 +237,11 @@ __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restric
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           u64 v = sm[r0 & (D::N - 1)];
-          if ((r0 & (u32)D::N) && v) v = qs - v;
+          // negated position and v != 0: v = qs - v, as two predicated subtractions (the C++ form compiles to two
+          // levels of 64-bit selects: 16 instructions per element instead of 10)
+          asm("{\n .reg .pred p;\n .reg .b32 lo, hi, t;\n mov.b64 {lo, hi}, %0;\n or.b32 t, lo, hi;\n setp.ne.u32 p, t, 0;\n"
+              " and.b32 t, %2, %3;\n setp.ne.and.u32 p, t, 0, p;\n @p sub.u64 %0, %1, %0;\n}"
+              : "+l"(v) : "l"(qs), "r"(r0), "r"((u32)D::N));
           x[g][r] = ar_from_canon<AR>(v);
           r0 += step;
         }
