@@ -141,19 +141,19 @@ __device__ __forceinline__ ModDownF64 moddown_f64(const ModDownRow &md, const Mo
 }
 __device__ __forceinline__ double moddown_one_f64(double vd, u64 t, bool has_base, u64 b, const ModDownF64 &f) {
   double a = f64_of(ar_from_canon<AR_F64>(t)) + f.p_half;
-  a = a >= f.pd ? a - f.pd : a;                                   // [t + p/2]_p, exact
+  a = csub_ge(a, f.pd);                                           // [t + p/2]_p, exact
   const double d = (vd - reduce_f64(a, f.qinv, f.qd)) + f.phm;    // |d| < 2.6q, exact integer
   const double Q = fma(d, f.ipc, ABC_RINT_MAGIC) - ABC_RINT_MAGIC;
   const double ph = d * f.ipd, pl = fma(d, f.ipd, -ph);
   double r = fma(-Q, f.qd, ph) + pl;                              // d * p^-1 mod q, |r| <= 0.6q
   if (has_base) r += f64_of(ar_from_canon<AR_F64>(b));
-  r = r < 0.0 ? r + f.qd : r;
-  return r >= f.qd ? r - f.qd : r;                                // canonical, as a double
+  r = cadd_neg(r, f.qd);
+  return csub_ge(r, f.qd);                                        // canonical, as a double
 }
 __device__ __forceinline__ u64 f64_canon_bits(double r) { return bits_of(r + 4503599627370496.0) & 0x000FFFFFFFFFFFFFULL; }
 __device__ __forceinline__ double add_canon_f64(double r, u64 ad, double qd) {
   r += f64_of(ar_from_canon<AR_F64>(ad));
-  return r >= qd ? r - qd : r;
+  return csub_ge(r, qd);
 }
 
 // ---- ModDown epilogue of one data row on the exact-double class: sm holds the INTT output as centred doubles

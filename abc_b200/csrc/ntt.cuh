@@ -158,9 +158,19 @@ __device__ __forceinline__ double reduce_f64(double x, double qinv, double qd) {
   const double Q = fma(x, qinv, ABC_RINT_MAGIC) - ABC_RINT_MAGIC;
   return fma(-Q, qd, x);
 }
+// r < 0 ? r + q : r  and  r >= q ? r - q : r  as a compare + ONE predicated add (the C++ ternary compiles to
+// add + compare + two selects)
+__device__ __forceinline__ double cadd_neg(double r, double q) {
+  asm("{\n .reg .pred p;\n setp.lt.f64 p, %0, 0d0000000000000000;\n @p add.f64 %0, %0, %1;\n}" : "+d"(r) : "d"(q));
+  return r;
+}
+__device__ __forceinline__ double csub_ge(double r, double q) {
+  asm("{\n .reg .pred p;\n setp.ge.f64 p, %0, %1;\n @p sub.f64 %0, %0, %1;\n}" : "+d"(r) : "d"(q));
+  return r;
+}
 // centred double in (-q, q) -> canonical u64
 __device__ __forceinline__ u64 f64_to_canon(double r, double qd) {
-  r = r < 0.0 ? r + qd : r;
+  r = cadd_neg(r, qd);
   return bits_of(r + 4503599627370496.0) & 0x000FFFFFFFFFFFFFULL;
 }
 template <int AR> __device__ __forceinline__ u64 canon_fwd(u64 x, const ModInfo &M, u64 q, u64 aux) {
