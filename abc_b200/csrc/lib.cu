@@ -43,6 +43,7 @@ struct abc_ctx {
   bool no_square = false;                        // ABC_NO_SQUARE: multiply(x, x) takes the general path
   bool lazy_rotate = true;                       // ABC_EAGER_ROTATE: rotate_rows runs its last key switch immediately
   bool ks_unmerged = false, ks_unfused = false;  // ABC_KS_UNMERGED / ABC_KS_UNFUSED: A/B switches for the key-switch tail
+  bool ks_no_discard = false;                    // ABC_KS_NO_DISCARD: leave the consumed ModUp rows to L2's write-back
   bool ks_no_image = false;                      // ABC_KS_NO_IMAGE: ModUp rows stored element by element instead of as bulk-copied images
   int ks_one_launch = -1;                        // ABC_KS_ONE_LAUNCH=0/1: force the single-launch key switch off / on (-1: by size)
   int ks1_threads = 1024;                        // ABC_KS1_THREADS: CTA size of the single-launch key switch at N = 8192
@@ -310,6 +311,7 @@ abc_status build_tables(abc_ctx *c) {
   if (const char *e = getenv("ABC_KS_ONE_LAUNCH")) c->ks_one_launch = atoi(e) ? 1 : 0;
   if (getenv("ABC_KS_TWO_LAUNCH")) c->ks_one_launch = 0;
   c->ks_no_image = getenv("ABC_KS_NO_IMAGE") != nullptr;
+  c->ks_no_discard = getenv("ABC_KS_NO_DISCARD") != nullptr;
   if (const char *e = getenv("ABC_KS_CHAIN")) c->ks_chain = atoi(e);
   if (const char *e = getenv("ABC_KS_CHAIN_SKEW")) c->ks_chain_skew = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("ABC_KS1_THREADS")) c->ks1_threads = atoi(e);
@@ -471,9 +473,9 @@ abc_status build_shard_maps(abc_ctx *c) {
     }
     TRY(upload(c, &c->ks_sched, sch));
     c->ks_sched_n = (int)sch.size();
-    CK(cudaMalloc((void **)&c->ks_done, (size_t)c->B * c->k * sizeof(u32)));
+    CK(cudaMalloc((void **)&c->ks_done, (size_t)2 * c->B * c->k * sizeof(u32)));   // [B][k] rows stored + [B][k] rows consumed
     c->owned.push_back(c->ks_done);
-    CK(cudaMemset(c->ks_done, 0, (size_t)c->B * c->k * sizeof(u32)));
+    CK(cudaMemset(c->ks_done, 0, (size_t)2 * c->B * c->k * sizeof(u32)));
     c->ks_chain_serial = 0;
   }
   if (!c->ks_flags) {
@@ -664,6 +666,7 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
         ch.up.n = ch.tail.n = N; ch.up.sub = ch.tail.sub = 0; ch.up.prefetch_ahead = 0; ch.tail.prefetch_ahead = c->prefetch_ahead;
         ch.up.k = k; ch.up.L = L;
         ch.up.done = ch.tail.done = c->ks_done;
+        ch.tail.t_used = c->ks_no_discard ? nullptr : c->ks_done + (size_t)c->B * k;
         ch.tail.done_target = ch.up.done_target = (u32)L * ++c->ks_chain_serial;
         Launch l(c, "ks_chain");
         const int e = ks_chain_launch(c->logN, ch, c->d_mods, c->stream);

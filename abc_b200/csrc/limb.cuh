@@ -50,6 +50,8 @@ struct LimbJob {
   int t_image;
   // chained ModUp + tail launch (kschain.cu): done[inst][modulus] counts the ModUp rows stored so far (L per key switch)
   u32 *done; u32 done_target;
+  u32 *t_used;   // [inst][modulus] tail rows that have consumed T[inst][modulus][*] (2 per key switch): the second one drops
+                 // the rows from L2 (discard.global.L2) so that their dirty lines are never written to DRAM
 };
 // physical 16-byte index of element pair e2 in the swizzled image of a limb (swz(2 * e2) / 2)
 __device__ __forceinline__ int swz2(int e2) { return e2 ^ ((e2 >> 3) & 7); }
@@ -306,6 +308,22 @@ __device__ __forceinline__ ulonglong2 ks_inner_pair_f64(const double2 *__restric
 }
 
 // ---- one limb (or, TAIL, one 2^LOGN-coefficient block of a larger limb) in shared memory: row w of instance inst
+#ifndef ABC_KS_DISCARD_T
+#define ABC_KS_DISCARD_T 0
+#endif
+// second consumer of T[inst][I][0..L): drop the rows from L2 (warp 0; `before` = the consumption count thread 0 took)
+template <int N>
+__device__ __forceinline__ void discard_consumed_T(const LimbJob &job, int inst, int srow, u32 before, int tid) {
+  if (job.t_used && tid < 32) {
+    const int I = srow >= job.k ? srow - job.k : srow;
+    if (__shfl_sync(0xffffffffu, before, 0) & 1u) {
+      const char *p = reinterpret_cast<const char *>(job.src + (size_t)inst * job.src_is + (size_t)I * job.L * N);
+      for (int line = tid; line < job.L * (N * 8 / 128); line += 32)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(p + (size_t)line * 128) : "memory");
+    }
+  }
+}
+
 // RowIds: the caller already knows modulus / destination row / source row of row w (the chained key switch packs them
 // into its schedule: no dependent loads from the row maps in front of the first copy); modidx < 0 = look them up
 struct RowIds { int modidx, drow, srow; };
@@ -405,6 +423,17 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
       *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = limb_load_pair<PRE>(job, M, mods, n, inst, srow, eoff + e2, h);
   }
   if (!LINSRC) __syncthreads();
+  // T[inst][I][0..L) is dead once both components' rows have read it (the barrier above: every thread of this row has).
+  // The count is taken now and looked at after the row is stored (its latency hides behind the transform); the row that
+  // finds it odd drops T's lines from L2 so that their dirty data never goes to DRAM.
+  // (compiled in with -DABC_KS_DISCARD_T=1 only: DRAM traffic of a key switch 1.55 -> 0.77 GB at B = 592, but the extra
+  // code costs the tail rows 2 % and DRAM is at 17 % of its peak either way)
+  u32 t_used_before = 0;
+#if ABC_KS_DISCARD_T
+  if constexpr (PRE == PRE_KS_INNER) {
+    if (job.t_used && tid == 0) t_used_before = atomicAdd(job.t_used + inst * job.k + (srow >= job.k ? srow - job.k : srow), 1u);
+  }
+#endif
 
   if (FWD) {
     if constexpr (LINSRC) {
@@ -476,6 +505,9 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
         __threadfence();
         __syncthreads();
         if (tid == 0) atomicExch(job.flags + inst * 2 + w, job.flag_serial);
+#if ABC_KS_DISCARD_T
+        if constexpr (PRE == PRE_KS_INNER) discard_consumed_T<D::N>(job, inst, srow, t_used_before, tid);
+#endif
         return;
       }
       wq = w - 2;
@@ -503,6 +535,10 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
       }
     }
   }
+#if ABC_KS_DISCARD_T
+  if constexpr (PRE == PRE_KS_INNER) discard_consumed_T<D::N>(job, inst, srow, t_used_before, tid);
+#endif
+  (void)t_used_before;
 }
 
 template <int LOGN, int PRE, bool FWD, bool MUL, bool INV, int POST, int AR, bool TAIL>
