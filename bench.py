@@ -98,6 +98,19 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def ncu_pipes_for(kernel, batch):
+    """pipe utilisation of `kernel` from the same committed ncu capture (profiles/traffic.json), else None."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
+        if rec and rec["batch"] == batch and rec["N"] == N_POLY and "fp64_pipe_pct_of_peak" in rec:
+            return {"fp64_pipe_pct_of_peak": rec["fp64_pipe_pct_of_peak"], "issue_active_pct": rec["issue_active_pct"],
+                    "l1_data_pipe_pct": rec["l1_data_pipe_pct"], "dram_pct_of_peak": rec["dram_pct_of_peak"],
+                    "source": rec["source"]}
+    except Exception:
+        pass
+    return None
+
+
 def traffic_for(kernel, batch):
     """dram bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json), else None."""
     try:
@@ -155,7 +168,20 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL announces its version on stdout when the communicator comes up; stdout carries the ONE JSON line, so the
+        # process-level descriptor points at stderr while NCCL initialises
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
@@ -289,7 +315,7 @@ def run_ours(args):
             "roofline": {"kernel": top["kernel"], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": ach / peaks["hbm_gbs"], "traffic": traffic_for(top["kernel"], B), "peak_source": how,
                          "algorithmic_bytes_per_launch": alg.get(top["kernel"], 0),
-                         "share_of_step": top["ms"] / tot,
+                         "share_of_step": top["ms"] / tot, "ncu": ncu_pipes_for(top["kernel"], B),
                          "note": "this kernel family is bound by the FP64 / integer pipes, not HBM: see int_roofline"},
             "int_roofline": {"unit": "64-bit modular NTT butterflies/s (all limb-pipeline kernels of the step)",
                              "achieved": ntt_bf / (ntt_ms * 1e-3), "peak": bf_peak,
