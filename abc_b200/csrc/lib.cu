@@ -227,7 +227,8 @@ void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, s
   // FP64-assisted class: companion = double(w/q) (correctly rounded: both operands are exact doubles)
   auto dbits = [q](u64 w) { double d = (double)w / (double)q; u64 b; memcpy(&b, &d, 8); return b; };
   m.ar_class = AR_SHOUP;
-  if ((q >> 49) == 0) m.ar_class = (q >> 45) == 0 ? AR_F64 : AR_FP;  // range plans in ntt.cuh (AR_FP_LAZY: ABC_FORCE_AR=2)
+  // exact-double class: q < 0.97 * 2^45 (the inverse transform's range plan keeps 7 stages between two reductions)
+  if ((q >> 49) == 0) m.ar_class = q < 34128100000000ull ? AR_F64 : AR_FP;  // range plans in ntt.cuh (AR_FP_LAZY: ABC_FORCE_AR=2)
   twf.clear(); itwf.clear();
   m.ninv_f = m.wl_ninv_f = m.qinv_bits = 0;
   if (m.ar_class != AR_SHOUP) {

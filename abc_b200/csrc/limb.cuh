@@ -54,7 +54,7 @@ struct LimbJob {
                  // the rows from L2 (discard.global.L2) so that their dirty lines are never written to DRAM
 };
 // physical 16-byte index of element pair e2 in the swizzled image of a limb (swz(2 * e2) / 2)
-__device__ __forceinline__ int swz2(int e2) { return e2 ^ ((e2 >> 3) & 7); }
+__device__ __forceinline__ int swz2(int e2) { return e2 ^ ((e2 >> 3) & 7) ^ ((e2 >> 4) & 4); }
 
 // combos of (PRE, FWD, MUL, INV, POST) the library uses
 enum {

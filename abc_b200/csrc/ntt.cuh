@@ -46,7 +46,17 @@ __device__ __forceinline__ double f64_of(u64 bits) { return __longlong_as_double
 __device__ __forceinline__ u64 bits_of(double d) { return (u64)__double_as_longlong(d); }
 
 // element index -> physical index; keeps (even, odd) pairs adjacent so 16-byte accesses stay legal
-__device__ __forceinline__ int swz(int e) { return e ^ ((e >> 3) & 14); }
+// (bits 4..6 of e onto bits 1..3: strided and contiguous passes are conflict free; bit 7 onto bit 3: neighbouring
+// 128-coefficient blocks are staggered by 64 bytes, which a pass with 8 lanes per block — the radix-16 plan's — needs)
+__device__ __forceinline__ int swz(int e) { return e ^ ((e >> 3) & 14) ^ ((e >> 4) & 8); }
+// sm address of element base + (r << LG) of a strided pass, given pbase = swz(base) with base's bits LG.. clear below bit 7
+// swz(8 * vt + 2 * i) = swz_row8(vt) ^ (2 * i): one XOR per access in the contiguous pass instead of a swizzle each
+__device__ __forceinline__ int swz_row8(int vt) { return (8 * vt) ^ (vt & 14) ^ ((vt >> 1) & 8); }
+template <int LG> __device__ __forceinline__ int swz_strided(int base, int pbase, int r) {
+  if (LG > 7) return pbase + (r << LG);                       // the swizzle never sees the bits r moves
+  if (LG == 7) return ((r & 1) ? (pbase ^ 8) : pbase) + (r << LG);  // bit 7 = r & 1 (it is 0 in base)
+  return swz(base + (r << LG));
+}
 
 // strided passes (radix 2^R each); the contiguous pass (NttLast) takes the remaining stages
 template <int LOGN> struct NttPlan;
@@ -63,6 +73,26 @@ template <int LOGN, int TT = 0> struct NttDims {
   static constexpr int IT = N / 8 / T;
   static constexpr size_t SMEM = (size_t)N * 8;
 };
+
+// ---- radix-16 plan (exact-double class at N = 8192 with 512-thread CTAs): strided passes of 3, 3 and FOUR stages, then a
+// contiguous pass of three in-register stages — no lane-pair shuffle stage, whose 16 shuffles + 48 selects per 8
+// coefficients were 7 % of a row's instructions.  The 4-stage pass keeps one group of 16 coefficients per thread (the
+// same 32 data registers as two interleaved groups of 8).  Thread mapping: the 128 threads that share a named barrier
+// after the second pass (tid >> 7 = g) wrote the 1024-coefficient blocks g and g + 4, so they also run those blocks'
+// 4-stage pass (64 groups of 16 each), and every warp of that pass then owns 64 consecutive 8-coefficient blocks,
+// which the same warp takes through the contiguous pass: the two new boundaries cost a named barrier and a warp barrier.
+#ifndef ABC_PLAN16
+#define ABC_PLAN16 1
+#endif
+template <int LOGN, int AR, int TT> struct UsePlan16 {
+  static constexpr bool value = ABC_PLAN16 && LOGN == 13 && AR == 3 /* AR_F64 */ && TT == 0 && NttDims<13, 0>::T == 512;
+};
+// 1024-coefficient block of thread tid in the 4-stage pass, and its group of 16 inside (0..63)
+__device__ __forceinline__ int p16_kblock(int tid) { return (tid >> 7) + 4 * ((tid >> 6) & 1); }
+// 8-coefficient block of (tid, g) in the contiguous pass
+__device__ __forceinline__ int p16_block8(int tid, int g) {
+  return (p16_kblock(tid) << 7) + (((tid >> 5) & 1) << 6) + (g << 5) + (tid & 31);
+}
 
 // lo64(a*b + c) as one IMAD.WIDE + two IMAD (no separate carry adds): the shape ptxas keeps on the fma pipe
 __device__ __forceinline__ u64 mad_lo64(u64 a, u64 b, u64 c) {
@@ -257,7 +287,7 @@ __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restric
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) x[g][r] = sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))];
+        for (int r = 0; r < 8; ++r) x[g][r] = sm[swz_strided<LG>(base[g], pbase[g], r)];
         if (S0 == 0) {  // first pass: canonical residues -> the class's representation
 #pragma unroll
           for (int r = 0; r < 8; ++r) x[g][r] = ar_from_canon<AR>(x[g][r]);
@@ -284,7 +314,7 @@ __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restric
 #pragma unroll
     for (int g = 0; g < G; ++g)
 #pragma unroll
-      for (int r = 0; r < 8; ++r) sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))] = x[g][r];
+      for (int r = 0; r < 8; ++r) sm[swz_strided<LG>(base[g], pbase[g], r)] = x[g][r];
   }
 }
 
@@ -313,7 +343,7 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
       base[g] = (blk[g] << (LG + 3)) | (vt & ((1 << LG) - 1));
       pbase[g] = swz(base[g]);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) x[g][r] = sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))];
+      for (int r = 0; r < 8; ++r) x[g][r] = sm[swz_strided<LG>(base[g], pbase[g], r)];
       if ((AR == AR_FP_LAZY || AR == AR_F64) && REDUCE) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
@@ -345,7 +375,7 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
 #pragma unroll
       for (int g = 0; g < G; ++g)
 #pragma unroll
-        for (int r = 0; r < 8; ++r) sm[LG >= 7 ? pbase[g] + (r << LG) : swz(base[g] + (r << LG))] = x[g][r];
+        for (int r = 0; r < 8; ++r) sm[swz_strided<LG>(base[g], pbase[g], r)] = x[g][r];
     } else {
 #pragma unroll
       for (int g = 0; g < G; ++g)
@@ -353,6 +383,57 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
         for (int r = 0; r < 8; ++r) epi(base[g] + (r << LG), x[g][r]);
     }
   }
+}
+
+// ---- the 4-stage strided pass of the radix-16 plan (stages 6..9 of N = 8192: gap 8 between a thread's 16 coefficients)
+template <int LOGN, int AR>
+__device__ __forceinline__ void ntt_fwd_mid16(u64 *sm, const ulonglong2 *__restrict__ tw, u64 q, u64 aux, int tid, double qinv) {
+  constexpr int S0 = 6, LG = LOGN - S0 - 4;
+  static_assert(LOGN == 13 && LG == 3, "radix-16 plan is laid out for N = 8192");
+  const int blk = (p16_kblock(tid) << 3) + ((tid & 63) >> LG);   // 128-coefficient block
+  // swz(base + 8r) = pb ^ C_r with C_r = (8r) ^ (r & 14) known at compile time (base = blk << 7 | column)
+  const int pb = ((blk << (LG + 4)) | (tid & ((1 << LG) - 1))) ^ ((blk & 1) << 3);
+  u64 x[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) x[r] = sm[pb ^ ((r << LG) ^ (r & 14))];
+#pragma unroll
+  for (int b = 3; b >= 0; --b) {
+    const int s = S0 + 3 - b;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (r & (1 << b)) continue;
+      const ulonglong2 w = mid_tw<AR>(tw, (1u << s) + ((u32)((blk << 4) + r) >> (b + 1)), qinv);
+      bf_fwd<AR>(x[r], x[r | (1 << b)], w, q, aux);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 16; ++r) sm[pb ^ ((r << LG) ^ (r & 14))] = x[r];
+}
+template <int LOGN, int AR, bool REDUCE>
+__device__ __forceinline__ void ntt_inv_mid16(u64 *sm, const ulonglong2 *__restrict__ tw, u64 q, u64 aux, int tid, double qinv) {
+  constexpr int S0 = 6, LG = LOGN - S0 - 4;
+  static_assert(LOGN == 13 && LG == 3 && AR == AR_F64, "radix-16 plan: exact-double class at N = 8192");
+  const int blk = (p16_kblock(tid) << 3) + ((tid & 63) >> LG);
+  const int pb = ((blk << (LG + 4)) | (tid & ((1 << LG) - 1))) ^ ((blk & 1) << 3);
+  u64 x[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) x[r] = sm[pb ^ ((r << LG) ^ (r & 14))];
+  if (REDUCE) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = bits_of(reduce_f64(f64_of(x[r]), qinv, f64_of(aux)));
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const int s = S0 + 3 - b;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (r & (1 << b)) continue;
+      const ulonglong2 w = mid_tw<AR>(tw, (1u << s) + ((u32)((blk << 4) + r) >> (b + 1)), qinv);
+      bf_inv<AR>(x[r], x[r | (1 << b)], w, q, aux);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 16; ++r) sm[pb ^ ((r << LG) ^ (r & 14))] = x[r];
 }
 
 // ---- contiguous pass: every thread owns E = 8 CONSECUTIVE coefficients per group: gaps 4,2,1 are in-register, the
@@ -377,13 +458,13 @@ __device__ __forceinline__ u32 last_tw_index(u32 twbase, int s, int b, int vt, i
 }
 
 // the butterflies of the contiguous forward pass on one thread's 8 consecutive coefficients (vt = first / 8)
-template <int LOGN, int AR, int TT = 0>
+template <int LOGN, int AR, int TT = 0, int NSH = NttLast<LOGN, TT>::NSH>
 __device__ __forceinline__ void ntt_fwd_last_math(u64 (&x)[8], const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 aux,
                                                   int vt, double qinv) {
   typedef NttLast<LOGN, TT> P;
   constexpr int E = P::E, H = E / 2;
 #pragma unroll
-  for (int j = P::NSH - 1; j >= 0; --j) {
+  for (int j = NSH - 1; j >= 0; --j) {
     const int s = LOGN - 1 - P::LOGE - j;
     const ulonglong2 w = tw_get<AR>(tw, (twbase << s) + ((u32)vt >> (1 + j)), qinv);
     const bool hi = (vt >> j) & 1;
@@ -418,28 +499,29 @@ __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twba
   const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.tw : (AR == AR_F64 ? M.twd : M.twf);
   const double qinv = f64_of(M.qinv_bits);
 #pragma unroll
+  constexpr bool P16 = UsePlan16<LOGN, AR, TT>::value;
   for (int g = 0; g < P::GROUPS; ++g) {
-    const int vt = tid + g * NttDims<LOGN, TT>::T;
+    const int vt = P16 ? p16_block8(tid, g) : tid + g * NttDims<LOGN, TT>::T;
     u64 x[E];
 #pragma unroll
     for (int i = 0; i < H; ++i) {
-      ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(E * vt + 2 * i)]);
+      ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz_row8(vt) ^ (2 * i)]);
       x[2 * i] = v.x; x[2 * i + 1] = v.y;
     }
-    ntt_fwd_last_math<LOGN, AR, TT>(x, tw, twbase, q, aux, vt, qinv);
+    ntt_fwd_last_math<LOGN, AR, TT, P16 ? 0 : P::NSH>(x, tw, twbase, q, aux, vt, qinv);
 #pragma unroll
     for (int i = 0; i < H; ++i) {
       ulonglong2 v;
       v.x = RAW ? x[2 * i] : canon_fwd<AR>(x[2 * i], M, q, aux);
       v.y = RAW ? x[2 * i + 1] : canon_fwd<AR>(x[2 * i + 1], M, q, aux);
-      *reinterpret_cast<ulonglong2 *>(&sm[swz(E * vt + 2 * i)]) = v;
+      *reinterpret_cast<ulonglong2 *>(&sm[swz_row8(vt) ^ (2 * i)]) = v;
     }
   }
 }
 
 // REPIN: shared memory already holds the class's representation (the fused key-switch inner product stores doubles)
 // the butterflies of the contiguous inverse pass on one thread's 8 consecutive coefficients (class representation in x)
-template <int LOGN, int AR, int TT = 0>
+template <int LOGN, int AR, int TT = 0, int NSH = NttLast<LOGN, TT>::NSH>
 __device__ __forceinline__ void ntt_inv_first_math(u64 (&x)[8], const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 aux,
                                                    int vt, double qinv) {
   typedef NttLast<LOGN, TT> P;
@@ -455,7 +537,7 @@ __device__ __forceinline__ void ntt_inv_first_math(u64 (&x)[8], const ulonglong2
     }
   }
 #pragma unroll
-  for (int j = 0; j < P::NSH; ++j) {
+  for (int j = 0; j < NSH; ++j) {
     const int s = LOGN - 1 - P::LOGE - j;
     const ulonglong2 w = tw_get<AR>(tw, (twbase << s) + ((u32)vt >> (1 + j)), qinv);
     const bool hi = (vt >> j) & 1;
@@ -478,19 +560,20 @@ __device__ __forceinline__ void ntt_inv_first(u64 *sm, const ModInfo &M, u32 twb
   const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.itw : (AR == AR_F64 ? M.itwd : M.itwf);
   const double qinv = f64_of(M.qinv_bits);
 #pragma unroll
+  constexpr bool P16 = UsePlan16<LOGN, AR, TT>::value;
   for (int g = 0; g < P::GROUPS; ++g) {
-    const int vt = tid + g * NttDims<LOGN, TT>::T;
+    const int vt = P16 ? p16_block8(tid, g) : tid + g * NttDims<LOGN, TT>::T;
     u64 x[E];
 #pragma unroll
     for (int i = 0; i < H; ++i) {
-      ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(E * vt + 2 * i)]);
+      ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz_row8(vt) ^ (2 * i)]);
       x[2 * i] = REPIN ? v.x : ar_from_canon<AR>(v.x); x[2 * i + 1] = REPIN ? v.y : ar_from_canon<AR>(v.y);
     }
-    ntt_inv_first_math<LOGN, AR, TT>(x, tw, twbase, q, aux, vt, qinv);
+    ntt_inv_first_math<LOGN, AR, TT, P16 ? 0 : P::NSH>(x, tw, twbase, q, aux, vt, qinv);
 #pragma unroll
     for (int i = 0; i < H; ++i) {
       ulonglong2 v; v.x = x[2 * i]; v.y = x[2 * i + 1];
-      *reinterpret_cast<ulonglong2 *>(&sm[swz(E * vt + 2 * i)]) = v;
+      *reinterpret_cast<ulonglong2 *>(&sm[swz_row8(vt) ^ (2 * i)]) = v;
     }
   }
 }
@@ -525,7 +608,10 @@ __device__ __forceinline__ void ntt_fwd_smem_mids(u64 *sm, const ModInfo &M, u32
   pass_sync<LOGN - P::R0, D::T>(tid);
   ntt_fwd_mid<LOGN, P::R0, P::R1, AR, false, TT>(sm, tw, twbase, q, aux, tid, qinv);
   pass_sync<LOGN - P::R0 - P::R1, D::T>(tid);
-  if constexpr (P::R2 > 0) {
+  if constexpr (UsePlan16<LOGN, AR, TT>::value) {
+    ntt_fwd_mid16<LOGN, AR>(sm, tw, q, aux, tid, qinv);
+    __syncwarp();
+  } else if constexpr (P::R2 > 0) {
     ntt_fwd_mid<LOGN, P::R0 + P::R1, P::R2, AR, false, TT>(sm, tw, twbase, q, aux, tid, qinv);
     pass_sync<LOGN - P::R0 - P::R1 - P::R2, D::T>(tid);
   }
@@ -548,10 +634,18 @@ __device__ __forceinline__ void ntt_inv_smem_mids(u64 *sm, const ModInfo &M, u32
   typedef NttPlan<LOGN> P;
   const u64 q = M.q, aux = ar_aux<AR>(q);
   typedef NttDims<LOGN, TT> D;
-  pass_sync<LOGN - P::R0 - P::R1 - P::R2, D::T>(tid);
-  if constexpr (P::R2 > 0) {
-    ntt_inv_mid<LOGN, P::R0 + P::R1, P::R2, false, true, AR, TT>(sm, M, twbase, q, aux, tid);
+  if constexpr (UsePlan16<LOGN, AR, TT>::value) {
+    // range plan (q < 0.97 * 2^45, lib.cu fill_mod): 3 contiguous stages leave |x| <= 4.1q; reduced here, the 4 + 3 stages
+    // up to the next reduction reach 0.51q * 2^7 = 65.3q, so the last product operand stays below 2^51
+    __syncwarp();
+    ntt_inv_mid16<LOGN, AR, true>(sm, (ABC_F64_TW_PAIRS ? M.itwp : M.itwd), q, aux, tid, f64_of(M.qinv_bits));
     pass_sync<LOGN - P::R0 - P::R1, D::T>(tid);
+  } else {
+    pass_sync<LOGN - P::R0 - P::R1 - P::R2, D::T>(tid);
+    if constexpr (P::R2 > 0) {
+      ntt_inv_mid<LOGN, P::R0 + P::R1, P::R2, false, true, AR, TT>(sm, M, twbase, q, aux, tid);
+      pass_sync<LOGN - P::R0 - P::R1, D::T>(tid);
+    }
   }
   ntt_inv_mid<LOGN, P::R0, P::R1, false, P::R2 == 0, AR, TT>(sm, M, twbase, q, aux, tid);
   pass_sync<LOGN - P::R0, D::T>(tid);
