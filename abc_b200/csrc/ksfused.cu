@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NttDims<LOGN, TT>::T, NttDims<LOGN, TT>::MINB)
     ulonglong2 *tlp = reinterpret_cast<ulonglong2 *>(job.tl + (size_t)inst * job.tl_is + (size_t)c * N);
     if (unit == 0) {
       for (int e2 = tid; e2 < N / 2; e2 += T) {
-        ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
+        ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz_pair(tid, e2)]);
         v.x = canon_inv<AR>(v.x, q, aux); v.y = canon_inv<AR>(v.y, q, aux);
         tlp[e2] = v;
       }

@@ -53,6 +53,9 @@ struct LimbJob {
   u32 *t_used;   // [inst][modulus] tail rows that have consumed T[inst][modulus][*] (2 per key switch): the second one drops
                  // the rows from L2 (discard.global.L2) so that their dirty lines are never written to DRAM
 };
+// sm word index of element pair e2 = tid + i * T (T >= 128): the swizzle only looks at bits 1..7, which i * 2T never
+// touches, so swz(2 * e2) = swz(2 * tid) + 2 * (e2 - tid) — the swizzle is computed once per thread, not per access
+__device__ __forceinline__ int swz_pair(int tid, int e2) { return swz(2 * tid) + 2 * (e2 - tid); }
 // physical 16-byte index of element pair e2 in the swizzled image of a limb (swz(2 * e2) / 2)
 __device__ __forceinline__ int swz2(int e2) { return e2 ^ ((e2 >> 3) & 7) ^ ((e2 >> 4) & 4); }
 
@@ -183,7 +186,7 @@ __device__ __forceinline__ void moddown_store_f64(const u64 *sm, const ModInfo &
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       const int e2 = tid + (i0 + i) * T;
-      const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
+      const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz_pair(tid, e2)]);
       ulonglong2 b = make_ulonglong2(0, 0);
       if (md.base) {
         if (einv) {
@@ -403,12 +406,12 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
     }
     if (job.t_image) {
       for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
-        *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) =
+        *reinterpret_cast<ulonglong2 *>(&sm[swz_pair(tid, e2)]) =
             ks_inner_pair_f64(reinterpret_cast<const double2 *>(t) + swz2(e2), reinterpret_cast<const double2 *>(kp) + e2, job.L,
                               D::N / 2, job.k * D::N, M);
     } else {
       for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
-        *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = ks_inner_pair(t + e2, kp + e2, job.L, D::N / 2, job.k * D::N, M);
+        *reinterpret_cast<ulonglong2 *>(&sm[swz_pair(tid, e2)]) = ks_inner_pair(t + e2, kp + e2, job.L, D::N / 2, job.k * D::N, M);
     }
   } else if (PRE == PRE_ENCODE) {
     // BatchEncoder::encode (SealCiphertextFactory.cpp:102-132): pad with the last value, scatter by the index map
@@ -420,7 +423,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
   } else {
     const u64 h = (PRE == PRE_TERNARY || PRE == PRE_CBD) ? stream_key(job.seed, job.domain, job.a0 + (u64)inst, job.b) : 0;
     for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
-      *reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]) = limb_load_pair<PRE>(job, M, mods, n, inst, srow, eoff + e2, h);
+      *reinterpret_cast<ulonglong2 *>(&sm[swz_pair(tid, e2)]) = limb_load_pair<PRE>(job, M, mods, n, inst, srow, eoff + e2, h);
   }
   if (!LINSRC) __syncthreads();
   // T[inst][I][0..L) is dead once both components' rows have read it (the barrier above: every thread of this row has).
@@ -467,7 +470,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
     const ulonglong2 *mp = reinterpret_cast<const ulonglong2 *>(job.mul + (size_t)inst * job.mul_is + (size_t)mrow * n) + eoff;
     for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
       ulonglong2 m = mp[e2];
-      ulonglong2 *p = reinterpret_cast<ulonglong2 *>(&sm[swz(2 * e2)]);
+      ulonglong2 *p = reinterpret_cast<ulonglong2 *>(&sm[swz_pair(tid, e2)]);
       ulonglong2 v = *p;
       v.x = mul_mod(v.x, m.x, q, M.mu_hi, M.mu_lo);
       v.y = mul_mod(v.y, m.y, q, M.mu_hi, M.mu_lo);
@@ -498,7 +501,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
         ulonglong2 *o = reinterpret_cast<ulonglong2 *>(const_cast<u64 *>(job.tl) + (size_t)inst * job.tl_is +
                                                        (size_t)(w * job.k + job.L) * n);
         for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
-          ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
+          ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz_pair(tid, e2)]);
           v.x = canon_inv<AR>(v.x, q, ar_aux<AR>(q)); v.y = canon_inv<AR>(v.y, q, ar_aux<AR>(q));
           o[e2] = v;
         }
@@ -529,7 +532,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
           job.add ? reinterpret_cast<const ulonglong2 *>(job.add + (size_t)inst * job.add_is + (size_t)drow * D::N) : nullptr, tid);
     } else {
       for (int e2 = tid; e2 < D::N / 2; e2 += D::T) {
-        ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz(2 * e2)]);
+        ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(&sm[swz_pair(tid, e2)]);
         if (INV && !TAIL) { v.x = canon_inv<AR>(v.x, q, ar_aux<AR>(q)); v.y = canon_inv<AR>(v.y, q, ar_aux<AR>(q)); }  // a tail block stays in [0,2q) for the head pass
         limb_store_pair<POST>(job, M, md, n, inst, drow, mrow, eoff + e2, v);
       }

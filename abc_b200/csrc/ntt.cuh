@@ -49,13 +49,13 @@ __device__ __forceinline__ u64 bits_of(double d) { return (u64)__double_as_longl
 // (bits 4..6 of e onto bits 1..3: strided and contiguous passes are conflict free; bit 7 onto bit 3: neighbouring
 // 128-coefficient blocks are staggered by 64 bytes, which a pass with 8 lanes per block — the radix-16 plan's — needs)
 __device__ __forceinline__ int swz(int e) { return e ^ ((e >> 3) & 14) ^ ((e >> 4) & 8); }
-// sm address of element base + (r << LG) of a strided pass, given pbase = swz(base) with base's bits LG.. clear below bit 7
 // swz(8 * vt + 2 * i) = swz_row8(vt) ^ (2 * i): one XOR per access in the contiguous pass instead of a swizzle each
 __device__ __forceinline__ int swz_row8(int vt) { return (8 * vt) ^ (vt & 14) ^ ((vt >> 1) & 8); }
+// sm address of element base + (r << LG) of a strided pass.  The swizzle is linear over XOR and base has no bit in
+// common with r << LG, so swz(base + (r << LG)) = swz(base) ^ swz(r << LG): ONE xor with a compile-time constant.
 template <int LG> __device__ __forceinline__ int swz_strided(int base, int pbase, int r) {
-  if (LG > 7) return pbase + (r << LG);                       // the swizzle never sees the bits r moves
-  if (LG == 7) return ((r & 1) ? (pbase ^ 8) : pbase) + (r << LG);  // bit 7 = r & 1 (it is 0 in base)
-  return swz(base + (r << LG));
+  (void)base;
+  return pbase ^ swz(r << LG);
 }
 
 // strided passes (radix 2^R each); the contiguous pass (NttLast) takes the remaining stages
