@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(NttDims<LOGN, TT>::T, NttDims<LOGN, TT>::MINB)
           for (int h = 0; h < 2; ++h) {
             const int r = 2 * i + h;
             const double kd = h ? k2.y : k2.x;
-            const double v = f64_of(mul_tw<AR>(x[g][r], bits_of(kd), bits_of(kd * qinv), q, aux));
+            const double v = f64_of(mul_tw<AR>(x[g][r], bits_of(kd), bits_of(qinv), q, aux));
             if (J == 0) a[r * T] = v; else a[r * T] += v;
           }
         }

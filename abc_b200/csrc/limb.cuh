@@ -304,8 +304,8 @@ __device__ __forceinline__ ulonglong2 ks_inner_pair_f64(const double2 *__restric
   for (int J = 0; J < L; ++J) {
     const double2 tv = __ldcg(t + (size_t)J * rowv);
     const double2 kv = __ldg(kp + (size_t)J * keyv2);
-    s0 += f64_of(mul_tw<AR_F64>(bits_of(tv.x), bits_of(kv.x), bits_of(kv.x * qinv), M.q, qb));
-    s1 += f64_of(mul_tw<AR_F64>(bits_of(tv.y), bits_of(kv.y), bits_of(kv.y * qinv), M.q, qb));
+    s0 += f64_of(mul_tw<AR_F64>(bits_of(tv.x), bits_of(kv.x), bits_of(qinv), M.q, qb));
+    s1 += f64_of(mul_tw<AR_F64>(bits_of(tv.y), bits_of(kv.y), bits_of(qinv), M.q, qb));
   }
   return make_ulonglong2(bits_of(reduce_f64(s0, qinv, qd)), bits_of(reduce_f64(s1, qinv, qd)));
 }

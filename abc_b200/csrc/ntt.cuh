@@ -26,8 +26,8 @@
 //              +2q offset (values grow by < 0.75q per stage); the inverse reduces its sum chain twice per
 //              transform instead of guarding every butterfly.
 //   AR_F64     q < 2^45: the whole transform runs on the FP64 pipe, on exact integer-valued doubles.  A modular product
-//              is 6 FP64 instructions: Q = rint(y*(w/q)) (DFMA + DADD with the 1.5*2^52 magic), the error-free product
-//              y*w = ph + pl (DMUL + DFMA), v = (ph - Q*q) + pl (DFMA, exact because the result is an integer below
+//              is 6 FP64 instructions: the error-free product y*w = ph + pl (DMUL + DFMA), Q = rint(ph * (1/q)) (DFMA +
+//              DADD with the 1.5*2^52 magic), v = (ph - Q*q) + pl (DFMA, exact because the result is an integer below
 //              2^53, + DADD); |v| <= 0.53q with a correctly rounded w/q (0.9q at worst with the DMUL companion of tw_get: exactness never depends on it, only the range plan).  A butterfly is 8 FP64 instructions and no integer instruction, so the
 //              FP64 pipe (64 lanes/clk/SM on B200, otherwise idle) does the arithmetic while the integer pipes do
 //              the addressing: 2156 G butterflies/s register-resident vs 863 G (Shoup) and 1544 G (signed-lazy IMAD).
@@ -132,14 +132,17 @@ template <int AR> __device__ __forceinline__ u64 ar_sub(u64 a, u64 b) { return A
 template <int AR> __device__ __forceinline__ ulonglong2 tw_get(const ulonglong2 *__restrict__ tw, u32 idx, double qinv) {
   if (AR == AR_F64) {
     const u64 w = __ldg(reinterpret_cast<const u64 *>(tw) + idx);
-    return make_ulonglong2(w, bits_of(f64_of(w) * qinv));
+    return make_ulonglong2(w, bits_of(qinv));
   }
   return __ldg(tw + idx);
 }
 
 // twiddle of a strided pass
 template <int AR> __device__ __forceinline__ ulonglong2 mid_tw(const ulonglong2 *__restrict__ tw, u32 idx, double qinv) {
-  if (AR == AR_F64 && !ABC_F64_TW_PAIRS) return tw_get<AR>(tw, idx, qinv);
+  if (AR == AR_F64) {
+    if (!ABC_F64_TW_PAIRS) return tw_get<AR>(tw, idx, qinv);
+    return make_ulonglong2(__ldg(tw + idx).x, bits_of(qinv));
+  }
   return __ldg(tw + idx);
 }
 
@@ -150,10 +153,12 @@ template <int AR> __device__ __forceinline__ ulonglong2 mid_tw(const ulonglong2 
 //            t = y*(w/q) + (2^52+2^51) rounds to an integer, so bits(t) = MAGIC_S + qr with qr = round(y*w/q);
 //            r = y*w - qr*q = y*w + bits(t)*(-q) + MAGIC_S*q  (mod 2^64): no mask, no offset.
 template <int AR> __device__ __forceinline__ u64 mul_tw(u64 y, u64 w, u64 c, u64 q, u64 aux) {
-  if (AR == AR_F64) {  // y, w: bits of integer-valued doubles; c: bits of double(w/q); aux: bits of double(q)
+  if (AR == AR_F64) {  // y, w: bits of integer-valued doubles; c: bits of double(1/q) (no per-twiddle companion); aux: bits of double(q)
+    // the quotient estimate comes from the rounded product itself, Q = rint(fl(y*w) * fl(1/q)): two roundings like the
+    // old companion w * (1/q), so the same |v| <= 0.6q, but no DMUL per twiddle and two registers fewer per twiddle
     const double yd = f64_of(y), wd = f64_of(w);
-    const double Q = fma(yd, f64_of(c), ABC_RINT_MAGIC) - ABC_RINT_MAGIC;
     const double ph = yd * wd;
+    const double Q = fma(ph, f64_of(c), ABC_RINT_MAGIC) - ABC_RINT_MAGIC;
     const double pl = fma(yd, wd, -ph);
     return bits_of(fma(-Q, f64_of(aux), ph) + pl);
   } else if (AR == AR_SHOUP) {
@@ -362,8 +367,10 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
             // last stage of the whole transform: fold N^-1 into both outputs
             const u64 u = x[g][r], v = x[g][r | (1 << b)];
             const u64 d = (AR == AR_FP_LAZY || AR == AR_F64) ? ar_sub<AR>(u, v) : u + aux - v;
-            x[g][r] = mul_tw<AR>(ar_add<AR>(u, v), AR == AR_F64 ? M.ninv_d : M.ninv, (AR == AR_SHOUP) ? M.ninv_s : M.ninv_f, q, aux);
-            x[g][r | (1 << b)] = mul_tw<AR>(d, AR == AR_F64 ? M.wl_ninv_d : M.wl_ninv, (AR == AR_SHOUP) ? M.wl_ninv_s : M.wl_ninv_f, q, aux);
+            x[g][r] = mul_tw<AR>(ar_add<AR>(u, v), AR == AR_F64 ? M.ninv_d : M.ninv,
+                                 (AR == AR_SHOUP) ? M.ninv_s : (AR == AR_F64 ? M.qinv_bits : M.ninv_f), q, aux);
+            x[g][r | (1 << b)] = mul_tw<AR>(d, AR == AR_F64 ? M.wl_ninv_d : M.wl_ninv,
+                                            (AR == AR_SHOUP) ? M.wl_ninv_s : (AR == AR_F64 ? M.qinv_bits : M.wl_ninv_f), q, aux);
           } else {
             const ulonglong2 w = mid_tw<AR>(tw, (twbase << s) + ((u32)((blk[g] << 3) + r) >> (b + 1)), qinv);
             bf_inv<AR>(x[g][r], x[g][r | (1 << b)], w, q, aux);
