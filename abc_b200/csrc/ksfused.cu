@@ -183,7 +183,6 @@ __global__ void __launch_bounds__(NttDims<LOGN, TT>::T, NttDims<LOGN, TT>::MINB)
 #pragma unroll
       for (int r = 0; r < 8; ++r) x[g][r] = bits_of(reduce_f64(a[r * T], qinv, qd));
     }
-#pragma unroll
     if (c == 0 && stage_base) {  // uniform over the CTA: every warp has taken its component-0 sums
       __syncwarp();
       if ((tid & 31) == 0) {
@@ -193,6 +192,7 @@ __global__ void __launch_bounds__(NttDims<LOGN, TT>::T, NttDims<LOGN, TT>::MINB)
           bulk_issue((u32)__cvta_generic_to_shared(accs), job.base0 + (size_t)inst * job.base0_is + (size_t)I * N, (u32)D::SMEM, mb);
       }
     }
+#pragma unroll
     for (int g = 0; g < G; ++g) ntt_inv_first_math<LOGN, AR, TT>(x[g], M.itwd, 1u, q, aux, tid + g * T, qinv);
 #pragma unroll
     for (int g = 0; g < G; ++g)

@@ -505,8 +505,8 @@ __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twba
   constexpr int E = P::E, H = E / 2;
   const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.tw : (AR == AR_F64 ? M.twd : M.twf);
   const double qinv = f64_of(M.qinv_bits);
-#pragma unroll
   constexpr bool P16 = UsePlan16<LOGN, AR, TT>::value;
+#pragma unroll
   for (int g = 0; g < P::GROUPS; ++g) {
     const int vt = P16 ? p16_block8(tid, g) : tid + g * NttDims<LOGN, TT>::T;
     u64 x[E];
@@ -566,8 +566,8 @@ __device__ __forceinline__ void ntt_inv_first(u64 *sm, const ModInfo &M, u32 twb
   constexpr int E = P::E, H = E / 2;
   const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.itw : (AR == AR_F64 ? M.itwd : M.itwf);
   const double qinv = f64_of(M.qinv_bits);
-#pragma unroll
   constexpr bool P16 = UsePlan16<LOGN, AR, TT>::value;
+#pragma unroll
   for (int g = 0; g < P::GROUPS; ++g) {
     const int vt = P16 ? p16_block8(tid, g) : tid + g * NttDims<LOGN, TT>::T;
     u64 x[E];
