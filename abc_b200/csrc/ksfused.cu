@@ -217,14 +217,7 @@ __global__ void __launch_bounds__(NttDims<LOGN, TT>::T, NttDims<LOGN, TT>::MINB)
       __syncthreads();
       if (tid == 0) atomicExch(job.flags + inst * 2 + c, job.serial);
     } else {
-      if ((tid & 31) == 0) {
-        const u32 *fp = job.flags + inst * 2 + c;
-        u32 seen;
-        do {
-          asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(fp) : "memory");
-          if (seen != job.serial) __nanosleep(64);
-        } while (seen != job.serial);
-      }
+      if ((tid & 31) == 0) wait_word<false>(job.flags + inst * 2 + c, job.serial, job.fault);
       __syncwarp();
       const DevConst *C = job.C;
       ModDownRow md;
@@ -255,14 +248,7 @@ __global__ void __launch_bounds__(NttDims<LOGN, TT>::T, NttDims<LOGN, TT>::MINB)
       __syncthreads();
       if (tid == 0) atomicExch(job.flags + inst * 2 + c, job.serial);
     } else {
-      if (tid == 0) {
-        const u32 *fp = job.flags + inst * 2 + c;
-        u32 seen;
-        do {
-          asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(fp) : "memory");
-          if (seen != job.serial) __nanosleep(64);
-        } while (seen != job.serial);
-      }
+      if (tid == 0) wait_word<false>(job.flags + inst * 2 + c, job.serial, job.fault);
       __syncthreads();
       const DevConst *C = job.C;
       ModDownRow md;

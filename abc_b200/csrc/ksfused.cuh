@@ -11,6 +11,7 @@ struct KsJob {
   const u64 *base0, *base1; long long base0_is, base1_is;  // polynomial added into component 0 / 1 (nullptr = 0)
   u32 einv;                                   // automorphism applied to target and bases while reading (0: none)
   u64 *tl; long long tl_is;                   // [2][N] per instance: INTT_p(acc_L[c]), published by the special unit
+  u32 *fault;                                 // host-mapped word raised when a dependency wait gives up (limb.cuh wait_word)
   u32 *flags; u32 serial; int skew;           // flags[inst][c] == serial when tl[inst][c] is ready
   const DevConst *C;
   const int *Iset; int nI;                    // output moduli: the data limbs this rank owns, then the special prime

@@ -75,6 +75,7 @@ struct abc_ctx {
   uint2 *ks_sched = nullptr; int ks_sched_n = 0;                                // chained key switch: block schedule (kschain.cu)
   u32 *ks_done = nullptr; u32 ks_chain_serial = 0;                            // ... [B][k] ModUp rows stored so far (L per launch)
   int ks_chain = 1, ks_chain_skew = 16;                                       // ABC_KS_CHAIN=0/1, ABC_KS_CHAIN_SKEW
+  u32 *ks_fault_h = nullptr, *ks_fault_d = nullptr;                           // host-mapped: a dependency wait of a key-switch grid gave up
   u32 *ks_flags = nullptr; u32 ks_serial = 0;                                 // [B][2] ready flags of the merged launch
   int *rs_zero = nullptr;   // [2k]  0
   u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;
@@ -127,6 +128,14 @@ namespace {
   } while (0)
 
 abc_status fail(abc_ctx *c, abc_status s, const std::string &msg) { c->err = msg; return s; }
+// after a stream synchronisation: did a key-switch grid give up waiting for one of its own producers?
+abc_status check_ks_fault(abc_ctx *c) {
+  if (c->ks_fault_h && *reinterpret_cast<volatile u32 *>(c->ks_fault_h)) {
+    *c->ks_fault_h = 0;
+    return fail(c, ABC_ERR_CUDA, "key switch: a dependency wait inside the grid timed out (results since the last synchronisation are invalid)");
+  }
+  return ABC_OK;
+}
 
 struct Launch {
   abc_ctx *c; const char *name; cudaEvent_t a = nullptr, b = nullptr;
@@ -479,6 +488,11 @@ abc_status build_shard_maps(abc_ctx *c) {
     CK(cudaMemset(c->ks_done, 0, (size_t)2 * c->B * c->k * sizeof(u32)));
     c->ks_chain_serial = 0;
   }
+  if (!c->ks_fault_h) {
+    CK(cudaHostAlloc((void **)&c->ks_fault_h, sizeof(u32), cudaHostAllocMapped));
+    *c->ks_fault_h = 0;
+    CK(cudaHostGetDevicePointer((void **)&c->ks_fault_d, c->ks_fault_h, 0));
+  }
   if (!c->ks_flags) {
     CK(cudaMalloc((void **)&c->ks_flags, (size_t)c->B * 2 * sizeof(u32)));
     c->owned.push_back(c->ks_flags);
@@ -612,7 +626,7 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
     kj.dst = dst; kj.dst_is = (long long)2 * L * N; kj.dst2 = dst_plain; kj.add = addend; kj.add_is = (long long)2 * L * N;
     kj.base0 = base0; kj.base0_is = base0_is; kj.base1 = base1; kj.base1_is = base1_is; kj.einv = einv;
     kj.tl = acc; kj.tl_is = (long long)2 * N;
-    kj.flags = c->ks_flags; kj.serial = ++c->ks_serial; kj.skew = c->ks1_skew;
+    kj.flags = c->ks_flags; kj.serial = ++c->ks_serial; kj.skew = c->ks1_skew; kj.fault = c->ks_fault_d;
     kj.C = c->dC; kj.Iset = c->ks_I; kj.nI = c->ks_nI; kj.L = L; kj.k = k; kj.B = B; kj.threads = c->ks1_threads;
     Launch l(c, "ks_fused");
     const int e = ks_fused_launch(c->logN, kj, c->d_mods, c->stream);
@@ -653,7 +667,7 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   j.dst2 = dst_plain;                                // ... and the result without it (same layout as dst)
   if (merged) {  // one launch: the two special-prime rows INTT and publish, the data rows INTT, wait, ModDown
     j.rowsrc = c->rs_mdm; j.rowdst = c->rd_mdm; j.rowmod = c->rm_mdm;
-    j.flags = c->ks_flags; j.flag_serial = ++c->ks_serial; j.skew = c->ks_skew;
+    j.flags = c->ks_flags; j.flag_serial = ++c->ks_serial; j.skew = c->ks_skew; j.fault = c->ks_fault_d;
     if (fused) {
       j.src = T; j.src_is = (long long)k * L * N; j.mul = key; j.t_image = t_image;
       if (t_image) {  // raw-double T rows are multiplied with the exact-double copy of the key
@@ -959,6 +973,7 @@ void abc_ctx_destroy(abc_ctx *c) {
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
   for (auto &kv : c->galois) cudaFree(kv.second);
   for (auto &kv : c->key_f64) cudaFree(kv.second);
+  if (c->ks_fault_h) cudaFreeHost(c->ks_fault_h);
   cudaFree(c->d_sk); cudaFree(c->d_pk); cudaFree(c->d_relin);
   for (void *p : c->owned) cudaFree(p);
   if (c->flush_buf) cudaFree(c->flush_buf);
@@ -971,7 +986,7 @@ void abc_ctx_destroy(abc_ctx *c) {
 }
 
 const char *abc_last_error(const abc_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
-abc_status abc_sync(abc_ctx *c) { CK(cudaStreamSynchronize(c->stream)); return ABC_OK; }
+abc_status abc_sync(abc_ctx *c) { CK(cudaStreamSynchronize(c->stream)); return check_ks_fault(c); }
 uint32_t abc_poly_degree(const abc_ctx *c) { return (uint32_t)c->N; }
 uint32_t abc_n_primes(const abc_ctx *c) { return (uint32_t)c->k; }
 uint32_t abc_n_limbs(const abc_ctx *c) { return (uint32_t)c->L; }
@@ -1161,7 +1176,7 @@ abc_status abc_ct_export(abc_ctx *c, const abc_ct *ct, uint64_t *host, size_t wo
   TRY(ct_resolve(c, ct));
   CK(cudaMemcpyAsync(host, ct->b->d, words * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  return ABC_OK;
+  return check_ks_fault(c);
 }
 // one instance of the batch (the unit of a SEAL stream); the other instances of the handle keep their content
 abc_status abc_ct_export_instance(abc_ctx *c, const abc_ct *ct, uint32_t inst, uint64_t *host, size_t words) {
@@ -1309,7 +1324,7 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
   CK(cudaMemcpyAsync(out_slots, d_out, (size_t)B * N * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   sfree(c, d_out);
-  return ABC_OK;
+  return check_ks_fault(c);
 }
 
 // ---- ciphertext ops

@@ -50,6 +50,7 @@ struct LimbJob {
   int t_image;
   // chained ModUp + tail launch (kschain.cu): done[inst][modulus] counts the ModUp rows stored so far (L per key switch)
   u32 *done; u32 done_target;
+  u32 *fault;    // host-mapped word raised when a dependency wait gives up (wait_word)
   u32 *t_used;   // [inst][modulus] tail rows that have consumed T[inst][modulus][*] (2 per key switch): the second one drops
                  // the rows from L2 (discard.global.L2) so that their dirty lines are never written to DRAM
 };
@@ -327,6 +328,20 @@ __device__ __forceinline__ void discard_consumed_T(const LimbJob &job, int inst,
   }
 }
 
+// Bounded wait for a word another CTA of the same grid sets (a producer dispatched earlier: normally it is set already).
+// After about a second it gives up, raises the context's fault word (host-mapped) and lets the row finish with whatever it
+// reads: a wrong result that the host reports at its next synchronisation point instead of a hung GPU.  GE: wait until
+// (int)(seen - target) >= 0, else until seen == target.
+template <bool GE> __device__ __forceinline__ void wait_word(const u32 *p, u32 target, u32 *fault) {
+  u32 seen;
+  for (u32 spins = 0;; ++spins) {
+    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(p) : "memory");
+    if (GE ? (int)(seen - target) >= 0 : seen == target) return;
+    if (spins > (1u << 22)) { if (fault) *reinterpret_cast<volatile u32 *>(fault) = 1u; return; }
+    __nanosleep(64);
+  }
+}
+
 // RowIds: the caller already knows modulus / destination row / source row of row w (the chained key switch packs them
 // into its schedule: no dependent loads from the row maps in front of the first copy); modidx < 0 = look them up
 struct RowIds { int modidx, drow, srow; };
@@ -373,14 +388,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
     const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(job.src + (size_t)inst * job.src_is + (size_t)I * job.L * D::N);
     const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(job.mul + (size_t)(comp * job.k + I) * D::N);
     if (job.done) {  // chained launch: T[inst][I][0..L) comes from blocks earlier in this grid
-      if (tid == 0) {
-        const u32 *dp = job.done + inst * job.k + I;
-        u32 seen;
-        do {
-          asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(dp) : "memory");
-          if ((int)(seen - job.done_target) < 0) __nanosleep(64);
-        } while ((int)(seen - job.done_target) < 0);
-      }
+      if (tid == 0) wait_word<true>(job.done + inst * job.k + I, job.done_target, job.fault);
       __syncthreads();
     }
     if (job.prefetch_ahead >= 0 && !job.done) {
@@ -514,14 +522,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
         return;
       }
       wq = w - 2;
-      if (tid == 0) {
-        const u32 *fp = job.flags + inst * 2 + (wq >= job.nrows ? 1 : 0);
-        u32 seen;
-        do {
-          asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(seen) : "l"(fp) : "memory");
-          if (seen != job.flag_serial) __nanosleep(64);
-        } while (seen != job.flag_serial);
-      }
+      if (tid == 0) wait_word<false>(job.flags + inst * 2 + (wq >= job.nrows ? 1 : 0), job.flag_serial, job.fault);
       __syncthreads();
     }
     if (POST == POST_MODDOWN) md = moddown_row(job, n, inst, wq);
