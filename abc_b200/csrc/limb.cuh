@@ -311,6 +311,42 @@ __device__ __forceinline__ ulonglong2 ks_inner_pair_f64(const double2 *__restric
   return make_ulonglong2(bits_of(reduce_f64(s0, qinv, qd)), bits_of(reduce_f64(s1, qinv, qd)));
 }
 
+// All pairs of a thread (e2 = tid + i * T), software-pipelined: the T values of pair i + 1 are requested before pair i is
+// multiplied, so the load phase of a tail row is not one L2 round trip per pair (ncu: this phase was 20 % of the chained
+// grid's stall samples, on the first use of the loaded values).  LT = number of data limbs, compile time.
+#ifndef ABC_KS_PIPE_INNER
+#define ABC_KS_PIPE_INNER 1
+#endif
+template <int LT, int NIT, int T>
+__device__ __forceinline__ void ks_inner_rows_f64(u64 *sm, const double2 *__restrict__ t, const double2 *__restrict__ kp,
+                                                  int rowv, int keyv2, const ModInfo &M, int tid) {
+  const double qinv = f64_of(M.qinv_bits), qd = (double)M.q;
+  const u64 qb = bits_of(qd), qib = bits_of(qinv);
+  const int p0 = swz(2 * tid);
+  const double2 *tp = t + swz2(tid);   // swz2(tid + i * T) = swz2(tid) + i * T: the swizzle looks at bits 0..6 only
+  double2 tv[LT], tn[LT];
+#pragma unroll
+  for (int J = 0; J < LT; ++J) tv[J] = __ldcg(tp + (size_t)J * rowv);
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) {
+    if (i + 1 < NIT) {
+#pragma unroll
+      for (int J = 0; J < LT; ++J) tn[J] = __ldcg(tp + (i + 1) * T + (size_t)J * rowv);
+    }
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int J = 0; J < LT; ++J) {
+      const double2 kv = __ldg(kp + tid + i * T + (size_t)J * keyv2);
+      s0 += f64_of(mul_tw<AR_F64>(bits_of(tv[J].x), bits_of(kv.x), qib, M.q, qb));
+      s1 += f64_of(mul_tw<AR_F64>(bits_of(tv[J].y), bits_of(kv.y), qib, M.q, qb));
+    }
+    *reinterpret_cast<ulonglong2 *>(&sm[p0 + 2 * i * T]) =
+        make_ulonglong2(bits_of(reduce_f64(s0, qinv, qd)), bits_of(reduce_f64(s1, qinv, qd)));
+#pragma unroll
+    for (int J = 0; J < LT; ++J) tv[J] = tn[J];
+  }
+}
+
 // ---- one limb (or, TAIL, one 2^LOGN-coefficient block of a larger limb) in shared memory: row w of instance inst
 #ifndef ABC_KS_DISCARD_T
 #define ABC_KS_DISCARD_T 0
@@ -412,7 +448,10 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
         }
       }
     }
-    if (job.t_image) {
+    if (job.t_image && ABC_KS_PIPE_INNER && job.L == 4) {
+      ks_inner_rows_f64<4, D::N / 2 / D::T, D::T>(sm, reinterpret_cast<const double2 *>(t), reinterpret_cast<const double2 *>(kp),
+                                                 D::N / 2, job.k * D::N, M, tid);
+    } else if (job.t_image) {
       for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
         *reinterpret_cast<ulonglong2 *>(&sm[swz_pair(tid, e2)]) =
             ks_inner_pair_f64(reinterpret_cast<const double2 *>(t) + swz2(e2), reinterpret_cast<const double2 *>(kp) + e2, job.L,
