@@ -30,6 +30,13 @@ enum { DOM_SK = 1, DOM_PK = 2, DOM_KSK = 3, DOM_ENC = 4 };
 struct abc_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // host slots travel on their own stream into one of two staging buffers, so the copy of the next operand overlaps the
+  // kernels of the previous one (createCiphertext(x); createCiphertext(y): y's H2D runs under x's encryption)
+  cudaStream_t copy_stream = nullptr;
+  long long *h2d_buf[2] = {nullptr, nullptr};
+  size_t h2d_words[2] = {0, 0};
+  cudaEvent_t h2d_copied[2] = {nullptr, nullptr}, h2d_consumed[2] = {nullptr, nullptr};
+  unsigned h2d_next = 0;
   int N = 0, logN = 0, k = 0, L = 0, nB = 0, nbsk = 0, B = 1, W = 0;
   u64 t = 0, seed = 0, enc_nonce = 0, gamma = 0, msk = 0;
   std::vector<u64> primes, bsk;
@@ -793,8 +800,20 @@ abc_status encode_device(abc_ctx *c, const int64_t *slots, size_t n, int broadca
                                       std::to_string(N) + ". ");
   long long *d_slots = nullptr;
   u64 *plain = nullptr;
-  CK(cudaMallocAsync((void **)&d_slots, (size_t)Bp * n * sizeof(long long), c->stream));
-  CK(cudaMemcpyAsync(d_slots, slots, (size_t)Bp * n * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  const size_t words = (size_t)Bp * n;
+  const unsigned hb = c->h2d_next++ & 1u;
+  if (c->h2d_words[hb] < words) {  // grow-only staging buffer (rare: first use, or a larger operand)
+    CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->copy_stream));
+    if (c->h2d_buf[hb]) CK(cudaFree(c->h2d_buf[hb]));
+    c->h2d_buf[hb] = nullptr; c->h2d_words[hb] = 0;
+    CK(cudaMalloc((void **)&c->h2d_buf[hb], words * sizeof(long long)));
+    c->h2d_words[hb] = words;
+  }
+  d_slots = c->h2d_buf[hb];
+  CK(cudaStreamWaitEvent(c->copy_stream, c->h2d_consumed[hb], 0));  // the encode kernel that last read this buffer is done
+  CK(cudaMemcpyAsync(d_slots, slots, words * sizeof(long long), cudaMemcpyHostToDevice, c->copy_stream));
+  CK(cudaEventRecord(c->h2d_copied[hb], c->copy_stream));
+  CK(cudaStreamWaitEvent(c->stream, c->h2d_copied[hb], 0));
   TRY(salloc(c, &plain, (size_t)Bp * N));
   LimbJob j = blank_job();
   j.dst = plain; j.dst_is = N; j.rowmod = c->rm_t;
@@ -810,7 +829,7 @@ abc_status encode_device(abc_ctx *c, const int64_t *slots, size_t n, int broadca
   } else {
     TRY(launch_limb(c, LIMB_ENCODE_INV, c->ar_t, j, 1, Bp, "encode_intt"));
   }
-  sfree(c, d_slots);
+  CK(cudaEventRecord(c->h2d_consumed[hb], c->stream));
   *plain_out = plain;
   return ABC_OK;
 }
@@ -951,6 +970,11 @@ abc_status abc_ctx_create(const abc_params *p, abc_ctx **out) {
         if (c->primes[i] == c->primes[j]) return bail(ABC_ERR_PARAM, "coefficient primes must be distinct");
     if (!hm::is_prime(c->t) || (c->t - 1) % (2 * N)) return bail(ABC_ERR_PARAM, "plain_modulus must be a prime = 1 mod 2N (batching)");
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ABC_ERR_CUDA, "stream creation failed");
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ABC_ERR_CUDA, "stream creation failed");
+    for (int i = 0; i < 2; ++i) {
+      cudaEventCreateWithFlags(&c->h2d_copied[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&c->h2d_consumed[i], cudaEventDisableTiming);
+    }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
@@ -981,6 +1005,12 @@ void abc_ctx_destroy(abc_ctx *c) {
   for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  for (int i = 0; i < 2; ++i) {
+    if (c->h2d_buf[i]) cudaFree(c->h2d_buf[i]);
+    if (c->h2d_copied[i]) cudaEventDestroy(c->h2d_copied[i]);
+    if (c->h2d_consumed[i]) cudaEventDestroy(c->h2d_consumed[i]);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
