@@ -240,3 +240,33 @@ def test_chained_key_switch_large_batch_matches_two_launch(monkeypatch):
     a_in, rot = outs["chained"][0], outs["chained"][1]
     for i in (0, B - 1):
         assert np.array_equal(rot[i], o.rotate_rows(a_in[i], -24))
+
+
+def test_bench_batch_identical_instances_agree():
+    """Size-independent property at the bench's full batch (592 instances, N = 8192): the same ciphertext pair imported
+    into every instance must give bit-identical coefficients in every instance after mul+relin, a NAF rotation and the
+    fused rotate+add (17 760 rows per key-switch grid, every dependency of the chained schedule exercised), and instance 0
+    must equal the oracle."""
+    from abc_b200 import CudaCiphertextFactory
+    from oracle.bfv_oracle import Oracle
+    N, B = 8192, 592
+    o = Oracle(N, seed=SEED)
+    rng = np.random.default_rng(11)
+    a_w, b_w = o.encrypt_slots(rng.integers(0, 1025, N), 1), o.encrypt_slots(rng.integers(0, 1025, N), 2)
+    f = CudaCiphertextFactory(N, seed=SEED, batch=B)
+    try:
+        a = f.importCiphertext(np.broadcast_to(a_w, (B,) + a_w.shape))
+        b = f.importCiphertext(np.broadcast_to(b_w, (B,) + b_w.shape))
+        m_w = o.mul_relin(a_w, b_w)
+        r_w = o.rotate_rows(m_w, -24)
+        s_w = o.add(b_w, o.rotate_rows(r_w, 4))
+        m = a.multiply(b)
+        r = m.rotateRows(-24)
+        s = b.add(r.rotateRows(4))
+        for name, ct, want in (("mul+relin", m, m_w), ("rotate(-24)", r, r_w), ("rotate(4)+add", s, s_w)):
+            got = ct.export()
+            assert np.array_equal(got[0], want), name + ": instance 0 vs oracle"
+            assert (got == got[0]).all(), name + ": instances differ"
+        assert np.array_equal(f.decryptCiphertext(s)[B - 1], o.decrypt_slots(s_w))
+    finally:
+        f.close()
