@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "ksfused.cuh"
 #include "kschain.cuh"
+#include "behz_f64.cuh"
 
 namespace {
 thread_local std::string g_create_error;
@@ -60,6 +61,12 @@ struct abc_ctx {
   u32 *d_index_map = nullptr;
   int *rm_ct = nullptr;     // [3L]  w % L
   int *rm_key = nullptr;    // [2k]  w % k
+  // BEHZ product on the FP64 pipe over a sub-2^45 auxiliary base (behz_f64.cuh); exact-double class contexts, L <= 8
+  bool behz_f64 = false;                       // ABC_BEHZ_F64=0 keeps SEAL's 61-bit base and the integer kernels
+  int nbsk2 = 0, W2 = 0, idx_b2 = 0;           // |Bsk'|, rows per polynomial, index of its first modulus in d_mods
+  std::vector<u64> bsk2;                       // B' primes, then m_sk'
+  BehzF64 *dF = nullptr;
+  int *rm_behz2 = nullptr;                     // [4 W2] modulus of X row
   int *rm_behz = nullptr;   // [4W]  q / Bsk modulus of X row
   int *rm_behz_q = nullptr, *rd_behz_q = nullptr;  // [4L]    q rows of X: modulus, row
   int *rm_behz_b = nullptr, *rd_behz_b = nullptr;  // [4nbsk] Bsk rows of X: modulus, row
@@ -301,12 +308,35 @@ abc_status build_tables(abc_ctx *c) {
   c->nB = nB; c->nbsk = nB + 1; c->W = L + c->nbsk;
   c->idx_t = k + c->nbsk;
 
+  // ---- second auxiliary base for the FP64 BEHZ path: 44-bit primes, product above 32 + bits(t) + bits(Q) + 8 bits
+  c->behz_f64 = false; c->bsk2.clear();
+  {
+    bool all_small = L <= BF_MAXQ;
+    for (int i = 0; i < k; ++i) all_small = all_small && c->primes[i] < 34128100000000ull;
+    const char *e = getenv("ABC_BEHZ_F64");
+    if (all_small && !(e && atoi(e) == 0) && logN <= 14) {
+      const int need_bits = 32 + bits_of(t) + prod_bits(Q) + 8;
+      const int cnt = (need_bits + 42) / 43;                       // a 44-bit prime carries more than 43 bits
+      if (cnt <= BF_MAXB) {
+        std::vector<u64> cand = get_primes((u64)N, 44, (size_t)cnt + k + 3);
+        for (u64 p44 : cand) {
+          bool used = p44 == t || p44 == c->gamma;
+          for (int i = 0; i < k; ++i) used = used || p44 == c->primes[i];
+          if (!used && (int)c->bsk2.size() < cnt) c->bsk2.push_back(p44);
+        }
+        if ((int)c->bsk2.size() == cnt) {   // B' = bsk2[0 .. cnt-2], m_sk' = bsk2[cnt-1]
+          c->behz_f64 = true; c->nbsk2 = cnt; c->W2 = L + cnt; c->idx_b2 = k + c->nbsk + 1;
+        }
+      }
+    }
+  }
+
   // ---- per-modulus tables
-  const int nmods = k + c->nbsk + 1;
+  const int nmods = k + c->nbsk + 1 + (c->behz_f64 ? c->nbsk2 : 0);
   std::vector<ModInfo> mods(nmods);
   std::vector<ulonglong2> tw, itw, twf, itwf, twd, itwd, twp, itwp;
   for (int i = 0; i < nmods; ++i) {
-    const u64 q = i < k ? c->primes[i] : (i < k + c->nbsk ? c->bsk[i - k] : t);
+    const u64 q = i < k ? c->primes[i] : (i < k + c->nbsk ? c->bsk[i - k] : (i == k + c->nbsk ? t : c->bsk2[i - k - c->nbsk - 1]));
     fill_mod(mods[i], q, N, logN, tw, itw, twf, itwf, twd, itwd, twp, itwp);
     ulonglong2 *d_tw = nullptr, *d_itw = nullptr, *d_twf = nullptr, *d_itwf = nullptr, *d_twd = nullptr, *d_itwd = nullptr;
     ulonglong2 *d_twp = nullptr, *d_itwp = nullptr;
@@ -392,6 +422,45 @@ abc_status build_tables(abc_ctx *c) {
   CK(cudaMalloc((void **)&c->dC, sizeof(DevConst)));
   c->owned.push_back(c->dC);
   CK(cudaMemcpy(c->dC, &C, sizeof(DevConst), cudaMemcpyHostToDevice));
+  if (c->behz_f64) {   // the same constants as above for the sub-2^45 base, as exact doubles
+    BehzF64 F;
+    memset(&F, 0, sizeof F);
+    const int nb2 = c->nbsk2 - 1;
+    std::vector<u64> B2(c->bsk2.begin(), c->bsk2.begin() + nb2);
+    const u64 msk2 = c->bsk2[nb2];
+    F.L = L; F.nB = nb2; F.nbsk = c->nbsk2;
+    for (int i = 0; i < L; ++i) {
+      const u64 qi = Q[i];
+      F.q[i] = (double)qi; F.qinv[i] = 1.0 / (double)qi;
+      F.lift_c[i] = (double)C.lift_c[i]; F.scale_c[i] = (double)C.scale_c[i];
+      F.punct_q_mt[i] = C.punct_q_mt[i];
+      F.B_mod_q[i] = (double)prod_mod(B2, qi);
+      for (int j = 0; j < nb2; ++j) F.punct_B_q[i][j] = (double)prod_mod(B2, qi, j);
+    }
+    F.neg_inv_q_mt = C.neg_inv_q_mt;
+    for (int j = 0; j < c->nbsk2; ++j) {
+      const u64 pj = c->bsk2[j];
+      F.b[j] = (double)pj; F.binv[j] = 1.0 / (double)pj;
+      for (int i = 0; i < L; ++i) F.punct_q_b[j][i] = (double)prod_mod(Q, pj, i);
+      const u64 qmb = prod_mod(Q, pj);
+      F.q_mod_b[j] = (double)qmb;
+      F.inv_mt_b[j] = (double)invmod(mt % pj, pj);
+      F.t_mod_b[j] = (double)(t % pj);
+      F.inv_q_b[j] = (double)invmod(qmb, pj);
+    }
+    for (int j = 0; j < nb2; ++j) {
+      F.inv_punct_B[j] = (double)invmod(prod_mod(B2, B2[j], j), B2[j]);
+      F.punct_B_msk[j] = (double)prod_mod(B2, msk2, j);
+    }
+    F.inv_B_msk = (double)invmod(prod_mod(B2, msk2), msk2);
+    F.msk_half = (double)(msk2 >> 1);
+    CK(cudaMalloc((void **)&c->dF, sizeof(BehzF64)));
+    c->owned.push_back(c->dF);
+    CK(cudaMemcpy(c->dF, &F, sizeof(BehzF64), cudaMemcpyHostToDevice));
+    std::vector<int> rm(4 * c->W2);
+    for (int w = 0; w < 4 * c->W2; ++w) { const int r = w % c->W2; rm[w] = r < L ? r : c->idx_b2 + (r - L); }
+    TRY(upload(c, &c->rm_behz2, rm));
+  }
 
   // ---- BatchEncoder index map (populate_matrix_reps_index_map)
   std::vector<u32> imap(N);
@@ -706,7 +775,50 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
 }
 
 // Evaluator::bfv_multiply (size 2 x size 2 -> size 3): out3 [B][3][L][N]
+#define DISPATCH_BF(c, EXPR)                                                                         \
+  switch ((c)->L * 16 + (c)->nbsk2) {                                                               \
+    case 2 * 16 + 4: { constexpr int LL = 2, NK = 4; EXPR; } break;                                 \
+    case 2 * 16 + 5: { constexpr int LL = 2, NK = 5; EXPR; } break;                                 \
+    case 3 * 16 + 5: { constexpr int LL = 3, NK = 5; EXPR; } break;                                 \
+    case 4 * 16 + 6: { constexpr int LL = 4, NK = 6; EXPR; } break;                                 \
+    case 4 * 16 + 7: { constexpr int LL = 4, NK = 7; EXPR; } break;                                 \
+    default: return fail(c, ABC_ERR_UNSUPPORTED, "FP64 BEHZ: no kernel for this (L, |Bsk|)");       \
+  }
+bool behz_f64_has_kernel(const abc_ctx *c) {
+  const int key = c->L * 16 + c->nbsk2;
+  return key == 2 * 16 + 4 || key == 2 * 16 + 5 || key == 3 * 16 + 5 || key == 4 * 16 + 6 || key == 4 * 16 + 7;
+}
+// the same product over the sub-2^45 auxiliary base, every transform on the exact-double class (behz_f64.cuh)
+abc_status behz_multiply_f64(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
+  const int N = c->N, B = c->B, W = c->W2;
+  u64 *X = nullptr;
+  TRY(scratch(c, SC_X, &X, (size_t)B * 4 * W * N));
+  const bool square = a == b && !c->no_square;
+  const int np = square ? 2 : 4;
+  {
+    Launch l(c, "behz_lift");
+    DISPATCH_BF(c, (k_behz_lift_f64<LL, NK><<<dim3(N / 128, np, B), 128, 0, c->stream>>>(a, b, X, c->dF, N)));
+    CK(cudaGetLastError());
+  }
+  LimbJob j = blank_job();
+  j.dst = X; j.src = X; j.dst_is = j.src_is = (long long)4 * W * N; j.rowmod = c->rm_behz2;
+  TRY(launch_limb(c, LIMB_FWD, AR_F64, j, np * W, B, "behz_ntt"));
+  {
+    Launch l(c, "behz_tensor");
+    k_behz_tensor_f64<<<dim3(N / 256, W, B), 256, 0, c->stream>>>(X, c->d_mods, c->rm_behz2, N, W, square ? 1 : 0);
+    CK(cudaGetLastError());
+  }
+  TRY(launch_limb(c, LIMB_INV, AR_F64, j, 3 * W, B, "behz_intt"));
+  {
+    Launch l(c, "behz_scale");
+    DISPATCH_BF(c, (k_behz_scale_f64<LL, NK><<<dim3(N / 128, 3, B), 128, 0, c->stream>>>(X, out3, c->dF, N)));
+    CK(cudaGetLastError());
+  }
+  return ABC_OK;
+}
+
 abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
+  if (c->behz_f64 && c->world == 1 && c->force_ar < 0 && behz_f64_has_kernel(c)) return behz_multiply_f64(c, a, b, out3);
   const int N = c->N, L = c->L, B = c->B, W = c->W;
   u64 *X = nullptr;
   TRY(scratch(c, SC_X, &X, (size_t)B * 4 * W * N));
