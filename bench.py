@@ -263,6 +263,9 @@ def run_ours(args):
         row = N_POLY * 8
         # algorithmic bytes per launch of each kernel family (DESIGN.md "kernels")
         nb = L + 1
+        # rows per polynomial of the FP64 BEHZ path: L + ceil((32 + bits(t) + bits(Q) + 8) / 43) (lib.cu build_tables)
+        qbits = sum(int(p).bit_length() for p in f.primes[:L])
+        W2 = L + (32 + int(f.t).bit_length() + qbits + 8 + 42) // 43
         alg = {"ks_modup_ntt": B * (L + k * L) * row, "ks_inner": B * (k * L + 2 * k) * row + 2 * k * L * row,
                "ks_intt_special": B * 4 * row, "ks_intt_moddown": B * (2 * L + 2 + 2 * L + 2 * L) * row,
                # fused tail of a rotation's key switch: T rows in, sigma(c0) and the addend in, sum out, + key
@@ -273,6 +276,7 @@ def run_ours(args):
                "ks_fused": B * (L + L + 2 * L + 2 * L) * row + 2 * k * L * row,
                "behz_ntt_q": B * 4 * L * row, "behz_ntt_bsk": B * 4 * nb * row,      # d *** d: squaring path, 2 of 4 polys
                "behz_intt_q": B * 6 * L * row, "behz_intt_bsk": B * 6 * nb * row,
+               "behz_ntt": B * 4 * W2 * row, "behz_intt": B * 6 * W2 * row,
                "behz_lift": B * 2 * (L + 2 * L + 1) * row, "behz_tensor": B * 7 * (2 * L + 1) * row,
                "behz_scale": B * 3 * (3 * L + 1) * row, "add": B * 6 * L * row, "sub": B * 6 * L * row}
         peaks, how = measured_peaks()
@@ -288,7 +292,9 @@ def run_ours(args):
                     "ks_intt_moddown": (2 * L + (0 if any(r["kernel"] == "ks_intt_special" for r in prof) else 2), arq),
                     "ks_inner_intt_moddown": (2 * L + 2, arq), "ks_chain": (k * L + 2 * L + 2, arq),
                     "ks_fused": (k * L + 2 * L + 2, arq), "behz_ntt_q": (2 * L, arq), "behz_ntt_bsk": (2 * nb, 0),
-                    "behz_intt_q": (3 * L, arq), "behz_intt_bsk": (3 * nb, 0)}
+                    "behz_intt_q": (3 * L, arq), "behz_intt_bsk": (3 * nb, 0),
+                    # FP64 BEHZ (behz_f64.cuh): q rows + the sub-2^45 auxiliary rows in one launch each, squaring path
+                    "behz_ntt": (2 * W2, arq), "behz_intt": (3 * W2, arq)}
         bf_peaks = {arq: bf_peak, 0: f.measure_butterfly_peak(0)}
         ntt_ms = sum(r["ms"] for r in prof if r["kernel"] in ntt_rows)
         bf_per_row = (N_POLY // 2) * logn
