@@ -295,3 +295,35 @@ def test_n32768_ops_bit_exact(pair32768):
     assert np.array_equal(a.multiplyPlain([5, -3, 7]).export()[0], o.multiply_plain(a_w, pl))
     assert np.array_equal(a.addPlain([5, -3, 7]).export()[0], o.add_plain(a_w, pl))
     assert np.array_equal(f.decryptCiphertext(a.multiply(b)), (da * db + f.t // 2) % f.t - f.t // 2)
+
+
+@pytest.mark.parametrize("which", ["4096", "8192"])
+def test_behz_product_extreme_and_random_residues(which, pair4096, pair8192):
+    """The BEHZ product as a function of raw residues (not of valid encryptions): all q_i - 1, all zero, alternating
+    0 / q_i - 1, a single non-zero coefficient, and uniformly random residues — the inputs that stretch the ranges of the
+    base conversions.  The CUDA path (on the exact-double class: its own sub-2^45 auxiliary base, csrc/behz_f64.cuh)
+    must equal the oracle (SEAL's 61-bit base) bit for bit, also when both operands are the same handle (squaring)."""
+    f, o = pair4096 if which == "4096" else pair8192
+    L, N = f.L, f.N
+    q = np.array(f.primes[:L], dtype=np.uint64)
+    rng = np.random.default_rng(99)
+
+    def fill(kind):
+        ct = np.zeros((2, L, N), dtype=np.uint64)
+        for i in range(L):
+            if kind == "max":
+                ct[:, i, :] = q[i] - np.uint64(1)
+            elif kind == "alt":
+                ct[:, i, ::2] = q[i] - np.uint64(1)
+            elif kind == "one":
+                ct[0, i, 0] = q[i] - np.uint64(1); ct[1, i, N - 1] = np.uint64(1)
+            elif kind == "rand":
+                ct[:, i, :] = rng.integers(0, int(q[i]), size=(2, N), dtype=np.uint64)
+        return ct
+
+    cases = [("max", "max"), ("max", "rand"), ("zero", "rand"), ("alt", "one"), ("rand", "rand"), ("one", "max")]
+    for ka, kb in cases:
+        a_w, b_w = fill(ka), fill(kb)
+        a, b = f.importCiphertext(a_w[None]), f.importCiphertext(b_w[None])
+        assert np.array_equal(f.probe_multiply(a, b)[0], o.multiply(a_w, b_w)), "product %s x %s" % (ka, kb)
+        assert np.array_equal(f.probe_multiply(a, a)[0], o.multiply(a_w, a_w)), "square %s" % ka
