@@ -56,6 +56,50 @@ def program_gpu(x, y):
     return s
 
 
+class NvmlSampler:
+    """SM clock and throttle reasons of ONE device through NVML, sampled every 5 ms from a thread (nvidia-smi needs longer
+    to start than a timed region lasts, and on 8-GPU boxes produced no sample at all)."""
+
+    def __init__(self, device):
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        self.sm, self.reasons, self.run = [], 0, False
+        self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+
+    def start(self):
+        self.run = True
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def _loop(self):
+        nv = self.nv
+        while self.run:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.reasons |= nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def stop(self):
+        self.run = False
+        self.t.join(timeout=2)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        return {"sm_mhz": int(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(k for k, v in names.items() if self.reasons & v), "samples": len(self.sm)}
+
+
+def make_sampler(device):
+    try:
+        return NvmlSampler(device)
+    except Exception:
+        return ClockSampler(device)
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -202,7 +246,7 @@ def run_ours(args):
     got = f.decryptCiphertext(s)
     got0 = got[:, 0] if B > 1 else got[:1]
     assert np.array_equal(got0, want0), "program result mismatch"
-    sampler = ClockSampler(local)
+    sampler = make_sampler(local)
     sampler.start()
     for _ in range(3):                     # let the sampler come up while the GPU is under the same load
         program_gpu(x, y)
@@ -216,6 +260,13 @@ def run_ours(args):
     launches = f.launch_count() - l0
     barrier()
     clocks = sampler.stop()
+    if world > 1:   # every rank samples its own device: report the slowest median and the union of the reasons
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        meds = [c["sm_mhz"] for c in allc if c["sm_mhz"] is not None]
+        clocks = {"sm_mhz": min(meds) if meds else None, "sm_max_mhz": clocks["sm_max_mhz"],
+                  "reasons": sorted({r for c in allc for r in c["reasons"]}), "samples": sum(c["samples"] for c in allc),
+                  "sm_mhz_per_rank": [c["sm_mhz"] for c in allc]}
 
     # ---- end to end through the factory with host buffers (pinned), copies inside the timed region
     hx = torch.from_numpy(xs).pin_memory()
