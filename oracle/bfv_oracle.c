@@ -231,6 +231,18 @@ static int prod_bit_count(const u64 *ps, size_t n) {
 }
 static int bit_count64(u64 v) { int b = 0; while (v) { b++; v >>= 1; } return b; }
 
+/* aux_bits != 0 (test hook, NOT SEAL behaviour): take the BEHZ auxiliary base B U {m_sk} as aux_count + 1 primes of aux_bits
+   bits from get_primes (skipping the coefficient primes) instead of SEAL's 61-bit ones.  The product of bfv_multiply must not
+   depend on that choice as long as the base satisfies SEAL's size rule; tests/test_oracle.py checks exactly this, which is
+   what lets the CUDA path run the product over a sub-2^45 base (abc_b200/csrc/behz_f64.cuh).  gamma stays SEAL's. */
+static int g_aux_bits = 0; static size_t g_aux_count = 0;
+obfv_ctx *obfv_create(size_t N, const u64 *primes, size_t k, u64 t);
+obfv_ctx *obfv_create_aux(size_t N, const u64 *primes, size_t k, u64 t, int aux_bits, size_t aux_count) {
+  g_aux_bits = aux_bits; g_aux_count = aux_count;
+  obfv_ctx *c = obfv_create(N, primes, k, t);
+  g_aux_bits = 0; g_aux_count = 0;
+  return c;
+}
 obfv_ctx *obfv_create(size_t N, const u64 *primes, size_t k, u64 t) {
   int logN = 0; while (((size_t)1 << logN) < N) logN++;
   if (((size_t)1 << logN) != N || N < 16 || N > 65536) return NULL;
@@ -288,6 +300,18 @@ obfv_ctx *obfv_create(size_t N, const u64 *primes, size_t k, u64 t) {
   if (obfv_get_primes(N, 61, nB + 2, aux) != nB + 2) { obfv_destroy(c); return NULL; }
   c->nB = nB; c->nbsk = nB + 1; c->msk = aux[0]; c->gamma = aux[1];
   for (size_t i = 0; i < nB; i++) { c->B[i] = aux[2 + i]; c->bsk[i] = aux[2 + i]; }
+  if (g_aux_bits) {   /* test hook: see obfv_create_aux */
+    u64 cand[MAXK], pick[MAXK]; size_t m = 0;
+    size_t got = obfv_get_primes(N, g_aux_bits, g_aux_count + 1 + c->k + 2, cand);
+    for (size_t a = 0; a < got && m < g_aux_count + 1; a++) {
+      int used = cand[a] == t;
+      for (size_t i = 0; i < c->k; i++) if (cand[a] == c->q[i]) used = 1;
+      if (!used) pick[m++] = cand[a];
+    }
+    if (m != g_aux_count + 1) { obfv_destroy(c); return NULL; }
+    nB = g_aux_count; c->nB = nB; c->nbsk = nB + 1; c->msk = pick[nB];
+    for (size_t i = 0; i < nB; i++) { c->B[i] = pick[i]; c->bsk[i] = pick[i]; }
+  }
   c->bsk[nB] = c->msk;
   for (size_t j = 0; j < c->nbsk; j++) { c->bbsk[j] = bmod_init(c->bsk[j]); ntt_tab_init(&c->nbskt[j], c->bsk[j], N, logN); }
   c->bgamma = bmod_init(c->gamma);

@@ -32,6 +32,8 @@ typedef struct obfv_ctx obfv_ctx;
 /* primes==NULL -> SEAL CoeffModulus::BFVDefault(N) (k is ignored); t==0 -> PlainModulus::Batching(N,20).
  * Returns NULL on invalid parameters. */
 obfv_ctx *obfv_create(size_t N, const uint64_t *primes, size_t k, uint64_t t);
+/* test hook (not SEAL behaviour): BEHZ auxiliary base of aux_count + 1 primes of aux_bits bits, see bfv_oracle.c */
+obfv_ctx *obfv_create_aux(size_t N, const uint64_t *primes, size_t k, uint64_t t, int aux_bits, size_t aux_count);
 void obfv_destroy(obfv_ctx *c);
 
 size_t obfv_N(const obfv_ctx *c);

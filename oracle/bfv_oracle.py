@@ -33,6 +33,7 @@ def _load():
     vp, sz, u64, i32, u32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_int, C.c_uint32
     sig = {
         "obfv_create": (vp, [sz, vp, sz, u64]),
+        "obfv_create_aux": (vp, [sz, vp, sz, u64, i32, sz]),
         "obfv_destroy": (None, [vp]),
         "obfv_N": (sz, [vp]), "obfv_k": (sz, [vp]), "obfv_L": (sz, [vp]), "obfv_t": (u64, [vp]),
         "obfv_primes": (None, [vp, u64p]),
@@ -91,13 +92,16 @@ class Oracle:
     """SEAL-3.6.5-restatement BFV context.  Mirrors what SealCiphertextFactory sets up
     (/root/reference/src/runtime/SealCiphertextFactory.cpp:72-100)."""
 
-    def __init__(self, N, primes=None, t=0, seed=None, galois_steps=None):
+    def __init__(self, N, primes=None, t=0, seed=None, galois_steps=None, aux=None):
+        """aux = (bits, count): test hook, BEHZ auxiliary base of `count` + 1 primes of `bits` bits instead of SEAL's
+        61-bit ones (obfv_create_aux); None = SEAL's base."""
         L_ = lib()
-        if primes is None:
-            self._c = L_.obfv_create(N, None, 0, t)
+        arr = None if primes is None else np.asarray(primes, dtype=np.uint64)
+        ptr, n = (None, 0) if arr is None else (arr.ctypes.data, len(arr))
+        if aux is None:
+            self._c = L_.obfv_create(N, ptr, n, t)
         else:
-            arr = np.asarray(primes, dtype=np.uint64)
-            self._c = L_.obfv_create(N, arr.ctypes.data, len(arr), t)
+            self._c = L_.obfv_create_aux(N, ptr, n, t, int(aux[0]), int(aux[1]))
         if not self._c:
             raise ValueError("invalid BFV parameters")
         self.N, self.k, self.L, self.t = N, L_.obfv_k(self._c), L_.obfv_L(self._c), L_.obfv_t(self._c)

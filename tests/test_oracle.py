@@ -8,6 +8,8 @@ import pytest
 
 from oracle.bfv_oracle import Oracle, get_primes
 
+SEED = 4673838
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 KATS = json.load(open(os.path.join(HERE, "golden", "abc_kats.json")))
 
@@ -228,3 +230,43 @@ def test_noise_budget_tracks_decryptability(oracle4096):
         assert ok or budgets[-1] == 0, "a positive budget guarantees decryption"
     assert budgets[1] < budgets[0] and budgets[-1] == 0
     assert all(a >= b for a, b in zip(budgets, budgets[1:]))
+
+
+def test_behz_product_does_not_depend_on_the_auxiliary_base():
+    """bfv_multiply lifts q -> Bsk = B U {m_sk}, multiplies, and comes back (fast_floor + Shenoy-Kumaresan).  Every
+    conversion is exact or has an error term that depends on the q residues only, so WHICH primes make up B and m_sk must
+    not show in the product as long as their product passes SEAL's size rule (more than 32 + bits(t) + bits(Q) bits).
+    The CUDA path relies on this to run the product over 44-bit auxiliary primes on the FP64 pipe
+    (abc_b200/csrc/behz_f64.cuh); here the oracle itself is run with SEAL's base and with such bases (test hook
+    obfv_create_aux), on fresh encryptions, on a chain of three products, and on extreme raw residues.  A base below the
+    size rule must (and does) give a different product, which shows the comparison is sensitive."""
+    from oracle.bfv_oracle import Oracle
+    N = 4096
+    ref = Oracle(N, seed=SEED)
+    L = ref.L
+    q = np.array(ref.primes[:L], dtype=np.uint64)
+    rng = np.random.default_rng(3)
+    a = ref.encrypt_slots(rng.integers(0, 1025, N), 1)
+    b = ref.encrypt_slots(rng.integers(0, 1025, N), 2)
+    mx = np.zeros((2, L, N), dtype=np.uint64)
+    rnd = np.zeros((2, L, N), dtype=np.uint64)
+    for i in range(L):
+        mx[:, i, :] = q[i] - np.uint64(1)
+        rnd[:, i, :] = rng.integers(0, int(q[i]), size=(2, N), dtype=np.uint64)
+
+    def products(o):
+        m1 = o.multiply(a, b)
+        r1 = o.relinearize(m1)
+        m2 = o.multiply(r1, r1)
+        m3 = o.multiply(o.relinearize(m2), a)
+        return [m1, m2, m3, o.multiply(mx, mx), o.multiply(mx, rnd), o.multiply(rnd, rnd)]
+
+    want = products(ref)
+    # N = 4096: Q has 72 bits, t 20: the rule asks for more than 124 bits; 4 x 44 = 176 (what the CUDA path takes), 3 x 45, 5 x 40
+    for aux in ((44, 3), (45, 2), (40, 4)):
+        o = Oracle(N, seed=SEED, aux=aux)
+        assert o.nbsk == aux[1] + 1
+        for x, y in zip(want, products(o)):
+            assert np.array_equal(x, y), "auxiliary base %r changes the product" % (aux,)
+    small = Oracle(N, seed=SEED, aux=(44, 1))      # 88 bits: below the rule
+    assert not all(np.array_equal(x, y) for x, y in zip(want, products(small)))
