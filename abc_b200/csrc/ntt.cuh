@@ -12,8 +12,10 @@
 // N <= 8192 a CTA is 512 threads doing two such groups per pass, so two CTAs share an SM and one CTA's
 // barriers and global-memory phases overlap the other's butterflies.  The contiguous pass owns 8 CONSECUTIVE
 // coefficients: gaps 4,2,1 are in-register and the stage above them is a warp-shuffle butterfly between lane
-// pairs, each lane computing half of the pair's butterflies.  Shared memory is XOR-swizzled at 16-byte
-// granularity so the strided and the contiguous passes are bank-conflict free.
+// pairs, each lane computing half of the pair's butterflies.  (Exact-double class at N = 8192: strided passes of 3, 3 and 4
+// stages and a shuffle-free contiguous pass, see "radix-16 plan" below.)  Shared memory is XOR-swizzled at 16-byte
+// granularity so the strided and the contiguous passes are bank-conflict free; the swizzle is linear over XOR, so a
+// strided access costs one XOR with a compile-time constant (swz_strided, swz_row8).
 //
 // Arithmetic classes (AR), chosen per launch from the largest modulus among its rows:
 //   AR_SHOUP   64-bit Harvey butterflies, Shoup twiddles (w, floor(w*2^64/q)); any q < 2^62.  29 SASS
@@ -25,10 +27,11 @@
 //              |y*w - round(y*w/q)*q| <= 0.75q.  The forward butterfly is x+v, x-v with no range guard and no
 //              +2q offset (values grow by < 0.75q per stage); the inverse reduces its sum chain twice per
 //              transform instead of guarding every butterfly.
-//   AR_F64     q < 2^45: the whole transform runs on the FP64 pipe, on exact integer-valued doubles.  A modular product
+//   AR_F64     q < 0.97 * 2^45: the whole transform runs on the FP64 pipe, on exact integer-valued doubles.  A modular product
 //              is 6 FP64 instructions: the error-free product y*w = ph + pl (DMUL + DFMA), Q = rint(ph * (1/q)) (DFMA +
-//              DADD with the 1.5*2^52 magic), v = (ph - Q*q) + pl (DFMA, exact because the result is an integer below
-//              2^53, + DADD); |v| <= 0.53q with a correctly rounded w/q (0.9q at worst with the DMUL companion of tw_get: exactness never depends on it, only the range plan).  A butterfly is 8 FP64 instructions and no integer instruction, so the
+//              DADD with the 1.5*2^52 magic: the estimate comes from the rounded product, a twiddle needs no companion),
+//              v = (ph - Q*q) + pl (DFMA, exact because the result is an integer below 2^53, + DADD); |v| <= 0.6q (exactness
+//              never depends on the estimate, only the range plan).  A butterfly is 8 FP64 instructions and no integer instruction, so the
 //              FP64 pipe (64 lanes/clk/SM on B200, otherwise idle) does the arithmetic while the integer pipes do
 //              the addressing: 2156 G butterflies/s register-resident vs 863 G (Shoup) and 1544 G (signed-lazy IMAD).
 #pragma once
