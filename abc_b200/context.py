@@ -38,7 +38,9 @@ class CudaCiphertextFactory:
     """Owns one device context: parameters, tables, keys, stream (SealCiphertextFactory.cpp:72-100)."""
 
     def __init__(self, numElementsPerCiphertextSlot=16384, primes=None, plain_modulus=0, device=0, batch=1,
-                 seed=4673838, keygen=True, galois_steps=None):
+                 seed=None, keygen=True, galois_steps=None):
+        """seed=None: keys from the OS generator, like the reference's randomly seeded SEAL PRNG; an explicit seed
+        makes the keys reproducible (tests, or the same keys on every GPU of a job)."""
         self._lib = _capi.load()
         p = _capi.AbcParams()
         p.poly_degree = numElementsPerCiphertextSlot
@@ -46,7 +48,7 @@ class CudaCiphertextFactory:
         if primes:
             self._primes_arr = (C.c_uint64 * len(primes))(*primes)
             p.n_primes, p.primes = len(primes), self._primes_arr
-        p.plain_modulus, p.device, p.batch, p.seed = plain_modulus, device, batch, seed
+        p.plain_modulus, p.device, p.batch, p.seed = plain_modulus, device, batch, seed or 0
         h = C.c_void_p()
         st = self._lib.abc_ctx_create(C.byref(p), C.byref(h))
         if st != 0:

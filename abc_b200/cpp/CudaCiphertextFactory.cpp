@@ -26,11 +26,14 @@ void CudaCiphertextFactory::setup(int device, unsigned int batch, uint64_t seed)
   check(abc_keygen(ctx));
 }
 
-CudaCiphertextFactory::CudaCiphertextFactory() { setup(0, 1, 4673838); }
+// The reference's factory draws its keys from SEAL's randomly seeded PRNG; seed 0 asks the library for the same
+// behaviour (key seed and encryption salt from the OS generator).  A fixed seed is for tests and for sharing keys
+// between the per-GPU factories of one job (extended constructor).
+CudaCiphertextFactory::CudaCiphertextFactory() { setup(0, 1, 0); }
 
 CudaCiphertextFactory::CudaCiphertextFactory(unsigned int numElementsPerCiphertextSlot)
     : ciphertextSlotSize(numElementsPerCiphertextSlot) {
-  setup(0, 1, 4673838);
+  setup(0, 1, 0);
 }
 
 CudaCiphertextFactory::CudaCiphertextFactory(unsigned int numElementsPerCiphertextSlot, int device,

@@ -31,7 +31,7 @@ struct BehzF64 {
 // a * b mod m for integer-valued doubles, |a| < 2^51, 0 <= b < m < 2^45; centred result, |r| <= 0.6 m
 __device__ __forceinline__ double bf_mul(double a, double b, double m, double minv) {
   const double ph = a * b;
-  const double Q = fma(ph, minv, ABC_RINT_MAGIC) - ABC_RINT_MAGIC;
+  const double Q = rint_mul(ph, minv);
   const double pl = fma(a, b, -ph);
   return fma(-Q, m, ph) + pl;
 }

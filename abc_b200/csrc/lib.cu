@@ -5,6 +5,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <sys/random.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -40,6 +41,10 @@ struct abc_ctx {
   unsigned h2d_next = 0;
   int N = 0, logN = 0, k = 0, L = 0, nB = 0, nbsk = 0, B = 1, W = 0;
   u64 t = 0, seed = 0, enc_nonce = 0, gamma = 0, msk = 0;
+  // encryption randomness: stream id = enc_salt + nonce * batch + instance.  The salt is drawn from the OS per context,
+  // so two contexts that share a key seed (one factory per GPU) never reuse (u, e0, e1); abc_set_encrypt_nonce makes the
+  // stream reproducible (salt 0) for parity tests.
+  u64 enc_salt = 0;
   std::vector<u64> primes, bsk;
   DevConst hC;
   DevConst *dC = nullptr;
@@ -949,7 +954,7 @@ abc_status encode_device(abc_ctx *c, const int64_t *slots, size_t n, int broadca
 abc_status encrypt_device(abc_ctx *c, const u64 *plain, int broadcast, u64 *ct) {
   if (!c->have_keys) return fail(c, ABC_ERR_STATE, "keys not generated");
   const int N = c->N, L = c->L, k = c->k, B = c->B;
-  const u64 nonce0 = c->enc_nonce * (u64)B;
+  const u64 nonce0 = c->enc_salt + c->enc_nonce * (u64)B;
   c->enc_nonce++;
   u64 *u = nullptr, *tmp = nullptr;
   TRY(scratch(c, SC_U, &u, (size_t)B * k * N));
@@ -1069,6 +1074,12 @@ abc_status abc_ctx_create(const abc_params *p, abc_ctx **out) {
   while ((1ull << logN) < N) ++logN;
   if ((1ull << logN) != N || logN < 12 || logN > 16) return bail(ABC_ERR_PARAM, "poly_degree must be a power of two in [4096, 65536]");
   c->N = (int)N; c->logN = logN; c->B = p->batch ? (int)p->batch : 1; c->seed = p->seed;
+  {  // seed 0 = not reproducible: key seed and encryption salt from the OS generator
+    u64 r[2] = {0, 0};
+    if (getrandom(r, sizeof r, 0) != (ssize_t)sizeof r) return bail(ABC_ERR_STATE, "getrandom failed: no entropy for keys / encryption randomness");
+    if (c->seed == 0) c->seed = r[0] | 1ull;
+    c->enc_salt = r[1];
+  }
   try {
     if (p->n_primes == 0) c->primes = hm::bfv_default_primes(N);
     else c->primes.assign(p->primes, p->primes + p->n_primes);
@@ -1378,7 +1389,7 @@ abc_status abc_encode_encrypt(abc_ctx *c, const int64_t *slots, size_t n, int br
   abc_pt_free(pt);
   return s;
 }
-abc_status abc_set_encrypt_nonce(abc_ctx *c, uint64_t nonce) { c->enc_nonce = nonce; return ABC_OK; }
+abc_status abc_set_encrypt_nonce(abc_ctx *c, uint64_t nonce) { c->enc_nonce = nonce; c->enc_salt = 0; return ABC_OK; }
 
 // c0 + c1 * s mod q in coefficient form (Decryptor::dot_product_ct_sk_array), x [B][L][N] in the SC_DECX scratch slot
 static abc_status dot_ct_sk(abc_ctx *c, const abc_ct *ct, u64 **x_out) {

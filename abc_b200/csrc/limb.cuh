@@ -149,7 +149,7 @@ __device__ __forceinline__ double moddown_one_f64(double vd, u64 t, bool has_bas
   double a = f64_of(ar_from_canon<AR_F64>(t)) + f.p_half;
   a = csub_ge(a, f.pd);                                           // [t + p/2]_p, exact
   const double d = (vd - reduce_f64(a, f.qinv, f.qd)) + f.phm;    // |d| < 2.6q, exact integer
-  const double Q = fma(d, f.ipc, ABC_RINT_MAGIC) - ABC_RINT_MAGIC;
+  const double Q = rint_mul(d, f.ipc);
   const double ph = d * f.ipd, pl = fma(d, f.ipd, -ph);
   double r = fma(-Q, f.qd, ph) + pl;                              // d * p^-1 mod q, |r| <= 0.6q
   if (has_base) r += f64_of(ar_from_canon<AR_F64>(b));
@@ -249,6 +249,9 @@ __device__ __forceinline__ void limb_store_pair(const LimbJob &job, const ModInf
 // issues it, no registers are staged, and the whole row is in flight from the first cycle of the CTA
 __device__ __forceinline__ void bulk_row_to_smem(u64 *sm, const u64 *src, u32 bytes, u64 *mbar, int tid) {
   const u32 mb = (u32)__cvta_generic_to_shared(mbar), dst = (u32)__cvta_generic_to_shared(sm);
+#if ABC_WHATIF & 2
+  (void)mb; (void)dst; (void)src; (void)bytes; __syncthreads(); return;   // what-if: the source row costs nothing
+#endif
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -448,6 +451,12 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
         }
       }
     }
+#if ABC_WHATIF & 4
+    if (true) {  // what-if: the inner product costs nothing
+      for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
+        *reinterpret_cast<ulonglong2 *>(&sm[swz_pair(tid, e2)]) = make_ulonglong2(bits_of((double)e2), bits_of((double)tid));
+    } else
+#endif
     if (job.t_image && ABC_KS_PIPE_INNER && job.L == 4) {
       ks_inner_rows_f64<4, D::N / 2 / D::T, D::T>(sm, reinterpret_cast<const double2 *>(t), reinterpret_cast<const double2 *>(kp),
                                                  D::N / 2, job.k * D::N, M, tid);
@@ -572,6 +581,12 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
       __syncthreads();
     }
     if (POST == POST_MODDOWN) md = moddown_row(job, n, inst, wq);
+#if ABC_WHATIF & 8
+    if (POST == POST_MODDOWN && PRE == PRE_KS_INNER) {  // what-if: the ModDown epilogue costs nothing (one store per thread keeps the row alive)
+      job.dst[(size_t)inst * job.dst_is + (size_t)drow * D::N + tid] = sm[swz(tid)] ^ sm[swz(tid + 4096)];
+      return;
+    }
+#endif
     if constexpr (POST == POST_MODDOWN && AR == AR_F64 && !TAIL) {
       moddown_store_f64<LOGN, D::T>(
           sm, M, md, job.base_einv, reinterpret_cast<ulonglong2 *>(job.dst + (size_t)inst * job.dst_is + (size_t)drow * D::N),

@@ -43,10 +43,29 @@
 #ifndef ABC_F64_TW_PAIRS
 #define ABC_F64_TW_PAIRS 0  /* exact-double class, strided passes: 16-byte {w, w/q} twiddles (0: 8-byte w + one DMUL) */
 #endif
+#ifndef ABC_F64_FRND
+#define ABC_F64_FRND 0      /* exact-double class: quotient estimate as DMUL + FRND.F64 (1) or DFMA + DADD on the 1.5*2^52 magic (0) */
+#endif
+#ifndef ABC_WHATIF
+#define ABC_WHATIF 0        /* timing-only experiments (wrong results): see tools/ks_time.py; 0 in every shipped build */
+#endif
 enum { AR_SHOUP = 0, AR_FP = 1, AR_FP_LAZY = 2, AR_F64 = 3 };
 #define ABC_RINT_MAGIC 6755399441055744.0 /* 1.5 * 2^52: x + MAGIC - MAGIC = rint(x) for |x| < 2^51 */
 __device__ __forceinline__ double f64_of(u64 bits) { return __longlong_as_double((long long)bits); }
 __device__ __forceinline__ u64 bits_of(double d) { return (u64)__double_as_longlong(d); }
+// rint(x * c) for the quotient estimates of the exact-double class.  FRND.F64 runs beside the FP64 pipe (ubench:
+// 16 lanes/clk/SM against 64 for DFMA), so the estimate costs one FP64-pipe instruction instead of two; the two forms
+// may differ by one unit on near-ties, which moves a centred remainder by q inside its range plan and never shows in a
+// canonical result.
+__device__ __forceinline__ double rint_mul(double x, double c) {
+#if ABC_F64_FRND
+  double r;
+  asm("cvt.rni.f64.f64 %0, %1;" : "=d"(r) : "d"(x * c));
+  return r;
+#else
+  return fma(x, c, ABC_RINT_MAGIC) - ABC_RINT_MAGIC;
+#endif
+}
 
 // element index -> physical index; keeps (even, odd) pairs adjacent so 16-byte accesses stay legal
 // (bits 4..6 of e onto bits 1..3: strided and contiguous passes are conflict free; bit 7 onto bit 3: neighbouring
@@ -134,6 +153,9 @@ template <int AR> __device__ __forceinline__ u64 ar_sub(u64 a, u64 b) { return A
 // needs for its c-th butterfly group of stage s lives at 2^s + c * (N/8) + vt, so a warp's load is one 256-byte run.
 template <int AR> __device__ __forceinline__ ulonglong2 tw_get(const ulonglong2 *__restrict__ tw, u32 idx, double qinv) {
   if (AR == AR_F64) {
+#if ABC_WHATIF & 1
+    idx &= 63u;   // what-if: every twiddle of the contiguous pass L1-hot
+#endif
     const u64 w = __ldg(reinterpret_cast<const u64 *>(tw) + idx);
     return make_ulonglong2(w, bits_of(qinv));
   }
@@ -161,7 +183,7 @@ template <int AR> __device__ __forceinline__ u64 mul_tw(u64 y, u64 w, u64 c, u64
     // old companion w * (1/q), so the same |v| <= 0.6q, but no DMUL per twiddle and two registers fewer per twiddle
     const double yd = f64_of(y), wd = f64_of(w);
     const double ph = yd * wd;
-    const double Q = fma(ph, f64_of(c), ABC_RINT_MAGIC) - ABC_RINT_MAGIC;
+    const double Q = rint_mul(ph, f64_of(c));
     const double pl = fma(yd, wd, -ph);
     return bits_of(fma(-Q, f64_of(aux), ph) + pl);
   } else if (AR == AR_SHOUP) {
@@ -193,7 +215,7 @@ template <bool SIGNED> __device__ __forceinline__ u64 reduce_fp(u64 x, double qi
 // canonical residue of a value as the class leaves it after a transform
 // AR_F64: x - rint(x/q)*q, |result| <= 0.51q, exact
 __device__ __forceinline__ double reduce_f64(double x, double qinv, double qd) {
-  const double Q = fma(x, qinv, ABC_RINT_MAGIC) - ABC_RINT_MAGIC;
+  const double Q = rint_mul(x, qinv);
   return fma(-Q, qd, x);
 }
 // r < 0 ? r + q : r  and  r >= q ? r - q : r  as a compare + ONE predicated add (the C++ ternary compiles to
@@ -614,6 +636,10 @@ __device__ __forceinline__ void ntt_fwd_smem_mids(u64 *sm, const ModInfo &M, u32
   const ulonglong2 *tw = (AR == AR_SHOUP) ? M.tw : (AR == AR_F64 ? (ABC_F64_TW_PAIRS ? M.twp : M.twd) : M.twf);
   const double qinv = f64_of(M.qinv_bits);
   typedef NttDims<LOGN, TT> D;
+#if ABC_WHATIF & 16
+  if constexpr (LINSRC) ntt_fwd_mid<LOGN, P::R0, P::R0, AR, false, TT>(sm, tw, twbase, q, aux, tid, qinv);  // what-if: first pass as cheap as a plain one
+  else
+#endif
   ntt_fwd_mid<LOGN, 0, P::R0, AR, LINSRC, TT>(sm, tw, twbase, q, aux, tid, qinv, qs, einv);
   pass_sync<LOGN - P::R0, D::T>(tid);
   ntt_fwd_mid<LOGN, P::R0, P::R1, AR, false, TT>(sm, tw, twbase, q, aux, tid, qinv);

@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/.."
 name=$1; flags=$2
-od=abc_b200/lib/obj_$name; mkdir -p $od
+od=/tmp/abc_obj_$name; mkdir -p $od
 for f in abc_b200/csrc/*.cu; do
   b=$(basename $f .cu)
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $flags -c -o $od/$b.o $f &
