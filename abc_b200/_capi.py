@@ -24,6 +24,8 @@ SYMBOLS = {
     "abc_ctx_destroy": (None, [vp]),
     "abc_last_error": (C.c_char_p, [vp]),
     "abc_sync": (i32, [vp]),
+    "abc_faulted": (i32, [vp]),
+    "abc_clear_fault": (i32, [vp]),
     "abc_poly_degree": (u32, [vp]),
     "abc_n_primes": (u32, [vp]),
     "abc_n_limbs": (u32, [vp]),

@@ -180,6 +180,56 @@ void runKats() {
     } catch (std::runtime_error &) { threw = true; }
     report("visitor.unsupported '/' on ciphertexts throws std::runtime_error", threw);
   }
+  {
+    // all 15 operations a ciphertext rejects (SealCiphertext.cpp:241-309) throw the same exception type
+    auto c1 = f.createCiphertext(data1), c2 = f.createCiphertext(data2);
+    using BinOp = void (AbstractValue::*)(const AbstractValue &);
+    const std::vector<std::pair<const char *, BinOp>> binary = {
+        {"divide", &AbstractValue::divide_inplace}, {"modulo", &AbstractValue::modulo_inplace},
+        {"logicalAnd", &AbstractValue::logicalAnd_inplace}, {"logicalOr", &AbstractValue::logicalOr_inplace},
+        {"logicalLess", &AbstractValue::logicalLess_inplace}, {"logicalLessEqual", &AbstractValue::logicalLessEqual_inplace},
+        {"logicalGreater", &AbstractValue::logicalGreater_inplace},
+        {"logicalGreaterEqual", &AbstractValue::logicalGreaterEqual_inplace},
+        {"logicalEqual", &AbstractValue::logicalEqual_inplace}, {"logicalNotEqual", &AbstractValue::logicalNotEqual_inplace},
+        {"bitwiseAnd", &AbstractValue::bitwiseAnd_inplace}, {"bitwiseXor", &AbstractValue::bitwiseXor_inplace},
+        {"bitwiseOr", &AbstractValue::bitwiseOr_inplace}};
+    Cleartext<int> pt(std::vector<int>{1, 2, 3});
+    for (const auto &[name, op] : binary) {
+      int threw = 0;
+      try { ((*c1).*op)(*c2); } catch (std::runtime_error &) { ++threw; }
+      try { ((*c1).*op)(pt); } catch (std::runtime_error &) { ++threw; }
+      report(std::string("unsupported.") + name + "_inplace(ciphertext | cleartext) throws std::runtime_error", threw == 2);
+    }
+    int threw = 0;
+    try { c1->logicalNot_inplace(); } catch (std::runtime_error &) { ++threw; }
+    try { c1->bitwiseNot_inplace(); } catch (std::runtime_error &) { ++threw; }
+    report("unsupported.logicalNot_inplace / bitwiseNot_inplace throw std::runtime_error", threw == 2);
+    checkCiphertextData(f, *c1, data1, "unsupported.operand unchanged after 15 rejected operations");
+  }
+  {
+    // Cleartext<int>::subtract_inplace(ciphertext) (include/ast_opt/runtime/Cleartext.h:349-360) encrypts
+    // the cleartext through the ciphertext's factory, subtracts, and DISCARDS the result: the cleartext is unchanged.  The
+    // quirk is the reference's; what is checked is that it runs through this factory (a ciphertext is created and a
+    // subtraction is launched) and leaves both operands as they were.
+    Cleartext<int> plain(std::vector<int>{50, 60, 70, 80, 90, 100});
+    auto c = f.createCiphertext(data1);
+    const uint64_t before = f.launchCount();
+    plain.subtract_inplace(*c);
+    const uint64_t used = f.launchCount() - before;
+    const std::vector<int> want = {50, 60, 70, 80, 90, 100};
+    report("a16.Cleartext<int>::subtract_inplace(ciphertext): cleartext unchanged, encrypt + sub launched through the factory",
+           plain.getData() == want && used >= 2, "launches " + std::to_string(used));
+    checkCiphertextData(f, *c, data1, "a16.ciphertext operand unchanged");
+    // the same through the interpreter: `i --- x` with a plain left operand keeps the cleartext (RuntimeVisitor.cpp:69-71),
+    // which the secret declaration then encrypts
+    auto r = runProgram(f, "secret int __input0__ = {43,  1,   1,  22, 11, 7};",
+                        "int i = 19;\nsecret int result = i --- __input0__;\nreturn result;", "y = result;", in0);
+    report("a16.visitor `plain --- cipher` yields the (encrypted) cleartext operand", prefixEquals(r["y"], {19, 19, 19, 19, 19, 19}));
+    // and the well-defined direction for comparison
+    r = runProgram(f, "secret int __input0__ = {43,  1,   1,  22, 11, 7};",
+                   "int i = 19;\nsecret int result = __input0__ --- i;\nreturn result;", "y = result;", in0);
+    report("a16.visitor `cipher --- plain`", prefixEquals(r["y"], {24, -18, -18, 3, -8, -12}));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ programs

@@ -6,7 +6,8 @@
 // rows of instance g + S1 are dispatched together with the tail rows of instance g (linear block order), so only about
 // S1 instances' worth of T is alive at any time (L2-resident), and an SM holds a transform-bound ModUp CTA next to a
 // load-bound tail CTA instead of two of the same kind.  A tail row waits (acquire on a counter its L ModUp rows bump
-// after their bulk stores complete) only for blocks with a smaller linear index, so the grid cannot deadlock.
+// after their bulk stores complete) only for blocks that took a smaller ticket (limb.cuh grid_ticket: the schedule is
+// indexed by the order in which blocks actually start, not by blockIdx), so the grid cannot deadlock.
 // Schedule (host-built, abc_ctx::ks_sched): entry.x = role << 31 | inst, entry.y = row | modulus << 8 | drow << 16 | srow << 24.
 #define ABC_LIMB_IMPL
 #include "kschain.cuh"
@@ -16,7 +17,7 @@ namespace {
 template <int LOGN, bool GAL>
 __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_ks_chain(KsChain ch, const ModInfo *__restrict__ mods) {
   // schedule entry: x = role << 31 | inst, y = w | modulus << 8 | drow << 16 | srow << 24
-  const uint2 s = __ldg(ch.sched + blockIdx.x);
+  const uint2 s = __ldg(ch.sched + grid_ticket(ch.ticket, ch.ticket_base));
   const int inst = (int)(s.x & 0x7fffffffu), w = (int)(s.y & 0xff);
   const RowIds ids{(int)((s.y >> 8) & 0xff), (int)((s.y >> 16) & 0xff), (int)(s.y >> 24)};
   if ((s.x >> 31) == 0)

@@ -7,6 +7,7 @@ struct KsChain {
   LimbJob tail;        // inner product + INTT + ModDown rows (flags / done set)
   const uint2 *sched;  // [n_blocks] in dependency order: x = role << 31 | inst, y = row | modulus << 8 | drow << 16 | srow << 24
   int n_blocks;
+  u32 *ticket; u32 ticket_base;   // schedule position of a block = the ticket it takes when it starts (limb.cuh grid_ticket)
 };
 
 // returns a cudaError_t as int; logN in {12, 13}, every key-level prime < 2^45

@@ -15,7 +15,8 @@
 //     I <  L:                   wait for that flag, ModDown (+ sigma(c0) / base, + addend), store
 //
 // The special-prime unit of instance g + skew is dispatched with the data units of instance g (linear block order), so
-// a data unit only ever waits for a block with a smaller index: no deadlock, and normally no waiting at all.
+// a data unit only ever waits for a block with a smaller ticket (the order blocks start in, limb.cuh grid_ticket): no
+// deadlock whatever the dispatch order, and normally no waiting at all.
 // Shared memory: N words of transform buffer + 2N words of accumulators (192 KiB at N = 8192: one 1024-thread CTA per
 // SM; 96 KiB at N = 4096: two 512-thread CTAs).
 #include "ksfused.cuh"
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(NttDims<LOGN, TT>::T, NttDims<LOGN, TT>::MINB)
   int inst, unit;  // unit 0 = special prime, 1.. = data modulus Iset[unit - 1]
   {
     const int nI = job.nI, nd = nI - 1, Bn = job.B, S = job.skew < Bn ? job.skew : Bn;
-    const int b = blockIdx.x;
+    const int b = (int)grid_ticket(job.ticket, job.ticket_base);
     if (b < S) { inst = b; unit = 0; }
     else {
       const int b1 = b - S, full = (Bn - S) * nI;

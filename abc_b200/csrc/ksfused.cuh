@@ -13,6 +13,7 @@ struct KsJob {
   u64 *tl; long long tl_is;                   // [2][N] per instance: INTT_p(acc_L[c]), published by the special unit
   u32 *fault;                                 // host-mapped word raised when a dependency wait gives up (limb.cuh wait_word)
   u32 *flags; u32 serial; int skew;           // flags[inst][c] == serial when tl[inst][c] is ready
+  u32 *ticket; u32 ticket_base;               // unit of a block = the ticket it takes when it starts (limb.cuh grid_ticket)
   const DevConst *C;
   const int *Iset; int nI;                    // output moduli: the data limbs this rank owns, then the special prime
   int L, k, B;

@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "ksfused.cuh"
 #include "kschain.cuh"
+#include "ksred.cuh"
 #include "behz_f64.cuh"
 
 namespace {
@@ -96,6 +97,11 @@ struct abc_ctx {
   int ks_chain = 1, ks_chain_skew = 16;                                       // ABC_KS_CHAIN=0/1, ABC_KS_CHAIN_SKEW
   u32 *ks_fault_h = nullptr, *ks_fault_d = nullptr;                           // host-mapped: a dependency wait of a key-switch grid gave up
   u32 *ks_flags = nullptr; u32 ks_serial = 0;                                 // [B][2] ready flags of the merged launch
+  // accumulating key switch (ksred.cu): accumulator ring [ring][k][2][N] doubles, [B][k] done / freed counters
+  // ABC_KS_RED=1 selects it; measured 9 % slower than the chained grid at N = 8192 (the bulk reductions wait on the L2 atomic units)
+  int ks_red = 0, ksr_ring = 0; double *ksr_acc = nullptr; u32 *ksr_done = nullptr, *ksr_freed = nullptr; u32 ksr_serial = 0;
+  u32 *ks_ticket = nullptr; u32 ks_ticket_total = 0;                          // start-order tickets of the dependency-ordered grids (limb.cuh grid_ticket)
+  bool faulted = false;                                                       // sticky: a dependency wait timed out; every later call fails until abc_clear_fault
   int *rs_zero = nullptr;   // [2k]  0
   u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;
   u64 *d_noise_tab = nullptr; int q_bits = 0;   // abc_noise_budget: (Q/q_i), Q, (Q+1)/2 as L-word integers; bit_count(Q)
@@ -148,13 +154,15 @@ namespace {
 
 abc_status fail(abc_ctx *c, abc_status s, const std::string &msg) { c->err = msg; return s; }
 // after a stream synchronisation: did a key-switch grid give up waiting for one of its own producers?
+const char *kFaultMsg = "key switch: a dependency wait inside the grid timed out; ciphertexts computed since the last "
+                        "successful synchronisation are invalid (context poisoned until abc_clear_fault)";
+// after a stream synchronisation: did a key-switch grid give up waiting for one of its own producers?  Sticky: once seen,
+// every call that computes on or exports ciphertexts fails until the caller acknowledges it with abc_clear_fault.
 abc_status check_ks_fault(abc_ctx *c) {
-  if (c->ks_fault_h && *reinterpret_cast<volatile u32 *>(c->ks_fault_h)) {
-    *c->ks_fault_h = 0;
-    return fail(c, ABC_ERR_CUDA, "key switch: a dependency wait inside the grid timed out (results since the last synchronisation are invalid)");
-  }
-  return ABC_OK;
+  if (c->ks_fault_h && *reinterpret_cast<volatile u32 *>(c->ks_fault_h)) c->faulted = true;
+  return c->faulted ? fail(c, ABC_ERR_CUDA, kFaultMsg) : ABC_OK;
 }
+#define CHECK_POISON(c) do { if ((c)->faulted) return fail((c), ABC_ERR_CUDA, kFaultMsg); } while (0)
 
 struct Launch {
   abc_ctx *c; const char *name; cudaEvent_t a = nullptr, b = nullptr;
@@ -256,7 +264,10 @@ void fill_mod(ModInfo &m, u64 q, int N, int logN, std::vector<ulonglong2> &tw, s
   auto dbits = [q](u64 w) { double d = (double)w / (double)q; u64 b; memcpy(&b, &d, 8); return b; };
   m.ar_class = AR_SHOUP;
   // exact-double class: q < 0.97 * 2^45 (the inverse transform's range plan keeps 7 stages between two reductions)
-  if ((q >> 49) == 0) m.ar_class = q < 34128100000000ull ? AR_F64 : AR_FP;  // range plans in ntt.cuh (AR_FP_LAZY: ABC_FORCE_AR=2)
+  // (range plans in ntt.cuh; AR_FP_LAZY: ABC_FORCE_AR=2).  Wide primes (up to 2^49: SEAL's N = 16384 defaults) run the
+  // exact-double class with its extra reductions on the generic stage plan, i.e. at N = 16384; ABC_F64_WIDE=0 keeps them on AR_FP.
+  const bool wide_ok = ABC_F64_FRND && !(getenv("ABC_F64_WIDE") && atoi(getenv("ABC_F64_WIDE")) == 0);
+  if ((q >> 49) == 0) m.ar_class = (q < ABC_F64_NARROW_MAX || (wide_ok && logN == 14)) ? AR_F64 : AR_FP;
   twf.clear(); itwf.clear();
   m.ninv_f = m.wl_ninv_f = m.qinv_bits = 0;
   if (m.ar_class != AR_SHOUP) {
@@ -317,7 +328,11 @@ abc_status build_tables(abc_ctx *c) {
   c->behz_f64 = false; c->bsk2.clear();
   {
     bool all_small = L <= BF_MAXQ;
-    for (int i = 0; i < k; ++i) all_small = all_small && c->primes[i] < 34128100000000ull;
+    {
+      const bool wide_ok = ABC_F64_FRND && !(getenv("ABC_F64_WIDE") && atoi(getenv("ABC_F64_WIDE")) == 0);
+      for (int i = 0; i < k; ++i)
+        all_small = all_small && (c->primes[i] < ABC_F64_NARROW_MAX || (wide_ok && logN == 14 && (c->primes[i] >> 49) == 0));
+    }
     const char *e = getenv("ABC_BEHZ_F64");
     if (all_small && !(e && atoi(e) == 0) && logN <= 14) {
       const int need_bits = 32 + bits_of(t) + prod_bits(Q) + 8;
@@ -365,6 +380,7 @@ abc_status build_tables(abc_ctx *c) {
   c->ks_no_image = getenv("ABC_KS_NO_IMAGE") != nullptr;
   c->ks_no_discard = getenv("ABC_KS_NO_DISCARD") != nullptr;
   if (const char *e = getenv("ABC_KS_CHAIN")) c->ks_chain = atoi(e);
+  if (const char *e = getenv("ABC_KS_RED")) c->ks_red = atoi(e);
   if (const char *e = getenv("ABC_KS_CHAIN_SKEW")) c->ks_chain_skew = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("ABC_KS1_THREADS")) c->ks1_threads = atoi(e);
   if (const char *e = getenv("ABC_KS1_SKEW")) c->ks1_skew = atoi(e) < 0 ? 0 : atoi(e);
@@ -568,6 +584,20 @@ abc_status build_shard_maps(abc_ctx *c) {
     c->owned.push_back(c->ks_done);
     CK(cudaMemset(c->ks_done, 0, (size_t)2 * c->B * c->k * sizeof(u32)));
     c->ks_chain_serial = 0;
+    // accumulating key switch: a ring of 2 * S1 instances' accumulators (a slot is reused once its tail rows, scheduled S1
+    // instances after its ModUp rows, are done: every wait points at a smaller ticket)
+    if (c->ksr_acc) { cudaStreamSynchronize(c->stream); cudaFree(c->ksr_acc); c->ksr_acc = nullptr; }
+    if (c->ks_red) {
+    c->ksr_ring = std::min(Bn, 2 * S1);
+    const size_t accw = (size_t)c->ksr_ring * c->k * 2 * c->N;
+    CK(cudaMalloc((void **)&c->ksr_acc, accw * sizeof(double)));
+    CK(cudaMemset(c->ksr_acc, 0, accw * sizeof(double)));
+    CK(cudaMalloc((void **)&c->ksr_done, (size_t)2 * c->B * c->k * sizeof(u32)));
+    c->owned.push_back(c->ksr_done);
+    CK(cudaMemset(c->ksr_done, 0, (size_t)2 * c->B * c->k * sizeof(u32)));
+    c->ksr_freed = c->ksr_done + (size_t)c->B * c->k;
+    c->ksr_serial = 0;
+    }
   }
   if (!c->ks_fault_h) {
     CK(cudaHostAlloc((void **)&c->ks_fault_h, sizeof(u32), cudaHostAllocMapped));
@@ -575,9 +605,11 @@ abc_status build_shard_maps(abc_ctx *c) {
     CK(cudaHostGetDevicePointer((void **)&c->ks_fault_d, c->ks_fault_h, 0));
   }
   if (!c->ks_flags) {
-    CK(cudaMalloc((void **)&c->ks_flags, (size_t)c->B * 2 * sizeof(u32)));
+    CK(cudaMalloc((void **)&c->ks_flags, ((size_t)c->B * 2 + 1) * sizeof(u32)));
     c->owned.push_back(c->ks_flags);
-    CK(cudaMemset(c->ks_flags, 0, (size_t)c->B * 2 * sizeof(u32)));
+    CK(cudaMemset(c->ks_flags, 0, ((size_t)c->B * 2 + 1) * sizeof(u32)));
+    c->ks_ticket = c->ks_flags + (size_t)c->B * 2;
+    c->ks_ticket_total = 0;
   }
   return ABC_OK;
 }
@@ -708,23 +740,25 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
     kj.base0 = base0; kj.base0_is = base0_is; kj.base1 = base1; kj.base1_is = base1_is; kj.einv = einv;
     kj.tl = acc; kj.tl_is = (long long)2 * N;
     kj.flags = c->ks_flags; kj.serial = ++c->ks_serial; kj.skew = c->ks1_skew; kj.fault = c->ks_fault_d;
+    kj.ticket = c->ks_ticket; kj.ticket_base = c->ks_ticket_total; c->ks_ticket_total += (u32)(B * c->ks_nI);
     kj.C = c->dC; kj.Iset = c->ks_I; kj.nI = c->ks_nI; kj.L = L; kj.k = k; kj.B = B; kj.threads = c->ks1_threads;
     Launch l(c, "ks_fused");
     const int e = ks_fused_launch(c->logN, kj, c->d_mods, c->stream);
     if (e != 0) { c->err = std::string("ks_fused: ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
     return ABC_OK;
   }
-  TRY(scratch(c, SC_T, &T, (size_t)B * k * L * N));
-  TRY(scratch(c, SC_ACC, &acc, (size_t)B * 2 * k * N));
-  LimbJob j = blank_job();
-  j.dst = T; j.dst_is = (long long)k * L * N; j.src = target; j.src_is = target_is;
-  j.rowmod = c->rm_modup_s; j.rowdst = c->rd_modup_s; j.rowsrc = c->rs_modup_s; j.galois_einv = einv;
   const bool merged = c->logN <= 14 && (c->own_hi - c->own_lo) > 0 && !c->ks_unmerged;
   // exact-double class: the inner product runs in the load of the INTT + ModDown launch (no accumulator round trip)
   const bool fused = merged && abc_ntt_arith_class(c) == AR_F64 && !c->ks_unfused;
   const int t_image = fused && c->logN <= 14 && !c->ks_no_image ? 1 : 0;  // T rows as bulk-stored images of the swizzled limb
-  j.t_image = t_image;
   const bool chain = t_image && c->ks_chain && c->ks_sched && c->logN <= 13 && c->force_ar < 0;
+  const bool red = chain && c->ks_red && c->ksr_acc;   // no ModUp block at all (ksred.cu)
+  if (!red) TRY(scratch(c, SC_T, &T, (size_t)B * k * L * N));
+  TRY(scratch(c, SC_ACC, &acc, (size_t)B * 2 * k * N));
+  LimbJob j = blank_job();
+  j.dst = T; j.dst_is = (long long)k * L * N; j.src = target; j.src_is = target_is;
+  j.rowmod = c->rm_modup_s; j.rowdst = c->rd_modup_s; j.rowsrc = c->rs_modup_s; j.galois_einv = einv;
+  j.t_image = t_image;
   LimbJob jup = j;
   if (!chain) TRY(launch_limb(c, einv ? LIMB_GALOIS_REDUCE_FWD : LIMB_REDUCE_FWD, c->ar_q, j, c->ks_nI * L, B, "ks_modup_ntt"));
   if (!fused) {
@@ -749,12 +783,34 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   if (merged) {  // one launch: the two special-prime rows INTT and publish, the data rows INTT, wait, ModDown
     j.rowsrc = c->rs_mdm; j.rowdst = c->rd_mdm; j.rowmod = c->rm_mdm;
     j.flags = c->ks_flags; j.flag_serial = ++c->ks_serial; j.skew = c->ks_skew; j.fault = c->ks_fault_d;
+    j.ticket = c->ks_ticket; j.ticket_base = c->ks_ticket_total;
     if (fused) {
       j.src = T; j.src_is = (long long)k * L * N; j.mul = key; j.t_image = t_image;
       if (t_image) {  // raw-double T rows are multiplied with the exact-double copy of the key
         const double *keyd = nullptr;
         TRY(key_as_f64(c, key, &keyd));
         j.mul = reinterpret_cast<const u64 *>(keyd);
+      }
+      if (red) {   // ModUp rows accumulate into the output accumulators: no T (ksred.cu)
+        KsRed kr;
+        memset(&kr, 0, sizeof kr);
+        const double *keyd = nullptr;
+        TRY(key_as_f64(c, key, &keyd));
+        kr.target = target; kr.target_is = target_is; kr.key = keyd;
+        kr.acc = c->ksr_acc; kr.ring = c->ksr_ring; kr.tl = acc; kr.tl_is = (long long)2 * k * N;
+        kr.dst = dst; kr.dst_is = (long long)2 * L * N; kr.dst2 = dst_plain; kr.add = addend; kr.add_is = (long long)2 * L * N;
+        kr.base0 = base0; kr.base0_is = base0_is; kr.base1 = base1; kr.base1_is = base1_is; kr.einv = einv;
+        kr.sched = c->ks_sched; kr.n_blocks = c->ks_sched_n;
+        kr.ticket = c->ks_ticket; kr.ticket_base = c->ks_ticket_total; c->ks_ticket_total += (u32)kr.n_blocks;
+        ++c->ksr_serial;
+        kr.done = c->ksr_done; kr.done_target = (u32)L * c->ksr_serial;
+        kr.freed = c->ksr_freed; kr.freed_target = 2u * c->ksr_serial;
+        kr.flags = c->ks_flags; kr.flag_serial = j.flag_serial; kr.fault = c->ks_fault_d;
+        kr.C = c->dC; kr.L = L; kr.k = k; kr.B = B;
+        Launch l(c, einv ? "ks_red" : "ks_red_relin");
+        const int e = ks_red_launch(c->logN, kr, c->d_mods, c->stream);
+        if (e != 0) { c->err = std::string("ks_red: ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
+        return ABC_OK;
       }
       if (chain) {
         KsChain ch;
@@ -764,13 +820,16 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
         ch.up.done = ch.tail.done = c->ks_done;
         ch.tail.t_used = c->ks_no_discard ? nullptr : c->ks_done + (size_t)c->B * k;
         ch.tail.done_target = ch.up.done_target = (u32)L * ++c->ks_chain_serial;
-        Launch l(c, "ks_chain");
+        ch.ticket = c->ks_ticket; ch.ticket_base = c->ks_ticket_total; c->ks_ticket_total += (u32)ch.n_blocks;
+        Launch l(c, einv ? "ks_chain" : "ks_chain_relin");
         const int e = ks_chain_launch(c->logN, ch, c->d_mods, c->stream);
         if (e != 0) { c->err = std::string("ks_chain: ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
         return ABC_OK;
       }
+      c->ks_ticket_total += (u32)((2 + 2 * nown) * B);
       TRY(launch_limb(c, LIMB_KSINNER_INV_MODDOWN, c->ar_q, j, 2 + 2 * nown, B, "ks_inner_intt_moddown"));
     } else {
+      c->ks_ticket_total += (u32)((2 + 2 * nown) * B);
       TRY(launch_limb(c, LIMB_INV_MODDOWN, c->ar_q, j, 2 + 2 * nown, B, "ks_intt_moddown"));
     }
   } else if (nown > 0) {
@@ -787,11 +846,12 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
     case 3 * 16 + 5: { constexpr int LL = 3, NK = 5; EXPR; } break;                                 \
     case 4 * 16 + 6: { constexpr int LL = 4, NK = 6; EXPR; } break;                                 \
     case 4 * 16 + 7: { constexpr int LL = 4, NK = 7; EXPR; } break;                                 \
+    case 8 * 16 + 11: { constexpr int LL = 8, NK = 11; EXPR; } break;                               \
     default: return fail(c, ABC_ERR_UNSUPPORTED, "FP64 BEHZ: no kernel for this (L, |Bsk|)");       \
   }
 bool behz_f64_has_kernel(const abc_ctx *c) {
   const int key = c->L * 16 + c->nbsk2;
-  return key == 2 * 16 + 4 || key == 2 * 16 + 5 || key == 3 * 16 + 5 || key == 4 * 16 + 6 || key == 4 * 16 + 7;
+  return key == 2 * 16 + 4 || key == 2 * 16 + 5 || key == 3 * 16 + 5 || key == 4 * 16 + 6 || key == 4 * 16 + 7 || key == 8 * 16 + 11;
 }
 // the same product over the sub-2^45 auxiliary base, every transform on the exact-double class (behz_f64.cuh)
 abc_status behz_multiply_f64(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
@@ -1121,6 +1181,7 @@ void abc_ctx_destroy(abc_ctx *c) {
   for (auto &kv : c->galois) cudaFree(kv.second);
   for (auto &kv : c->key_f64) cudaFree(kv.second);
   if (c->ks_fault_h) cudaFreeHost(c->ks_fault_h);
+  if (c->ksr_acc) cudaFree(c->ksr_acc);
   cudaFree(c->d_sk); cudaFree(c->d_pk); cudaFree(c->d_relin);
   for (void *p : c->owned) cudaFree(p);
   if (c->flush_buf) cudaFree(c->flush_buf);
@@ -1140,6 +1201,13 @@ void abc_ctx_destroy(abc_ctx *c) {
 
 const char *abc_last_error(const abc_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 abc_status abc_sync(abc_ctx *c) { CK(cudaStreamSynchronize(c->stream)); return check_ks_fault(c); }
+int abc_faulted(const abc_ctx *c) { return c->faulted ? 1 : 0; }
+abc_status abc_clear_fault(abc_ctx *c) {
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->ks_fault_h) *c->ks_fault_h = 0;
+  c->faulted = false;
+  return ABC_OK;
+}
 uint32_t abc_poly_degree(const abc_ctx *c) { return (uint32_t)c->N; }
 uint32_t abc_n_primes(const abc_ctx *c) { return (uint32_t)c->k; }
 uint32_t abc_n_limbs(const abc_ctx *c) { return (uint32_t)c->L; }
@@ -1326,6 +1394,7 @@ int abc_ct_shared(const abc_ct *ct) { return ct && ct->b ? ct->b->refs : 0; }
 int abc_ct_deferred(const abc_ct *ct) { return ct && ct->b && !ct->b->d ? 1 : 0; }
 abc_status abc_ct_export(abc_ctx *c, const abc_ct *ct, uint64_t *host, size_t words) {
   if (!valid_ct(c, ct) || words != abc_ct_words(c)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle or size");
+  CHECK_POISON(c);
   TRY(ct_resolve(c, ct));
   CK(cudaMemcpyAsync(host, ct->b->d, words * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -1338,7 +1407,7 @@ abc_status abc_ct_export_instance(abc_ctx *c, const abc_ct *ct, uint32_t inst, u
   TRY(ct_resolve(c, ct));
   CK(cudaMemcpyAsync(host, ct->b->d + (size_t)inst * words, words * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  return ABC_OK;
+  return check_ks_fault(c);
 }
 abc_status abc_ct_import_instance(abc_ctx *c, abc_ct *ct, uint32_t inst, const uint64_t *host, size_t words) {
   if (!valid_ct(c, ct) || words != ct_words1(c) || inst >= (uint32_t)c->B)
@@ -1394,6 +1463,7 @@ abc_status abc_set_encrypt_nonce(abc_ctx *c, uint64_t nonce) { c->enc_nonce = no
 // c0 + c1 * s mod q in coefficient form (Decryptor::dot_product_ct_sk_array), x [B][L][N] in the SC_DECX scratch slot
 static abc_status dot_ct_sk(abc_ctx *c, const abc_ct *ct, u64 **x_out) {
   if (!valid_ct(c, ct)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+  CHECK_POISON(c);
   if (!c->d_sk) return fail(c, ABC_ERR_STATE, "secret key not present");
   CK(cudaSetDevice(c->device));
   TRY(ct_resolve(c, ct));
@@ -1447,7 +1517,7 @@ abc_status abc_noise_budget(abc_ctx *c, const abc_ct *ct, int32_t *out_bits) {
   CK(cudaStreamSynchronize(c->stream));
   sfree(c, d_bits);
   for (int i = 0; i < B; ++i) { const int d = c->q_bits - bits[i] - 1; out_bits[i] = d > 0 ? d : 0; }
-  return ABC_OK;
+  return check_ks_fault(c);
 }
 
 abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) {
@@ -1485,6 +1555,7 @@ static abc_status fused_rotate_add(abc_ctx *c, abc_ct *dst, const abc_ct *rot, c
 static abc_status addsub(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct *b, int op) {
   if (!valid_ct(c, dst) || !valid_ct(c, a) || (op != 2 && !valid_ct(c, b)))
     return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+  CHECK_POISON(c);
   if (op == 0) {  // add with a deferred rotation: accumulate in its key switch
     if (!a->b->d && !b->b->d) TRY(ct_resolve(c, a));
     if (!b->b->d) return fused_rotate_add(c, dst, b, a);
@@ -1533,6 +1604,7 @@ abc_status abc_negate(abc_ctx *c, abc_ct *dst, const abc_ct *a) { return addsub(
 abc_status abc_mul_relin(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct *b) {
   if (!valid_ct(c, dst) || !valid_ct(c, a) || !valid_ct(c, b)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
   if (!c->d_relin) return fail(c, ABC_ERR_STATE, "relinearisation key not present");
+  CHECK_POISON(c);
   const size_t LN = (size_t)c->L * c->N;
   u64 *out3 = nullptr;
   TRY(scratch(c, SC_OUT3, &out3, (size_t)c->B * 3 * LN));
@@ -1552,6 +1624,7 @@ abc_status abc_mul_relin(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct 
 static abc_status rotate_impl(abc_ctx *c, abc_ct *dst, const abc_ct *a, int steps, const abc_ct *addend) {
   if (!valid_ct(c, dst) || !valid_ct(c, a) || (addend && !valid_ct(c, addend)))
     return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+  CHECK_POISON(c);
   const int as = steps < 0 ? -steps : steps;
   if (as >= (c->N >> 1)) return fail(c, ABC_ERR_PARAM, "step count too large");
   std::vector<u32> plan;
@@ -1598,6 +1671,7 @@ abc_status abc_rotate_rows_add(abc_ctx *c, abc_ct *dst, const abc_ct *a, int ste
 // ---- plaintext operands
 abc_status abc_add_plain_pt(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_pt *pt) {
   if (!valid_ct(c, dst) || !valid_ct(c, a) || !pt || pt->ctx != c) return fail(c, ABC_ERR_PARAM, "invalid handle");
+  CHECK_POISON(c);
   TRY(ct_resolve(c, a));
   const u64 *pa = a->b->d;
   TRY(ct_make_private(c, dst));
@@ -1605,6 +1679,7 @@ abc_status abc_add_plain_pt(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_
 }
 abc_status abc_sub_plain_pt(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_pt *pt) {
   if (!valid_ct(c, dst) || !valid_ct(c, a) || !pt || pt->ctx != c) return fail(c, ABC_ERR_PARAM, "invalid handle");
+  CHECK_POISON(c);
   TRY(ct_resolve(c, a));
   const u64 *pa = a->b->d;
   TRY(ct_make_private(c, dst));
@@ -1612,6 +1687,7 @@ abc_status abc_sub_plain_pt(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_
 }
 abc_status abc_mul_plain_pt(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_pt *pt) {
   if (!valid_ct(c, dst) || !valid_ct(c, a) || !pt || pt->ctx != c) return fail(c, ABC_ERR_PARAM, "invalid handle");
+  CHECK_POISON(c);
   TRY(ct_resolve(c, a));
   const u64 *pa = a->b->d;
   TRY(ct_make_private(c, dst));

@@ -51,6 +51,7 @@ struct LimbJob {
   // chained ModUp + tail launch (kschain.cu): done[inst][modulus] counts the ModUp rows stored so far (L per key switch)
   u32 *done; u32 done_target;
   u32 *fault;    // host-mapped word raised when a dependency wait gives up (wait_word)
+  u32 *ticket; u32 ticket_base;  // grids with internal dependencies: logical block index = atomicAdd(ticket) - ticket_base
   u32 *t_used;   // [inst][modulus] tail rows that have consumed T[inst][modulus][*] (2 per key switch): the second one drops
                  // the rows from L2 (discard.global.L2) so that their dirty lines are never written to DRAM
 };
@@ -138,11 +139,11 @@ __device__ __forceinline__ ModDownRow moddown_row(const LimbJob &job, int n, int
 }
 // ModDown on the exact-double class: vd = INTT output as a centred double (|vd| < q), result canonical.
 // Same value as the integer formulation below: base + p^-1 * (v - ([t + p/2]_p mod q) + [p/2]_q) mod q.
-struct ModDownF64 { double pd, p_half, phm, ipd, ipc, qd, qinv; };
+struct ModDownF64 { double pd, p_half, phm, ipd, ipc, qd, qinv; bool wide; };
 __device__ __forceinline__ ModDownF64 moddown_f64(const ModDownRow &md, const ModInfo &M) {
   ModDownF64 f;
   f.pd = (double)md.p; f.p_half = (double)md.p_half; f.phm = (double)md.phm; f.ipd = (double)md.ip;
-  f.qd = (double)M.q; f.qinv = f64_of(M.qinv_bits); f.ipc = f.ipd * f.qinv;
+  f.qd = (double)M.q; f.qinv = f64_of(M.qinv_bits); f.ipc = f.ipd * f.qinv; f.wide = f64_wide(M.q);
   return f;
 }
 __device__ __forceinline__ double moddown_one_f64(double vd, u64 t, bool has_base, u64 b, const ModDownF64 &f) {
@@ -152,6 +153,7 @@ __device__ __forceinline__ double moddown_one_f64(double vd, u64 t, bool has_bas
   const double Q = rint_mul(d, f.ipc);
   const double ph = d * f.ipd, pl = fma(d, f.ipd, -ph);
   double r = fma(-Q, f.qd, ph) + pl;                              // d * p^-1 mod q, |r| <= 0.6q
+  if (f.wide) r = reduce_f64(r, f.qinv, f.qd);                    // wide primes: the estimate's error can leave |r| ~ q
   if (has_base) r += f64_of(ar_from_canon<AR_F64>(b));
   r = cadd_neg(r, f.qd);
   return csub_ge(r, f.qd);                                        // canonical, as a double
@@ -379,6 +381,17 @@ template <bool GE> __device__ __forceinline__ void wait_word(const u32 *p, u32 t
     if (spins > (1u << 22)) { if (fault) *reinterpret_cast<volatile u32 *>(fault) = 1u; return; }
     __nanosleep(64);
   }
+}
+
+// Logical block index of a grid whose rows wait for rows "earlier" in the grid.  CUDA does not promise that blocks start in
+// blockIdx order, so "earlier" is defined by a ticket taken when the block starts running (as in decoupled look-back
+// scans): a block only ever waits for blocks that hold smaller tickets, i.e. that are already running or done, so the
+// waits cannot deadlock whatever the dispatch order.  base = tickets handed out by earlier launches on this counter.
+__device__ __forceinline__ unsigned grid_ticket(u32 *counter, u32 base) {
+  __shared__ unsigned s_ticket;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(counter, 1u) - base;
+  __syncthreads();
+  return s_ticket;
 }
 
 // RowIds: the caller already knows modulus / destination row / source row of row w (the chained key switch packs them
@@ -611,11 +624,11 @@ __global__ void __launch_bounds__(NttDims<LOGN>::T, NttDims<LOGN>::MINB) k_limb(
                                                                                const ModInfo *__restrict__ mods) {
   int inst = blockIdx.y, w = TAIL ? (int)(blockIdx.x >> job.sub) : (int)blockIdx.x;
   if (POST == POST_MODDOWN && !TAIL && job.flags) {
-    // merged special-row + ModDown launch: CTAs are dispatched in linear block order, and the two special-prime rows
-    // of instance g + S are issued with the data rows of instance g, so they have published INTT_p(acc_L) long before
-    // their own data rows ask for it (a data row only ever waits for blocks with a smaller linear index: no deadlock)
+    // merged special-row + ModDown launch: in ticket order the two special-prime rows of instance g + S come with the
+    // data rows of instance g, so they have published INTT_p(acc_L) long before their own data rows ask for it (a data
+    // row only ever waits for blocks with a smaller ticket: no deadlock)
     const int W = gridDim.x, Bn = gridDim.y, nd = W - 2, S = job.skew < Bn ? job.skew : Bn;
-    const int b = blockIdx.y * W + blockIdx.x;
+    const int b = (int)grid_ticket(job.ticket, job.ticket_base);
     if (b < 2 * S) { inst = b >> 1; w = b & 1; }
     else {
       const int b1 = b - 2 * S, full = (Bn - S) * W;

@@ -44,7 +44,7 @@
 #define ABC_F64_TW_PAIRS 0  /* exact-double class, strided passes: 16-byte {w, w/q} twiddles (0: 8-byte w + one DMUL) */
 #endif
 #ifndef ABC_F64_FRND
-#define ABC_F64_FRND 0      /* exact-double class: quotient estimate as DMUL + FRND.F64 (1) or DFMA + DADD on the 1.5*2^52 magic (0) */
+#define ABC_F64_FRND 1      /* exact-double class: quotient estimate as DMUL + FRND.F64 (1) or DFMA + DADD on the 1.5*2^52 magic (0) */
 #endif
 #ifndef ABC_WHATIF
 #define ABC_WHATIF 0        /* timing-only experiments (wrong results): see tools/ks_time.py; 0 in every shipped build */
@@ -66,6 +66,24 @@ __device__ __forceinline__ double rint_mul(double x, double c) {
   return fma(x, c, ABC_RINT_MAGIC) - ABC_RINT_MAGIC;
 #endif
 }
+
+// ---- exact-double class on WIDE primes (0.97 * 2^45 <= q < 2^49: SEAL's N = 16384 defaults are 48- and 49-bit).
+// The modular product itself is exact for any q < 2^51 once the quotient estimate is FRND(ph * (1/q)) (no 2^51 magic
+// range); what a wider prime costs is headroom: every value must stay an exact integer below 2^53 = 16 q, and the
+// estimate's three roundings make a centred product |v| <= (0.5 + 3 q |y| / 2^53) q <= (0.5 + 0.1875 |y| / q) q.  Range
+// plan (generic stage plan only: N = 16384, and N = 4096 if asked), magnitudes in units of q, input <= 2.1 (a source
+// residue of a 49-bit prime under a 48-bit target):
+//   forward : 6 stages unreduced reach 10.4; ONE reduction (to 0.5) in the load of the third strided pass; the remaining
+//             3 + 5 stages reach 9.9.  Raw outputs for the key switch's ModUp block are reduced once more (0.5), so a
+//             sum of L <= 15 key products stays below 15 * 0.6 = 9.
+//   inverse : sums double per stage, so at most 3 stages follow a reduction: after the in-register stages of the
+//             contiguous pass, in the load of every strided pass, and after the folded last stage (its outputs feed
+//             canon_inv / ModDown, which expect |x| < q).
+// The extra reductions are taken at run time (`wide`, uniform per row: q of the row's modulus), so one instantiation
+// serves rows of both kinds (the BEHZ product mixes 49-bit q rows with 44-bit auxiliary rows in one launch).
+#define ABC_F64_NARROW_MAX 34128100000000ull      /* 0.97 * 2^45 */
+#define ABC_F64_WIDE_MAX   562949953421312ull     /* 2^49 */
+__device__ __forceinline__ bool f64_wide(u64 q) { return ABC_F64_FRND && q >= ABC_F64_NARROW_MAX; }
 
 // element index -> physical index; keeps (even, odd) pairs adjacent so 16-byte accesses stay legal
 // (bits 4..6 of e onto bits 1..3: strided and contiguous passes are conflict free; bit 7 onto bit 3: neighbouring
@@ -282,7 +300,7 @@ template <int AR> __device__ __forceinline__ void bf_inv(u64 &x, u64 &y, ulonglo
 // it is no longer in place, separates its loads from its stores with a barrier.
 template <int LOGN, int S0, int R, int AR, bool LINSRC = false, int TT = 0>
 __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 aux,
-                                            int tid, double qinv, u64 qs = 0, u32 einv = 0) {
+                                            int tid, double qinv, u64 qs = 0, u32 einv = 0, bool wide_reduce = false) {
   typedef NttDims<LOGN, TT> D;
   constexpr int LG = LOGN - S0 - R;
   static_assert(!LINSRC || (AR == AR_F64 && S0 == 0), "linear-source gather is the first pass of the exact-double class");
@@ -315,12 +333,20 @@ __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restric
           x[g][r] = ar_from_canon<AR>(v);
           r0 += step;
         }
+        if (qs >= ABC_F64_NARROW_MAX && qs > q) {   // a wide source prime above the target: bring the residues to |x| <= 0.5 q first
+#pragma unroll
+          for (int r = 0; r < 8; ++r) x[g][r] = bits_of(reduce_f64(f64_of(x[g][r]), qinv, f64_of(aux)));
+        }
       } else {
 #pragma unroll
         for (int r = 0; r < 8; ++r) x[g][r] = sm[swz_strided<LG>(base[g], pbase[g], r)];
         if (S0 == 0) {  // first pass: canonical residues -> the class's representation
 #pragma unroll
           for (int r = 0; r < 8; ++r) x[g][r] = ar_from_canon<AR>(x[g][r]);
+        }
+        if (AR == AR_F64 && S0 != 0 && wide_reduce) {  // wide primes: the one reduction of the forward range plan
+#pragma unroll
+          for (int r = 0; r < 8; ++r) x[g][r] = bits_of(reduce_f64(f64_of(x[g][r]), qinv, f64_of(aux)));
         }
       }
     }
@@ -374,7 +400,7 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
       pbase[g] = swz(base[g]);
 #pragma unroll
       for (int r = 0; r < 8; ++r) x[g][r] = sm[swz_strided<LG>(base[g], pbase[g], r)];
-      if ((AR == AR_FP_LAZY || AR == AR_F64) && REDUCE) {
+      if ((AR == AR_FP_LAZY || AR == AR_F64) && (REDUCE || (AR == AR_F64 && f64_wide(q)))) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
           x[g][r] = AR == AR_F64 ? bits_of(reduce_f64(f64_of(x[g][r]), qinv, f64_of(aux))) : reduce_fp<true>(x[g][r], qinv, q, aux);
@@ -396,6 +422,10 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
                                  (AR == AR_SHOUP) ? M.ninv_s : (AR == AR_F64 ? M.qinv_bits : M.ninv_f), q, aux);
             x[g][r | (1 << b)] = mul_tw<AR>(d, AR == AR_F64 ? M.wl_ninv_d : M.wl_ninv,
                                             (AR == AR_SHOUP) ? M.wl_ninv_s : (AR == AR_F64 ? M.qinv_bits : M.wl_ninv_f), q, aux);
+            if (AR == AR_F64 && f64_wide(q)) {   // wide primes: |product| can reach 1.25 q; consumers expect |x| < q
+              x[g][r] = bits_of(reduce_f64(f64_of(x[g][r]), qinv, f64_of(aux)));
+              x[g][r | (1 << b)] = bits_of(reduce_f64(f64_of(x[g][r | (1 << b)]), qinv, f64_of(aux)));
+            }
           } else {
             const ulonglong2 w = mid_tw<AR>(tw, (twbase << s) + ((u32)((blk[g] << 3) + r) >> (b + 1)), qinv);
             bf_inv<AR>(x[g][r], x[g][r | (1 << b)], w, q, aux);
@@ -541,6 +571,10 @@ __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twba
       x[2 * i] = v.x; x[2 * i + 1] = v.y;
     }
     ntt_fwd_last_math<LOGN, AR, TT, P16 ? 0 : P::NSH>(x, tw, twbase, q, aux, vt, qinv);
+    if (RAW && AR == AR_F64 && f64_wide(q)) {   // wide primes: the ModUp block's raw values back to |x| <= 0.5 q
+#pragma unroll
+      for (int r = 0; r < E; ++r) x[r] = bits_of(reduce_f64(f64_of(x[r]), qinv, f64_of(aux)));
+    }
 #pragma unroll
     for (int i = 0; i < H; ++i) {
       ulonglong2 v;
@@ -567,6 +601,10 @@ __device__ __forceinline__ void ntt_inv_first_math(u64 (&x)[8], const ulonglong2
       const ulonglong2 w = tw_get<AR>(tw, last_tw_index<LOGN, AR>(twbase, s, b, vt, r), qinv);
       bf_inv<AR>(x[r], x[r | (1 << b)], w, q, aux);
     }
+  }
+  if (AR == AR_F64 && NSH > 0 && f64_wide(q)) {   // wide primes: at most 3 stages between reductions
+#pragma unroll
+    for (int r = 0; r < E; ++r) x[r] = bits_of(reduce_f64(f64_of(x[r]), qinv, f64_of(aux)));
   }
 #pragma unroll
   for (int j = 0; j < NSH; ++j) {
@@ -648,7 +686,7 @@ __device__ __forceinline__ void ntt_fwd_smem_mids(u64 *sm, const ModInfo &M, u32
     ntt_fwd_mid16<LOGN, AR>(sm, tw, q, aux, tid, qinv);
     __syncwarp();
   } else if constexpr (P::R2 > 0) {
-    ntt_fwd_mid<LOGN, P::R0 + P::R1, P::R2, AR, false, TT>(sm, tw, twbase, q, aux, tid, qinv);
+    ntt_fwd_mid<LOGN, P::R0 + P::R1, P::R2, AR, false, TT>(sm, tw, twbase, q, aux, tid, qinv, 0, 0, AR == AR_F64 && f64_wide(q));
     pass_sync<LOGN - P::R0 - P::R1 - P::R2, D::T>(tid);
   }
 }

@@ -325,6 +325,7 @@ def run_ours(args):
                # sigma(c0) in, the addend ciphertext in, the sum out, + key; the ModUp block T is not algorithmic traffic
                "ks_chain": B * (L + L + 2 * L + 2 * L) * row + 2 * k * L * row,
                "ks_fused": B * (L + L + 2 * L + 2 * L) * row + 2 * k * L * row,
+               "ks_chain_relin": B * (L + 2 * L + 2 * L) * row + 2 * k * L * row,   # relinearisation: c2 in, (c0, c1) in, sum out
                "behz_ntt_q": B * 4 * L * row, "behz_ntt_bsk": B * 4 * nb * row,      # d *** d: squaring path, 2 of 4 polys
                "behz_intt_q": B * 6 * L * row, "behz_intt_bsk": B * 6 * nb * row,
                "behz_ntt": B * 4 * W2 * row, "behz_intt": B * 6 * W2 * row,
@@ -342,7 +343,7 @@ def run_ours(args):
         ntt_rows = {"ks_modup_ntt": (k * L, arq), "ks_intt_special": (2, arq),
                     "ks_intt_moddown": (2 * L + (0 if any(r["kernel"] == "ks_intt_special" for r in prof) else 2), arq),
                     "ks_inner_intt_moddown": (2 * L + 2, arq), "ks_chain": (k * L + 2 * L + 2, arq),
-                    "ks_fused": (k * L + 2 * L + 2, arq), "behz_ntt_q": (2 * L, arq), "behz_ntt_bsk": (2 * nb, 0),
+                    "ks_fused": (k * L + 2 * L + 2, arq), "ks_chain_relin": (k * L + 2 * L + 2, arq), "behz_ntt_q": (2 * L, arq), "behz_ntt_bsk": (2 * nb, 0),
                     "behz_intt_q": (3 * L, arq), "behz_intt_bsk": (3 * nb, 0),
                     # FP64 BEHZ (behz_f64.cuh): q rows + the sub-2^45 auxiliary rows in one launch each, squaring path
                     "behz_ntt": (2 * W2, arq), "behz_intt": (3 * W2, arq)}
