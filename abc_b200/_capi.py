@@ -48,6 +48,8 @@ SYMBOLS = {
     "abc_ct_import": (i32, [vp, vp, vp, sz]),
     "abc_encode_encrypt": (i32, [vp, vp, sz, i32, vpp]),
     "abc_decrypt_decode": (i32, [vp, vp, vp]),
+    "abc_decrypt_decode_async": (i32, [vp, vp, vp]),
+    "abc_decrypt_wait": (i32, [vp]),
     "abc_set_encrypt_nonce": (i32, [vp, u64]),
     "abc_noise_budget": (i32, [vp, vp, vp]),
     "abc_add": (i32, [vp, vp, vp, vp]),

@@ -51,6 +51,7 @@ int ks_chain_launch(int logN, const KsChain &ch, const ModInfo *mods, cudaStream
   switch (logN) {
     case 12: return gal ? launch<12, true>(ch, mods, stream) : launch<12, false>(ch, mods, stream);
     case 13: return gal ? launch<13, true>(ch, mods, stream) : launch<13, false>(ch, mods, stream);
+    case 14: return gal ? launch<14, true>(ch, mods, stream) : launch<14, false>(ch, mods, stream);
     default: return (int)cudaErrorInvalidValue;
   }
 }

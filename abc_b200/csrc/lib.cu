@@ -40,6 +40,13 @@ struct abc_ctx {
   size_t h2d_words[2] = {0, 0};
   cudaEvent_t h2d_copied[2] = {nullptr, nullptr}, h2d_consumed[2] = {nullptr, nullptr};
   unsigned h2d_next = 0;
+  // decrypted slots leave on their own stream from one of two device buffers: the D2H of one decryptCiphertext runs under
+  // the kernels of whatever is enqueued next (abc_decrypt_decode_async + abc_decrypt_wait)
+  cudaStream_t d2h_stream = nullptr;
+  long long *d2h_buf[2] = {nullptr, nullptr};
+  size_t d2h_words[2] = {0, 0};
+  cudaEvent_t d2h_ready[2] = {nullptr, nullptr}, d2h_done[2] = {nullptr, nullptr};
+  unsigned d2h_next = 0;
   int N = 0, logN = 0, k = 0, L = 0, nB = 0, nbsk = 0, B = 1, W = 0;
   u64 t = 0, seed = 0, enc_nonce = 0, gamma = 0, msk = 0;
   // encryption randomness: stream id = enc_salt + nonce * batch + instance.  The salt is drawn from the OS per context,
@@ -561,7 +568,11 @@ abc_status build_shard_maps(abc_ctx *c) {
     // chained key switch: ModUp rows of instance g, the two special-prime tail rows of instance g - (S1 - S2) and the
     // data tail rows of instance g - S1, for g = 0 .. B + S1 - 1 (every wait points at an earlier block).  Every entry
     // carries its row's modulus, destination row and source row (the row maps of the two-launch sequence, resolved here)
-    const int Bn = c->B, S1 = c->ks_chain_skew, S2 = std::min(c->ks_skew, S1 - 1) < 0 ? 0 : std::min(c->ks_skew, S1 - 1);
+    // instances in flight: 16 at N <= 8192 (20 MiB of ModUp rows); fewer when an instance's block is larger (N = 16384,
+    // k = 9: 9.4 MiB each) so that what is in flight stays L2-resident
+    const size_t t_bytes = (size_t)c->ks_nI * L * c->N * 8;
+    const int s1_fit = (int)std::max<size_t>(2, (size_t)(48u << 20) / std::max<size_t>(t_bytes, 1));
+    const int Bn = c->B, S1 = getenv("ABC_KS_CHAIN_SKEW") ? c->ks_chain_skew : std::min(c->ks_chain_skew, s1_fit), S2 = std::min(c->ks_skew, S1 - 1) < 0 ? 0 : std::min(c->ks_skew, S1 - 1);
     std::vector<uint2> sch;
     auto up_row = [&](int g, int w) {      // w = idx(I) * L + J: T row I * L + J from target limb J, modulus I
       const int Iv = I[w / L], J = w % L;
@@ -751,8 +762,8 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   // exact-double class: the inner product runs in the load of the INTT + ModDown launch (no accumulator round trip)
   const bool fused = merged && abc_ntt_arith_class(c) == AR_F64 && !c->ks_unfused;
   const int t_image = fused && c->logN <= 14 && !c->ks_no_image ? 1 : 0;  // T rows as bulk-stored images of the swizzled limb
-  const bool chain = t_image && c->ks_chain && c->ks_sched && c->logN <= 13 && c->force_ar < 0;
-  const bool red = chain && c->ks_red && c->ksr_acc;   // no ModUp block at all (ksred.cu)
+  const bool chain = t_image && c->ks_chain && c->ks_sched && c->logN <= 14 && c->force_ar < 0;
+  const bool red = chain && c->ks_red && c->ksr_acc && c->logN <= 13;   // no ModUp block at all (ksred.cu)
   if (!red) TRY(scratch(c, SC_T, &T, (size_t)B * k * L * N));
   TRY(scratch(c, SC_ACC, &acc, (size_t)B * 2 * k * N));
   LimbJob j = blank_job();
@@ -1154,9 +1165,12 @@ abc_status abc_ctx_create(const abc_params *p, abc_ctx **out) {
     if (!hm::is_prime(c->t) || (c->t - 1) % (2 * N)) return bail(ABC_ERR_PARAM, "plain_modulus must be a prime = 1 mod 2N (batching)");
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ABC_ERR_CUDA, "stream creation failed");
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ABC_ERR_CUDA, "stream creation failed");
+    if (cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ABC_ERR_CUDA, "stream creation failed");
     for (int i = 0; i < 2; ++i) {
       cudaEventCreateWithFlags(&c->h2d_copied[i], cudaEventDisableTiming);
       cudaEventCreateWithFlags(&c->h2d_consumed[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&c->d2h_ready[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&c->d2h_done[i], cudaEventDisableTiming);
     }
     cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
     cudaMemPool_t pool;
@@ -1190,6 +1204,12 @@ void abc_ctx_destroy(abc_ctx *c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->d2h_stream) { cudaStreamSynchronize(c->d2h_stream); cudaStreamDestroy(c->d2h_stream); }
+  for (int i = 0; i < 2; ++i) {
+    if (c->d2h_buf[i]) cudaFree(c->d2h_buf[i]);
+    if (c->d2h_ready[i]) cudaEventDestroy(c->d2h_ready[i]);
+    if (c->d2h_done[i]) cudaEventDestroy(c->d2h_done[i]);
+  }
   for (int i = 0; i < 2; ++i) {
     if (c->h2d_buf[i]) cudaFree(c->h2d_buf[i]);
     if (c->h2d_copied[i]) cudaEventDestroy(c->h2d_copied[i]);
@@ -1200,7 +1220,11 @@ void abc_ctx_destroy(abc_ctx *c) {
 }
 
 const char *abc_last_error(const abc_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
-abc_status abc_sync(abc_ctx *c) { CK(cudaStreamSynchronize(c->stream)); return check_ks_fault(c); }
+abc_status abc_sync(abc_ctx *c) {
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->d2h_stream) CK(cudaStreamSynchronize(c->d2h_stream));
+  return check_ks_fault(c);
+}
 int abc_faulted(const abc_ctx *c) { return c->faulted ? 1 : 0; }
 abc_status abc_clear_fault(abc_ctx *c) {
   CK(cudaStreamSynchronize(c->stream));
@@ -1520,13 +1544,26 @@ abc_status abc_noise_budget(abc_ctx *c, const abc_ct *ct, int32_t *out_bits) {
   return check_ks_fault(c);
 }
 
-abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) {
+// Decryptor::decrypt + BatchEncoder::decode, enqueued: the slots land in out_slots (pinned host memory for a truly
+// asynchronous copy) once abc_decrypt_wait / abc_sync returns.  The device-side result sits in one of two buffers and
+// leaves on the context's D2H stream, so the copy overlaps the kernels of the ops enqueued after this call.
+abc_status abc_decrypt_decode_async(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) {
   u64 *x = nullptr, *plain = nullptr;
   TRY(dot_ct_sk(c, ct, &x));
   const int N = c->N, B = c->B;
-  long long *d_out = nullptr;
   TRY(scratch(c, SC_DECP, &plain, (size_t)B * N));
-  CK(cudaMallocAsync((void **)&d_out, (size_t)B * N * sizeof(long long), c->stream));
+  const unsigned hb = c->d2h_next++ & 1u;
+  const size_t words = (size_t)B * N;
+  if (c->d2h_words[hb] < words) {   // grow-only (first use)
+    CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->d2h_stream));
+    if (c->d2h_buf[hb]) CK(cudaFree(c->d2h_buf[hb]));
+    c->d2h_buf[hb] = nullptr; c->d2h_words[hb] = 0;
+    CK(cudaMalloc((void **)&c->d2h_buf[hb], words * sizeof(long long)));
+    c->d2h_words[hb] = words;
+    CK(cudaEventRecord(c->d2h_done[hb], c->d2h_stream));
+  }
+  long long *d_out = c->d2h_buf[hb];
+  CK(cudaStreamWaitEvent(c->stream, c->d2h_done[hb], 0));   // the copy that last read this buffer has finished
   LimbJob j = blank_job();
   {
     Launch l(c, "dec_scale_round");
@@ -1544,10 +1581,19 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
   } else {
     TRY(launch_limb(c, LIMB_FWD_DECODE, c->ar_t, j, 1, B, "decode_ntt"));
   }
-  CK(cudaMemcpyAsync(out_slots, d_out, (size_t)B * N * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  sfree(c, d_out);
+  CK(cudaEventRecord(c->d2h_ready[hb], c->stream));
+  CK(cudaStreamWaitEvent(c->d2h_stream, c->d2h_ready[hb], 0));
+  CK(cudaMemcpyAsync(out_slots, d_out, words * sizeof(long long), cudaMemcpyDeviceToHost, c->d2h_stream));
+  CK(cudaEventRecord(c->d2h_done[hb], c->d2h_stream));
+  return ABC_OK;
+}
+abc_status abc_decrypt_wait(abc_ctx *c) {
+  CK(cudaStreamSynchronize(c->d2h_stream));
   return check_ks_fault(c);
+}
+abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) {
+  TRY(abc_decrypt_decode_async(c, ct, out_slots));
+  return abc_decrypt_wait(c);
 }
 
 // ---- ciphertext ops

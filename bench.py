@@ -35,6 +35,15 @@ WORKLOAD = ("l2distance_batched: BFV N=8192 k=5 t=1032193, n=4096; per instance 
             "12 rotateRows(2^j) + 12 add, through CudaCiphertextFactory")
 
 
+def config_dict(batch, world):
+    """The `config` object of the JSON line: both arms print exactly this (the reference arm times a bounded sample of the
+    same workload on the host cores and says so in cpu_baseline.sample)."""
+    L, row = 4, N_POLY * 8   # BFVDefault(8192): k = 5 primes, L = 4 data limbs
+    return {"workload": WORKLOAD, "batch_per_gpu": batch, "instances_total": batch * world,
+            "parallelism": "independent instances sharded across GPUs, no collectives",
+            "l2": "inputs+intermediates exceed L2 (%.0f MiB of ciphertext per operand)" % (batch * 2 * L * row / 2**20)}
+
+
 def synth_inputs(batch, rank):
     """i.i.d. ints in [0,1024] (the reference's test distribution, BoxBlurTest.cpp:123), seeded per rank."""
     rng = np.random.default_rng(SEED + rank)
@@ -135,6 +144,26 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def pin_to_gpu_local_cores(device):
+    """Bind this process to the CPU cores NVML reports as local to `device` (the host leg of the end-to-end path —
+    pinned-buffer copies, the ctypes call sequence — otherwise wanders across sockets when 8 ranks share a box).
+    Returns the number of cores bound, or 0 when NVML / the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -202,6 +231,32 @@ def cpu_baseline_port(cores, seconds_budget=12.0):
                       "(oracle/), SEAL itself not installable; result check %s" % (n, cores, dt, "ok" if ok else "FAILED")}
 
 
+def per_op_numbers(f, x, y, B, reps=30):
+    """BASELINE.json's metric names the ops separately: mul+relin, rotateRows and add alone at the bench batch, device-resident,
+    each timed `reps` times between two synchronisations (CUDA events on the library stream): ops/s from the median,
+    p50 / p99 of the batched launch-sequence latency.  rotateRows is timed eagerly (the default defers its key switch to
+    the consumer) through abc_rotate_rows_add's sibling with no addend: ABC_EAGER_ROTATE semantics via rotate + export-free add."""
+    lib = f._lib
+    out = f.allocCiphertext()
+    ops = {"mul_relin": lambda: f._ck(lib.abc_mul_relin(f._h, out._h, x._h, y._h)),
+           # rotate_rows_add runs the key switch immediately (the addend rides in its ModDown): one rotation + one add
+           "rotate_add": lambda: f._ck(lib.abc_rotate_rows_add(f._h, out._h, x._h, 1, y._h)),
+           "add": lambda: f._ck(lib.abc_add(f._h, out._h, x._h, y._h))}
+    res = {}
+    for name, fn in ops.items():
+        fn(); fn()
+        f.sync()
+        ts = []
+        for _ in range(reps):
+            f.timer_start()
+            fn()
+            ts.append(f.timer_stop())
+        ts.sort()
+        p50, p99 = ts[len(ts) // 2], ts[min(len(ts) - 1, int(0.99 * len(ts)))]
+        res[name] = {"ops_per_s": B / (p50 * 1e-3), "p50_ms": round(p50, 4), "p99_ms": round(p99, 4)}
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -211,6 +266,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    host_cores_bound = pin_to_gpu_local_cores(local)
     if world > 1:
         # NCCL announces its version on stdout when the communicator comes up; stdout carries the ONE JSON line, so the
         # process-level descriptor points at stderr while NCCL initialises
@@ -271,29 +327,63 @@ def run_ours(args):
     # ---- end to end through the factory with host buffers (pinned), copies inside the timed region
     hx = torch.from_numpy(xs).pin_memory()
     hy = torch.from_numpy(ys).pin_memory()
-    hout = torch.empty((B, N_POLY), dtype=torch.int64).pin_memory()
+    houts = [torch.empty((B, N_POLY), dtype=torch.int64).pin_memory() for _ in range(2)]
     lib, C = f._lib, __import__("ctypes")
+    from abc_b200 import CudaCiphertext
 
-    def e2e_step():
+    def e2e_step(i):
+        """createCiphertext(x), createCiphertext(y) from pinned host slots; the program; decryptCiphertext to pinned host
+        memory.  The decrypted slots of step i leave on the library's D2H stream while step i + 1 computes
+        (abc_decrypt_decode_async); every copy is inside the timed region, which ends with abc_sync."""
         hx_ct, hy_ct = C.c_void_p(), C.c_void_p()
         f._ck(lib.abc_encode_encrypt(f._h, hx.data_ptr(), N_VEC, 0, C.byref(hx_ct)))
         f._ck(lib.abc_encode_encrypt(f._h, hy.data_ptr(), N_VEC, 0, C.byref(hy_ct)))
-        from abc_b200 import CudaCiphertext
         cx, cy = CudaCiphertext(f, hx_ct), CudaCiphertext(f, hy_ct)
         r = program_gpu(cx, cy)
-        f._ck(lib.abc_decrypt_decode(f._h, r._h, hout.data_ptr()))
+        f._ck(lib.abc_decrypt_decode_async(f._h, r._h, houts[i & 1].data_ptr()))
 
-    for _ in range(max(1, args.warmup)):
-        e2e_step()
-    assert np.array_equal(hout[:, 0].numpy(), want0), "e2e result mismatch"
+    for i in range(max(2, args.warmup)):
+        e2e_step(i)
+    f.sync()
+    assert np.array_equal(houts[0][:, 0].numpy(), want0) and np.array_equal(houts[1][:, 0].numpy(), want0), "e2e result mismatch"
     barrier()
     t0 = time.perf_counter()
     f.timer_start()
-    for _ in range(args.steps):
-        e2e_step()
-    e2e_ms = f.timer_stop()
+    for i in range(args.steps):
+        e2e_step(i)
+    f.sync()                                   # the last steps' D2H copies are part of the timed region
     e2e_wall = (time.perf_counter() - t0) * 1e3
+    e2e_ms = f.timer_stop()
+    assert np.array_equal(houts[(args.steps - 1) & 1][:, 0].numpy(), want0), "e2e result mismatch (timed region)"
     barrier()
+
+    # ---- where an end-to-end step spends its time (one more step, phase by phase, each ended by a synchronisation)
+    def phase(fn):
+        f.sync()
+        t = time.perf_counter()
+        out = fn()
+        f.sync()
+        return (time.perf_counter() - t) * 1e3, out
+
+    def enc_both():
+        hx_ct, hy_ct = C.c_void_p(), C.c_void_p()
+        f._ck(lib.abc_encode_encrypt(f._h, hx.data_ptr(), N_VEC, 0, C.byref(hx_ct)))
+        f._ck(lib.abc_encode_encrypt(f._h, hy.data_ptr(), N_VEC, 0, C.byref(hy_ct)))
+        return CudaCiphertext(f, hx_ct), CudaCiphertext(f, hy_ct)
+
+    d_in = torch.empty((B, N_VEC), dtype=torch.int64, device="cuda")
+    d_res = torch.empty((B, N_POLY), dtype=torch.int64, device="cuda")
+    for _ in range(2):   # the first round pays one-time costs (first torch copy, pool growth); the second is reported
+        ms_h2d, _ = phase(lambda: (d_in.copy_(hx, non_blocking=True), d_in.copy_(hy, non_blocking=True), torch.cuda.synchronize()))
+        ms_enc, (cx, cy) = phase(enc_both)
+        ms_prog, res = phase(lambda: program_gpu(cx, cy))
+        ms_dec, _ = phase(lambda: f._ck(lib.abc_decrypt_decode(f._h, res._h, houts[0].data_ptr())))
+        ms_d2h, _ = phase(lambda: (houts[1].copy_(d_res, non_blocking=True), torch.cuda.synchronize()))
+    breakdown = {"h2d_copy_alone": round(ms_h2d, 3), "encode_encrypt_incl_h2d": round(ms_enc, 3), "program": round(ms_prog, 3),
+                 "decrypt_decode_incl_d2h": round(ms_dec, 3), "d2h_copy_alone": round(ms_d2h, 3),
+                 "note": "phases run back to back with a synchronisation after each (no overlap); in the timed region the "
+                         "H2D of y runs under the encryption of x and the D2H of step i under the kernels of step i+1"}
+    del cx, cy, res
 
     # max over ranks
     from abc_b200.sharding import max_over_ranks
@@ -354,27 +444,47 @@ def run_ours(args):
         # time the same butterflies would take register-resident, class by class
         ideal_ms = sum(r["launches"] * ntt_rows[r["kernel"]][0] * B * bf_per_row / bf_peaks[ntt_rows[r["kernel"]][1]] * 1e3
                        for r in prof if r["kernel"] in ntt_rows)
+        top_rows = ntt_rows.get(top["kernel"], (0, arq))[0]
+        top_bf = top_rows * B * bf_per_row                                  # butterflies of one launch of the dominant kernel
+        top_inner = (2 * k * L * N_POLY * B) if top["kernel"].startswith("ks_") else 0   # key inner-product modular products
+        t_hbm = alg.get(top["kernel"], 0) / (peaks["hbm_gbs"] * 1e9)
+        t_pipe = (top_bf + 0.75 * top_inner) / bf_peak
+        bound = "fp64" if t_pipe >= t_hbm else "hbm"
+        roofline = {"kernel": top["kernel"], "bound": bound,
+                    "achieved": (top_bf + 0.75 * top_inner) / (per_launch_ms * 1e-3) / 1e9 if bound == "fp64" else ach,
+                    "peak": bf_peak / 1e9 if bound == "fp64" else peaks["hbm_gbs"],
+                    "unit": "G butterfly-equivalents/s (8 FP64-pipe instructions each)" if bound == "fp64" else "GB/s",
+                    "frac": max(t_pipe, t_hbm) / (per_launch_ms * 1e-3),
+                    "frac_butterflies_only": top_bf / bf_peak / (per_launch_ms * 1e-3),
+                    "ms_per_launch": per_launch_ms, "t_roof_ms": max(t_pipe, t_hbm) * 1e3,
+                    "work_per_launch": {"ntt_butterflies": top_bf, "inner_product_modmuls": top_inner},
+                    "traffic": traffic_for(top["kernel"], B), "algorithmic_bytes_per_launch": alg.get(top["kernel"], 0),
+                    "share_of_step": top["ms"] / tot, "ncu": ncu_pipes_for(top["kernel"], B),
+                    "peak_source": "k_peak_butterfly_f64, measured in this run" if bound == "fp64" else how,
+                    "hbm_view": {"achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                                 "peak_source": how, "note": "the non-binding roof: algorithmic bytes / launch time"}}
         ops_total = B * OPS_PER_INSTANCE * world
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
         cpu = cpu_baseline_port(cores) if world == 1 and not args.no_cpu else None
+        per_op = per_op_numbers(f, x, y, B)
         line = {
             "metric": METRIC, "value": ops_total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "instances_total": B * world,
-                       "parallelism": "independent instances sharded across GPUs, no collectives",
-                       "l2": "inputs+intermediates exceed L2 (%.0f MiB of ciphertext per operand)" % (B * 2 * L * row / 2**20)},
+            "config": config_dict(B, world),
             "e2e": {"value": ops_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": 2 * B * N_VEC * 8, "d2h_bytes_per_step": B * N_POLY * 8,
                     "device_ms_per_step": e2e_dev / args.steps, "wall_ms_per_step": e2e_wall / args.steps,
-                    "includes": "createCiphertext(x), createCiphertext(y) from pinned host slots, program, decryptCiphertext to host"},
+                    "frac_of_device_resident": (ms / args.steps) / (e2e_ms / args.steps),
+                    "breakdown_ms": breakdown, "host_cores_bound_to_gpu": host_cores_bound,
+                    "includes": "createCiphertext(x), createCiphertext(y) from pinned host slots, program, decryptCiphertext to pinned host "
+                                "memory; the D2H of step i overlaps step i+1 (abc_decrypt_decode_async), the region ends with abc_sync"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": top["kernel"], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm_gbs"], "traffic": traffic_for(top["kernel"], B), "peak_source": how,
-                         "algorithmic_bytes_per_launch": alg.get(top["kernel"], 0),
-                         "share_of_step": top["ms"] / tot, "ncu": ncu_pipes_for(top["kernel"], B),
-                         "note": "this kernel family is bound by the FP64 / integer pipes, not HBM: see int_roofline"},
+            # t_roof = max(algorithmic bytes / HBM, work / pipe peak).  For the key switch the FP64 pipe binds:
+            # work = the launch's NTT butterflies (8 FP64 instructions each) + its key inner-product modular products
+            # (6 FP64 instructions = 0.75 butterfly each), peak = register-resident butterflies/s measured in this run.
+            "roofline": roofline,
             "int_roofline": {"unit": "64-bit modular NTT butterflies/s (all limb-pipeline kernels of the step)",
                              "achieved": ntt_bf / (ntt_ms * 1e-3), "peak": bf_peak,
                              "frac": ideal_ms / ntt_ms, "ntt_share_of_step": ntt_ms / tot,
@@ -388,7 +498,7 @@ def run_ours(args):
                                             "rates from k_peak_imad / k_peak_iadd"},
             "kernels": [{"kernel": r["kernel"], "launches": r["launches"], "ms": round(r["ms"], 4),
                          "share": round(r["ms"] / tot, 4)} for r in sorted(prof, key=lambda r: -r["ms"])],
-            "per_op": {"programs_per_s": B * world * args.steps / (ms * 1e-3)},
+            "per_op": dict(per_op, programs_per_s=B * world * args.steps / (ms * 1e-3)),
         }
         if cpu:
             line["cpu_baseline"] = cpu
@@ -446,7 +556,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": config_dict(args.batch, world),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample + "; SEAL-3.6.5 restatement (oracle/), SEAL itself not installable here"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -32,8 +32,7 @@ def _patterns(q, N, rng):
     return rows
 
 
-@pytest.mark.parametrize("N", [4096, 8192])
-@pytest.mark.parametrize("cls", sorted(CLASSES))
+@pytest.mark.parametrize("N,cls", [(n, c) for n in (4096, 8192) for c in sorted(CLASSES)] + [(16384, "f64"), (16384, "fp")])
 def test_probe_ntt_extreme_rows_every_class(N, cls, monkeypatch):
     from abc_b200 import CudaCiphertextFactory
     from oracle.bfv_oracle import Oracle
@@ -75,8 +74,9 @@ KS_PATHS = {"default": {}, "two_launch": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAI
             "one_launch": {"ABC_KS_ONE_LAUNCH": "1"}, "accumulating": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_RED": "1"}}
 
 
-@pytest.mark.parametrize("N", [4096, 8192])
-@pytest.mark.parametrize("cls,path", [("f64", p) for p in sorted(KS_PATHS)] + [(c, "default") for c in ("shoup", "fp", "fp_lazy")])
+@pytest.mark.parametrize("N,cls,path", [(n, "f64", p) for n in (4096, 8192) for p in sorted(KS_PATHS)] +
+                         [(n, c, "default") for n in (4096, 8192) for c in ("shoup", "fp", "fp_lazy")] +
+                         [(16384, "f64", "default"), (16384, "fp", "default")])   # 16384: 48/49-bit primes, the wide exact-double plan
 def test_key_switch_extreme_residues_and_keys(N, cls, path, monkeypatch):
     """rotate_rows with an imported Galois key whose every residue is q_I - 1 (then alternating, then random) applied to
     ciphertexts of extreme residues; expected value = (sigma(c0), 0) + switch_key(sigma(c1), key) from the oracle."""
