@@ -74,6 +74,7 @@ SYMBOLS = {
     "abc_bench_ntt": (i32, [vp, i32, u32, sz, i32, f32p]),
     "abc_comm_unique_id": (i32, [vp, vp]),
     "abc_comm_init": (i32, [vp, i32, i32, vp]),
+    "abc_comm_stats": (i32, [vp, C.POINTER(u64), C.POINTER(u64)]),
     "abc_comm_rank": (i32, [vp]),
     "abc_comm_world": (i32, [vp]),
     "abc_owned_limbs": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),

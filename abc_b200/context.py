@@ -135,6 +135,12 @@ class CudaCiphertextFactory:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self._ck(self._lib.abc_comm_init(self._h, rank, world, buf))
 
+    def comm_stats(self):
+        """(bytes received through all-gathers so far, NCCL collectives issued) on this rank."""
+        b, n = C.c_uint64(), C.c_uint64()
+        self._ck(self._lib.abc_comm_stats(self._h, C.byref(b), C.byref(n)))
+        return b.value, n.value
+
     def owned_limbs(self):
         lo, hi = C.c_uint32(), C.c_uint32()
         self._ck(self._lib.abc_owned_limbs(self._h, C.byref(lo), C.byref(hi)))

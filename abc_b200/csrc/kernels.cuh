@@ -40,10 +40,13 @@ __global__ void __launch_bounds__(256) k_addsub(u64 *__restrict__ dst, const u64
 // LT = 0: generic limb count Lrt <= ABC_MAXL (loops not unrolled, residues in local memory).
 template <int LT>
 __global__ void __launch_bounds__(128) k_behz_lift(const u64 *__restrict__ a, const u64 *__restrict__ b,
-                                                   u64 *__restrict__ X, const DevConst *__restrict__ C, int N, int Lrt) {
+                                                   u64 *__restrict__ X, const DevConst *__restrict__ C, int N, int Lrt,
+                                                   int col0 = 0, int copy_q = 1) {
+  // col0: first coefficient of this launch (limb-sharded contexts convert N / world coefficients per rank: the base
+  // conversion is independent per coefficient); copy_q = 0: the q rows of X are filled elsewhere
   constexpr int CAP = LT ? LT : ABC_MAXL;
   const int L = LT ? LT : Lrt;
-  const int n = blockIdx.x * 128 + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
+  const int n = col0 + blockIdx.x * 128 + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
   const int W = 2 * L + 1;
   const u64 *src = (poly < 2 ? a : b) + ((size_t)inst * 2 + (poly & 1)) * L * N + n;
   u64 *dst = X + ((size_t)inst * 4 + poly) * W * N + n;
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(128) k_behz_lift(const u64 *__restrict__ a, co
 #pragma unroll
   for (int i = 0; i < L; ++i) {
     u64 x = src[(size_t)i * N];
-    dst[(size_t)i * N] = x;
+    if (copy_q) dst[(size_t)i * N] = x;
     z[i] = mul_shoup(x, C->lift_c[i], C->lift_c_s[i], C->q[i]);
     xm += (u32)z[i] * C->punct_q_mt[i];
   }
@@ -95,10 +98,10 @@ __global__ void __launch_bounds__(256) k_behz_tensor(u64 *__restrict__ X, const 
 // X [inst][4][W][N] (polys 0..2, coefficient form) -> dst3 [inst][3][L][N].  grid: (N/128, 3, B)
 template <int LT>
 __global__ void __launch_bounds__(128) k_behz_scale(const u64 *__restrict__ X, u64 *__restrict__ dst,
-                                                    const DevConst *__restrict__ C, int N, int Lrt) {
+                                                    const DevConst *__restrict__ C, int N, int Lrt, int col0 = 0) {
   constexpr int CAP = LT ? LT : ABC_MAXL;
   const int L = LT ? LT : Lrt;
-  const int n = blockIdx.x * 128 + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
+  const int n = col0 + blockIdx.x * 128 + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
   const int W = 2 * L + 1;
   const u64 *src = X + ((size_t)inst * 4 + poly) * W * N + n;
   u64 *out = dst + ((size_t)inst * 3 + poly) * L * N + n;

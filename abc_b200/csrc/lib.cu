@@ -93,6 +93,12 @@ struct abc_ctx {
   // computes the key-switch output moduli own U {special}; world == 1 owns everything.  Maps below follow the own set.
   int rank = 0, world = 1, own_lo = 0, own_hi = 0;
   ncclComm_t comm = nullptr;
+  cudaStream_t comm_stream = nullptr;               // all-gathers that overlap compute (ModUp of locally owned source limbs)
+  cudaEvent_t comm_ready = nullptr, comm_done = nullptr;
+  int *rm_up_own = nullptr, *rd_up_own = nullptr, *rs_up_own = nullptr, n_up_own = 0;   // ModUp rows whose source limb this rank owns
+  int *rm_up_oth = nullptr, *rd_up_oth = nullptr, *rs_up_oth = nullptr, n_up_oth = 0;   // ... and the rows that wait for the all-gather
+  bool shard_overlap = true, shard_cols = true;     // ABC_SHARD_OVERLAP=0 / ABC_SHARD_COLS=0: A/B switches
+  uint64_t gathered_bytes = 0, gather_calls = 0;    // payload this rank received through all-gathers / NCCL calls issued
   int ks_nI = 0;                                    // |own| + 1
   int *ks_I = nullptr;                              // [ks_nI] output moduli of the key switch (own..., special)
   int *rm_modup_s = nullptr, *rd_modup_s = nullptr, *rs_modup_s = nullptr;   // [ks_nI * L]
@@ -125,8 +131,8 @@ struct abc_ctx {
   void *flush_buf = nullptr;
   // grow-only scratch slots reused by every op (one stream: an op's scratch is dead before the next op starts).
   // Allocating these per op from the stream-ordered pool fragmented it (135 MB / 335 MB / 170 MB blocks) and cost ms.
-  u64 *sc_ptr[12] = {nullptr};
-  size_t sc_words[12] = {0};
+  u64 *sc_ptr[16] = {nullptr};
+  size_t sc_words[16] = {0};
 };
 // A ciphertext handle.  The device buffer is shared between clones (copy-on-write): RuntimeVisitor clones on every
 // variable read (RuntimeVisitor.cpp:436), so clone is O(1) and an op gives its destination a private buffer first.
@@ -187,7 +193,7 @@ abc_status salloc(abc_ctx *c, u64 **p, size_t words) {
   return ABC_OK;
 }
 void sfree(abc_ctx *c, void *p) { if (p) cudaFreeAsync(p, c->stream); }
-enum { SC_T = 0, SC_ACC, SC_X, SC_OUT3, SC_U, SC_TMP, SC_DECX, SC_DECP, SC_P, SC_NK, SC_ENTT };
+enum { SC_T = 0, SC_ACC, SC_X, SC_OUT3, SC_U, SC_TMP, SC_DECX, SC_DECP, SC_P, SC_NK, SC_ENTT, SC_COMM_SEND, SC_COMM_ALL, SC_NSLOTS };
 abc_status scratch(abc_ctx *c, int slot, u64 **p, size_t words) {
   if (c->sc_words[slot] < words) {
     if (c->sc_ptr[slot]) cudaFreeAsync(c->sc_ptr[slot], c->stream);
@@ -552,6 +558,16 @@ abc_status build_shard_maps(abc_ctx *c) {
   std::vector<int> m, d, sr;
   for (int I_ : I) for (int J = 0; J < L; ++J) { m.push_back(I_); d.push_back(I_ * L + J); sr.push_back(J); }
   TRY(upload(c, &c->rm_modup_s, m)); TRY(upload(c, &c->rd_modup_s, d)); TRY(upload(c, &c->rs_modup_s, sr));
+  {  // the same rows split by where their SOURCE limb lives: owned here (can start before the all-gather lands) or not
+    std::vector<int> mo, dob, so, mt, dt, st;
+    for (size_t w = 0; w < m.size(); ++w) {
+      const bool mine = sr[w] >= lo && sr[w] < hi;
+      (mine ? mo : mt).push_back(m[w]); (mine ? dob : dt).push_back(d[w]); (mine ? so : st).push_back(sr[w]);
+    }
+    c->n_up_own = (int)mo.size(); c->n_up_oth = (int)mt.size();
+    if (c->n_up_own) { TRY(upload(c, &c->rm_up_own, mo)); TRY(upload(c, &c->rd_up_own, dob)); TRY(upload(c, &c->rs_up_own, so)); }
+    if (c->n_up_oth) { TRY(upload(c, &c->rm_up_oth, mt)); TRY(upload(c, &c->rd_up_oth, dt)); TRY(upload(c, &c->rs_up_oth, st)); }
+  }
   m.clear(); d.clear(); sr.clear();
   std::vector<int> od;
   for (int comp = 0; comp < 2; ++comp) for (int i = lo; i < hi; ++i) {
@@ -635,6 +651,7 @@ struct NcclApi {
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi *nccl_api() {
@@ -651,8 +668,9 @@ NcclApi *nccl_api() {
       api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
       api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
       api.Broadcast = (decltype(api.Broadcast))dlsym(h, "ncclBroadcast");
+      api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
       api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
-      if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Broadcast) api.h = h;
+      if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Broadcast && api.AllGather) api.h = h;
     }
   }
   return api.h ? &api : nullptr;
@@ -672,26 +690,86 @@ void limb_range(int L, int world, int rank, int *lo, int *hi) {
   *hi = *lo + base + (rank < extra ? 1 : 0);
 }
 
-// all-gather of the limb-sharded polynomials `poly_mask` (bit 0: c0, bit 1: c1) of ciphertext block d, in place:
-// every rank broadcasts the limbs it owns (NCCL over NVLink; the exchange step of the limb-sharded key switch)
-abc_status allgather_limbs(abc_ctx *c, u64 *d, int poly_mask) {
+// all-gather of the limb-sharded polynomials `poly_mask` (bit 0: c0, bit 1: c1) of ciphertext block d, in place: the
+// exchange step of the limb-sharded key switch (NCCL over NVLink).  Owned limb ranges are contiguous and ordered by rank,
+// so with an even split (L % world == 0) a polynomial is ONE in-place ncclAllGather; an uneven split falls back to one
+// broadcast per rank.
+abc_status allgather_limbs(abc_ctx *c, u64 *d, int poly_mask, cudaStream_t stream = nullptr) {
   if (c->world == 1) return ABC_OK;
+  if (!stream) stream = c->stream;
   NcclApi *n = nccl_api();
   const size_t N = c->N, L = c->L;
+  const bool even = c->L % c->world == 0;
   c->launches++;
   NCK(n->GroupStart());
-  for (int r = 0; r < c->world; ++r) {
-    int lo, hi;
-    limb_range(c->L, c->world, r, &lo, &hi);
-    if (hi == lo) continue;
-    for (int inst = 0; inst < c->B; ++inst)
-      for (int p = 0; p < 2; ++p) {
-        if (!(poly_mask & (1 << p))) continue;
-        u64 *ptr = d + ((size_t)inst * 2 + p) * L * N + (size_t)lo * N;
-        NCK(n->Broadcast(ptr, ptr, (size_t)(hi - lo) * N, ncclUint64, r, c->comm, c->stream));
+  for (int inst = 0; inst < c->B; ++inst)
+    for (int p = 0; p < 2; ++p) {
+      if (!(poly_mask & (1 << p))) continue;
+      u64 *poly = d + ((size_t)inst * 2 + p) * L * N;
+      if (even) {
+        const size_t cnt = (L / c->world) * N;
+        NCK(n->AllGather(poly + (size_t)c->rank * cnt, poly, cnt, ncclUint64, c->comm, stream));
+        c->gather_calls++;
+      } else {
+        for (int r = 0; r < c->world; ++r) {
+          int lo, hi;
+          limb_range(c->L, c->world, r, &lo, &hi);
+          if (hi == lo) continue;
+          NCK(n->Broadcast(poly + (size_t)lo * N, poly + (size_t)lo * N, (size_t)(hi - lo) * N, ncclUint64, r, c->comm, stream));
+          c->gather_calls++;
+        }
       }
-  }
+      c->gathered_bytes += (uint64_t)(L - (c->own_hi - c->own_lo)) * N * 8;
+    }
   NCK(n->GroupEnd());
+  return ABC_OK;
+}
+// all-gather by COLUMNS: `rows` rows of N words starting at `base` (row stride N, per-instance stride inst_stride), of
+// which this rank has filled coefficients [rank * N / world, (rank + 1) * N / world) — the exchange after a
+// coefficient-sharded base conversion.  The slices are packed into one contiguous block, exchanged with ONE
+// ncclAllGather, and the other ranks' slices are scattered back into the rows (two copy kernels at HBM speed instead of
+// one small collective per row: 125 collectives per multiply cost as much as the conversions saved).
+// (a block of rows = `groups` groups of `rows` consecutive rows, group stride group_stride: e.g. the Bsk rows of the 2 or 4
+// operand polynomials of the BEHZ block; blockIdx.z = inst * groups + group)
+__global__ void k_cols_pack(const u64 *__restrict__ base, u64 *__restrict__ send, int rows, int N, int ncols, int col0,
+                            size_t inst_stride, int groups, size_t group_stride) {
+  const int r = blockIdx.y, inst = blockIdx.z / groups, g = blockIdx.z % groups;
+  const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(base + (size_t)inst * inst_stride + (size_t)g * group_stride + (size_t)r * N + col0);
+  ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(send + ((size_t)blockIdx.z * rows + r) * ncols);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncols / 2; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void k_cols_unpack(u64 *__restrict__ base, const u64 *__restrict__ all, int rows, int N, int ncols, int world,
+                              int rank, size_t inst_stride, int groups, size_t group_stride) {
+  const int r = blockIdx.y, inst = blockIdx.z / groups, g = blockIdx.z % groups;
+  for (int w = 0; w < world; ++w) {
+    if (w == rank) continue;
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(all + (((size_t)w * gridDim.z + blockIdx.z) * rows + r) * ncols);
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(base + (size_t)inst * inst_stride + (size_t)g * group_stride + (size_t)r * N + (size_t)w * ncols);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ncols / 2; i += gridDim.x * blockDim.x) dst[i] = src[i];
+  }
+}
+abc_status allgather_columns(abc_ctx *c, u64 *base, size_t rows, size_t inst_stride, int groups = 1, size_t group_stride = 0) {
+  if (c->world == 1) return ABC_OK;
+  NcclApi *n = nccl_api();
+  const size_t N = c->N, cnt = N / c->world, per_rank = (size_t)c->B * groups * rows * cnt;
+  u64 *send = nullptr, *all = nullptr;
+  TRY(scratch(c, SC_COMM_SEND, &send, per_rank));
+  TRY(scratch(c, SC_COMM_ALL, &all, per_rank * c->world));
+  const dim3 grid((unsigned)std::max<size_t>(1, std::min<size_t>(8, cnt / 2 / 256)), (unsigned)rows, (unsigned)(c->B * groups));
+  {
+    Launch l(c, "shard_cols_pack");
+    k_cols_pack<<<grid, 256, 0, c->stream>>>(base, send, (int)rows, (int)N, (int)cnt, (int)(c->rank * cnt), inst_stride, groups, group_stride);
+    CK(cudaGetLastError());
+  }
+  c->launches++;
+  NCK(n->AllGather(send, all, per_rank, ncclUint64, c->comm, c->stream));
+  c->gather_calls++;
+  c->gathered_bytes += (uint64_t)per_rank * (c->world - 1) * 8;
+  {
+    Launch l(c, "shard_cols_unpack");
+    k_cols_unpack<<<grid, 256, 0, c->stream>>>(base, all, (int)rows, (int)N, (int)cnt, c->world, c->rank, inst_stride, groups, group_stride);
+    CK(cudaGetLastError());
+  }
   return ABC_OK;
 }
 
@@ -731,7 +809,10 @@ size_t ct_words1(const abc_ctx *c) { return (size_t)2 * c->L * c->N; }
 //   4. INTT of the 2L data rows fused with ModDown (rounded division by p) and the base accumulate            [limb pipeline]
 abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u64 *key, const u64 *base0,
                      long long base0_is, const u64 *base1, long long base1_is, u32 einv, u64 *dst,
-                     const u64 *addend = nullptr, u64 *dst_plain = nullptr) {
+                     const u64 *addend = nullptr, u64 *dst_plain = nullptr, u64 *gather_ct = nullptr) {
+  // gather_ct (limb-sharded contexts): the ciphertext block whose c1 is `target`; its limbs are all-gathered in front of
+  // ModUp.  With overlap on, the exchange runs on the communication stream while the ModUp rows whose source limb is
+  // local are already transforming; the rows fed by remote limbs follow once it has landed.
   const int N = c->N, L = c->L, k = c->k, B = c->B;
   u64 *T = nullptr, *acc = nullptr;
   // exact-double class: the whole key switch can be one launch (ksfused.cu), nothing but INTT_p(acc_L) goes through HBM.
@@ -741,6 +822,7 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   const bool one_launch = c->ks_one_launch >= 0 ? c->ks_one_launch == 1 : c->logN <= 12;
   if (one_launch && c->logN <= 13 && (c->own_hi - c->own_lo) > 0 && abc_ntt_arith_class(c) == AR_F64 && !c->ks_unmerged &&
       !c->ks_unfused) {
+    if (gather_ct && c->world > 1) TRY(allgather_limbs(c, gather_ct, 2));
     TRY(scratch(c, SC_ACC, &acc, (size_t)B * 2 * N));
     KsJob kj;
     memset(&kj, 0, sizeof kj);
@@ -771,7 +853,24 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   j.rowmod = c->rm_modup_s; j.rowdst = c->rd_modup_s; j.rowsrc = c->rs_modup_s; j.galois_einv = einv;
   j.t_image = t_image;
   LimbJob jup = j;
-  if (!chain) TRY(launch_limb(c, einv ? LIMB_GALOIS_REDUCE_FWD : LIMB_REDUCE_FWD, c->ar_q, j, c->ks_nI * L, B, "ks_modup_ntt"));
+  if (gather_ct && c->world > 1) {
+    const int combo = einv ? LIMB_GALOIS_REDUCE_FWD : LIMB_REDUCE_FWD;
+    if (c->shard_overlap && c->comm_stream && c->n_up_own > 0 && c->n_up_oth > 0 && !chain) {
+      CK(cudaEventRecord(c->comm_ready, c->stream));                  // the producer of target has been enqueued
+      CK(cudaStreamWaitEvent(c->comm_stream, c->comm_ready, 0));
+      TRY(allgather_limbs(c, gather_ct, 2, c->comm_stream));
+      CK(cudaEventRecord(c->comm_done, c->comm_stream));
+      LimbJob jo = j;
+      jo.rowmod = c->rm_up_own; jo.rowdst = c->rd_up_own; jo.rowsrc = c->rs_up_own;
+      TRY(launch_limb(c, combo, c->ar_q, jo, c->n_up_own, B, "ks_modup_ntt_local"));
+      CK(cudaStreamWaitEvent(c->stream, c->comm_done, 0));
+      jo.rowmod = c->rm_up_oth; jo.rowdst = c->rd_up_oth; jo.rowsrc = c->rs_up_oth;
+      TRY(launch_limb(c, combo, c->ar_q, jo, c->n_up_oth, B, "ks_modup_ntt_remote"));
+    } else {
+      TRY(allgather_limbs(c, gather_ct, 2));
+      if (!chain) TRY(launch_limb(c, combo, c->ar_q, j, c->ks_nI * L, B, "ks_modup_ntt"));
+    }
+  } else if (!chain) TRY(launch_limb(c, einv ? LIMB_GALOIS_REDUCE_FWD : LIMB_REDUCE_FWD, c->ar_q, j, c->ks_nI * L, B, "ks_modup_ntt"));
   if (!fused) {
     Launch l(c, "ks_inner");
     DISPATCH_L(c, (k_ks_inner<LL><<<dim3(N / 512, c->ks_nI, B), 256, 0, c->stream>>>(T, key, acc, c->d_mods, N, k, c->L, c->ks_I)));
@@ -902,10 +1001,24 @@ abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
   // repeat the first's, so only polys 0,1 are prepared; the products are the same modular expressions, bit for bit
   const bool square = a == b && !c->no_square;
   const int np = square ? 2 : 4;
+  // Limb-sharded contexts: the base conversions (O(L^2) modular products per coefficient, half of the product's time at
+  // L = 30) are independent per coefficient, so every rank converts N / world coefficients and the ranks exchange the
+  // converted columns (in-place all-gathers of row slices); the transforms in between run on whole rows on every rank.
+  const bool cols = c->world > 1 && c->shard_cols && (N / c->world) % 128 == 0;
+  const int ncols = cols ? N / c->world : N, col0 = cols ? c->rank * ncols : 0;
   {
     Launch l(c, "behz_lift");
-    DISPATCH_L(c, (k_behz_lift<LL><<<dim3(N / 128, np, B), 128, 0, c->stream>>>(a, b, X, c->dC, N, c->L)));
+    DISPATCH_L(c, (k_behz_lift<LL><<<dim3(ncols / 128, np, B), 128, 0, c->stream>>>(a, b, X, c->dC, N, c->L, col0, cols ? 0 : 1)));
     CK(cudaGetLastError());
+  }
+  if (cols) {
+    for (int inst = 0; inst < B; ++inst)
+      for (int p = 0; p < np; ++p) {   // q rows of X = the operand polynomials (every rank holds them whole)
+        const u64 *srcp = (p < 2 ? a : b) + ((size_t)inst * 2 + (p & 1)) * L * N;
+        CK(cudaMemcpyAsync(X + ((size_t)inst * 4 + p) * W * N, srcp, (size_t)L * N * 8, cudaMemcpyDeviceToDevice, c->stream));
+      }
+    // Bsk rows of the np operand polynomials: every rank's column slice to everybody, one exchange
+    TRY(allgather_columns(c, X + (size_t)L * N, (size_t)c->nbsk, (size_t)4 * W * N, np, (size_t)W * N));
   }
   LimbJob j = blank_job();
   j.dst = X; j.src = X; j.dst_is = j.src_is = (long long)4 * W * N; j.rowmod = c->rm_behz;
@@ -931,9 +1044,11 @@ abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
   }
   {
     Launch l(c, "behz_scale");
-    DISPATCH_L(c, (k_behz_scale<LL><<<dim3(N / 128, 3, B), 128, 0, c->stream>>>(X, out3, c->dC, N, c->L)));
+    DISPATCH_L(c, (k_behz_scale<LL><<<dim3(ncols / 128, 3, B), 128, 0, c->stream>>>(X, out3, c->dC, N, c->L, col0)));
     CK(cudaGetLastError());
   }
+  // c2 is needed whole by every rank (ModUp of the relinearisation); c0, c1 only on their owners, but as whole rows
+  if (cols) TRY(allgather_columns(c, out3, (size_t)3 * L, (size_t)3 * L * N));
   return ABC_OK;
 }
 
@@ -944,8 +1059,9 @@ abc_status apply_galois(abc_ctx *c, const u64 *src, u64 *dst, u32 elt, const u64
   if (it == c->galois.end()) return fail(c, ABC_ERR_STATE, "Galois key not present");
   const long long LN = (long long)c->L * c->N;
   const u32 elt_inv = (u32)hm::invmod(elt, 2ull * c->N);
-  TRY(allgather_limbs(c, const_cast<u64 *>(src), 2));  // limb-sharded: ModUp needs every limb of c1 on every rank
-  return keyswitch(c, src + LN, 2 * LN, it->second, src, 2 * LN, nullptr, 0, elt_inv, dst, addend, dst_plain);
+  // limb-sharded: ModUp needs every limb of c1 on every rank (all-gathered inside keyswitch, overlapped with the local rows)
+  return keyswitch(c, src + LN, 2 * LN, it->second, src, 2 * LN, nullptr, 0, elt_inv, dst, addend, dst_plain,
+                   c->world > 1 ? const_cast<u64 *>(src) : nullptr);
 }
 
 u32 elt_from_step(const abc_ctx *c, int step) {
@@ -1191,6 +1307,9 @@ void abc_ctx_destroy(abc_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); }
+  if (c->comm_ready) cudaEventDestroy(c->comm_ready);
+  if (c->comm_done) cudaEventDestroy(c->comm_done);
   if (c->comm && nccl_api()) nccl_api()->CommDestroy(c->comm);
   for (auto &kv : c->galois) cudaFree(kv.second);
   for (auto &kv : c->key_f64) cudaFree(kv.second);
@@ -1829,9 +1948,32 @@ abc_status abc_comm_init(abc_ctx *c, int rank, int world, const uint8_t *id128) 
   memcpy(&id, id128, sizeof id);
   NCK(n->CommInitRank(&c->comm, world, id, rank));
   c->rank = rank; c->world = world;
+  if (!c->comm_stream) {
+    CK(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->comm_ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->comm_done, cudaEventDisableTiming));
+  }
+  if (const char *e = getenv("ABC_SHARD_OVERLAP")) c->shard_overlap = atoi(e) != 0;
+  if (const char *e = getenv("ABC_SHARD_COLS")) c->shard_cols = atoi(e) != 0;
   limb_range(c->L, world, rank, &c->own_lo, &c->own_hi);
+  // the ranks jointly hold ONE ciphertext per handle, so an encryption must draw the same (u, e0, e1) on every rank:
+  // rank 0's encryption salt replaces the per-context one (unless abc_set_encrypt_nonce already zeroed it everywhere)
+  if (world > 1) {
+    u64 *d_salt = nullptr;
+    CK(cudaMalloc((void **)&d_salt, sizeof(u64)));
+    CK(cudaMemcpyAsync(d_salt, &c->enc_salt, sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+    NCK(n->Broadcast(d_salt, d_salt, 1, ncclUint64, 0, c->comm, c->stream));
+    CK(cudaMemcpyAsync(&c->enc_salt, d_salt, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_salt);
+  }
   CK(cudaStreamSynchronize(c->stream));
   return build_shard_maps(c);
+}
+abc_status abc_comm_stats(const abc_ctx *c, uint64_t *bytes_received, uint64_t *nccl_calls) {
+  if (bytes_received) *bytes_received = c->gathered_bytes;
+  if (nccl_calls) *nccl_calls = c->gather_calls;
+  return ABC_OK;
 }
 int abc_comm_rank(const abc_ctx *c) { return c->rank; }
 int abc_comm_world(const abc_ctx *c) { return c->world; }

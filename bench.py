@@ -563,6 +563,33 @@ def run_reference(args):
     }))
 
 
+def run_deep_chain(args):
+    """BASELINE.json configs[4] through the same launch contract: one (mul+relin, rotate) x depth chain per step on ONE
+    ciphertext whose RNS limbs are sharded over the ranks (NCCL all-gather in front of the key-switch ModUp, column
+    all-gathers around the base conversions).  Strong scaling: the work is fixed, value = ops of the chain / device time
+    (max over ranks)."""
+    from types import SimpleNamespace
+    from tools import deep_chain_bench
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    a = SimpleNamespace(depth=args.depth, n=65536, limbs=0, reps=max(1, args.steps), profile=True, out="")
+    r = deep_chain_bench.run(a, emit=False)
+    if r is not None:
+        print(json.dumps({
+            "metric": METRIC, "value": r["ops_per_s"], "unit": UNIT, "n_gpus": world, "steps": a.reps, "warmup": 1,
+            "ms_per_step": r["ms_per_pair"] * args.depth, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": {"workload": r["workload"], "parallelism": "RNS limbs sharded over the ranks"},
+            "ms_per_pair": r["ms_per_pair"], "limbs_per_rank": r["limbs_per_rank"],
+            "allgather_bytes_received_per_pair_per_rank": r["allgather_bytes_received_per_pair_per_rank"],
+            "nccl_collectives_per_pair": r["nccl_collectives_per_pair"], "decrypt_check": r["decrypt_check"],
+            "gpu_launches": r["gpu_launches_rank0"], "kernels": r.get("kernels_rank0_one_chain")}))
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -572,7 +599,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-instances-per-core", type=int, default=2)
+    ap.add_argument("--workload", default="l2distance", choices=["l2distance", "deep_chain"],
+                    help="deep_chain: BASELINE.json configs[4], N=65536 multiplicative chain, RNS limbs sharded over the ranks")
+    ap.add_argument("--depth", type=int, default=8, help="deep_chain: (mul+relin, rotate) pairs per step")
     args = ap.parse_args()
+    if args.workload == "deep_chain":
+        return run_deep_chain(args)
     if args.impl == "reference":
         run_reference(args)
     else:

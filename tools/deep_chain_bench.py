@@ -30,9 +30,18 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--depth", type=int, default=8)
     ap.add_argument("--n", type=int, default=65536)
-    ap.add_argument("--limbs", type=int, default=31, help="k, including the special prime")
+    ap.add_argument("--limbs", type=int, default=0, help="k, including the special prime (0: 25 = 24 data limbs, divisible by 2/4/8 ranks)")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--profile", action="store_true", help="rank 0: per-kernel device time of one more chain")
+    ap.add_argument("--out", default="", help="rank 0: also write the JSON line to this file")
     args = ap.parse_args()
+    run(args)
+
+
+def run(args, emit=True):
+    """Returns the result dict on rank 0 (None elsewhere)."""
+    if not args.limbs:
+        args.limbs = 25
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     dist = None
@@ -40,7 +49,8 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("gloo")
+        if not dist.is_initialized():
+            dist.init_process_group("gloo")
     N = args.n
     data = get_primes(N, 55, args.limbs - 1)
     primes = data + get_primes(N, 56, 1, skip=data)
@@ -75,21 +85,41 @@ def main():
         times.append(f.timer_stop())
     (ms,) = max_over_ranks([min(times)], dist)
     lo, hi = f.owned_limbs()
+    b0, n0 = f.comm_stats()
+    chain(x0)
+    f.sync()
+    b1, n1 = f.comm_stats()
+    prof = None
+    if args.profile:                               # every rank runs the profiled chain (it contains collectives)
+        f.profile_enable(True)
+        chain(x0)
+        prof = sorted(f.profile(), key=lambda r: -r["ms"])
+        f.profile_enable(False)
+    result = None
     if rank == 0:
         pair_ms = ms / args.depth
-        # all-gather payload per pair: operands of the multiply (2 polys) + c1 of the rotation, all L limbs
-        gathered = 3 * L * N * 8 * (world - 1) / world if world > 1 else 0
-        print(json.dumps({
-            "workload": "deep chain: %d x (x = x***x; x = rotate(x,1)), BFV N=%d k=%d (30x55+56-bit primes), batch 1" % (
-                args.depth, N, f.k),
+        gathered = (b1 - b0) / args.depth          # all-gather payload this rank received per (mul+relin, rotate) pair
+        line = json.dumps({
+            "workload": "deep chain: %d x (x = x***x; x = rotate(x,1)), BFV N=%d k=%d (%dx55-bit + one 56-bit prime), batch 1" % (
+                args.depth, N, f.k, f.k - 1),
             "n_gpus": world, "ops_per_s": 2 * args.depth / (ms * 1e-3), "ms_per_pair": pair_ms, "scaling": "strong",
             "limbs_per_rank": hi - lo, "allgather_bytes_received_per_pair_per_rank": int(gathered),
-            "decrypt_check": "ok" if ok else "FAILED", "gpu_launches_rank0": f.launch_count()}), flush=True)
+            "nccl_collectives_per_pair": (n1 - n0) / args.depth,
+            "allgather_gbs_if_serial": None if not gathered else gathered / (pair_ms * 1e-3) / 1e9,
+            "decrypt_check": "ok" if ok else "FAILED", "gpu_launches_rank0": f.launch_count(),
+            "kernels_rank0_one_chain": prof})
+        result = json.loads(line)
+        if emit:
+            print(line, flush=True)
+        if args.out:
+            open(args.out, "w").write(line + "\n")
     assert ok, "deep chain result mismatch on rank %d" % rank
     f.close()
     if dist:
         dist.barrier()
-        dist.destroy_process_group()
+        if emit:
+            dist.destroy_process_group()
+    return result
 
 
 if __name__ == "__main__":
