@@ -24,6 +24,10 @@ SYMBOLS = {
     "abc_ctx_destroy": (None, [vp]),
     "abc_last_error": (C.c_char_p, [vp]),
     "abc_sync": (i32, [vp]),
+    "abc_host_alloc": (i32, [vp, sz, vpp]),
+    "abc_host_free": (None, [vp]),
+    "abc_host_register": (i32, [vp, vp, sz]),
+    "abc_host_unregister": (None, [vp]),
     "abc_faulted": (i32, [vp]),
     "abc_clear_fault": (i32, [vp]),
     "abc_poly_degree": (u32, [vp]),

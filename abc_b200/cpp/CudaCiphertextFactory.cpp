@@ -42,7 +42,18 @@ CudaCiphertextFactory::CudaCiphertextFactory(unsigned int numElementsPerCipherte
   setup(device, batch, seed);
 }
 
-CudaCiphertextFactory::~CudaCiphertextFactory() { abc_ctx_destroy(ctx); }
+CudaCiphertextFactory::~CudaCiphertextFactory() {
+  releaseBatchTables();
+  abc_host_free(pinnedOut);
+  abc_ctx_destroy(ctx);
+}
+
+void CudaCiphertextFactory::releaseBatchTables() const {
+  for (auto &t : batchTables) abc_host_unregister(t.data());
+  batchTables.clear();
+  batchTableWidth.clear();
+  nextBatchTable = 0;
+}
 
 std::unique_ptr<AbstractCiphertext> CudaCiphertextFactory::loadCiphertext(const std::vector<uint8_t> &sealStream,
                                                                           unsigned int instance) const {
@@ -100,11 +111,51 @@ std::unique_ptr<AbstractCiphertext> CudaCiphertextFactory::createCiphertext(
     std::unique_ptr<AbstractValue> &&abstractValue) const {
   if (auto castedCleartext = dynamic_cast<Cleartext<int> *>(abstractValue.get())) {
     auto castedCleartextData = castedCleartext->getData();
+    if (nextBatchTable < batchTables.size()) {   // lock-step batch: this declaration's values for every instance
+      // the table decides the values AND their count: the literal in the program text is a placeholder (a one-element
+      // literal keeps the interpreter from evaluating thousands of LiteralInt nodes per declaration: 28 ms each at n = 4096)
+      const size_t d = nextBatchTable++;
+      return createCiphertextBatch(batchTables[d], batchTableWidth[d]);
+    }
     std::vector<int64_t> data(castedCleartextData.begin(), castedCleartextData.end());
     return createCiphertext(data);
   }
   throw std::runtime_error("Cannot create ciphertext from any other than a Cleartext<int> as used ciphertext factory "
                            "(CudaCiphertextFactory) uses BFV that only supports integers.");
+}
+
+void CudaCiphertextFactory::setBatchInputs(std::vector<std::vector<int64_t>> tables) const {
+  const size_t B = getBatchSize();
+  std::vector<size_t> widths;
+  for (const auto &t : tables) {
+    if (t.empty() || t.size() % B) throw std::runtime_error("setBatchInputs: every table needs batch * n values");
+    widths.push_back(t.size() / B);
+  }
+  releaseBatchTables();
+  batchTableWidth = std::move(widths);
+  batchTables = std::move(tables);
+  for (auto &t : batchTables) check(abc_host_register(ctx, t.data(), t.size() * sizeof(int64_t)));   // H2D straight from the tables
+  nextBatchTable = 0;
+}
+
+const int64_t *CudaCiphertextFactory::decryptCiphertextBatchPinnedAsync(AbstractCiphertext &abstractCiphertext) const {
+  auto c = dynamic_cast<CudaCiphertext *>(&abstractCiphertext);
+  if (!c) throw std::runtime_error("Cast of AbstractCiphertext to CudaCiphertext failed!");
+  const size_t words = static_cast<size_t>(getBatchSize()) * ciphertextSlotSize;
+  if (!pinnedOut) {
+    void *p = nullptr;
+    check(abc_host_alloc(ctx, 2 * words * sizeof(int64_t), &p));
+    pinnedOut = static_cast<int64_t *>(p);
+  }
+  int64_t *dst = pinnedOut + (pinnedNext++ & 1u) * words;
+  check(abc_decrypt_decode_async(ctx, c->getHandle(), dst));
+  return dst;
+}
+void CudaCiphertextFactory::waitDecryptions() const { check(abc_decrypt_wait(ctx)); }
+const int64_t *CudaCiphertextFactory::decryptCiphertextBatchPinned(AbstractCiphertext &abstractCiphertext) const {
+  const int64_t *r = decryptCiphertextBatchPinnedAsync(abstractCiphertext);
+  waitDecryptions();
+  return r;
 }
 
 std::unique_ptr<AbstractCiphertext> CudaCiphertextFactory::createCiphertextBatch(const std::vector<int64_t> &data,

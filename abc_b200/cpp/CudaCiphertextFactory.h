@@ -27,6 +27,15 @@ class CudaCiphertextFactory : public AbstractCiphertextFactory {
   /// mutable device state lives behind this pointer.
   abc_ctx *ctx = nullptr;
 
+  /// Lock-step batch driver: per-instance values of the next `secret` declarations, in declaration order.
+  /// The factory virtuals are const (RuntimeVisitor holds a const reference), hence mutable.
+  mutable std::vector<std::vector<int64_t>> batchTables;   // [declaration][batch * n], instance-major
+  mutable std::vector<size_t> batchTableWidth;             // n of each table
+  mutable size_t nextBatchTable = 0;
+  mutable int64_t *pinnedOut = nullptr;                    // page-locked 2 x batch * N slots: decryptCiphertextBatchPinned
+  mutable unsigned pinnedNext = 0;
+  void releaseBatchTables() const;
+
   void setup(int device, unsigned int batch, uint64_t seed);
 
  public:
@@ -51,9 +60,25 @@ class CudaCiphertextFactory : public AbstractCiphertextFactory {
   [[nodiscard]] unsigned int getCiphertextSlotSize() const;
   /// Instances carried by every ciphertext handle (1 unless constructed with a batch).
   [[nodiscard]] unsigned int getBatchSize() const;
+  /// Lock-step batch driver: ONE interpreter walk (RuntimeVisitor unchanged) drives `batch` independent encrypted
+  /// programs.  Register, in the order the walk will declare them, the values of every `secret` input for all
+  /// instances (table d holds batch * n values, instance-major).  The next createCiphertext(unique_ptr<AbstractValue>&&)
+  /// calls — the ones RuntimeVisitor makes for `secret` declarations (src/runtime/RuntimeVisitor.cpp:413) — consume the
+  /// tables instead of the literal in the program text (a placeholder: the table decides values and count); calls after the
+  /// last table broadcast their literal to every instance as before.
+  void setBatchInputs(std::vector<std::vector<int64_t>> tables) const;
+  /// The next interpreter walk starts again at the first registered table (same inputs, e.g. a timed repetition).
+  void rewindBatchInputs() const { nextBatchTable = 0; }
   /// Batched variants: data holds batch*n slot values (instance-major); out gets batch*N values.
   std::unique_ptr<AbstractCiphertext> createCiphertextBatch(const std::vector<int64_t> &data, size_t n) const;
   void decryptCiphertextBatch(AbstractCiphertext &abstractCiphertext, std::vector<int64_t> &out) const;
+  /// The same into page-locked staging owned by the factory (no pageable copy of batch * N * 8 bytes): the pointer is
+  /// valid until the next call.
+  const int64_t *decryptCiphertextBatchPinned(AbstractCiphertext &abstractCiphertext) const;
+  /// Enqueued variant: returns where the slots WILL be once waitDecryptions() (or synchronize()) has returned; two staging
+  /// buffers alternate, so the D2H copy of one walk's result runs under the next walk's kernels.
+  const int64_t *decryptCiphertextBatchPinnedAsync(AbstractCiphertext &abstractCiphertext) const;
+  void waitDecryptions() const;
   /// Raw coefficients [batch][2][L][N] of a ciphertext (the bit-exactness probe).
   std::vector<uint64_t> exportCoefficients(const AbstractCiphertext &abstractCiphertext) const;
   /// Microsoft SEAL 3.6 binary streams (seal::Ciphertext::save/load, SecretKey/PublicKey/RelinKeys/GaloisKeys::save/load):

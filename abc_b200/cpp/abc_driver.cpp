@@ -6,6 +6,12 @@
 //   abc_driver programs [N]    the hand-written batched programs of SURVEY.md 8(d) at N (default 8192), secret
 //                              inputs: HammingDistance, L2Distance (n = N/2), BoxBlur, GxKernel (64x64 image),
 //                              checked against plain C++ evaluations of the same functions
+//   abc_driver programs N --batch B [--steps K]
+//                              the lock-step batch driver: ONE RuntimeVisitor walk per step drives B
+//                              independent instances of each program; the per-instance values of the `secret` inputs are
+//                              registered with the factory (setBatchInputs), every instance is checked against the plain
+//                              evaluation, and the L2Distance line reports the metric of bench.py's end-to-end leg
+//                              (mul+relin + rotate ops/s, encrypt and decrypt included)
 // Prints one line per case and a JSON summary; exit code 1 on any mismatch.
 #include <chrono>
 #include <cmath>
@@ -232,6 +238,52 @@ void runKats() {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ lock-step batch
+// One interpreter walk for `batch` instances: the ASTs are parsed and type-checked once (outside the clock); a step =
+// RuntimeVisitor construction (evaluates the input declarations: createCiphertext pulls every instance's values from the
+// registered tables), executeAst, getOutput, decryptCiphertextBatchPinned.
+struct BatchProgram {
+  std::unique_ptr<AbstractNode> astInput, astProgram, astOutput;
+  SecretTaintedNodesMap tainted;
+  BatchProgram(const std::string &inputs, const std::string &program, const std::string &outputs, const std::vector<Var> &inputVars) {
+    astInput = Parser::parse(inputs);
+    astProgram = Parser::parse(program);
+    astOutput = Parser::parse(outputs);
+    TypeCheckingVisitor tcv;
+    auto rootScope = std::make_unique<Scope>(*astProgram);
+    for (const auto &v : inputVars) {
+      auto scopedIdentifier = std::make_unique<ScopedIdentifier>(*rootScope, v.name);
+      rootScope->addIdentifier(v.name);
+      tcv.addVariableDatatype(*scopedIdentifier, Datatype(Type::INT, v.secret));
+    }
+    tcv.setRootScope(std::move(rootScope));
+    astProgram->accept(tcv);
+    tainted = tcv.getSecretTaintedNodes();
+  }
+  // returns the factory's pinned staging: batch * N decrypted slots of the (single) ciphertext output
+  const int64_t *step(CudaCiphertextFactory &factory, bool async = false) {
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
+    factory.rewindBatchInputs();
+    RuntimeVisitor srv(factory, *astInput, tainted);
+    const auto t1 = now();
+    srv.executeAst(*astProgram);
+    const auto t2 = now();
+    auto output = srv.getOutput(*astOutput);
+    const auto t3 = now();
+    for (const auto &[identifier, value] : output)
+      if (auto ciphertext = dynamic_cast<AbstractCiphertext *>(value.get())) {
+        const int64_t *r = async ? factory.decryptCiphertextBatchPinnedAsync(*ciphertext) : factory.decryptCiphertextBatchPinned(*ciphertext);
+        if (getenv("ABC_DRIVER_TIMING"))
+          std::cout << "  host ms: inputs+encrypt (enqueue) " << ms(t0, t1) << ", executeAst (enqueue) " << ms(t1, t2)
+                    << ", getOutput " << ms(t2, t3) << ", decrypt (sync) " << ms(t3, now()) << std::endl;
+        return r;
+      }
+    throw std::runtime_error("batch program: no ciphertext output");
+  }
+};
+
 // ------------------------------------------------------------------------------------------------ programs
 std::vector<int> randomVector(size_t n, unsigned seed) {
   // the reference's generator: std::default_random_engine(4673838), uniform ints in [0,1024]
@@ -330,13 +382,99 @@ void runPrograms(unsigned N) {
   }
   std::cout << "launches=" << f.launchCount() << std::endl;
 }
+void runProgramsBatch(unsigned N, unsigned B, int steps) {
+  CudaCiphertextFactory f(N, 0, B, 0);
+  const size_t n = N / 2;
+  const int64_t t = N <= 8192 ? 1032193 : 786433;
+  auto centre = [&](int64_t v) { v %= t; if (v < 0) v += t; return v > t / 2 ? v - t : v; };
+  // per-instance inputs, instance-major tables
+  std::vector<std::vector<int>> xs(B), ys(B);
+  std::vector<int64_t> tx((size_t)B * n), ty((size_t)B * n);
+  for (unsigned b = 0; b < B; ++b) {
+    xs[b] = randomVector(n, 4673838 + 2 * b); ys[b] = randomVector(n, 4673839 + 2 * b);
+    for (size_t i = 0; i < n; ++i) { tx[b * n + i] = xs[b][i]; ty[b * n + i] = ys[b][i]; }
+  }
+  std::stringstream ladder;
+  ladder << "secret int d = x --- y;\nsecret int s = d *** d;\n";
+  int rotations = 0;
+  for (size_t k = n / 2; k >= 1; k /= 2) { ladder << "s = s +++ rotate(s, " << k << ");\n"; ++rotations; }
+  ladder << "return s;\n";
+  const std::vector<Var> xy = {{"x", true}, {"y", true}};
+  {
+    // the literals are placeholders: every instance's values come from the registered tables
+    BatchProgram prog("secret int x = {0};\nsecret int y = {0};", ladder.str(), "s = s;", xy);
+    f.setBatchInputs({tx, ty});                  // registered (and page-locked) once; every walk rewinds to the first table
+    const int64_t *out = prog.step(f);           // warm-up (scratch growth, key copies) + check of every instance
+    bool ok = true;
+    for (unsigned b = 0; b < B && ok; ++b) {
+      int64_t want = 0;
+      for (size_t i = 0; i < n; ++i) want += (int64_t)(xs[b][i] - ys[b][i]) * (xs[b][i] - ys[b][i]);
+      ok = out[(size_t)b * N] == centre(want);
+    }
+    f.synchronize();
+    auto t0 = std::chrono::steady_clock::now();
+    for (int s_ = 0; s_ < steps; ++s_) out = prog.step(f, true);   // the D2H of walk i runs under walk i + 1
+    f.waitDecryptions();
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (unsigned b = 0; b < B && ok; ++b) {                          // the last walk's result, every instance again
+      int64_t want = 0;
+      for (size_t i = 0; i < n; ++i) want += (int64_t)(xs[b][i] - ys[b][i]) * (xs[b][i] - ys[b][i]);
+      ok = out[(size_t)b * N] == centre(want);
+    }
+    const double ops = (double)B * (1 + rotations) * steps / secs;
+    report("batch.L2Distance n=" + std::to_string(n) + " B=" + std::to_string(B), ok,
+           std::to_string(secs / steps * 1e3) + " ms per walk, " + std::to_string((long)ops) + " mul+relin & rotate ops/s end to end");
+    std::cout << "{\"program\": \"L2Distance\", \"N\": " << N << ", \"batch\": " << B << ", \"steps\": " << steps
+              << ", \"ms_per_walk\": " << secs / steps * 1e3 << ", \"ops_per_s\": " << ops
+              << ", \"instances_per_s\": " << (double)B * steps / secs << ", \"all_instances_checked\": " << (ok ? "true" : "false") << "}"
+              << std::endl;
+  }
+  if (const int size = (int)std::lround(std::sqrt((double)n)); (size_t)size * size == n) {
+    const int box[3][3] = {{1, 1, 1}, {1, 1, 1}, {1, 1, 1}};
+    const int gx[3][3] = {{1, 2, 1}, {0, 0, 0}, {-1, -2, -1}};
+    std::vector<std::vector<int>> imgs(B);
+    std::vector<int64_t> ti((size_t)B * n);
+    for (unsigned b = 0; b < B; ++b) {
+      imgs[b] = randomVector(n, 99 + b);
+      for (size_t i = 0; i < n; ++i) ti[b * n + i] = imgs[b][i];
+    }
+    for (int which = 0; which < 2; ++which) {
+      const auto &w = which == 0 ? box : gx;
+      BatchProgram prog("secret int img = {0};", stencilProgram(size, w), "acc = acc;", {{"img", true}});
+      f.setBatchInputs({ti});
+      const int64_t *out = prog.step(f);
+      bool ok = true;
+      for (unsigned b = 0; b < B && ok; b += std::max(1u, B / 16)) {   // every 1/16th instance in full
+        auto want = stencil(imgs[b], size, w);
+        for (size_t i = 0; ok && i < want.size(); ++i) ok = out[(size_t)b * N + i] == centre(want[i]);
+      }
+      f.synchronize();
+      auto t0 = std::chrono::steady_clock::now();
+      for (int s_ = 0; s_ < steps; ++s_) out = prog.step(f);
+      const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      report(std::string("batch.") + (which == 0 ? "BoxBlur " : "GxKernel ") + std::to_string(size) + "x" + std::to_string(size) +
+                 " B=" + std::to_string(B), ok,
+             std::to_string(secs / steps * 1e3) + " ms per walk, " + std::to_string((long)(B * steps / secs)) + " instances/s end to end");
+    }
+  }
+  std::cout << "launches=" << f.launchCount() << std::endl;
+}
 }  // namespace
 
 int main(int argc, char **argv) {
   const std::string mode = argc > 1 ? argv[1] : "kats";
   try {
     if (mode == "kats") runKats();
-    else if (mode == "programs") runPrograms(argc > 2 ? (unsigned)std::stoul(argv[2]) : 8192);
+    else if (mode == "programs") {
+      const unsigned N = argc > 2 ? (unsigned)std::stoul(argv[2]) : 8192;
+      unsigned batch = 0; int steps = 5;
+      for (int i = 3; i + 1 < argc; i += 2) {
+        if (std::string(argv[i]) == "--batch") batch = (unsigned)std::stoul(argv[i + 1]);
+        if (std::string(argv[i]) == "--steps") steps = std::stoi(argv[i + 1]);
+      }
+      if (batch) runProgramsBatch(N, batch, steps);
+      else runPrograms(N);
+    }
     else { std::cerr << "usage: abc_driver kats|programs [N]" << std::endl; return 2; }
   } catch (const std::exception &e) {
     std::cout << "[FAIL] uncaught exception: " << e.what() << std::endl;

@@ -5,6 +5,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler is attached
 #include <sys/random.h>
 
 #include <algorithm>
@@ -177,9 +178,15 @@ abc_status check_ks_fault(abc_ctx *c) {
 }
 #define CHECK_POISON(c) do { if ((c)->faulted) return fail((c), ABC_ERR_CUDA, kFaultMsg); } while (0)
 
+// NVTX range around one ABI call ("abc_mul_relin", "abc_rotate_rows", ...): what nsys / ncu --nvtx group kernels by
+struct NvtxOp {
+  explicit NvtxOp(const char *name) { nvtxRangePushA(name); }
+  ~NvtxOp() { nvtxRangePop(); }
+};
 struct Launch {
   abc_ctx *c; const char *name; cudaEvent_t a = nullptr, b = nullptr;
-  Launch(abc_ctx *c_, const char *n) : c(c_), name(n) {
+  NvtxOp range;
+  Launch(abc_ctx *c_, const char *n) : c(c_), name(n), range(n) {
     c->launches++;
     if (c->prof) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
   }
@@ -1344,6 +1351,18 @@ abc_status abc_sync(abc_ctx *c) {
   if (c->d2h_stream) CK(cudaStreamSynchronize(c->d2h_stream));
   return check_ks_fault(c);
 }
+abc_status abc_host_alloc(abc_ctx *c, size_t bytes, void **out) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return ABC_OK;
+}
+void abc_host_free(void *p) { if (p) cudaFreeHost(p); }
+abc_status abc_host_register(abc_ctx *c, void *p, size_t bytes) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+  return ABC_OK;
+}
+void abc_host_unregister(void *p) { if (p) cudaHostUnregister(p); }
 int abc_faulted(const abc_ctx *c) { return c->faulted ? 1 : 0; }
 abc_status abc_clear_fault(abc_ctx *c) {
   CK(cudaStreamSynchronize(c->stream));
@@ -1395,7 +1414,7 @@ static abc_status keygen_impl(abc_ctx *c, const std::vector<u32> &elts) {
   c->have_keys = true;
   return ABC_OK;
 }
-abc_status abc_keygen(abc_ctx *c) { return keygen_impl(c, galois_elts_all(c)); }
+abc_status abc_keygen(abc_ctx *c) { NvtxOp nvtx_("abc_keygen"); return keygen_impl(c, galois_elts_all(c)); }
 abc_status abc_keygen_select(abc_ctx *c, const uint32_t *galois_elts, size_t n) {
   return keygen_impl(c, std::vector<u32>(galois_elts, galois_elts + n));
 }
@@ -1595,6 +1614,7 @@ abc_status abc_encrypt_pt(abc_ctx *c, const abc_pt *pt, abc_ct **out) {
   return s;
 }
 abc_status abc_encode_encrypt(abc_ctx *c, const int64_t *slots, size_t n, int broadcast, abc_ct **out) {
+  NvtxOp nvtx_("abc_encode_encrypt");
   abc_pt *pt = nullptr;
   TRY(abc_pt_encode(c, slots, n, broadcast, &pt));
   abc_status s = abc_encrypt_pt(c, pt, out);
@@ -1627,6 +1647,7 @@ static abc_status dot_ct_sk(abc_ctx *c, const abc_ct *ct, u64 **x_out) {
 // Decryptor::invariant_noise_budget (SealCiphertext::noiseBits, SealCiphertext.cpp:80-83), per instance:
 // bit_count(Q) - bit_count(|| t * (c0 + c1*s) mod Q ||_inf, centred) - 1, floored at 0.
 abc_status abc_noise_budget(abc_ctx *c, const abc_ct *ct, int32_t *out_bits) {
+  NvtxOp nvtx_("abc_noise_budget");
   u64 *x = nullptr;
   TRY(dot_ct_sk(c, ct, &x));
   const int N = c->N, L = c->L, B = c->B;
@@ -1667,6 +1688,7 @@ abc_status abc_noise_budget(abc_ctx *c, const abc_ct *ct, int32_t *out_bits) {
 // asynchronous copy) once abc_decrypt_wait / abc_sync returns.  The device-side result sits in one of two buffers and
 // leaves on the context's D2H stream, so the copy overlaps the kernels of the ops enqueued after this call.
 abc_status abc_decrypt_decode_async(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) {
+  NvtxOp nvtx_("abc_decrypt_decode_async");
   u64 *x = nullptr, *plain = nullptr;
   TRY(dot_ct_sk(c, ct, &x));
   const int N = c->N, B = c->B;
@@ -1718,6 +1740,7 @@ abc_status abc_decrypt_decode(abc_ctx *c, const abc_ct *ct, int64_t *out_slots) 
 // ---- ciphertext ops
 static abc_status fused_rotate_add(abc_ctx *c, abc_ct *dst, const abc_ct *rot, const abc_ct *other);
 static abc_status addsub(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct *b, int op) {
+  NvtxOp nvtx_(op == 0 ? "abc_add" : op == 1 ? "abc_sub" : "abc_negate");
   if (!valid_ct(c, dst) || !valid_ct(c, a) || (op != 2 && !valid_ct(c, b)))
     return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
   CHECK_POISON(c);
@@ -1767,6 +1790,7 @@ abc_status abc_sub(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct *b) { 
 abc_status abc_negate(abc_ctx *c, abc_ct *dst, const abc_ct *a) { return addsub(c, dst, a, nullptr, 2); }
 
 abc_status abc_mul_relin(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct *b) {
+  NvtxOp nvtx_("abc_mul_relin");
   if (!valid_ct(c, dst) || !valid_ct(c, a) || !valid_ct(c, b)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
   if (!c->d_relin) return fail(c, ABC_ERR_STATE, "relinearisation key not present");
   CHECK_POISON(c);
@@ -1787,6 +1811,7 @@ abc_status abc_mul_relin(abc_ctx *c, abc_ct *dst, const abc_ct *a, const abc_ct 
 // dst = rotate_rows(a, steps) [+ addend].  The addend is accumulated in the ModDown of the last key switch, which
 // gives exactly add(rotate_rows(a), addend): modular addition of canonical residues is associative.
 static abc_status rotate_impl(abc_ctx *c, abc_ct *dst, const abc_ct *a, int steps, const abc_ct *addend) {
+  NvtxOp nvtx_(addend ? "abc_rotate_rows_add" : "abc_rotate_rows");
   if (!valid_ct(c, dst) || !valid_ct(c, a) || (addend && !valid_ct(c, addend)))
     return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
   CHECK_POISON(c);

@@ -37,3 +37,20 @@ def test_batched_programs_n16384():
     # 8192 slots per row is not a square image: distance programs only
     summary, _ = run("programs", "16384")
     assert summary["cases"] == 2
+
+
+def test_lock_step_batch_driver():
+    """ONE RuntimeVisitor walk drives B instances (the per-instance `secret` inputs come from the tables
+    registered with the factory); every instance of L2Distance and sampled instances of the stencils are checked against
+    the plain evaluation inside the driver."""
+    summary, out = run("programs", "8192", "--batch", "24", "--steps", "2")
+    assert summary["cases"] == 3
+    for name in ("L2Distance", "BoxBlur", "GxKernel"):
+        assert "[ ok ] batch." + name in out
+    assert '"all_instances_checked": true' in out
+
+
+def test_a16_and_unsupported_ops_are_in_the_kats():
+    _, out = run("kats")
+    assert "[ ok ] a16.Cleartext<int>::subtract_inplace(ciphertext)" in out
+    assert out.count("[ ok ] unsupported.") >= 15
