@@ -46,7 +46,7 @@ __device__ __forceinline__ u64 bf_out(double r) { return f64_canon_bits(r); }
 // X layout [inst][4][W = L + NBSK][N]: q rows (a copy of the input), then the Bsk rows.  grid: (N/128, polys, B)
 template <int L, int NBSK>
 __global__ void __launch_bounds__(128) k_behz_lift_f64(const u64 *__restrict__ a, const u64 *__restrict__ b,
-                                                       u64 *__restrict__ X, const BehzF64 *__restrict__ F, int N) {
+                                                       u64 *__restrict__ X, const BehzF64 *__restrict__ F, int N, int copy_q = 1) {
   const int n = blockIdx.x * 128 + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
   constexpr int W = L + NBSK;
   const u64 *src = (poly < 2 ? a : b) + ((size_t)inst * 2 + (poly & 1)) * L * N + n;
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128) k_behz_lift_f64(const u64 *__restrict__ a
 #pragma unroll
   for (int i = 0; i < L; ++i) {
     const u64 x = src[(size_t)i * N];
-    dst[(size_t)i * N] = x;
+    if (copy_q) dst[(size_t)i * N] = x;   // (0: the forward transforms read the operand's own limbs)
     z[i] = bf_mulc(bf_in(x), F->lift_c[i], F->q[i], F->qinv[i]);
     xm += (u32)bf_out(z[i]) * F->punct_q_mt[i];
   }
@@ -90,10 +90,10 @@ __global__ void __launch_bounds__(256) k_behz_tensor_f64(u64 *__restrict__ X, co
 // ---- steps 6-8: * t, fast_floor (q U Bsk -> Bsk), fastbconv_sk (Bsk -> q).  grid: (N/128, 3, B)
 template <int L, int NBSK>
 __global__ void __launch_bounds__(128) k_behz_scale_f64(const u64 *__restrict__ X, u64 *__restrict__ dst,
-                                                        const BehzF64 *__restrict__ F, int N) {
+                                                        const BehzF64 *__restrict__ F, int N, int polys_per_inst = 4) {
   constexpr int W = L + NBSK, NB = NBSK - 1;
   const int n = blockIdx.x * 128 + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
-  const u64 *src = X + ((size_t)inst * 4 + poly) * W * N + n;
+  const u64 *src = X + ((size_t)inst * polys_per_inst + poly) * W * N + n;
   u64 *out = dst + ((size_t)inst * 3 + poly) * L * N + n;
   double z[L], zb[NB];
 #pragma unroll

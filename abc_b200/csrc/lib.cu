@@ -77,6 +77,7 @@ struct abc_ctx {
   int *rm_key = nullptr;    // [2k]  w % k
   // BEHZ product on the FP64 pipe over a sub-2^45 auxiliary base (behz_f64.cuh); exact-double class contexts, L <= 8
   bool behz_f64 = false;                       // ABC_BEHZ_F64=0 keeps SEAL's 61-bit base and the integer kernels
+  bool behz_fused = true;                      // ABC_BEHZ_FUSED=0: separate tensor launch, canonical rows between the launches
   int nbsk2 = 0, W2 = 0, idx_b2 = 0;           // |Bsk'|, rows per polynomial, index of its first modulus in d_mods
   std::vector<u64> bsk2;                       // B' primes, then m_sk'
   BehzF64 *dF = nullptr;
@@ -200,7 +201,7 @@ abc_status salloc(abc_ctx *c, u64 **p, size_t words) {
   return ABC_OK;
 }
 void sfree(abc_ctx *c, void *p) { if (p) cudaFreeAsync(p, c->stream); }
-enum { SC_T = 0, SC_ACC, SC_X, SC_OUT3, SC_U, SC_TMP, SC_DECX, SC_DECP, SC_P, SC_NK, SC_ENTT, SC_COMM_SEND, SC_COMM_ALL, SC_NSLOTS };
+enum { SC_T = 0, SC_ACC, SC_X, SC_OUT3, SC_U, SC_TMP, SC_DECX, SC_DECP, SC_P, SC_NK, SC_ENTT, SC_COMM_SEND, SC_COMM_ALL, SC_Y, SC_NSLOTS };
 abc_status scratch(abc_ctx *c, int slot, u64 **p, size_t words) {
   if (c->sc_words[slot] < words) {
     if (c->sc_ptr[slot]) cudaFreeAsync(c->sc_ptr[slot], c->stream);
@@ -401,6 +402,7 @@ abc_status build_tables(abc_ctx *c) {
   c->ks_no_discard = getenv("ABC_KS_NO_DISCARD") != nullptr;
   if (const char *e = getenv("ABC_KS_CHAIN")) c->ks_chain = atoi(e);
   if (const char *e = getenv("ABC_KS_RED")) c->ks_red = atoi(e);
+  if (const char *e = getenv("ABC_BEHZ_FUSED")) c->behz_fused = atoi(e) != 0;
   if (const char *e = getenv("ABC_KS_CHAIN_SKEW")) c->ks_chain_skew = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("ABC_KS1_THREADS")) c->ks1_threads = atoi(e);
   if (const char *e = getenv("ABC_KS1_SKEW")) c->ks1_skew = atoi(e) < 0 ? 0 : atoi(e);
@@ -979,11 +981,29 @@ abc_status behz_multiply_f64(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) 
   const int np = square ? 2 : 4;
   {
     Launch l(c, "behz_lift");
-    DISPATCH_BF(c, (k_behz_lift_f64<LL, NK><<<dim3(N / 128, np, B), 128, 0, c->stream>>>(a, b, X, c->dF, N)));
+    DISPATCH_BF(c, (k_behz_lift_f64<LL, NK><<<dim3(N / 128, np, B), 128, 0, c->stream>>>(a, b, X, c->dF, N, c->behz_fused ? 0 : 1)));
     CK(cudaGetLastError());
   }
   LimbJob j = blank_job();
   j.dst = X; j.src = X; j.dst_is = j.src_is = (long long)4 * W * N; j.rowmod = c->rm_behz2;
+  if (c->behz_fused) {
+    // forward rows like the key switch's ModUp rows: bulk copy in, conversion in the first pass, raw-double image out
+    // (reduced to |x| <= 0.5 q: the images feed products); then the tensor product in the LOAD of the inverse transforms
+    // (no tensor launch, no round trip of the products through HBM)
+    u64 *Y = nullptr;
+    TRY(scratch(c, SC_Y, &Y, (size_t)B * 3 * W * N));
+    j.t_image = 1; j.src_same_mod = 1; j.raw_reduce = 1;
+    j.bz_W = W; j.bz_a = a; j.bz_b = b; j.L = c->L;
+    TRY(launch_limb(c, LIMB_REDUCE_FWD, AR_F64, j, np * W, B, "behz_ntt"));
+    LimbJob jt = blank_job();
+    jt.src = X; jt.src_is = (long long)4 * W * N; jt.dst = Y; jt.dst_is = (long long)3 * W * N; jt.rowmod = c->rm_behz2;
+    jt.bz_W = W; jt.bz_square = square ? 1 : 0;
+    TRY(launch_limb(c, LIMB_BEHZTENSOR_INV, AR_F64, jt, 3 * W, B, "behz_tensor_intt"));
+    Launch l(c, "behz_scale");
+    DISPATCH_BF(c, (k_behz_scale_f64<LL, NK><<<dim3(N / 128, 3, B), 128, 0, c->stream>>>(Y, out3, c->dF, N, 3)));
+    CK(cudaGetLastError());
+    return ABC_OK;
+  }
   TRY(launch_limb(c, LIMB_FWD, AR_F64, j, np * W, B, "behz_ntt"));
   {
     Launch l(c, "behz_tensor");

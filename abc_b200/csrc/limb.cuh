@@ -14,7 +14,7 @@
 #include "ntt.cuh"
 
 enum { PRE_LOAD = 0, PRE_REDUCE = 1, PRE_PLAIN_LIFT = 2, PRE_TERNARY = 3, PRE_CBD = 4, PRE_ENCODE = 5, PRE_GALOIS_REDUCE = 6,
-       PRE_KS_INNER = 7 };
+       PRE_KS_INNER = 7, PRE_BEHZ_TENSOR = 8 };
 enum { POST_STORE = 0, POST_ADD = 1, POST_DECODE = 2, POST_MODDOWN = 3 };
 
 struct LimbJob {
@@ -51,6 +51,16 @@ struct LimbJob {
   // chained ModUp + tail launch (kschain.cu): done[inst][modulus] counts the ModUp rows stored so far (L per key switch)
   u32 *done; u32 done_target;
   u32 *fault;    // host-mapped word raised when a dependency wait gives up (wait_word)
+  // ModUp-style rows whose source is already a residue of the row's own modulus (the BEHZ block's forward transforms):
+  // no source prime to negate / compare against
+  int src_same_mod;
+  int raw_reduce;                // t_image rows: reduce the raw outputs to |x| <= 0.5 q before the bulk store (they feed products)
+  // PRE_BEHZ_TENSOR: src = the transformed operand block [inst][4][bz_W][N] as raw-double images (polys a0, a1, b0, b1;
+  // bz_square: b = a); output row w = poly * bz_W + r takes a0*b0 / a0*b1 + a1*b0 / a1*b1 of row r
+  int bz_W, bz_square;
+  // forward rows of the BEHZ block (src_same_mod): rows r < L of polynomial p are the operand ciphertexts' own limbs, read
+  // where they lie (bz_a: polys 0,1; bz_b: polys 2,3; [inst][2][L][N]) instead of from a copy inside the block
+  const u64 *bz_a, *bz_b;
   u32 *ticket; u32 ticket_base;  // grids with internal dependencies: logical block index = atomicAdd(ticket) - ticket_base
   u32 *t_used;   // [inst][modulus] tail rows that have consumed T[inst][modulus][*] (2 per key switch): the second one drops
                  // the rows from L2 (discard.global.L2) so that their dirty lines are never written to DRAM
@@ -77,7 +87,8 @@ enum {
   LIMB_GALOIS_REDUCE_FWD = 11,  // Galois gather + reduce mod q, NTT  (rotate: sigma(c1) ModUp)
   LIMB_INV_MODDOWN = 12,   // INTT, ModDown with rounding, + base (key-switch tail)
   LIMB_KSINNER_INV_MODDOWN = 13,  // key-switch inner product over J in the load, INTT, ModDown (AR_F64 only)
-  LIMB_NCOMBOS = 14
+  LIMB_BEHZTENSOR_INV = 14,       // BEHZ tensor product of the transformed operand rows in the load, INTT (AR_F64 only)
+  LIMB_NCOMBOS = 15
 };
 
 __device__ __forceinline__ u64 small_to_mod(int v, u64 q) { return v < 0 ? q - (u64)(-v) : (u64)v; }
@@ -433,7 +444,12 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
   // ---- load
   if constexpr (LINSRC) {
     __shared__ __align__(8) u64 mbar;
-    bulk_row_to_smem(sm, job.src + (size_t)inst * job.src_is + (size_t)srow * D::N, (u32)D::SMEM, &mbar, tid);
+    const u64 *sp = job.src + (size_t)inst * job.src_is + (size_t)srow * D::N;
+    if (job.bz_a) {
+      const int p = w / job.bz_W, r = w - p * job.bz_W;
+      if (r < job.L) sp = (p < 2 ? job.bz_a : job.bz_b) + (((size_t)inst * 2 + (p & 1)) * job.L + r) * D::N;
+    }
+    bulk_row_to_smem(sm, sp, (u32)D::SMEM, &mbar, tid);
   } else if (PRE == PRE_KS_INNER) {
     // srow = comp * k + I: row of the accumulator block this CTA produces
     const int comp = srow >= job.k ? 1 : 0, I = srow - comp * job.k;  // srow < 2k
@@ -482,6 +498,31 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
       for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
         *reinterpret_cast<ulonglong2 *>(&sm[swz_pair(tid, e2)]) = ks_inner_pair(t + e2, kp + e2, job.L, D::N / 2, job.k * D::N, M);
     }
+  } else if (PRE == PRE_BEHZ_TENSOR) {
+    // Evaluator::bfv_multiply's dyadic products (behz_ciphertext_product) in the load of the inverse transform: the
+    // operand rows are the raw-double images their forward transforms left (|x| <= 0.5 q, same element order as this
+    // CTA's shared memory, so image pair j goes straight to shared-memory pair j); every product is six FP64 instructions
+    const int Wb = job.bz_W, p = w / Wb, r = w - p * Wb;
+    const double2 *a0 = reinterpret_cast<const double2 *>(job.src + (size_t)inst * job.src_is + (size_t)r * D::N);
+    const size_t ps = (size_t)Wb * (D::N / 2);
+    const double2 *a1 = a0 + ps, *b0 = job.bz_square ? a0 : a0 + 2 * ps, *b1 = job.bz_square ? a1 : a0 + 3 * ps;
+    const double qinv = f64_of(M.qinv_bits), qd = (double)q;
+    const u64 qb = bits_of(qd);
+    auto mul = [&](double x, double y) { return f64_of(mul_tw<AR_F64>(bits_of(x), bits_of(y), M.qinv_bits, q, qb)); };
+    const double2 *x = p == 2 ? a1 : a0, *y = p == 0 ? b0 : b1;
+    for (int j = tid; j < D::N / 2; j += D::T) {
+      const double2 xv = __ldcs(x + j), yv = __ldcs(y + j);
+      double2 o = make_double2(mul(xv.x, yv.x), mul(xv.y, yv.y));
+      if (p == 1) {   // a0*b1 + a1*b0 (squaring: 2 * a0*a1)
+        if (job.bz_square) { o.x += o.x; o.y += o.y; }
+        else {
+          const double2 uv = __ldcs(a1 + j), vv = __ldcs(b0 + j);
+          o.x += mul(uv.x, vv.x); o.y += mul(uv.y, vv.y);
+        }
+        o.x = reduce_f64(o.x, qinv, qd); o.y = reduce_f64(o.y, qinv, qd);
+      }
+      *reinterpret_cast<double2 *>(&sm[2 * j]) = o;
+    }
   } else if (PRE == PRE_ENCODE) {
     // BatchEncoder::encode (SealCiphertextFactory.cpp:102-132): pad with the last value, scatter by the index map
     const long long *sl = job.slots_in + (size_t)inst * job.slots_is;
@@ -510,8 +551,9 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
   if (FWD) {
     if constexpr (LINSRC) {
       if (job.t_image) {  // (uniform) the row leaves as the image of the swizzled limb: one bulk copy, issued by one thread
-        ntt_fwd_smem_mids<LOGN, AR, true>(sm, M, twbase, tid, mods[srow].q, PRE == PRE_GALOIS_REDUCE ? job.galois_einv : 0u);
-        ntt_fwd_last<LOGN, AR, 0, true>(sm, M, twbase, q, ar_aux<AR>(q), tid);  // raw doubles: the tail multiplies them as they are
+        ntt_fwd_smem_mids<LOGN, AR, true>(sm, M, twbase, tid, job.src_same_mod ? q : mods[srow].q,
+                                          PRE == PRE_GALOIS_REDUCE ? job.galois_einv : 0u);
+        ntt_fwd_last<LOGN, AR, 0, true>(sm, M, twbase, q, ar_aux<AR>(q), tid, job.raw_reduce != 0);  // raw doubles: the consumer multiplies them as they are
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
         __syncthreads();
         if (tid == 0) {
@@ -555,7 +597,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
     __syncthreads();
   }
 
-  if (INV) ntt_inv_smem<LOGN, !TAIL, AR, PRE == PRE_KS_INNER>(sm, M, twbase, tid);
+  if (INV) ntt_inv_smem<LOGN, !TAIL, AR, PRE == PRE_KS_INNER || PRE == PRE_BEHZ_TENSOR>(sm, M, twbase, tid);
 
   // ---- store
   if (POST == POST_DECODE) {
@@ -762,6 +804,9 @@ static int limb_dispatch_ar(int combo, const LimbJob &j, const ModInfo *m, int W
     case LIMB_INV_MODDOWN: return limb_launch<LOGN, PRE_LOAD, false, false, true, POST_MODDOWN, AR, false>(j, m, W, B, s);
     case LIMB_KSINNER_INV_MODDOWN:
       if constexpr (AR == AR_F64) return limb_launch<LOGN, PRE_KS_INNER, false, false, true, POST_MODDOWN, AR, false>(j, m, W, B, s);
+      return (int)cudaErrorInvalidValue;
+    case LIMB_BEHZTENSOR_INV:
+      if constexpr (AR == AR_F64) return limb_launch<LOGN, PRE_BEHZ_TENSOR, false, false, true, POST_STORE, AR, false>(j, m, W, B, s);
       return (int)cudaErrorInvalidValue;
     default: return (int)cudaErrorInvalidValue;
   }

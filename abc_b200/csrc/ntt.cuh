@@ -555,7 +555,7 @@ __device__ __forceinline__ void ntt_fwd_last_math(u64 (&x)[8], const ulonglong2 
 // RAW (exact-double class): leave the outputs as the lazy doubles they are (|x| < (log2(N) + 2) q) instead of canonical
 // residues — for consumers that multiply them in the same arithmetic (the key switch's ModUp block)
 template <int LOGN, int AR, int TT = 0, bool RAW = false>
-__device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 aux, int tid) {
+__device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twbase, u64 q, u64 aux, int tid, bool raw_reduce = false) {
   typedef NttLast<LOGN, TT> P;
   constexpr int E = P::E, H = E / 2;
   const ulonglong2 *__restrict__ tw = (AR == AR_SHOUP) ? M.tw : (AR == AR_F64 ? M.twd : M.twf);
@@ -571,7 +571,7 @@ __device__ __forceinline__ void ntt_fwd_last(u64 *sm, const ModInfo &M, u32 twba
       x[2 * i] = v.x; x[2 * i + 1] = v.y;
     }
     ntt_fwd_last_math<LOGN, AR, TT, P16 ? 0 : P::NSH>(x, tw, twbase, q, aux, vt, qinv);
-    if (RAW && AR == AR_F64 && f64_wide(q)) {   // wide primes: the ModUp block's raw values back to |x| <= 0.5 q
+    if (RAW && AR == AR_F64 && (raw_reduce || f64_wide(q))) {   // wide primes (or on request): raw values back to |x| <= 0.5 q
 #pragma unroll
       for (int r = 0; r < E; ++r) x[r] = bits_of(reduce_f64(f64_of(x[r]), qinv, f64_of(aux)));
     }

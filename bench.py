@@ -419,6 +419,7 @@ def run_ours(args):
                "behz_ntt_q": B * 4 * L * row, "behz_ntt_bsk": B * 4 * nb * row,      # d *** d: squaring path, 2 of 4 polys
                "behz_intt_q": B * 6 * L * row, "behz_intt_bsk": B * 6 * nb * row,
                "behz_ntt": B * 4 * W2 * row, "behz_intt": B * 6 * W2 * row,
+               "behz_tensor_intt": B * (4 + 3) * W2 * row,   # d *** d: 2 operand rows read by 3 products (1 + 2 + 1 row reads), 3 out
                "behz_lift": B * 2 * (L + 2 * L + 1) * row, "behz_tensor": B * 7 * (2 * L + 1) * row,
                "behz_scale": B * 3 * (3 * L + 1) * row, "add": B * 6 * L * row, "sub": B * 6 * L * row}
         peaks, how = measured_peaks()
@@ -436,7 +437,7 @@ def run_ours(args):
                     "ks_fused": (k * L + 2 * L + 2, arq), "ks_chain_relin": (k * L + 2 * L + 2, arq), "behz_ntt_q": (2 * L, arq), "behz_ntt_bsk": (2 * nb, 0),
                     "behz_intt_q": (3 * L, arq), "behz_intt_bsk": (3 * nb, 0),
                     # FP64 BEHZ (behz_f64.cuh): q rows + the sub-2^45 auxiliary rows in one launch each, squaring path
-                    "behz_ntt": (2 * W2, arq), "behz_intt": (3 * W2, arq)}
+                    "behz_ntt": (2 * W2, arq), "behz_intt": (3 * W2, arq), "behz_tensor_intt": (3 * W2, arq)}
         bf_peaks = {arq: bf_peak, 0: f.measure_butterfly_peak(0)}
         ntt_ms = sum(r["ms"] for r in prof if r["kernel"] in ntt_rows)
         bf_per_row = (N_POLY // 2) * logn
