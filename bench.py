@@ -193,7 +193,38 @@ def traffic_for(kernel, batch):
         return None
 
 
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "abc_ref_driver")
+
+
+def run_ref_driver(cores, per_core, steps, warmup):
+    """The CPU arm through the reference's own interpreter: oracle/_ref/abc_ref_driver = Parser + TypeCheckingVisitor +
+    RuntimeVisitor of /root/reference (compiled unchanged into libabc_ref.a) over OracleCiphertextFactory (oracle/cpp), one
+    walk per instance, `cores` forked workers.  Returns its JSON line, or None when the binary is not built."""
+    if not os.path.exists(REF_DRIVER):
+        return None
+    p = subprocess.run([REF_DRIVER, str(N_POLY), str(cores), str(per_core), str(steps), str(warmup)],
+                       capture_output=True, text=True, timeout=1200)
+    if p.returncode != 0:
+        raise RuntimeError("abc_ref_driver failed: " + p.stdout[-500:] + p.stderr[-500:])
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
 def cpu_baseline_port(cores, seconds_budget=12.0):
+    """The CPU baseline on the box's host cores, bounded sample (about `seconds_budget` s of wall time): through the
+    reference's RuntimeVisitor when the driver is built (encrypt x, y + program + decrypt per instance), else the oracle
+    driven from Python threads."""
+    cal = run_ref_driver(cores, 1, 1, 0)
+    if cal is not None:
+        per = max(1, int(seconds_budget / max(cal["ms_per_step"] * 1e-3, 1e-3)))
+        r = run_ref_driver(cores, per, 1, 0)
+        return {"value": r["ops_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d instances on %d host processes (%.1f s): encrypt x, y + program + decrypt through the reference's "
+                          "RuntimeVisitor over OracleCiphertextFactory (oracle/cpp; SEAL-3.6.5 restatement, SEAL itself not "
+                          "installable); result check %s" % (r["instances_per_step"], cores, r["ms_per_step"] * 1e-3, r["result_check"])}
+    return cpu_baseline_python_threads(cores, seconds_budget)
+
+
+def cpu_baseline_python_threads(cores, seconds_budget=12.0):
     """The oracle (SEAL-3.6.5 restatement) running the same program on host cores; bounded sample."""
     from oracle.bfv_oracle import Oracle
     o = Oracle(N_POLY, seed=SEED)
@@ -519,10 +550,31 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     if rank != 0:
         return
-    from oracle.bfv_oracle import Oracle
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    o = Oracle(N_POLY, seed=SEED)
     n = cores * args.ref_instances_per_core
+    r = run_ref_driver(cores, args.ref_instances_per_core, args.steps, args.warmup)
+    if r is not None:
+        v, dt_ms = r["ops_per_s"], r["ms_per_step"]
+        assert r["result_check"] == "ok", "reference arm result mismatch"
+        sample = ("%d instances per step on %d host processes: encrypt x,y + program + decrypt, one RuntimeVisitor walk per "
+                  "instance over OracleCiphertextFactory" % (n, cores))
+    else:
+        v, dt_ms, sample = reference_python_threads(args, cores, n)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": config_dict(args.batch, world),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample + "; SEAL-3.6.5 restatement (oracle/), SEAL itself not installable here"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def reference_python_threads(args, cores, n):
+    """Fallback of the reference arm when abc_ref_driver is not built: the oracle driven from Python threads."""
+    from oracle.bfv_oracle import Oracle
+    o = Oracle(N_POLY, seed=SEED)
     xs, ys = synth_inputs(n, 0)
     res = np.zeros(n, dtype=np.int64)
 
@@ -551,17 +603,8 @@ def run_reference(args):
     want = expected_slot0(xs, ys) % o.t
     want = np.where(want > o.t // 2, want - o.t, want)
     assert np.array_equal(res, want), "reference arm result mismatch"
-    v = n * OPS_PER_INSTANCE * args.steps / dt
     sample = "%d instances per step on %d host threads: encrypt x,y + program + decrypt" % (n, cores)
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": config_dict(args.batch, world),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample + "; SEAL-3.6.5 restatement (oracle/), SEAL itself not installable here"},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    return n * OPS_PER_INSTANCE * args.steps / dt, dt / args.steps * 1e3, sample
 
 
 def run_deep_chain(args):
@@ -599,7 +642,7 @@ def main():
     ap.add_argument("--batch", type=int, default=592, help="independent instances per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--ref-instances-per-core", type=int, default=2)
+    ap.add_argument("--ref-instances-per-core", type=int, default=8)
     ap.add_argument("--workload", default="l2distance", choices=["l2distance", "deep_chain"],
                     help="deep_chain: BASELINE.json configs[4], N=65536 multiplicative chain, RNS limbs sharded over the ranks")
     ap.add_argument("--depth", type=int, default=8, help="deep_chain: (mul+relin, rotate) pairs per step")
