@@ -1,0 +1,29 @@
+// ks14.cuh — descriptor + launchers of the split key switch at N = 16384 (ks14.cu)
+#pragma once
+#include "limb.cuh"
+
+struct Ks14 {
+  const u64 *target; long long target_is;     // polynomial being switched: [L][N] per instance, coefficient form
+  double *sx;                                 // [B][L][N]: sigma(target) as exact doubles, natural order (k_ks14_prep)
+  const double *key;                          // KSwitchKey [L][2][k][N], NTT form at key level, as exact doubles
+  double *T;                                  // ModUp block [B][k][L][N]: row (I, J) = two 8192-blocks, each the raw-double image of its swizzled block
+  double *xch;                                // [B][2k][N]: block h of accumulator row (c*k + I) after its 13 local inverse stages (image)
+  u64 *tl; long long tl_is;                   // accumulator block [2][k][N] per instance: rows (c*k + L) receive INTT_p(acc_L[c]) (canonical)
+  u64 *dst; long long dst_is;                 // result ciphertext [2][L][N]
+  u64 *dst2;                                  // with `add`: also the result without the addend
+  const u64 *add; long long add_is;           // a whole ciphertext accumulated into the result (rotate + add)
+  const u64 *base0, *base1; long long base0_is, base1_is;  // polynomial added into component 0 / 1 (nullptr = 0)
+  u32 einv;                                   // automorphism applied to target and bases while reading (0: none)
+  const uint2 *sched; int n_blocks;           // x = role << 31 | block << 30 | inst, y = w | modulus << 8 | drow << 16 | srow << 24
+  u32 *ticket; u32 ticket_base;
+  u32 *done; u32 done_target;                 // [B][k][2]: ModUp half-rows of (modulus, block) stored so far (L per launch)
+  u32 *xflag; u32 serial;                     // [B][2k][2] == serial when xch[inst][row][block] is written
+  u32 *flags;                                 // [B][2][2] == serial when tl[inst][c] block h is published
+  u32 *fault;
+  const DevConst *C;
+  int L, k, B;
+};
+
+// returns a cudaError_t as int
+int ks14_prep_launch(const Ks14 &ks, const ModInfo *mods, cudaStream_t stream);
+int ks14_launch(const Ks14 &ks, const ModInfo *mods, cudaStream_t stream);

@@ -21,6 +21,7 @@
 #include "ksfused.cuh"
 #include "kschain.cuh"
 #include "ksred.cuh"
+#include "ks14.cuh"
 #include "behz_f64.cuh"
 
 namespace {
@@ -115,6 +116,9 @@ struct abc_ctx {
   // accumulating key switch (ksred.cu): accumulator ring [ring][k][2][N] doubles, [B][k] done / freed counters
   // ABC_KS_RED=1 selects it; measured 9 % slower than the chained grid at N = 8192 (the bulk reductions wait on the L2 atomic units)
   int ks_red = 0, ksr_ring = 0; double *ksr_acc = nullptr; u32 *ksr_done = nullptr, *ksr_freed = nullptr; u32 ksr_serial = 0;
+  // split key switch at N = 16384 (ks14.cu): schedule of half-rows, [B][k][2] done + [B][2k][2] exchange + [B][2][2] special flags
+  int ks14 = 1; uint2 *ks14_sched = nullptr; int ks14_sched_n = 0; u32 *ks14_done = nullptr, *ks14_xflag = nullptr, *ks14_flags = nullptr;
+  u32 ks14_serial = 0;
   u32 *ks_ticket = nullptr; u32 ks_ticket_total = 0;                          // start-order tickets of the dependency-ordered grids (limb.cuh grid_ticket)
   bool faulted = false;                                                       // sticky: a dependency wait timed out; every later call fails until abc_clear_fault
   int *rs_zero = nullptr;   // [2k]  0
@@ -201,7 +205,7 @@ abc_status salloc(abc_ctx *c, u64 **p, size_t words) {
   return ABC_OK;
 }
 void sfree(abc_ctx *c, void *p) { if (p) cudaFreeAsync(p, c->stream); }
-enum { SC_T = 0, SC_ACC, SC_X, SC_OUT3, SC_U, SC_TMP, SC_DECX, SC_DECP, SC_P, SC_NK, SC_ENTT, SC_COMM_SEND, SC_COMM_ALL, SC_Y, SC_NSLOTS };
+enum { SC_T = 0, SC_ACC, SC_X, SC_OUT3, SC_U, SC_TMP, SC_DECX, SC_DECP, SC_P, SC_NK, SC_ENTT, SC_COMM_SEND, SC_COMM_ALL, SC_Y, SC_SX, SC_XCH, SC_NSLOTS };
 abc_status scratch(abc_ctx *c, int slot, u64 **p, size_t words) {
   if (c->sc_words[slot] < words) {
     if (c->sc_ptr[slot]) cudaFreeAsync(c->sc_ptr[slot], c->stream);
@@ -402,6 +406,7 @@ abc_status build_tables(abc_ctx *c) {
   c->ks_no_discard = getenv("ABC_KS_NO_DISCARD") != nullptr;
   if (const char *e = getenv("ABC_KS_CHAIN")) c->ks_chain = atoi(e);
   if (const char *e = getenv("ABC_KS_RED")) c->ks_red = atoi(e);
+  if (const char *e = getenv("ABC_KS14_SPLIT")) c->ks14 = atoi(e);
   if (const char *e = getenv("ABC_BEHZ_FUSED")) c->behz_fused = atoi(e) != 0;
   if (const char *e = getenv("ABC_KS_CHAIN_SKEW")) c->ks_chain_skew = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("ABC_KS1_THREADS")) c->ks1_threads = atoi(e);
@@ -635,6 +640,40 @@ abc_status build_shard_maps(abc_ctx *c) {
     c->ksr_serial = 0;
     }
   }
+  if (nown > 0 && c->logN == 14 && c->ks14 && c->ks_nI * L < 256 && 2 * k < 256) {
+    // split key switch (ks14.cu): the chained schedule with every row as two half-rows holding adjacent tickets
+    const int Bn = c->B;
+    const size_t t_bytes = (size_t)c->ks_nI * L * c->N * 8;
+    const int S1 = std::max(2, std::min(c->ks_chain_skew, (int)((size_t)(48u << 20) / std::max<size_t>(t_bytes, 1))));
+    const int S2 = std::max(0, std::min(c->ks_skew, S1 - 1));
+    std::vector<uint2> sch;
+    auto up_row = [&](int g, int w) {
+      const int Iv = I[w / L], J = w % L;
+      for (u32 h = 0; h < 2; ++h)
+        sch.push_back(make_uint2(h << 30 | (u32)g, (u32)w | (u32)Iv << 8 | (u32)(Iv * L + J) << 16 | (u32)J << 24));
+    };
+    auto tail_row = [&](int g, int w) {
+      const int comp = w < 2 ? w : (w - 2) / nown, Iv = w < 2 ? L : lo + (w - 2) % nown;
+      const int drow = w < 2 ? (w == 0 ? L : k + L) : comp * L + Iv;
+      for (u32 h = 0; h < 2; ++h)
+        sch.push_back(make_uint2(1u << 31 | h << 30 | (u32)g, (u32)w | (u32)Iv << 8 | (u32)drow << 16 | (u32)(comp * k + Iv) << 24));
+    };
+    for (int g = 0; g < Bn + S1; ++g) {
+      if (g < Bn) for (int w = 0; w < c->ks_nI * L; ++w) up_row(g, w);
+      const int gs = g - (S1 - S2), gd = g - S1;
+      if (gs >= 0 && gs < Bn) for (int w = 0; w < 2; ++w) tail_row(gs, w);
+      if (gd >= 0 && gd < Bn) for (int w = 2; w < 2 + 2 * nown; ++w) tail_row(gd, w);
+    }
+    TRY(upload(c, &c->ks14_sched, sch));
+    c->ks14_sched_n = (int)sch.size();
+    const size_t nflag = (size_t)c->B * (2 * k + 4 * k + 4);
+    CK(cudaMalloc((void **)&c->ks14_done, nflag * sizeof(u32)));
+    c->owned.push_back(c->ks14_done);
+    CK(cudaMemset(c->ks14_done, 0, nflag * sizeof(u32)));
+    c->ks14_xflag = c->ks14_done + (size_t)c->B * 2 * k;
+    c->ks14_flags = c->ks14_xflag + (size_t)c->B * 4 * k;
+    c->ks14_serial = 0;
+  }
   if (!c->ks_fault_h) {
     CK(cudaHostAlloc((void **)&c->ks_fault_h, sizeof(u32), cudaHostAllocMapped));
     *c->ks_fault_h = 0;
@@ -855,6 +894,38 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   const int t_image = fused && c->logN <= 14 && !c->ks_no_image ? 1 : 0;  // T rows as bulk-stored images of the swizzled limb
   const bool chain = t_image && c->ks_chain && c->ks_sched && c->logN <= 14 && c->force_ar < 0;
   const bool red = chain && c->ks_red && c->ksr_acc && c->logN <= 13;   // no ModUp block at all (ksred.cu)
+  if (chain && c->logN == 14 && c->ks14 && c->ks14_sched) {   // N = 16384: rows of half a limb, two CTAs per SM (ks14.cu)
+    if (gather_ct && c->world > 1) TRY(allgather_limbs(c, gather_ct, 2));
+    Ks14 kq;
+    memset(&kq, 0, sizeof kq);
+    const double *keyd = nullptr;
+    TRY(key_as_f64(c, key, &keyd));
+    u64 *sx = nullptr, *xch = nullptr;
+    TRY(scratch(c, SC_T, &T, (size_t)B * k * L * N));
+    TRY(scratch(c, SC_ACC, &acc, (size_t)B * 2 * k * N));
+    TRY(scratch(c, SC_SX, &sx, (size_t)B * L * N));
+    TRY(scratch(c, SC_XCH, &xch, (size_t)B * 2 * k * N));
+    kq.target = target; kq.target_is = target_is; kq.sx = reinterpret_cast<double *>(sx); kq.key = keyd;
+    kq.T = reinterpret_cast<double *>(T); kq.xch = reinterpret_cast<double *>(xch);
+    kq.tl = acc; kq.tl_is = (long long)2 * k * N;
+    kq.dst = dst; kq.dst_is = (long long)2 * L * N; kq.dst2 = dst_plain; kq.add = addend; kq.add_is = (long long)2 * L * N;
+    kq.base0 = base0; kq.base0_is = base0_is; kq.base1 = base1; kq.base1_is = base1_is; kq.einv = einv;
+    kq.sched = c->ks14_sched; kq.n_blocks = c->ks14_sched_n;
+    kq.ticket = c->ks_ticket; kq.ticket_base = c->ks_ticket_total; c->ks_ticket_total += (u32)kq.n_blocks;
+    kq.serial = ++c->ks14_serial;
+    kq.done = c->ks14_done; kq.done_target = (u32)L * kq.serial;
+    kq.xflag = c->ks14_xflag; kq.flags = c->ks14_flags; kq.fault = c->ks_fault_d;
+    kq.C = c->dC; kq.L = L; kq.k = k; kq.B = B;
+    {
+      Launch l(c, "ks14_prep");
+      const int e = ks14_prep_launch(kq, c->d_mods, c->stream);
+      if (e != 0) { c->err = std::string("ks14_prep: ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
+    }
+    Launch l(c, einv ? "ks14" : "ks14_relin");
+    const int e = ks14_launch(kq, c->d_mods, c->stream);
+    if (e != 0) { c->err = std::string("ks14: ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
+    return ABC_OK;
+  }
   if (!red) TRY(scratch(c, SC_T, &T, (size_t)B * k * L * N));
   TRY(scratch(c, SC_ACC, &acc, (size_t)B * 2 * k * N));
   LimbJob j = blank_job();

@@ -333,7 +333,9 @@ __device__ __forceinline__ ulonglong2 ks_inner_pair_f64(const double2 *__restric
 #ifndef ABC_KS_PIPE_INNER
 #define ABC_KS_PIPE_INNER 1
 #endif
-template <int LT, int NIT, int T>
+// ACC: add to what shared memory already holds (the sum over an earlier chunk of LT limbs, |x| <= 0.51 q): L = 8 runs as
+// two chunks of 4, which keeps the software pipeline inside the register budget
+template <int LT, int NIT, int T, bool ACC = false>
 __device__ __forceinline__ void ks_inner_rows_f64(u64 *sm, const double2 *__restrict__ t, const double2 *__restrict__ kp,
                                                   int rowv, int keyv2, const ModInfo &M, int tid) {
   const double qinv = f64_of(M.qinv_bits), qd = (double)M.q;
@@ -350,6 +352,10 @@ __device__ __forceinline__ void ks_inner_rows_f64(u64 *sm, const double2 *__rest
       for (int J = 0; J < LT; ++J) tn[J] = __ldcg(tp + (i + 1) * T + (size_t)J * rowv);
     }
     double s0 = 0.0, s1 = 0.0;
+    if (ACC) {
+      const double2 prev = *reinterpret_cast<const double2 *>(&sm[p0 + 2 * i * T]);
+      s0 = prev.x; s1 = prev.y;
+    }
 #pragma unroll
     for (int J = 0; J < LT; ++J) {
       const double2 kv = __ldg(kp + tid + i * T + (size_t)J * keyv2);

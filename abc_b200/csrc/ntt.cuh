@@ -298,7 +298,9 @@ template <int AR> __device__ __forceinline__ void bf_inv(u64 &x, u64 &y, ulonglo
 // +-sm[e * einv mod 2N] (GaloisTool::apply_galois as a gather, einv = 0: identity), takes NO reduction modulo the
 // target prime (an exact-double transform accepts any |x| < 2^45 and canon_fwd reduces at the end), and, because
 // it is no longer in place, separates its loads from its stores with a barrier.
-template <int LOGN, int S0, int R, int AR, bool LINSRC = false, int TT = 0>
+// PRECONV: shared memory already holds the class's representation (the first pass of a block whose stage above it was
+// done while loading)
+template <int LOGN, int S0, int R, int AR, bool LINSRC = false, int TT = 0, bool PRECONV = false>
 __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 aux,
                                             int tid, double qinv, u64 qs = 0, u32 einv = 0, bool wide_reduce = false) {
   typedef NttDims<LOGN, TT> D;
@@ -340,7 +342,7 @@ __device__ __forceinline__ void ntt_fwd_mid(u64 *sm, const ulonglong2 *__restric
       } else {
 #pragma unroll
         for (int r = 0; r < 8; ++r) x[g][r] = sm[swz_strided<LG>(base[g], pbase[g], r)];
-        if (S0 == 0) {  // first pass: canonical residues -> the class's representation
+        if (S0 == 0 && !PRECONV) {  // first pass: canonical residues -> the class's representation
 #pragma unroll
           for (int r = 0; r < 8; ++r) x[g][r] = ar_from_canon<AR>(x[g][r]);
         }
@@ -449,7 +451,8 @@ __device__ __forceinline__ void ntt_inv_mid(u64 *sm, const ModInfo &M, u32 twbas
 
 // ---- the 4-stage strided pass of the radix-16 plan (stages 6..9 of N = 8192: gap 8 between a thread's 16 coefficients)
 template <int LOGN, int AR>
-__device__ __forceinline__ void ntt_fwd_mid16(u64 *sm, const ulonglong2 *__restrict__ tw, u64 q, u64 aux, int tid, double qinv) {
+__device__ __forceinline__ void ntt_fwd_mid16(u64 *sm, const ulonglong2 *__restrict__ tw, u64 q, u64 aux, int tid, double qinv,
+                                              u32 twbase = 1u, bool wide_reduce = false) {
   constexpr int S0 = 6, LG = LOGN - S0 - 4;
   static_assert(LOGN == 13 && LG == 3, "radix-16 plan is laid out for N = 8192");
   const int blk = (p16_kblock(tid) << 3) + ((tid & 63) >> LG);   // 128-coefficient block
@@ -458,13 +461,17 @@ __device__ __forceinline__ void ntt_fwd_mid16(u64 *sm, const ulonglong2 *__restr
   u64 x[16];
 #pragma unroll
   for (int r = 0; r < 16; ++r) x[r] = sm[pb ^ ((r << LG) ^ (r & 14))];
+  if (AR == AR_F64 && wide_reduce) {   // wide primes: the forward range plan's one reduction (7 stages in, 7 to go)
+#pragma unroll
+    for (int r = 0; r < 16; ++r) x[r] = bits_of(reduce_f64(f64_of(x[r]), qinv, f64_of(aux)));
+  }
 #pragma unroll
   for (int b = 3; b >= 0; --b) {
     const int s = S0 + 3 - b;
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       if (r & (1 << b)) continue;
-      const ulonglong2 w = mid_tw<AR>(tw, (1u << s) + ((u32)((blk << 4) + r) >> (b + 1)), qinv);
+      const ulonglong2 w = mid_tw<AR>(tw, (twbase << s) + ((u32)((blk << 4) + r) >> (b + 1)), qinv);
       bf_fwd<AR>(x[r], x[r | (1 << b)], w, q, aux);
     }
   }
@@ -472,7 +479,8 @@ __device__ __forceinline__ void ntt_fwd_mid16(u64 *sm, const ulonglong2 *__restr
   for (int r = 0; r < 16; ++r) sm[pb ^ ((r << LG) ^ (r & 14))] = x[r];
 }
 template <int LOGN, int AR, bool REDUCE>
-__device__ __forceinline__ void ntt_inv_mid16(u64 *sm, const ulonglong2 *__restrict__ tw, u64 q, u64 aux, int tid, double qinv) {
+__device__ __forceinline__ void ntt_inv_mid16(u64 *sm, const ulonglong2 *__restrict__ tw, u64 q, u64 aux, int tid, double qinv,
+                                              u32 twbase = 1u) {
   constexpr int S0 = 6, LG = LOGN - S0 - 4;
   static_assert(LOGN == 13 && LG == 3 && AR == AR_F64, "radix-16 plan: exact-double class at N = 8192");
   const int blk = (p16_kblock(tid) << 3) + ((tid & 63) >> LG);
@@ -490,7 +498,7 @@ __device__ __forceinline__ void ntt_inv_mid16(u64 *sm, const ulonglong2 *__restr
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       if (r & (1 << b)) continue;
-      const ulonglong2 w = mid_tw<AR>(tw, (1u << s) + ((u32)((blk << 4) + r) >> (b + 1)), qinv);
+      const ulonglong2 w = mid_tw<AR>(tw, (twbase << s) + ((u32)((blk << 4) + r) >> (b + 1)), qinv);
       bf_inv<AR>(x[r], x[r | (1 << b)], w, q, aux);
     }
   }
@@ -513,9 +521,15 @@ template <int LOGN, int TT = 0> struct NttLast {
 
 // twiddle index of the in-register stage with partner distance 2^b of the contiguous pass (E = 8): natural order
 // 2^s + ((8*vt + r) >> (b+1)); AR_F64 stores the last two stages lane-contiguously (see tw_get)
+// When this limb is block `blk` of a 2^sub times larger transform (twbase = 2^sub + blk; exact-double class: sub <= 1, the
+// split N = 16384 key switch), local stage s is global stage s + sub, the lane-contiguous stride is the larger transform's
+// N / 8 and this block's contiguous-pass threads are blk * (N_local / 8) + vt of it.
 template <int LOGN, int AR>
 __device__ __forceinline__ u32 last_tw_index(u32 twbase, int s, int b, int vt, int r) {
-  if (AR == AR_F64 && b < 2) return (1u << s) + (u32)(r >> (b + 1)) * (u32)(NttDims<LOGN>::N / 8) + (u32)vt;
+  if (AR == AR_F64 && b < 2) {
+    const u32 sub = twbase >> 1 ? 1u : 0u, blk = twbase - (1u << sub);   // twbase in {1, 2, 3}
+    return (1u << (s + sub)) + (u32)(r >> (b + 1)) * (u32)((NttDims<LOGN>::N << sub) / 8) + blk * (u32)(NttDims<LOGN>::N / 8) + (u32)vt;
+  }
   return (twbase << s) + ((u32)(8 * vt + r) >> (b + 1));
 }
 
@@ -667,7 +681,7 @@ template <int LG, int T> __device__ __forceinline__ void pass_sync(int tid) {
 // ---- whole-limb transforms on a swizzled shared-memory limb.  Caller has filled sm[swz(e)] and synced.
 // Forward: input canonical (guarded classes accept < 4q), output canonical.  Returns after a barrier.
 // the strided passes of the forward transform; returns after the barrier in front of the contiguous pass
-template <int LOGN, int AR, bool LINSRC = false, int TT = 0>
+template <int LOGN, int AR, bool LINSRC = false, int TT = 0, bool PRECONV = false>
 __device__ __forceinline__ void ntt_fwd_smem_mids(u64 *sm, const ModInfo &M, u32 twbase, int tid, u64 qs = 0, u32 einv = 0) {
   typedef NttPlan<LOGN> P;
   const u64 q = M.q, aux = ar_aux<AR>(q);
@@ -678,12 +692,12 @@ __device__ __forceinline__ void ntt_fwd_smem_mids(u64 *sm, const ModInfo &M, u32
   if constexpr (LINSRC) ntt_fwd_mid<LOGN, P::R0, P::R0, AR, false, TT>(sm, tw, twbase, q, aux, tid, qinv);  // what-if: first pass as cheap as a plain one
   else
 #endif
-  ntt_fwd_mid<LOGN, 0, P::R0, AR, LINSRC, TT>(sm, tw, twbase, q, aux, tid, qinv, qs, einv);
+  ntt_fwd_mid<LOGN, 0, P::R0, AR, LINSRC, TT, PRECONV>(sm, tw, twbase, q, aux, tid, qinv, qs, einv);
   pass_sync<LOGN - P::R0, D::T>(tid);
   ntt_fwd_mid<LOGN, P::R0, P::R1, AR, false, TT>(sm, tw, twbase, q, aux, tid, qinv);
   pass_sync<LOGN - P::R0 - P::R1, D::T>(tid);
   if constexpr (UsePlan16<LOGN, AR, TT>::value) {
-    ntt_fwd_mid16<LOGN, AR>(sm, tw, q, aux, tid, qinv);
+    ntt_fwd_mid16<LOGN, AR>(sm, tw, q, aux, tid, qinv, twbase, AR == AR_F64 && f64_wide(q));
     __syncwarp();
   } else if constexpr (P::R2 > 0) {
     ntt_fwd_mid<LOGN, P::R0 + P::R1, P::R2, AR, false, TT>(sm, tw, twbase, q, aux, tid, qinv, 0, 0, AR == AR_F64 && f64_wide(q));
@@ -712,7 +726,7 @@ __device__ __forceinline__ void ntt_inv_smem_mids(u64 *sm, const ModInfo &M, u32
     // range plan (q < 0.97 * 2^45, lib.cu fill_mod): 3 contiguous stages leave |x| <= 4.1q; reduced here, the 4 + 3 stages
     // up to the next reduction reach 0.51q * 2^7 = 65.3q, so the last product operand stays below 2^51
     __syncwarp();
-    ntt_inv_mid16<LOGN, AR, true>(sm, (ABC_F64_TW_PAIRS ? M.itwp : M.itwd), q, aux, tid, f64_of(M.qinv_bits));
+    ntt_inv_mid16<LOGN, AR, true>(sm, (ABC_F64_TW_PAIRS ? M.itwp : M.itwd), q, aux, tid, f64_of(M.qinv_bits), twbase);
     pass_sync<LOGN - P::R0 - P::R1, D::T>(tid);
   } else {
     pass_sync<LOGN - P::R0 - P::R1 - P::R2, D::T>(tid);
