@@ -20,10 +20,11 @@
 
 namespace {
 
-constexpr int LG = 13, NG_LOG = 14;
-typedef NttDims<LG> D;                    // the block: 8192 coefficients, 512 threads, 64 KiB
-constexpr int NB = D::N, NGL = 2 * NB;    // block / whole-limb coefficient counts
+// LG = log2 of the block: 13 for N = 16384 (block = 8192 coefficients, 512 threads, 64 KiB); 12 for N = 8192, where the
+// split is used for SMALL batches only (B <= 8: twice as many, half as long rows fill more of the 148 SMs and the
+// critical path ModUp row -> special tail row -> data tail row shortens: batch-1 rotateRows 43 -> about 27 us)
 constexpr int AR = AR_F64;
+#define KS14_DIMS typedef NttDims<LG> D; constexpr int NB = D::N, NGL = 2 * NB, NP = NB / 2 / D::T;
 
 __device__ __forceinline__ void mbar_wait0(u32 mb) {
   u32 ok;
@@ -36,8 +37,10 @@ __device__ __forceinline__ double mulc(double x, double w, const ModInfo &M, u64
   return f64_of(mul_tw<AR>(bits_of(x), bits_of(w), M.qinv_bits, q, aux));
 }
 
-// ---- sigma(target limb J) as doubles, once per source limb.  grid (L, B), 1024 threads, 128 KiB
+// ---- sigma(target limb J) as doubles, once per source limb.  grid (L, B), 1024 threads, the whole limb in shared memory
+template <int LG>
 __global__ void __launch_bounds__(1024, 1) k_ks14_prep(Ks14 ks, const ModInfo *__restrict__ mods) {
+  KS14_DIMS; (void)NP;
   extern __shared__ __align__(128) u64 sm[];
   __shared__ __align__(8) u64 mbar;
   const int J = blockIdx.x, inst = blockIdx.y, tid = threadIdx.x;
@@ -57,8 +60,10 @@ __global__ void __launch_bounds__(1024, 1) k_ks14_prep(Ks14 ks, const ModInfo *_
 }
 
 // ---- ModUp half-row
+template <int LG>
 __device__ __forceinline__ void ks14_up(const Ks14 &ks, const ModInfo *__restrict__ mods, int inst, int I, int J, int h, u64 *sm,
                                         u64 *mbar) {
+  KS14_DIMS;
   const int tid = threadIdx.x;
   const ModInfo M = mods[I];
   const u64 q = M.q, aux = ar_aux<AR>(q);
@@ -73,16 +78,16 @@ __device__ __forceinline__ void ks14_up(const Ks14 &ks, const ModInfo *__restric
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"((u32)__cvta_generic_to_shared(sm)), "l"(srow + NB), "r"((u32)D::SMEM), "r"(mb) : "memory");
   }
-  double2 a[8];
+  double2 a[NP];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) a[i] = __ldcs(reinterpret_cast<const double2 *>(srow) + tid + i * D::T);
+  for (int i = 0; i < NP; ++i) a[i] = __ldcs(reinterpret_cast<const double2 *>(srow) + tid + i * D::T);
   const double w0 = f64_of(__ldg(reinterpret_cast<const u64 *>(M.twd) + 1));   // the single twiddle of stage 0
   const u64 qs = mods[J].q;
   const bool red_in = qs >= ABC_F64_NARROW_MAX && qs > q;   // a wide source prime above the target: reduce first (ntt.cuh range plan)
   __syncthreads();   // the barrier object is initialised before anyone polls it
   mbar_wait0(mb);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < NP; ++i) {
     double2 b = *reinterpret_cast<const double2 *>(&sm[2 * (tid + i * D::T)]);
     if (red_in) {
       a[i].x = reduce_f64(a[i].x, qinv, qd); a[i].y = reduce_f64(a[i].y, qinv, qd);
@@ -94,7 +99,7 @@ __device__ __forceinline__ void ks14_up(const Ks14 &ks, const ModInfo *__restric
   }
   __syncthreads();   // every thread has taken its b's: the buffer becomes the swizzled block
 #pragma unroll
-  for (int i = 0; i < 8; ++i) *reinterpret_cast<double2 *>(&sm[swz_pair(tid, tid + i * D::T)]) = a[i];
+  for (int i = 0; i < NP; ++i) *reinterpret_cast<double2 *>(&sm[swz_pair(tid, tid + i * D::T)]) = a[i];
   __syncthreads();
   ntt_fwd_smem_mids<LG, AR, false, 0, true>(sm, M, twbase, tid);
   ntt_fwd_last<LG, AR, 0, true>(sm, M, twbase, q, aux, tid);
@@ -112,8 +117,10 @@ __device__ __forceinline__ void ks14_up(const Ks14 &ks, const ModInfo *__restric
 }
 
 // ---- tail half-row
+template <int LG>
 __device__ __forceinline__ void ks14_tail(const Ks14 &ks, const ModInfo *__restrict__ mods, int inst, int I, int comp, int h,
                                           u64 *sm) {
+  KS14_DIMS;
   const int tid = threadIdx.x;
   const ModInfo M = mods[I];
   const u64 q = M.q, aux = ar_aux<AR>(q);
@@ -215,32 +222,44 @@ __device__ __forceinline__ void ks14_tail(const Ks14 &ks, const ModInfo *__restr
   }
 }
 
-__global__ void __launch_bounds__(D::T, D::MINB) k_ks14(Ks14 ks, const ModInfo *__restrict__ mods) {
+template <int LG>
+__global__ void __launch_bounds__(NttDims<LG>::T, NttDims<LG>::MINB) k_ks14(Ks14 ks, const ModInfo *__restrict__ mods) {
   extern __shared__ __align__(128) u64 sm[];
   __shared__ __align__(8) u64 mbar;
   const uint2 s = __ldg(ks.sched + grid_ticket(ks.ticket, ks.ticket_base));
   const int inst = (int)(s.x & 0x3fffffffu), h = (int)((s.x >> 30) & 1u), I = (int)((s.y >> 8) & 0xff);
-  if ((s.x >> 31) == 0) ks14_up(ks, mods, inst, I, (int)(s.y >> 24), h, sm, &mbar);
-  else ks14_tail(ks, mods, inst, I, (int)(s.y >> 24) >= ks.k ? 1 : 0, h, sm);
+  if ((s.x >> 31) == 0) ks14_up<LG>(ks, mods, inst, I, (int)(s.y >> 24), h, sm, &mbar);
+  else ks14_tail<LG>(ks, mods, inst, I, (int)(s.y >> 24) >= ks.k ? 1 : 0, h, sm);
 }
 
-}  // namespace
 
-int ks14_prep_launch(const Ks14 &ks, const ModInfo *mods, cudaStream_t stream) {
+
+template <int LG> int prep_launch(const Ks14 &ks, const ModInfo *mods, cudaStream_t stream) {
+  KS14_DIMS; (void)NP;
   static bool done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!done[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(k_ks14_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, NGL * 8);
+    cudaError_t e = cudaFuncSetAttribute(k_ks14_prep<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, NGL * 8);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(k_ks14, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::SMEM);
+    e = cudaFuncSetAttribute(k_ks14<LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::SMEM);
     if (e != cudaSuccess) return (int)e;
     done[dev & 63] = true;
   }
-  k_ks14_prep<<<dim3(ks.L, ks.B), 1024, NGL * 8, stream>>>(ks, mods);
+  k_ks14_prep<LG><<<dim3(ks.L, ks.B), 1024, NGL * 8, stream>>>(ks, mods);
   return (int)cudaGetLastError();
 }
-int ks14_launch(const Ks14 &ks, const ModInfo *mods, cudaStream_t stream) {
-  k_ks14<<<(unsigned)ks.n_blocks, D::T, D::SMEM, stream>>>(ks, mods);
+template <int LG> int main_launch(const Ks14 &ks, const ModInfo *mods, cudaStream_t stream) {
+  k_ks14<LG><<<(unsigned)ks.n_blocks, NttDims<LG>::T, NttDims<LG>::SMEM, stream>>>(ks, mods);
   return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// logN = log2 of the whole limb: 14 (blocks of 8192) or 13 (blocks of 4096)
+int ks14_prep_launch(int logN, const Ks14 &ks, const ModInfo *mods, cudaStream_t stream) {
+  return logN == 14 ? prep_launch<13>(ks, mods, stream) : logN == 13 ? prep_launch<12>(ks, mods, stream) : (int)cudaErrorInvalidValue;
+}
+int ks14_launch(int logN, const Ks14 &ks, const ModInfo *mods, cudaStream_t stream) {
+  return logN == 14 ? main_launch<13>(ks, mods, stream) : logN == 13 ? main_launch<12>(ks, mods, stream) : (int)cudaErrorInvalidValue;
 }

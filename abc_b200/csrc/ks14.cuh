@@ -25,5 +25,6 @@ struct Ks14 {
 };
 
 // returns a cudaError_t as int
-int ks14_prep_launch(const Ks14 &ks, const ModInfo *mods, cudaStream_t stream);
-int ks14_launch(const Ks14 &ks, const ModInfo *mods, cudaStream_t stream);
+// logN = log2 of the whole limb: 14 (rows of 8192-coefficient blocks) or 13 (4096-coefficient blocks, small batches)
+int ks14_prep_launch(int logN, const Ks14 &ks, const ModInfo *mods, cudaStream_t stream);
+int ks14_launch(int logN, const Ks14 &ks, const ModInfo *mods, cudaStream_t stream);

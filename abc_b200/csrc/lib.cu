@@ -117,6 +117,7 @@ struct abc_ctx {
   // ABC_KS_RED=1 selects it; measured 9 % slower than the chained grid at N = 8192 (the bulk reductions wait on the L2 atomic units)
   int ks_red = 0, ksr_ring = 0; double *ksr_acc = nullptr; u32 *ksr_done = nullptr, *ksr_freed = nullptr; u32 ksr_serial = 0;
   // split key switch at N = 16384 (ks14.cu): schedule of half-rows, [B][k][2] done + [B][2k][2] exchange + [B][2][2] special flags
+  int ks_split_maxb = 8;   // ABC_KS_SPLIT_MAXB: N = 8192 contexts of at most this many instances use the split rows too (latency)
   int ks14 = 1; uint2 *ks14_sched = nullptr; int ks14_sched_n = 0; u32 *ks14_done = nullptr, *ks14_xflag = nullptr, *ks14_flags = nullptr;
   u32 ks14_serial = 0;
   u32 *ks_ticket = nullptr; u32 ks_ticket_total = 0;                          // start-order tickets of the dependency-ordered grids (limb.cuh grid_ticket)
@@ -407,6 +408,7 @@ abc_status build_tables(abc_ctx *c) {
   if (const char *e = getenv("ABC_KS_CHAIN")) c->ks_chain = atoi(e);
   if (const char *e = getenv("ABC_KS_RED")) c->ks_red = atoi(e);
   if (const char *e = getenv("ABC_KS14_SPLIT")) c->ks14 = atoi(e);
+  if (const char *e = getenv("ABC_KS_SPLIT_MAXB")) c->ks_split_maxb = atoi(e);
   if (const char *e = getenv("ABC_BEHZ_FUSED")) c->behz_fused = atoi(e) != 0;
   if (const char *e = getenv("ABC_KS_CHAIN_SKEW")) c->ks_chain_skew = atoi(e) < 1 ? 1 : atoi(e);
   if (const char *e = getenv("ABC_KS1_THREADS")) c->ks1_threads = atoi(e);
@@ -640,7 +642,10 @@ abc_status build_shard_maps(abc_ctx *c) {
     c->ksr_serial = 0;
     }
   }
-  if (nown > 0 && c->logN == 14 && c->ks14 && c->ks_nI * L < 256 && 2 * k < 256) {
+  // N = 8192: measured per batch (tools/ks_time.py, us per rotateRows, split vs chained): 1-2: 28.7 vs 32.8; 3-4: 34-37 vs 33;
+  // 6: 37 vs 44; 8: 37 vs 47 -> split rows for B <= 2 and 5 <= B <= ks_split_maxb
+  const bool split13 = c->logN == 13 && c->ks_split_maxb > 0 && (c->B <= 2 || (c->B >= 5 && c->B <= c->ks_split_maxb));
+  if (nown > 0 && ((c->logN == 14 && c->ks14) || split13) && c->ks_nI * L < 256 && 2 * k < 256) {
     // split key switch (ks14.cu): the chained schedule with every row as two half-rows holding adjacent tickets
     const int Bn = c->B;
     const size_t t_bytes = (size_t)c->ks_nI * L * c->N * 8;
@@ -894,7 +899,8 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   const int t_image = fused && c->logN <= 14 && !c->ks_no_image ? 1 : 0;  // T rows as bulk-stored images of the swizzled limb
   const bool chain = t_image && c->ks_chain && c->ks_sched && c->logN <= 14 && c->force_ar < 0;
   const bool red = chain && c->ks_red && c->ksr_acc && c->logN <= 13;   // no ModUp block at all (ksred.cu)
-  if (chain && c->logN == 14 && c->ks14 && c->ks14_sched) {   // N = 16384: rows of half a limb, two CTAs per SM (ks14.cu)
+  if (chain && c->ks14_sched && (c->logN == 14 || c->logN == 13) && c->ks_one_launch != 1 && !c->ks_red) {
+    // rows of half a limb (ks14.cu): N = 16384 (two CTAs per SM instead of one), N = 8192 at small batch (latency)
     if (gather_ct && c->world > 1) TRY(allgather_limbs(c, gather_ct, 2));
     Ks14 kq;
     memset(&kq, 0, sizeof kq);
@@ -918,11 +924,11 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
     kq.C = c->dC; kq.L = L; kq.k = k; kq.B = B;
     {
       Launch l(c, "ks14_prep");
-      const int e = ks14_prep_launch(kq, c->d_mods, c->stream);
+      const int e = ks14_prep_launch(c->logN, kq, c->d_mods, c->stream);
       if (e != 0) { c->err = std::string("ks14_prep: ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
     }
     Launch l(c, einv ? "ks14" : "ks14_relin");
-    const int e = ks14_launch(kq, c->d_mods, c->stream);
+    const int e = ks14_launch(c->logN, kq, c->d_mods, c->stream);
     if (e != 0) { c->err = std::string("ks14: ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
     return ABC_OK;
   }

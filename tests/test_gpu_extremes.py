@@ -70,7 +70,7 @@ def _galois_coeff(poly, elt, q):
     return out
 
 
-KS_PATHS = {"default": {}, "two_launch": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAIN": "0"},
+KS_PATHS = {"default": {}, "chained": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_SPLIT_MAXB": "0"}, "two_launch": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAIN": "0"},
             "one_launch": {"ABC_KS_ONE_LAUNCH": "1"}, "accumulating": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_RED": "1"}}
 
 
