@@ -23,6 +23,7 @@ void CudaCiphertextFactory::setup(int device, unsigned int batch, uint64_t seed)
   if (abc_ctx_create(&p, &ctx) != ABC_OK) {
     throw std::runtime_error(std::string("CudaCiphertextFactory: ") + abc_last_error(nullptr));
   }
+  st->ctx = ctx;
   check(abc_keygen(ctx));
 }
 
@@ -42,17 +43,17 @@ CudaCiphertextFactory::CudaCiphertextFactory(unsigned int numElementsPerCipherte
   setup(device, batch, seed);
 }
 
-CudaCiphertextFactory::~CudaCiphertextFactory() {
-  releaseBatchTables();
+CudaCiphertextFactory::State::~State() {
+  for (auto &t : batchTables) abc_host_unregister(t.data());
   abc_host_free(pinnedOut);
-  abc_ctx_destroy(ctx);
+  abc_ctx_destroy(ctx);   // completed by the last live ciphertext handle, if any (abc_b200.h)
 }
 
 void CudaCiphertextFactory::releaseBatchTables() const {
-  for (auto &t : batchTables) abc_host_unregister(t.data());
-  batchTables.clear();
-  batchTableWidth.clear();
-  nextBatchTable = 0;
+  for (auto &t : st->batchTables) abc_host_unregister(t.data());
+  st->batchTables.clear();
+  st->batchTableWidth.clear();
+  st->nextBatchTable = 0;
 }
 
 std::unique_ptr<AbstractCiphertext> CudaCiphertextFactory::loadCiphertext(const std::vector<uint8_t> &sealStream,
@@ -111,11 +112,11 @@ std::unique_ptr<AbstractCiphertext> CudaCiphertextFactory::createCiphertext(
     std::unique_ptr<AbstractValue> &&abstractValue) const {
   if (auto castedCleartext = dynamic_cast<Cleartext<int> *>(abstractValue.get())) {
     auto castedCleartextData = castedCleartext->getData();
-    if (nextBatchTable < batchTables.size()) {   // lock-step batch: this declaration's values for every instance
+    if (st->nextBatchTable < st->batchTables.size()) {   // lock-step batch: this declaration's values for every instance
       // the table decides the values AND their count: the literal in the program text is a placeholder (a one-element
       // literal keeps the interpreter from evaluating thousands of LiteralInt nodes per declaration: 28 ms each at n = 4096)
-      const size_t d = nextBatchTable++;
-      return createCiphertextBatch(batchTables[d], batchTableWidth[d]);
+      const size_t d = st->nextBatchTable++;
+      return createCiphertextBatch(st->batchTables[d], st->batchTableWidth[d]);
     }
     std::vector<int64_t> data(castedCleartextData.begin(), castedCleartextData.end());
     return createCiphertext(data);
@@ -132,22 +133,22 @@ void CudaCiphertextFactory::setBatchInputs(std::vector<std::vector<int64_t>> tab
     widths.push_back(t.size() / B);
   }
   releaseBatchTables();
-  batchTableWidth = std::move(widths);
-  batchTables = std::move(tables);
-  for (auto &t : batchTables) check(abc_host_register(ctx, t.data(), t.size() * sizeof(int64_t)));   // H2D straight from the tables
-  nextBatchTable = 0;
+  st->batchTableWidth = std::move(widths);
+  st->batchTables = std::move(tables);
+  for (auto &t : st->batchTables) check(abc_host_register(ctx, t.data(), t.size() * sizeof(int64_t)));   // H2D straight from the tables
+  st->nextBatchTable = 0;
 }
 
 const int64_t *CudaCiphertextFactory::decryptCiphertextBatchPinnedAsync(AbstractCiphertext &abstractCiphertext) const {
   auto c = dynamic_cast<CudaCiphertext *>(&abstractCiphertext);
   if (!c) throw std::runtime_error("Cast of AbstractCiphertext to CudaCiphertext failed!");
   const size_t words = static_cast<size_t>(getBatchSize()) * ciphertextSlotSize;
-  if (!pinnedOut) {
+  if (!st->pinnedOut) {
     void *p = nullptr;
     check(abc_host_alloc(ctx, 2 * words * sizeof(int64_t), &p));
-    pinnedOut = static_cast<int64_t *>(p);
+    st->pinnedOut = static_cast<int64_t *>(p);
   }
-  int64_t *dst = pinnedOut + (pinnedNext++ & 1u) * words;
+  int64_t *dst = st->pinnedOut + (st->pinnedNext++ & 1u) * words;
   check(abc_decrypt_decode_async(ctx, c->getHandle(), dst));
   return dst;
 }

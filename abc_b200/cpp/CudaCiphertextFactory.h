@@ -23,17 +23,21 @@ class CudaCiphertextFactory : public AbstractCiphertextFactory {
  private:
   /// The number of slots (= polynomial degree N) of every ciphertext created by this factory.
   const unsigned int ciphertextSlotSize = 16'384;  // same default as SealCiphertextFactory.h:13
-  /// Device context: parameters, NTT tables, keys, stream.  All factory virtuals are const, so the
-  /// mutable device state lives behind this pointer.
-  abc_ctx *ctx = nullptr;
-
-  /// Lock-step batch driver: per-instance values of the next `secret` declarations, in declaration order.
-  /// The factory virtuals are const (RuntimeVisitor holds a const reference), hence mutable.
-  mutable std::vector<std::vector<int64_t>> batchTables;   // [declaration][batch * n], instance-major
-  mutable std::vector<size_t> batchTableWidth;             // n of each table
-  mutable size_t nextBatchTable = 0;
-  mutable int64_t *pinnedOut = nullptr;                    // page-locked 2 x batch * N slots: decryptCiphertextBatchPinned
-  mutable unsigned pinnedNext = 0;
+  /// Device context (parameters, NTT tables, keys, stream) and the factory's host-side staging, shared between copies of
+  /// the factory: like SealCiphertextFactory, this class is copy-constructible — a copy refers to the same keys on the
+  /// same device.  All factory virtuals are const, so the mutable state lives behind this pointer.
+  struct State {
+    abc_ctx *ctx = nullptr;
+    // lock-step batch driver: per-instance values of the next `secret` declarations, in declaration order
+    std::vector<std::vector<int64_t>> batchTables;   // [declaration][batch * n], instance-major
+    std::vector<size_t> batchTableWidth;             // n of each table
+    size_t nextBatchTable = 0;
+    int64_t *pinnedOut = nullptr;                    // page-locked 2 x batch * N slots: decryptCiphertextBatchPinned
+    unsigned pinnedNext = 0;
+    ~State();
+  };
+  std::shared_ptr<State> st = std::make_shared<State>();
+  abc_ctx *ctx = nullptr;                            // = st->ctx
   void releaseBatchTables() const;
 
   void setup(int device, unsigned int batch, uint64_t seed);
@@ -44,10 +48,10 @@ class CudaCiphertextFactory : public AbstractCiphertextFactory {
   explicit CudaCiphertextFactory(unsigned int numElementsPerCiphertextSlot);
   /// Extended constructor: device ordinal, instances per handle (lock-step batch), sampler seed.
   CudaCiphertextFactory(unsigned int numElementsPerCiphertextSlot, int device, unsigned int batch, uint64_t seed);
-  ~CudaCiphertextFactory();
-
-  CudaCiphertextFactory(const CudaCiphertextFactory &) = delete;  // keys live on one device: not copyable
-  CudaCiphertextFactory &operator=(const CudaCiphertextFactory &) = delete;
+  ~CudaCiphertextFactory() = default;
+  /// A copy shares the device context (keys, stream) with the original; the context goes when the last copy — and the last
+  /// ciphertext created through it — is gone.  One host thread at a time per context (copies included).
+  CudaCiphertextFactory(const CudaCiphertextFactory &) = default;
 
   std::unique_ptr<AbstractCiphertext> createCiphertext(const std::vector<int64_t> &data) const override;
   std::unique_ptr<AbstractCiphertext> createCiphertext(const std::vector<int> &data) const override;
@@ -68,7 +72,7 @@ class CudaCiphertextFactory : public AbstractCiphertextFactory {
   /// last table broadcast their literal to every instance as before.
   void setBatchInputs(std::vector<std::vector<int64_t>> tables) const;
   /// The next interpreter walk starts again at the first registered table (same inputs, e.g. a timed repetition).
-  void rewindBatchInputs() const { nextBatchTable = 0; }
+  void rewindBatchInputs() const { st->nextBatchTable = 0; }
   /// Batched variants: data holds batch*n slot values (instance-major); out gets batch*N values.
   std::unique_ptr<AbstractCiphertext> createCiphertextBatch(const std::vector<int64_t> &data, size_t n) const;
   void decryptCiphertextBatch(AbstractCiphertext &abstractCiphertext, std::vector<int64_t> &out) const;

@@ -4,7 +4,13 @@
 #include "../../include/abc_b200.h"
 
 #include <dlfcn.h>
-#include <nccl.h>
+// NCCL is loaded with dlopen on first use (limb sharding only), so the library builds and runs without NCCL installed: the
+// few types of its C API this file needs are declared here (values as in nccl.h 2.x: ncclSuccess = 0, ncclUint64 = 5,
+// ncclUniqueId = 128 opaque bytes)
+typedef struct ncclComm *ncclComm_t;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclUint64 = 5 } ncclDataType_t;
+typedef struct { char internal[128]; } ncclUniqueId;
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges are no-ops unless a profiler is attached
 #include <sys/random.h>
 
@@ -121,6 +127,9 @@ struct abc_ctx {
   int ks14 = 1; uint2 *ks14_sched = nullptr; int ks14_sched_n = 0; u32 *ks14_done = nullptr, *ks14_xflag = nullptr, *ks14_flags = nullptr;
   u32 ks14_serial = 0;
   u32 *ks_ticket = nullptr; u32 ks_ticket_total = 0;                          // start-order tickets of the dependency-ordered grids (limb.cuh grid_ticket)
+  // handles (abc_ct / abc_pt) keep their context alive: abc_ctx_destroy with live handles only marks it, the last
+  // abc_ct_free / abc_pt_free completes the destruction (a ciphertext may outlive its factory, as with SealCiphertext)
+  long live_handles = 0; bool zombie = false;
   bool faulted = false;                                                       // sticky: a dependency wait timed out; every later call fails until abc_clear_fault
   int *rs_zero = nullptr;   // [2k]  0
   u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;
@@ -644,7 +653,8 @@ abc_status build_shard_maps(abc_ctx *c) {
   }
   // N = 8192: measured per batch (tools/ks_time.py, us per rotateRows, split vs chained): 1-2: 28.7 vs 32.8; 3-4: 34-37 vs 33;
   // 6: 37 vs 44; 8: 37 vs 47 -> split rows for B <= 2 and 5 <= B <= ks_split_maxb
-  const bool split13 = c->logN == 13 && c->ks_split_maxb > 0 && (c->B <= 2 || (c->B >= 5 && c->B <= c->ks_split_maxb));
+  const bool split13 = c->logN == 13 && c->ks_split_maxb > 0 &&
+                       (c->B <= 2 || (c->B >= 5 && c->B <= c->ks_split_maxb) || getenv("ABC_KS_SPLIT_FORCE") != nullptr);
   if (nown > 0 && ((c->logN == 14 && c->ks14) || split13) && c->ks_nI * L < 256 && 2 * k < 256) {
     // split key switch (ks14.cu): the chained schedule with every row as two half-rows holding adjacent tickets
     const int Bn = c->B;
@@ -1409,6 +1419,7 @@ abc_status abc_ctx_create(const abc_params *p, abc_ctx **out) {
 
 void abc_ctx_destroy(abc_ctx *c) {
   if (!c) return;
+  if (c->live_handles > 0) { c->zombie = true; return; }   // completed by the last handle's free
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); }
@@ -1586,6 +1597,7 @@ abc_status abc_ct_alloc(abc_ctx *c, abc_ct **out) {
   TRY(salloc(c, &d, abc_ct_words(c)));
   CtBuf *b = new CtBuf; b->d = d;
   *out = new abc_ct{c, b};
+  ++c->live_handles;
   return ABC_OK;
 }
 // drop one reference to a buffer (stream-ordered free when it was the last one)
@@ -1637,16 +1649,22 @@ static abc_status ct_make_private(abc_ctx *c, abc_ct *dst) {
   ct_adopt(dst, d);
   return ABC_OK;
 }
+static void handle_released(abc_ctx *c) {
+  if (--c->live_handles == 0 && c->zombie) abc_ctx_destroy(c);
+}
 void abc_ct_free(abc_ct *ct) {
   if (!ct) return;
-  buf_unref(ct->ctx, ct->b);
+  abc_ctx *c = ct->ctx;
+  buf_unref(c, ct->b);
   delete ct;
+  handle_released(c);
 }
 size_t abc_ct_words(const abc_ctx *c) { return (size_t)c->B * ct_words1(c); }
 abc_status abc_ct_clone(abc_ctx *c, const abc_ct *src, abc_ct **out) {
   if (!valid_ct(c, src)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
   ++src->b->refs;
   *out = new abc_ct{c, src->b};
+  ++c->live_handles;
   return ABC_OK;
 }
 int abc_ct_shared(const abc_ct *ct) { return ct && ct->b ? ct->b->refs : 0; }
@@ -1696,12 +1714,15 @@ abc_status abc_pt_encode(abc_ctx *c, const int64_t *slots, size_t n, int broadca
   u64 *plain = nullptr;
   TRY(encode_device(c, slots, n, broadcast, &plain));
   *out = new abc_pt{c, plain, broadcast};
+  ++c->live_handles;
   return ABC_OK;
 }
 void abc_pt_free(abc_pt *pt) {
   if (!pt) return;
-  sfree(pt->ctx, pt->d);
+  abc_ctx *c = pt->ctx;
+  sfree(c, pt->d);
   delete pt;
+  handle_released(c);
 }
 abc_status abc_encrypt_pt(abc_ctx *c, const abc_pt *pt, abc_ct **out) {
   if (!pt || pt->ctx != c) return fail(c, ABC_ERR_PARAM, "invalid plaintext handle");

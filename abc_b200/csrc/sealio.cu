@@ -142,25 +142,34 @@ bool deflate_all(const std::vector<unsigned char> &in, std::vector<unsigned char
   out.resize(cap);
   return true;
 }
-bool inflate_all(const unsigned char *in, size_t n, std::vector<unsigned char> &out, std::string &err) {
+// Streams are untrusted input: the decompressed size is capped (max_out: the largest record this context can legally hold,
+// see max_record_bytes) so a decompression bomb cannot exhaust host memory, and zlib is fed in pieces below UINT_MAX so
+// streams of 4 GiB or more are not silently truncated.
+bool inflate_all(const unsigned char *in, size_t n, std::vector<unsigned char> &out, std::string &err, size_t max_out) {
   z_stream z;
   memset(&z, 0, sizeof z);
   if (inflateInit(&z) != Z_OK) { err = "zlib init failed"; return false; }
-  z.next_in = const_cast<unsigned char *>(in); z.avail_in = (uInt)n;
   out.clear();
   unsigned char chunk[1 << 16];
+  size_t fed = 0;
   int r = Z_OK;
   while (r != Z_STREAM_END) {
+    if (z.avail_in == 0 && fed < n) {
+      const size_t piece = std::min<size_t>(n - fed, (size_t)1 << 30);
+      z.next_in = const_cast<unsigned char *>(in + fed); z.avail_in = (uInt)piece;
+      fed += piece;
+    }
     z.next_out = chunk; z.avail_out = sizeof chunk;
     r = inflate(&z, Z_NO_FLUSH);
     if (r != Z_OK && r != Z_STREAM_END) { inflateEnd(&z); err = "zlib stream corrupt"; return false; }
     out.insert(out.end(), chunk, chunk + (sizeof chunk - z.avail_out));
-    if (r == Z_OK && z.avail_in == 0 && z.avail_out != 0) { inflateEnd(&z); err = "zlib stream truncated"; return false; }
+    if (out.size() > max_out) { inflateEnd(&z); err = "compressed SEAL record expands beyond the largest record of this parameter set"; return false; }
+    if (r == Z_OK && z.avail_in == 0 && fed == n && z.avail_out != 0) { inflateEnd(&z); err = "zlib stream truncated"; return false; }
   }
   inflateEnd(&z);
   return true;
 }
-bool unzstd_all(const unsigned char *in, size_t n, std::vector<unsigned char> &out, std::string &err) {
+bool unzstd_all(const unsigned char *in, size_t n, std::vector<unsigned char> &out, std::string &err, size_t max_out) {
   if (!g_zstd.load()) { err = "zstd-compressed SEAL stream, and libzstd.so.1 is not loadable here"; return false; }
   void *ds = g_zstd.cds();
   ZBuf ib{in, n, 0};
@@ -171,10 +180,20 @@ bool unzstd_all(const unsigned char *in, size_t n, std::vector<unsigned char> &o
     const size_t r = g_zstd.ds(ds, &ob, &ib);
     if (g_zstd.iserr(r)) { g_zstd.fds(ds); err = "zstd stream corrupt"; return false; }
     out.insert(out.end(), chunk.data(), chunk.data() + ob.pos);
+    if (out.size() > max_out) { g_zstd.fds(ds); err = "compressed SEAL record expands beyond the largest record of this parameter set"; return false; }
     if (r == 0 && ib.pos < ib.size) continue;  // next frame
   }
   g_zstd.fds(ds);
   return true;
+}
+// the largest record a context can legally load: a Galois key set (2 * log2(N) keys of L * 2 * k * N words) plus headers;
+// without a context (parameter streams) a parameter record is a few hundred bytes
+size_t max_record_bytes(const abc_ctx *c) {
+  if (!c) return (size_t)1 << 20;
+  const size_t N = abc_poly_degree(c), k = abc_n_primes(c), L = abc_n_limbs(c);
+  size_t logn = 0;
+  while (((size_t)1 << logn) < N) ++logn;
+  return (2 * logn + 2) * (L * 2 * k * N * 8 + 4096) + ((size_t)1 << 20);
 }
 
 // outermost record: body bytes -> stream (with the requested compr_mode)
@@ -213,8 +232,8 @@ abc_status open_record(abc_ctx *c, const uint8_t *bytes, size_t len, std::vector
   const unsigned compr = bytes[5];
   std::string err;
   if (compr == ABC_SEAL_COMPR_NONE) body.assign(bytes + 16, bytes + size);
-  else if (compr == ABC_SEAL_COMPR_ZLIB) { if (!inflate_all(bytes + 16, size - 16, body, err)) return bad(err.c_str()); }
-  else if (compr == ABC_SEAL_COMPR_ZSTD) { if (!unzstd_all(bytes + 16, size - 16, body, err)) return bad(err.c_str()); }
+  else if (compr == ABC_SEAL_COMPR_ZLIB) { if (!inflate_all(bytes + 16, size - 16, body, err, max_record_bytes(c))) return bad(err.c_str()); }
+  else if (compr == ABC_SEAL_COMPR_ZSTD) { if (!unzstd_all(bytes + 16, size - 16, body, err, max_record_bytes(c))) return bad(err.c_str()); }
   else return bad("unknown compr_mode in SEAL record");
   return ABC_OK;
 }

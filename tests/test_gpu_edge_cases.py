@@ -177,7 +177,7 @@ KS_VARIANTS = {
     "one_launch": {"ABC_KS_ONE_LAUNCH": "1"},                                   # ksfused.cu: accumulators in shared memory
     "chained": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAIN": "1", "ABC_KS_SPLIT_MAXB": "0"},   # kschain.cu: ModUp + tail rows in one grid
     "accumulating": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAIN": "1", "ABC_KS_RED": "1"},  # ksred.cu: ModUp rows bulk-reduce into the accumulators
-    "split_rows": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAIN": "1", "ABC_KS_SPLIT_MAXB": "8"},  # ks14.cu: rows of half a limb (N = 8192 at batch <= 8)
+    "split_rows": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAIN": "1", "ABC_KS_SPLIT_MAXB": "8", "ABC_KS_SPLIT_FORCE": "1"},  # ks14.cu: rows of half a limb (N = 8192 at batch <= 8)
     "two_launch": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAIN": "0"},              # ModUp launch, tail launch (T as images)
     "two_launch_canonical_T": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAIN": "0", "ABC_KS_NO_IMAGE": "1"},
     "unfused_tail": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_UNFUSED": "1"},          # separate inner-product kernel
