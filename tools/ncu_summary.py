@@ -25,7 +25,11 @@ WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_selected_per_issue_active.ratio']
+        'smsp__average_warps_issue_stalled_selected_per_issue_active.ratio',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed', 'smsp__warps_eligible.avg.per_cycle_active',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__cycles_active.avg', 'sm__throughput.avg.pct_of_peak_sustained_elapsed']
 
 
 def main(path):
