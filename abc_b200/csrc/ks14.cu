@@ -234,6 +234,123 @@ __global__ void __launch_bounds__(NttDims<LG>::T, NttDims<LG>::MINB) k_ks14(Ks14
 
 
 
+// ---------------------------------------------------------------- BEHZ block at N = 16384 (LG = 13 only)
+// forward half-row: grid = B * np * W * 2 blocks, block index -> (inst, w, h) by ticket (no cross-row dependencies, but the
+// same launch shape as the inverse rows)
+__global__ void __launch_bounds__(NttDims<13>::T, NttDims<13>::MINB) k_behz14_fwd(Behz14 bz, const ModInfo *__restrict__ mods) {
+  constexpr int LG = 13;
+  KS14_DIMS;
+  extern __shared__ __align__(128) u64 sm[];
+  __shared__ __align__(8) u64 mbar;
+  const int tid = threadIdx.x;
+  const unsigned blk = blockIdx.x;
+  const int h = (int)(blk & 1u), w = (int)((blk >> 1) % (unsigned)(bz.np * bz.W)), inst = (int)((blk >> 1) / (unsigned)(bz.np * bz.W));
+  const int p = w / bz.W, r = w - p * bz.W;
+  const ModInfo M = mods[bz.rowmod[w]];
+  const u64 q = M.q, aux = ar_aux<AR>(q);
+  const u32 twbase = 2u + (u32)h;
+  const u64 *src = r < bz.L ? (p < 2 ? bz.a : bz.b) + (((size_t)inst * 2 + (p & 1)) * bz.L + r) * NGL
+                            : bz.X + (size_t)inst * bz.X_is + (size_t)w * NGL;
+  const u32 mb = (u32)__cvta_generic_to_shared(&mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((u32)D::SMEM) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((u32)__cvta_generic_to_shared(sm)), "l"(src + NB), "r"((u32)D::SMEM), "r"(mb) : "memory");
+  }
+  ulonglong2 a[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) a[i] = __ldcs(reinterpret_cast<const ulonglong2 *>(src) + tid + i * D::T);
+  const double w0 = f64_of(__ldg(reinterpret_cast<const u64 *>(M.twd) + 1));
+  __syncthreads();
+  mbar_wait0(mb);
+  double2 y[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const ulonglong2 b = *reinterpret_cast<const ulonglong2 *>(&sm[2 * (tid + i * D::T)]);
+    const double ax = f64_of(ar_from_canon<AR>(a[i].x)), ay = f64_of(ar_from_canon<AR>(a[i].y));
+    const double px = mulc(f64_of(ar_from_canon<AR>(b.x)), w0, M, q, aux), py = mulc(f64_of(ar_from_canon<AR>(b.y)), w0, M, q, aux);
+    y[i] = make_double2(h ? ax - px : ax + px, h ? ay - py : ay + py);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NP; ++i) *reinterpret_cast<double2 *>(&sm[swz_pair(tid, tid + i * D::T)]) = y[i];
+  __syncthreads();
+  ntt_fwd_smem_mids<LG, AR, false, 0, true>(sm, M, twbase, tid);
+  ntt_fwd_last<LG, AR, 0, true>(sm, M, twbase, q, aux, tid, true);   // raw, reduced to |x| <= 0.5 q: the images feed products
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    u64 *g = bz.XI + (size_t)inst * bz.XI_is + (size_t)w * NGL + (size_t)h * NB;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(g), "r"((u32)__cvta_generic_to_shared(sm)), "r"((u32)D::SMEM) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+}
+
+// inverse half-row with the tensor product in its load
+__global__ void __launch_bounds__(NttDims<13>::T, NttDims<13>::MINB) k_behz14_inv(Behz14 bz, const ModInfo *__restrict__ mods) {
+  constexpr int LG = 13;
+  KS14_DIMS; (void)NP;
+  extern __shared__ __align__(128) u64 sm[];
+  const int tid = threadIdx.x;
+  const unsigned blk = grid_ticket(bz.ticket, bz.ticket_base);   // partner blocks hold adjacent tickets
+  const int h = (int)(blk & 1u), w = (int)((blk >> 1) % (unsigned)(3 * bz.W)), inst = (int)((blk >> 1) / (unsigned)(3 * bz.W));
+  const int p = w / bz.W, r = w - p * bz.W;
+  const ModInfo M = mods[bz.rowmod[w]];
+  const u64 q = M.q, aux = ar_aux<AR>(q);
+  const double qinv = f64_of(M.qinv_bits), qd = f64_of(aux);
+  const u32 twbase = 2u + (u32)h;
+  {
+    // operand images: row (poly * W + r) of the image block, block h
+    const double2 *a0 = reinterpret_cast<const double2 *>(bz.XI + (size_t)inst * bz.XI_is + (size_t)r * NGL + (size_t)h * NB);
+    const size_t ps = (size_t)bz.W * (NGL / 2);
+    const double2 *a1 = a0 + ps, *b0 = bz.square ? a0 : a0 + 2 * ps, *b1 = bz.square ? a1 : a0 + 3 * ps;
+    const double2 *x = p == 2 ? a1 : a0, *y = p == 0 ? b0 : b1;
+    for (int j = tid; j < NB / 2; j += D::T) {
+      const double2 xv = __ldcs(x + j), yv = __ldcs(y + j);
+      double2 o = make_double2(mulc(xv.x, yv.x, M, q, aux), mulc(xv.y, yv.y, M, q, aux));
+      if (p == 1) {
+        if (bz.square) { o.x += o.x; o.y += o.y; }
+        else {
+          const double2 uv = __ldcs(a1 + j), vv = __ldcs(b0 + j);
+          o.x += mulc(uv.x, vv.x, M, q, aux); o.y += mulc(uv.y, vv.y, M, q, aux);
+        }
+        o.x = reduce_f64(o.x, qinv, qd); o.y = reduce_f64(o.y, qinv, qd);
+      }
+      *reinterpret_cast<double2 *>(&sm[2 * j]) = o;
+    }
+  }
+  __syncthreads();
+  ntt_inv_first<LG, AR, true>(sm, M, twbase, q, aux, tid);
+  ntt_inv_smem_mids<LG, false, AR>(sm, M, twbase, tid);
+  const size_t xrow = (size_t)inst * 3 * bz.W + w;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(bz.xch + xrow * NGL + (size_t)h * NB), "r"((u32)__cvta_generic_to_shared(sm)), "r"((u32)D::SMEM) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __threadfence();
+    atomicExch(bz.xflag + xrow * 2 + h, bz.serial);
+    wait_word<false>(bz.xflag + xrow * 2 + (1 - h), bz.serial, bz.fault);
+  }
+  __syncthreads();
+  const double2 *part = reinterpret_cast<const double2 *>(bz.xch + xrow * NGL + (size_t)(1 - h) * NB);
+  const double wlast = f64_of(h ? M.wl_ninv_d : M.ninv_d);
+  const bool wide = f64_wide(q);
+  ulonglong2 *out = reinterpret_cast<ulonglong2 *>(bz.Y + (size_t)inst * bz.Y_is + (size_t)w * NGL) + h * (NB / 2);
+  for (int e2 = tid; e2 < NB / 2; e2 += D::T) {
+    const double2 m = *reinterpret_cast<const double2 *>(&sm[swz_pair(tid, e2)]), pv = __ldcg(part + swz2(e2));
+    double zx = mulc(h ? pv.x - m.x : m.x + pv.x, wlast, M, q, aux), zy = mulc(h ? pv.y - m.y : m.y + pv.y, wlast, M, q, aux);
+    if (wide) { zx = reduce_f64(zx, qinv, qd); zy = reduce_f64(zy, qinv, qd); }
+    out[e2] = make_ulonglong2(f64_to_canon(zx, qd), f64_to_canon(zy, qd));
+  }
+}
+
 template <int LG> int prep_launch(const Ks14 &ks, const ModInfo *mods, cudaStream_t stream) {
   KS14_DIMS; (void)NP;
   static bool done[64] = {false};
@@ -262,4 +379,23 @@ int ks14_prep_launch(int logN, const Ks14 &ks, const ModInfo *mods, cudaStream_t
 }
 int ks14_launch(int logN, const Ks14 &ks, const ModInfo *mods, cudaStream_t stream) {
   return logN == 14 ? main_launch<13>(ks, mods, stream) : logN == 13 ? main_launch<12>(ks, mods, stream) : (int)cudaErrorInvalidValue;
+}
+
+int behz14_fwd_launch(const Behz14 &bz, const ModInfo *mods, cudaStream_t stream) {
+  static bool done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k_behz14_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttDims<13>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_behz14_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NttDims<13>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    done[dev & 63] = true;
+  }
+  k_behz14_fwd<<<(unsigned)(bz.B * bz.np * bz.W * 2), NttDims<13>::T, NttDims<13>::SMEM, stream>>>(bz, mods);
+  return (int)cudaGetLastError();
+}
+int behz14_inv_launch(const Behz14 &bz, const ModInfo *mods, cudaStream_t stream) {
+  k_behz14_inv<<<(unsigned)(bz.B * 3 * bz.W * 2), NttDims<13>::T, NttDims<13>::SMEM, stream>>>(bz, mods);
+  return (int)cudaGetLastError();
 }

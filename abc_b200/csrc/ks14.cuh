@@ -28,3 +28,22 @@ struct Ks14 {
 // logN = log2 of the whole limb: 14 (rows of 8192-coefficient blocks) or 13 (4096-coefficient blocks, small batches)
 int ks14_prep_launch(int logN, const Ks14 &ks, const ModInfo *mods, cudaStream_t stream);
 int ks14_launch(int logN, const Ks14 &ks, const ModInfo *mods, cudaStream_t stream);
+
+// ---- the BEHZ block's transforms at N = 16384 on the same half-limb rows (ks14.cu): forward rows (operand limb or lifted
+// Bsk row -> stage 0 while loading -> 13 local stages -> raw-double image, reduced to 0.5 q), and inverse rows with the
+// tensor product in their load (13 local inverse stages, partner exchange, last stage, canonical store)
+struct Behz14 {
+  const u64 *X; long long X_is;               // [inst][4][W][N]: the lifted Bsk rows (canonical), read only
+  u64 *XI; long long XI_is;                   // [inst][4][W][N]: the transformed rows as raw-double images (two blocks per row); a
+                                              // separate block: both half-rows read a whole source row before either stores
+  const u64 *a, *b;                           // operand ciphertexts [inst][2][L][N] (rows r < L of polys 0,1 / 2,3 are read from here)
+  u64 *Y; long long Y_is;                     // [inst][3][W][N]: the product in coefficient form (canonical)
+  double *xch;                                // [B][3W][N]: partner exchange of the inverse rows
+  u32 *xflag; u32 serial;                     // [B][3W][2]
+  u32 *ticket; u32 ticket_base;
+  u32 *fault;
+  const int *rowmod;                          // [4W] modulus index of row w
+  int W, L, np, square, B;
+};
+int behz14_fwd_launch(const Behz14 &bz, const ModInfo *mods, cudaStream_t stream);
+int behz14_inv_launch(const Behz14 &bz, const ModInfo *mods, cudaStream_t stream);

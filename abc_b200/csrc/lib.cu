@@ -126,10 +126,12 @@ struct abc_ctx {
   int ks_split_maxb = 8;   // ABC_KS_SPLIT_MAXB: N = 8192 contexts of at most this many instances use the split rows too (latency)
   int ks14 = 1; uint2 *ks14_sched = nullptr; int ks14_sched_n = 0; u32 *ks14_done = nullptr, *ks14_xflag = nullptr, *ks14_flags = nullptr;
   u32 ks14_serial = 0;
+  u32 *ks14_xflag_behz = nullptr; u32 ks14_behz_serial = 0;   // [B][3 W2][2] exchange flags of the BEHZ inverse half-rows
   u32 *ks_ticket = nullptr; u32 ks_ticket_total = 0;                          // start-order tickets of the dependency-ordered grids (limb.cuh grid_ticket)
   // handles (abc_ct / abc_pt) keep their context alive: abc_ctx_destroy with live handles only marks it, the last
   // abc_ct_free / abc_pt_free completes the destruction (a ciphertext may outlive its factory, as with SealCiphertext)
   long live_handles = 0; bool zombie = false;
+  bool sync_each = getenv("ABC_SYNC_EACH") != nullptr;
   bool faulted = false;                                                       // sticky: a dependency wait timed out; every later call fails until abc_clear_fault
   int *rs_zero = nullptr;   // [2k]  0
   u64 *d_sk = nullptr, *d_pk = nullptr, *d_relin = nullptr;
@@ -147,8 +149,8 @@ struct abc_ctx {
   void *flush_buf = nullptr;
   // grow-only scratch slots reused by every op (one stream: an op's scratch is dead before the next op starts).
   // Allocating these per op from the stream-ordered pool fragmented it (135 MB / 335 MB / 170 MB blocks) and cost ms.
-  u64 *sc_ptr[16] = {nullptr};
-  size_t sc_words[16] = {0};
+  u64 *sc_ptr[32] = {nullptr};
+  size_t sc_words[32] = {0};
 };
 // A ciphertext handle.  The device buffer is shared between clones (copy-on-write): RuntimeVisitor clones on every
 // variable read (RuntimeVisitor.cpp:436), so clone is O(1) and an op gives its destination a private buffer first.
@@ -207,6 +209,10 @@ struct Launch {
   }
   ~Launch() {
     if (c->prof) { cudaEventRecord(b, c->stream); c->prof_recs.push_back({name, a, b}); }
+    if (c->sync_each) {   // ABC_SYNC_EACH=1 (debugging): name the launch a device-side error belongs to
+      const cudaError_t e = cudaStreamSynchronize(c->stream);
+      if (e != cudaSuccess) fprintf(stderr, "[abc_b200] %s: %s\n", name, cudaGetErrorString(e));
+    }
   }
 };
 
@@ -215,7 +221,8 @@ abc_status salloc(abc_ctx *c, u64 **p, size_t words) {
   return ABC_OK;
 }
 void sfree(abc_ctx *c, void *p) { if (p) cudaFreeAsync(p, c->stream); }
-enum { SC_T = 0, SC_ACC, SC_X, SC_OUT3, SC_U, SC_TMP, SC_DECX, SC_DECP, SC_P, SC_NK, SC_ENTT, SC_COMM_SEND, SC_COMM_ALL, SC_Y, SC_SX, SC_XCH, SC_NSLOTS };
+enum { SC_T = 0, SC_ACC, SC_X, SC_OUT3, SC_U, SC_TMP, SC_DECX, SC_DECP, SC_P, SC_NK, SC_ENTT, SC_COMM_SEND, SC_COMM_ALL, SC_Y, SC_SX, SC_XCH, SC_XI, SC_NSLOTS };
+static_assert(SC_NSLOTS <= 32, "abc_ctx::sc_ptr / sc_words hold 32 slots");
 abc_status scratch(abc_ctx *c, int slot, u64 **p, size_t words) {
   if (c->sc_words[slot] < words) {
     if (c->sc_ptr[slot]) cudaFreeAsync(c->sc_ptr[slot], c->stream);
@@ -519,6 +526,12 @@ abc_status build_tables(abc_ctx *c) {
     std::vector<int> rm(4 * c->W2);
     for (int w = 0; w < 4 * c->W2; ++w) { const int r = w % c->W2; rm[w] = r < L ? r : c->idx_b2 + (r - L); }
     TRY(upload(c, &c->rm_behz2, rm));
+    if (logN == 14) {
+      const size_t nf = (size_t)c->B * 3 * c->W2 * 2;
+      CK(cudaMalloc((void **)&c->ks14_xflag_behz, nf * sizeof(u32)));
+      c->owned.push_back(c->ks14_xflag_behz);
+      CK(cudaMemset(c->ks14_xflag_behz, 0, nf * sizeof(u32)));
+    }
   }
 
   // ---- BatchEncoder index map (populate_matrix_reps_index_map)
@@ -1079,6 +1092,32 @@ abc_status behz_multiply_f64(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) 
     // (no tensor launch, no round trip of the products through HBM)
     u64 *Y = nullptr;
     TRY(scratch(c, SC_Y, &Y, (size_t)B * 3 * W * N));
+    if (c->logN == 14 && c->ks14 && c->ks14_xflag_behz) {   // N = 16384: the block's transforms on rows of half a limb (ks14.cu)
+      u64 *XI = nullptr, *xch = nullptr;
+      TRY(scratch(c, SC_XI, &XI, (size_t)B * 4 * W * N));
+      TRY(scratch(c, SC_XCH, &xch, (size_t)B * std::max(3 * W, 2 * c->k) * N));
+      Behz14 bz;
+      memset(&bz, 0, sizeof bz);
+      bz.X = X; bz.X_is = (long long)4 * W * N; bz.XI = XI; bz.XI_is = (long long)4 * W * N; bz.a = a; bz.b = b;
+      bz.Y = Y; bz.Y_is = (long long)3 * W * N; bz.xch = reinterpret_cast<double *>(xch);
+      bz.xflag = c->ks14_xflag_behz; bz.serial = ++c->ks14_behz_serial; bz.fault = c->ks_fault_d;
+      bz.rowmod = c->rm_behz2; bz.W = W; bz.L = c->L; bz.np = np; bz.square = square ? 1 : 0; bz.B = B;
+      {
+        Launch l(c, "behz14_ntt");
+        const int e = behz14_fwd_launch(bz, c->d_mods, c->stream);
+        if (e != 0) { c->err = std::string("behz14_ntt: ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
+      }
+      {
+        bz.ticket = c->ks_ticket; bz.ticket_base = c->ks_ticket_total; c->ks_ticket_total += (u32)(B * 3 * W * 2);
+        Launch l(c, "behz14_tensor_intt");
+        const int e = behz14_inv_launch(bz, c->d_mods, c->stream);
+        if (e != 0) { c->err = std::string("behz14_tensor_intt: ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
+      }
+      Launch l(c, "behz_scale");
+      DISPATCH_BF(c, (k_behz_scale_f64<LL, NK><<<dim3(N / 128, 3, B), 128, 0, c->stream>>>(Y, out3, c->dF, N, 3)));
+      CK(cudaGetLastError());
+      return ABC_OK;
+    }
     j.t_image = 1; j.src_same_mod = 1; j.raw_reduce = 1;
     j.bz_W = W; j.bz_a = a; j.bz_b = b; j.L = c->L;
     TRY(launch_limb(c, LIMB_REDUCE_FWD, AR_F64, j, np * W, B, "behz_ntt"));
