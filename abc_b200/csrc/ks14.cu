@@ -212,13 +212,13 @@ __device__ __forceinline__ void ks14_tail(const Ks14 &ks, const ModInfo *__restr
         b = reinterpret_cast<const ulonglong2 *>(md.base)[E2];
       }
     }
-    double rx = moddown_one_f64(last(m.x, p.x), t.x, md.base != nullptr, b.x, f);
-    double ry = moddown_one_f64(last(m.y, p.y), t.y, md.base != nullptr, b.y, f);
+    u64 rx = moddown_finish_int(moddown_core_f64(last(m.x, p.x), t.x, f), md.base != nullptr, b.x, q);
+    u64 ry = moddown_finish_int(moddown_core_f64(last(m.y, p.y), t.y, f), md.base != nullptr, b.y, q);
     if (addp) {
-      if (out2) out2[E2] = make_ulonglong2(f64_canon_bits(rx), f64_canon_bits(ry));
-      rx = add_canon_f64(rx, ad.x, f.qd); ry = add_canon_f64(ry, ad.y, f.qd);
+      if (out2) out2[E2] = make_ulonglong2(rx, ry);
+      rx = add_mod(rx, ad.x, q); ry = add_mod(ry, ad.y, q);
     }
-    out[E2] = make_ulonglong2(f64_canon_bits(rx), f64_canon_bits(ry));
+    out[E2] = make_ulonglong2(rx, ry);
   }
 }
 

@@ -157,7 +157,8 @@ __device__ __forceinline__ ModDownF64 moddown_f64(const ModDownRow &md, const Mo
   f.qd = (double)M.q; f.qinv = f64_of(M.qinv_bits); f.ipc = f.ipd * f.qinv; f.wide = f64_wide(M.q);
   return f;
 }
-__device__ __forceinline__ double moddown_one_f64(double vd, u64 t, bool has_base, u64 b, const ModDownF64 &f) {
+// the rounded division itself: p^-1 * (v - [t + p/2]_p + [p/2]) mod q as a centred double, |r| <= 0.6 q
+__device__ __forceinline__ double moddown_core_f64(double vd, u64 t, const ModDownF64 &f) {
   double a = f64_of(ar_from_canon<AR_F64>(t)) + f.p_half;
   a = csub_ge(a, f.pd);                                           // [t + p/2]_p, exact
   const double d = (vd - reduce_f64(a, f.qinv, f.qd)) + f.phm;    // |d| < 2.6q, exact integer
@@ -165,9 +166,26 @@ __device__ __forceinline__ double moddown_one_f64(double vd, u64 t, bool has_bas
   const double ph = d * f.ipd, pl = fma(d, f.ipd, -ph);
   double r = fma(-Q, f.qd, ph) + pl;                              // d * p^-1 mod q, |r| <= 0.6q
   if (f.wide) r = reduce_f64(r, f.qinv, f.qd);                    // wide primes: the estimate's error can leave |r| ~ q
+  return r;
+}
+__device__ __forceinline__ double moddown_one_f64(double vd, u64 t, bool has_base, u64 b, const ModDownF64 &f) {
+  double r = moddown_core_f64(vd, t, f);
   if (has_base) r += f64_of(ar_from_canon<AR_F64>(b));
   r = cadd_neg(r, f.qd);
   return csub_ge(r, f.qd);                                        // canonical, as a double
+}
+// The additions that follow the division (+ base, + addend, canonical ranges) on the INTEGER pipes, which the key switch
+// leaves idle: one DADD turns the centred double into a two's-complement integer (the 1.5 * 2^52 encoding), the rest is
+// 64-bit adds and compares instead of 7 .. 11 FP64-pipe instructions per coefficient.
+#ifndef ABC_MD_INT
+#define ABC_MD_INT 1
+#endif
+__device__ __forceinline__ u64 moddown_finish_int(double r, bool has_base, u64 b, u64 q) {
+  long long x = (long long)(bits_of(r + ABC_RINT_MAGIC) - 0x4338000000000000ULL);   // |r| <= 0.6 q < 2^51
+  if (has_base) x += (long long)b;                                                  // (-0.6 q, 1.6 q)
+  if (x < 0) x += (long long)q;
+  if (x >= (long long)q) x -= (long long)q;
+  return (u64)x;
 }
 __device__ __forceinline__ u64 f64_canon_bits(double r) { return bits_of(r + 4503599627370496.0) & 0x000FFFFFFFFFFFFFULL; }
 __device__ __forceinline__ double add_canon_f64(double r, u64 ad, double qd) {
@@ -212,6 +230,15 @@ __device__ __forceinline__ void moddown_store_f64(const u64 *sm, const ModInfo &
           b = reinterpret_cast<const ulonglong2 *>(md.base)[e2];
         }
       }
+#if ABC_MD_INT
+      u64 rx = moddown_finish_int(moddown_core_f64(f64_of(v.x), t[i].x, f), md.base != nullptr, b.x, q);
+      u64 ry = moddown_finish_int(moddown_core_f64(f64_of(v.y), t[i].y, f), md.base != nullptr, b.y, q);
+      if (addp) {
+        if (out2) out2[e2] = make_ulonglong2(rx, ry);
+        rx = add_mod(rx, ad[i].x, q); ry = add_mod(ry, ad[i].y, q);
+      }
+      out[e2] = make_ulonglong2(rx, ry);
+#else
       double rx = moddown_one_f64(f64_of(v.x), t[i].x, md.base != nullptr, b.x, f);
       double ry = moddown_one_f64(f64_of(v.y), t[i].y, md.base != nullptr, b.y, f);
       if (addp) {
@@ -219,6 +246,7 @@ __device__ __forceinline__ void moddown_store_f64(const u64 *sm, const ModInfo &
         rx = add_canon_f64(rx, ad[i].x, f.qd); ry = add_canon_f64(ry, ad[i].y, f.qd);
       }
       out[e2] = make_ulonglong2(f64_canon_bits(rx), f64_canon_bits(ry));
+#endif
     }
   }
 }

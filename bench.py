@@ -297,7 +297,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
-    host_cores_bound = pin_to_gpu_local_cores(local)
+    host_cores_bound = 0 if os.environ.get("ABC_BENCH_NO_PIN") else pin_to_gpu_local_cores(local)
     if world > 1:
         # NCCL announces its version on stdout when the communicator comes up; stdout carries the ONE JSON line, so the
         # process-level descriptor points at stderr while NCCL initialises
@@ -362,16 +362,28 @@ def run_ours(args):
     lib, C = f._lib, __import__("ctypes")
     from abc_b200 import CudaCiphertext
 
+    host_t = {"encode_encrypt_x": 0.0, "encode_encrypt_y": 0.0, "program": 0.0, "decrypt_async": 0.0, "release_handles": 0.0}
+
     def e2e_step(i):
         """createCiphertext(x), createCiphertext(y) from pinned host slots; the program; decryptCiphertext to pinned host
         memory.  The decrypted slots of step i leave on the library's D2H stream while step i + 1 computes
-        (abc_decrypt_decode_async); every copy is inside the timed region, which ends with abc_sync."""
+        (abc_decrypt_decode_async); every copy is inside the timed region, which ends with abc_sync.  host_t accumulates the
+        HOST time of each part of the call sequence (enqueue only)."""
+        t0 = time.perf_counter()
         hx_ct, hy_ct = C.c_void_p(), C.c_void_p()
         f._ck(lib.abc_encode_encrypt(f._h, hx.data_ptr(), N_VEC, 0, C.byref(hx_ct)))
+        t1 = time.perf_counter()
         f._ck(lib.abc_encode_encrypt(f._h, hy.data_ptr(), N_VEC, 0, C.byref(hy_ct)))
+        t2 = time.perf_counter()
         cx, cy = CudaCiphertext(f, hx_ct), CudaCiphertext(f, hy_ct)
         r = program_gpu(cx, cy)
+        t3 = time.perf_counter()
         f._ck(lib.abc_decrypt_decode_async(f._h, r._h, houts[i & 1].data_ptr()))
+        t4 = time.perf_counter()
+        del cx, cy, r
+        t5 = time.perf_counter()
+        for k, v in zip(host_t, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+            host_t[k] += v
 
     for i in range(max(2, args.warmup)):
         e2e_step(i)
@@ -380,8 +392,13 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     f.timer_start()
+    t_enq = 0.0
+    for k in host_t:
+        host_t[k] = 0.0
     for i in range(args.steps):
+        te = time.perf_counter()
         e2e_step(i)
+        t_enq += time.perf_counter() - te
     f.sync()                                   # the last steps' D2H copies are part of the timed region
     e2e_wall = (time.perf_counter() - t0) * 1e3
     e2e_ms = f.timer_stop()
@@ -428,6 +445,11 @@ def run_ours(args):
                          "timed region the H2D of y runs under the encryption of x and the D2H of step i under the kernels of step i+1"}
     del cx, cy, res
 
+    e2e_per_rank = [round(e2e_ms / args.steps, 3)]
+    if world > 1:
+        allv = [None] * world
+        dist.all_gather_object(allv, e2e_per_rank[0])
+        e2e_per_rank = allv
     # max over ranks
     from abc_b200.sharding import max_over_ranks
     ms, e2e_ms, e2e_wall = max_over_ranks([ms, e2e_ms, e2e_wall], dist if world > 1 else None, "cuda")
@@ -520,7 +542,9 @@ def run_ours(args):
                     "h2d_bytes_per_step": 2 * B * N_VEC * 8, "d2h_bytes_per_step": B * N_POLY * 8,
                     "device_ms_per_step": e2e_dev / args.steps, "wall_ms_per_step": e2e_wall / args.steps,
                     "frac_of_device_resident": (ms / args.steps) / (e2e_ms / args.steps),
-                    "breakdown_ms": breakdown, "host_cores_bound_to_gpu": host_cores_bound,
+                    "breakdown_ms": breakdown, "host_cores_bound_to_gpu": host_cores_bound, "device_ms_per_step_per_rank": e2e_per_rank,
+                    "host_enqueue_ms_per_step": round(t_enq * 1e3 / args.steps, 3),
+                    "host_enqueue_ms_by_call": {k: round(v * 1e3 / args.steps, 3) for k, v in host_t.items()},
                     "includes": "createCiphertext(x), createCiphertext(y) from pinned host slots, program, decryptCiphertext to pinned host "
                                 "memory; the D2H of step i overlaps step i+1 (abc_decrypt_decode_async), the region ends with abc_sync"},
             "gpu_launches": launches,
