@@ -176,9 +176,12 @@ __device__ __forceinline__ double moddown_one_f64(double vd, u64 t, bool has_bas
 }
 // The additions that follow the division (+ base, + addend, canonical ranges) on the INTEGER pipes, which the key switch
 // leaves idle: one DADD turns the centred double into a two's-complement integer (the 1.5 * 2^52 encoding), the rest is
-// 64-bit adds and compares instead of 7 .. 11 FP64-pipe instructions per coefficient.
+// 64-bit adds and compares instead of 7 .. 11 FP64-pipe instructions per coefficient.  Measured (tools/ab_ks.sh, rotate at
+// N = 8192, B = 592): 1.0152 vs 1.0167 ms — nothing: the key switch is bound by latency at 8 warps per scheduler, not by
+// FP64 issue, so trading FP64 instructions for integer ones does not show.  Kept as -DABC_MD_INT=1 (the half-limb rows of
+// ks14.cu use it); the whole-limb epilogue stays on the FP64 form.
 #ifndef ABC_MD_INT
-#define ABC_MD_INT 1
+#define ABC_MD_INT 0
 #endif
 __device__ __forceinline__ u64 moddown_finish_int(double r, bool has_base, u64 b, u64 q) {
   long long x = (long long)(bits_of(r + ABC_RINT_MAGIC) - 0x4338000000000000ULL);   // |r| <= 0.6 q < 2^51
