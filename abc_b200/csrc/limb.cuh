@@ -364,6 +364,9 @@ __device__ __forceinline__ ulonglong2 ks_inner_pair_f64(const double2 *__restric
 #ifndef ABC_KS_PIPE_INNER
 #define ABC_KS_PIPE_INNER 1
 #endif
+#ifndef ABC_KS_KEY_CG
+#define ABC_KS_KEY_CG 1
+#endif
 // ACC: add to what shared memory already holds (the sum over an earlier chunk of LT limbs, |x| <= 0.51 q): L = 8 runs as
 // two chunks of 4, which keeps the software pipeline inside the register budget
 template <int LT, int NIT, int T, bool ACC = false>
@@ -389,7 +392,11 @@ __device__ __forceinline__ void ks_inner_rows_f64(u64 *sm, const double2 *__rest
     }
 #pragma unroll
     for (int J = 0; J < LT; ++J) {
+#if ABC_KS_KEY_CG
+      const double2 kv = __ldcg(kp + tid + i * T + (size_t)J * keyv2);   // L2 only: the key rows stream through, L1 keeps the twiddles
+#else
       const double2 kv = __ldg(kp + tid + i * T + (size_t)J * keyv2);
+#endif
       s0 += f64_of(mul_tw<AR_F64>(bits_of(tv[J].x), bits_of(kv.x), qib, M.q, qb));
       s1 += f64_of(mul_tw<AR_F64>(bits_of(tv[J].y), bits_of(kv.y), qib, M.q, qb));
     }
@@ -523,6 +530,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
         *reinterpret_cast<ulonglong2 *>(&sm[swz_pair(tid, e2)]) = make_ulonglong2(bits_of((double)e2), bits_of((double)tid));
     } else
 #endif
+    if (job.t_image) tw_prefetch_last<LOGN, AR>(M.itwd, twbase, tid);   // the inverse transform starts with the contiguous pass
     if (job.t_image && ABC_KS_PIPE_INNER && job.L == 4) {
       ks_inner_rows_f64<4, D::N / 2 / D::T, D::T>(sm, reinterpret_cast<const double2 *>(t), reinterpret_cast<const double2 *>(kp),
                                                  D::N / 2, job.k * D::N, M, tid);

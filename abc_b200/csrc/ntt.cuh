@@ -533,6 +533,34 @@ __device__ __forceinline__ u32 last_tw_index(u32 twbase, int s, int b, int vt, i
   return (twbase << s) + ((u32)(8 * vt + r) >> (b + 1));
 }
 
+// L1 prefetch of the twiddles this thread's contiguous pass will ask for (exact-double class: 7 eight-byte entries per group
+// of 8 coefficients, lane-contiguous for the last two stages): issued a pass early, the lines arrive while the pass in between
+// does its butterflies, so the contiguous pass's loads hit L1 instead of waiting on L2 (the kernels are latency-bound at 8
+// warps per scheduler; timing what-if "twiddles always L1-hot": 3.7 % of the key switch)
+#ifndef ABC_TW_PREFETCH
+#define ABC_TW_PREFETCH 1
+#endif
+template <int LOGN, int AR, int TT = 0>
+__device__ __forceinline__ void tw_prefetch_last(const ulonglong2 *__restrict__ tw, u32 twbase, int tid) {
+#if ABC_TW_PREFETCH
+  if constexpr (AR == AR_F64) {
+    constexpr bool P16 = UsePlan16<LOGN, AR, TT>::value;
+    const u64 *t8 = reinterpret_cast<const u64 *>(tw);
+#pragma unroll
+    for (int g = 0; g < NttLast<LOGN, TT>::GROUPS; ++g) {
+      const int vt = P16 ? p16_block8(tid, g) : tid + g * NttDims<LOGN, TT>::T;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int s = LOGN - 1 - b;
+#pragma unroll
+        for (int r = 0; r < 8; r += (2 << b))
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(t8 + last_tw_index<LOGN, AR>(twbase, s, b, vt, r)));
+      }
+    }
+  }
+#endif
+}
+
 // the butterflies of the contiguous forward pass on one thread's 8 consecutive coefficients (vt = first / 8)
 template <int LOGN, int AR, int TT = 0, int NSH = NttLast<LOGN, TT>::NSH>
 __device__ __forceinline__ void ntt_fwd_last_math(u64 (&x)[8], const ulonglong2 *__restrict__ tw, u32 twbase, u64 q, u64 aux,
@@ -697,6 +725,7 @@ __device__ __forceinline__ void ntt_fwd_smem_mids(u64 *sm, const ModInfo &M, u32
   ntt_fwd_mid<LOGN, P::R0, P::R1, AR, false, TT>(sm, tw, twbase, q, aux, tid, qinv);
   pass_sync<LOGN - P::R0 - P::R1, D::T>(tid);
   if constexpr (UsePlan16<LOGN, AR, TT>::value) {
+    tw_prefetch_last<LOGN, AR, TT>(M.twd, twbase, tid);
     ntt_fwd_mid16<LOGN, AR>(sm, tw, q, aux, tid, qinv, twbase, AR == AR_F64 && f64_wide(q));
     __syncwarp();
   } else if constexpr (P::R2 > 0) {
