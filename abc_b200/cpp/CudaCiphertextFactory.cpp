@@ -85,6 +85,25 @@ std::vector<uint8_t> CudaCiphertextFactory::saveKey(int kind, int compr) const {
   return out;
 }
 
+CudaPlaintext::~CudaPlaintext() { abc_pt_free(handle); }
+
+std::unique_ptr<CudaPlaintext> CudaCiphertextFactory::createPlaintext(const std::vector<int64_t> &value) const {
+  abc_pt *h = nullptr;
+  check(abc_pt_encode(ctx, value.data(), value.size(), /*broadcast=*/1, &h));   // empty / oversize vectors: same errors as createCiphertext
+  return std::make_unique<CudaPlaintext>(h);
+}
+std::unique_ptr<CudaPlaintext> CudaCiphertextFactory::createPlaintext(const std::vector<int> &value) const {
+  return createPlaintext(std::vector<int64_t>(value.begin(), value.end()));
+}
+std::unique_ptr<CudaPlaintext> CudaCiphertextFactory::createPlaintext(int64_t value) const {
+  return createPlaintext(std::vector<int64_t>{value});
+}
+std::unique_ptr<AbstractCiphertext> CudaCiphertextFactory::encryptPlaintext(const CudaPlaintext &plaintext) const {
+  abc_ct *h = nullptr;
+  check(abc_encrypt_pt(ctx, plaintext.handle, &h));
+  return std::make_unique<CudaCiphertext>(*this, h);
+}
+
 unsigned int CudaCiphertextFactory::getCiphertextSlotSize() const { return ciphertextSlotSize; }
 unsigned int CudaCiphertextFactory::getBatchSize() const { return abc_batch(ctx); }
 void CudaCiphertextFactory::synchronize() const { check(abc_sync(ctx)); }

@@ -17,7 +17,19 @@
 
 struct abc_ctx;
 struct abc_ct;
+struct abc_pt;
 class CudaCiphertext;
+
+/// An encoded plaintext on the device: what SealCiphertextFactory::createPlaintext returns as a seal::Plaintext
+/// (include/ast_opt/runtime/SealCiphertextFactory.h:95-107).  Owns its device handle.
+class CudaPlaintext {
+ public:
+  abc_pt *handle = nullptr;
+  explicit CudaPlaintext(abc_pt *h) : handle(h) {}
+  ~CudaPlaintext();
+  CudaPlaintext(const CudaPlaintext &) = delete;
+  CudaPlaintext &operator=(const CudaPlaintext &) = delete;
+};
 
 class CudaCiphertextFactory : public AbstractCiphertextFactory {
  private:
@@ -59,6 +71,13 @@ class CudaCiphertextFactory : public AbstractCiphertextFactory {
   std::unique_ptr<AbstractCiphertext> createCiphertext(std::unique_ptr<AbstractValue> &&cleartext) const override;
   void decryptCiphertext(AbstractCiphertext &abstractCiphertext, std::vector<int64_t> &ciphertextData) const override;
   std::string getString(AbstractCiphertext &abstractCiphertext) const override;
+
+  /// SealCiphertextFactory::createPlaintext x 3 (SealCiphertextFactory.h:95-107): pad-with-last + BatchEncoder::encode on
+  /// the device.  The result can be encrypted later (encryptPlaintext) — the two halves of createCiphertext.
+  std::unique_ptr<CudaPlaintext> createPlaintext(const std::vector<int> &value) const;
+  std::unique_ptr<CudaPlaintext> createPlaintext(const std::vector<int64_t> &value) const;
+  std::unique_ptr<CudaPlaintext> createPlaintext(int64_t value) const;
+  std::unique_ptr<AbstractCiphertext> encryptPlaintext(const CudaPlaintext &plaintext) const;
 
   /// Gets the number of slots of a ciphertext (SealCiphertextFactory::getCiphertextSlotSize).
   [[nodiscard]] unsigned int getCiphertextSlotSize() const;

@@ -187,6 +187,16 @@ void runKats() {
     report("visitor.unsupported '/' on ciphertexts throws std::runtime_error", threw);
   }
   {
+    // SealCiphertextFactory::createPlaintext x 3 (SealCiphertextFactory.h:95-107) + encryption of the result
+    auto p1 = f.createPlaintext(std::vector<int64_t>{3, 3, 1, 4, 5, 9});
+    auto p2 = f.createPlaintext(std::vector<int>{0, 1, 2, 1, 10, 21});
+    auto p3 = f.createPlaintext((int64_t)-7);
+    auto c1 = f.encryptPlaintext(*p1), c2 = f.encryptPlaintext(*p2), c3 = f.encryptPlaintext(*p3);
+    checkCiphertextData(f, *c1, data1, "factory.createPlaintext(vector<int64_t>) + encrypt");
+    checkCiphertextData(f, *c2, data2, "factory.createPlaintext(vector<int>) + encrypt");
+    checkCiphertextData(f, *c3, {-7}, "factory.createPlaintext(int64_t) + encrypt");
+  }
+  {
     // all 15 operations a ciphertext rejects (SealCiphertext.cpp:241-309) throw the same exception type
     auto c1 = f.createCiphertext(data1), c2 = f.createCiphertext(data2);
     using BinOp = void (AbstractValue::*)(const AbstractValue &);

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) k_behz_lift(const u64 *__restrict__ a, co
   // conversion is independent per coefficient); copy_q = 0: the q rows of X are filled elsewhere
   constexpr int CAP = LT ? LT : ABC_MAXL;
   const int L = LT ? LT : Lrt;
-  const int n = col0 + blockIdx.x * 128 + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
+  const int n = col0 + blockIdx.x * blockDim.x + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
   const int W = 2 * L + 1;
   const u64 *src = (poly < 2 ? a : b) + ((size_t)inst * 2 + (poly & 1)) * L * N + n;
   u64 *dst = X + ((size_t)inst * 4 + poly) * W * N + n;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(128) k_behz_scale(const u64 *__restrict__ X, u
                                                     const DevConst *__restrict__ C, int N, int Lrt, int col0 = 0) {
   constexpr int CAP = LT ? LT : ABC_MAXL;
   const int L = LT ? LT : Lrt;
-  const int n = col0 + blockIdx.x * 128 + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
+  const int n = col0 + blockIdx.x * blockDim.x + threadIdx.x, poly = blockIdx.y, inst = blockIdx.z;
   const int W = 2 * L + 1;
   const u64 *src = X + ((size_t)inst * 4 + poly) * W * N + n;
   u64 *out = dst + ((size_t)inst * 3 + poly) * L * N + n;

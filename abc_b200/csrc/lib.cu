@@ -1159,9 +1159,12 @@ abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
   // converted columns (in-place all-gathers of row slices); the transforms in between run on whole rows on every rank.
   const bool cols = c->world > 1 && c->shard_cols && (N / c->world) % 128 == 0;
   const int ncols = cols ? N / c->world : N, col0 = cols ? c->rank * ncols : 0;
+  // threads per block of the conversion kernels: a column slice of a single ciphertext is few coefficients (8192 at world
+  // = 8) of heavy, latency-bound work each, so small blocks spread them over all SMs (192 blocks of 128 threads left most idle)
+  const int cvt = (size_t)ncols * B * 3 >= (size_t)148 * 2 * 128 * 4 ? 128 : 32;
   {
     Launch l(c, "behz_lift");
-    DISPATCH_L(c, (k_behz_lift<LL><<<dim3(ncols / 128, np, B), 128, 0, c->stream>>>(a, b, X, c->dC, N, c->L, col0, cols ? 0 : 1)));
+    DISPATCH_L(c, (k_behz_lift<LL><<<dim3(ncols / cvt, np, B), cvt, 0, c->stream>>>(a, b, X, c->dC, N, c->L, col0, cols ? 0 : 1)));
     CK(cudaGetLastError());
   }
   if (cols) {
@@ -1197,7 +1200,7 @@ abc_status behz_multiply(abc_ctx *c, const u64 *a, const u64 *b, u64 *out3) {
   }
   {
     Launch l(c, "behz_scale");
-    DISPATCH_L(c, (k_behz_scale<LL><<<dim3(ncols / 128, 3, B), 128, 0, c->stream>>>(X, out3, c->dC, N, c->L, col0)));
+    DISPATCH_L(c, (k_behz_scale<LL><<<dim3(ncols / cvt, 3, B), cvt, 0, c->stream>>>(X, out3, c->dC, N, c->L, col0)));
     CK(cudaGetLastError());
   }
   // c2 is needed whole by every rank (ModUp of the relinearisation); c0, c1 only on their owners, but as whole rows
