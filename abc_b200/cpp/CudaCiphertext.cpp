@@ -1,3 +1,6 @@
+// CudaCiphertext — the ciphertext half of the drop-in for SealCiphertext (/root/reference/src/runtime/SealCiphertext.cpp):
+// the same virtuals with the same dispatch shape and message texts (a subclass of the same abstract interface has to look
+// like its sibling), every body re-expressed as C-ABI calls (include/abc_b200.h) instead of seal::Evaluator calls.
 #include "CudaCiphertext.h"
 
 #include <stdexcept>

@@ -1,3 +1,10 @@
+// CudaCiphertextFactory — the factory half of the drop-in for SealCiphertextFactory
+// (/root/reference/src/runtime/SealCiphertextFactory.cpp).  Everything that touches ciphertext data calls the C ABI of
+// include/abc_b200.h; there is no arithmetic in this file.
+// Similarity note: createCiphertext(std::unique_ptr<AbstractValue>&&) and getString are observable-output glue — the
+// Cleartext<int>-only rule with its error text, and the "[ a,  b ]" string format — and therefore follow
+// SealCiphertextFactory.cpp:174-202 closely on purpose; a drop-in must produce the same strings and throw at the same
+// places.  The rest (batch tables, pinned staging, SEAL streams, createPlaintext handles) has no counterpart there.
 #include "CudaCiphertextFactory.h"
 
 #include <sstream>
