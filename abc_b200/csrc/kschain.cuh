@@ -12,3 +12,5 @@ struct KsChain {
 
 // returns a cudaError_t as int; logN in {12, 13}, every key-level prime < 2^45
 int ks_chain_launch(int logN, const KsChain &ch, const ModInfo *mods, cudaStream_t stream);
+// persistent grid of `grid` CTAs taking tickets in a loop (logN in {12, 13}); consumes n_blocks + grid tickets
+int ks_chain_launch_persistent(int logN, const KsChain &ch, const ModInfo *mods, cudaStream_t stream, int grid);

@@ -123,6 +123,7 @@ struct abc_ctx {
   // ABC_KS_RED=1 selects it; measured 9 % slower than the chained grid at N = 8192 (the bulk reductions wait on the L2 atomic units)
   int ks_red = 0, ksr_ring = 0; double *ksr_acc = nullptr; u32 *ksr_done = nullptr, *ksr_freed = nullptr; u32 ksr_serial = 0;
   // split key switch at N = 16384 (ks14.cu): schedule of half-rows, [B][k][2] done + [B][2k][2] exchange + [B][2][2] special flags
+  int ks_persist = 0, n_sms = 148;   // ABC_KS_PERSIST=1: the chained key switch on a persistent grid (2 CTAs per SM take tickets in a loop)
   int ks_split_maxb = 8;   // ABC_KS_SPLIT_MAXB: N = 8192 contexts of at most this many instances use the split rows too (latency)
   int ks14 = 1; uint2 *ks14_sched = nullptr; int ks14_sched_n = 0; u32 *ks14_done = nullptr, *ks14_xflag = nullptr, *ks14_flags = nullptr;
   u32 ks14_serial = 0;
@@ -424,6 +425,8 @@ abc_status build_tables(abc_ctx *c) {
   if (const char *e = getenv("ABC_KS_CHAIN")) c->ks_chain = atoi(e);
   if (const char *e = getenv("ABC_KS_RED")) c->ks_red = atoi(e);
   if (const char *e = getenv("ABC_KS14_SPLIT")) c->ks14 = atoi(e);
+  if (const char *e = getenv("ABC_KS_PERSIST")) c->ks_persist = atoi(e);
+  cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device);
   if (const char *e = getenv("ABC_KS_SPLIT_MAXB")) c->ks_split_maxb = atoi(e);
   if (const char *e = getenv("ABC_BEHZ_FUSED")) c->behz_fused = atoi(e) != 0;
   if (const char *e = getenv("ABC_KS_CHAIN_SKEW")) c->ks_chain_skew = atoi(e) < 1 ? 1 : atoi(e);
@@ -1041,6 +1044,14 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
         ch.tail.done_target = ch.up.done_target = (u32)L * ++c->ks_chain_serial;
         ch.ticket = c->ks_ticket; ch.ticket_base = c->ks_ticket_total; c->ks_ticket_total += (u32)ch.n_blocks;
         Launch l(c, einv ? "ks_chain" : "ks_chain_relin");
+        const int pgrid = c->ks_persist ? std::min(ch.n_blocks, 2 * c->n_sms) : 0;
+        if (pgrid > 0 && c->logN <= 13) {
+          ch.up.persist = ch.tail.persist = 1;
+          c->ks_ticket_total += (u32)pgrid;   // every CTA takes one ticket past the end
+          const int e = ks_chain_launch_persistent(c->logN, ch, c->d_mods, c->stream, pgrid);
+          if (e != 0) { c->err = std::string("ks_chain (persistent): ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
+          return ABC_OK;
+        }
         const int e = ks_chain_launch(c->logN, ch, c->d_mods, c->stream);
         if (e != 0) { c->err = std::string("ks_chain: ") + cudaGetErrorString((cudaError_t)e); return ABC_ERR_CUDA; }
         return ABC_OK;

@@ -53,6 +53,7 @@ struct LimbJob {
   u32 *fault;    // host-mapped word raised when a dependency wait gives up (wait_word)
   // ModUp-style rows whose source is already a residue of the row's own modulus (the BEHZ block's forward transforms):
   // no source prime to negate / compare against
+  int persist;                   // the CTA processes several rows one after another (persistent chained grid)
   int src_same_mod;
   int raw_reduce;                // t_image rows: reduce the raw outputs to |x| <= 0.5 q before the bulk store (they feed products)
   // PRE_BEHZ_TENSOR: src = the transformed operand block [inst][4][bz_W][N] as raw-double images (polys a0, a1, b0, b1;
@@ -291,7 +292,9 @@ __device__ __forceinline__ void limb_store_pair(const LimbJob &job, const ModInf
 
 // ---- bulk asynchronous copy of one row into shared memory (cp.async.bulk, completion on an mbarrier): one thread
 // issues it, no registers are staged, and the whole row is in flight from the first cycle of the CTA
-__device__ __forceinline__ void bulk_row_to_smem(u64 *sm, const u64 *src, u32 bytes, u64 *mbar, int tid) {
+// reuse: the CTA will bring in another row through the same barrier object later (persistent grids): invalidate it once every
+// thread has seen the copy complete
+__device__ __forceinline__ void bulk_row_to_smem(u64 *sm, const u64 *src, u32 bytes, u64 *mbar, int tid, bool reuse = false) {
   const u32 mb = (u32)__cvta_generic_to_shared(mbar), dst = (u32)__cvta_generic_to_shared(sm);
 #if ABC_WHATIF & 2
   (void)mb; (void)dst; (void)src; (void)bytes; __syncthreads(); return;   // what-if: the source row costs nothing
@@ -309,6 +312,10 @@ __device__ __forceinline__ void bulk_row_to_smem(u64 *sm, const u64 *src, u32 by
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                  : "=r"(ok) : "r"(mb) : "memory");
   } while (!ok);
+  if (reuse) {
+    __syncthreads();
+    if (tid == 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(mb) : "memory");
+  }
 }
 
 // ---- key-switch inner product in the load of the inverse transform (AR_F64: every prime < 2^45):
@@ -493,7 +500,7 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
       const int p = w / job.bz_W, r = w - p * job.bz_W;
       if (r < job.L) sp = (p < 2 ? job.bz_a : job.bz_b) + (((size_t)inst * 2 + (p & 1)) * job.L + r) * D::N;
     }
-    bulk_row_to_smem(sm, sp, (u32)D::SMEM, &mbar, tid);
+    bulk_row_to_smem(sm, sp, (u32)D::SMEM, &mbar, tid, job.persist != 0);
   } else if (PRE == PRE_KS_INNER) {
     // srow = comp * k + I: row of the accumulator block this CTA produces
     const int comp = srow >= job.k ? 1 : 0, I = srow - comp * job.k;  // srow < 2k

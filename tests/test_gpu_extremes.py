@@ -71,7 +71,8 @@ def _galois_coeff(poly, elt, q):
 
 
 KS_PATHS = {"default": {}, "chained": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_SPLIT_MAXB": "0"}, "two_launch": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_CHAIN": "0"},
-            "one_launch": {"ABC_KS_ONE_LAUNCH": "1"}, "accumulating": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_RED": "1"}}
+            "one_launch": {"ABC_KS_ONE_LAUNCH": "1"}, "accumulating": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_RED": "1"},
+            "persistent": {"ABC_KS_ONE_LAUNCH": "0", "ABC_KS_SPLIT_MAXB": "0", "ABC_KS_PERSIST": "1"}}
 
 
 @pytest.mark.parametrize("N,cls,path", [(n, "f64", p) for n in (4096, 8192) for p in sorted(KS_PATHS)] +
