@@ -56,6 +56,7 @@ SYMBOLS = {
     "abc_decrypt_wait": (i32, [vp]),
     "abc_set_encrypt_nonce": (i32, [vp, u64]),
     "abc_noise_budget": (i32, [vp, vp, vp]),
+    "abc_is_transparent": (i32, [vp, vp, vp]),
     "abc_add": (i32, [vp, vp, vp, vp]),
     "abc_sub": (i32, [vp, vp, vp, vp]),
     "abc_negate": (i32, [vp, vp, vp]),

@@ -331,6 +331,14 @@ class CudaCiphertext:
     def noiseBits(self):
         return self.factory.noiseBits(self)
 
+    def isTransparent(self):
+        """Ciphertext::is_transparent per instance (SEAL throws std::logic_error on such results, SURVEY A.8b):
+        bool [batch] (bool when batch == 1).  Synchronises."""
+        f = self.factory
+        out = np.zeros(f.batch, dtype=np.int32)
+        f._ck(f._lib.abc_is_transparent(f._h, self._h, out.ctypes.data))
+        return bool(out[0]) if f.batch == 1 else out.astype(bool)
+
     def _other(self, operand):
         if not isinstance(operand, CudaCiphertext) or operand.factory is not self.factory:
             raise AbcError("Cast of AbstractCiphertext to CudaCiphertext failed!")

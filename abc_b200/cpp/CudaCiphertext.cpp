@@ -70,79 +70,79 @@ std::unique_ptr<AbstractCiphertext> CudaCiphertext::clone() const { return std::
 // ---- rotation (Evaluator::rotate_rows, SealCiphertext.cpp:52-61)
 std::unique_ptr<AbstractCiphertext> CudaCiphertext::rotateRows(int steps) const {
   auto result = std::make_unique<CudaCiphertext>(getFactory());
-  getFactory().check(abc_rotate_rows(getFactory().context(), result->handle, handle, steps));
+  getFactory().checkResult(abc_rotate_rows(getFactory().context(), result->handle, handle, steps), result->handle);
   return result;
 }
 void CudaCiphertext::rotateRowsInplace(int steps) {
-  getFactory().check(abc_rotate_rows(getFactory().context(), handle, handle, steps));
+  getFactory().checkResult(abc_rotate_rows(getFactory().context(), handle, handle, steps), handle);
 }
 
 // ---- ctxt-ctxt (SealCiphertext.cpp:90-124)
 std::unique_ptr<AbstractCiphertext> CudaCiphertext::add(const AbstractCiphertext &operand) const {
   auto result = std::make_unique<CudaCiphertext>(getFactory());
-  getFactory().check(abc_add(getFactory().context(), result->handle, handle, cast(operand).handle));
+  getFactory().checkResult(abc_add(getFactory().context(), result->handle, handle, cast(operand).handle), result->handle);
   return result;
 }
 std::unique_ptr<AbstractCiphertext> CudaCiphertext::subtract(const AbstractCiphertext &operand) const {
   auto result = std::make_unique<CudaCiphertext>(getFactory());
-  getFactory().check(abc_sub(getFactory().context(), result->handle, handle, cast(operand).handle));
+  getFactory().checkResult(abc_sub(getFactory().context(), result->handle, handle, cast(operand).handle), result->handle);
   return result;
 }
 std::unique_ptr<AbstractCiphertext> CudaCiphertext::multiply(const AbstractCiphertext &operand) const {
   // multiply + relinearize_inplace in one call
   auto result = std::make_unique<CudaCiphertext>(getFactory());
-  getFactory().check(abc_mul_relin(getFactory().context(), result->handle, handle, cast(operand).handle));
+  getFactory().checkResult(abc_mul_relin(getFactory().context(), result->handle, handle, cast(operand).handle), result->handle);
   return result;
 }
 void CudaCiphertext::addInplace(const AbstractCiphertext &operand) {
-  getFactory().check(abc_add(getFactory().context(), handle, handle, cast(operand).handle));
+  getFactory().checkResult(abc_add(getFactory().context(), handle, handle, cast(operand).handle), handle);
 }
 void CudaCiphertext::subtractInplace(const AbstractCiphertext &operand) {
-  getFactory().check(abc_sub(getFactory().context(), handle, handle, cast(operand).handle));
+  getFactory().checkResult(abc_sub(getFactory().context(), handle, handle, cast(operand).handle), handle);
 }
 void CudaCiphertext::multiplyInplace(const AbstractCiphertext &operand) {
-  getFactory().check(abc_mul_relin(getFactory().context(), handle, handle, cast(operand).handle));
+  getFactory().checkResult(abc_mul_relin(getFactory().context(), handle, handle, cast(operand).handle), handle);
 }
 
 // ---- ctxt-plain (SealCiphertext.cpp:130-202)
 std::unique_ptr<AbstractCiphertext> CudaCiphertext::addPlain(const ICleartext &operand) const {
   auto data = widen(intCleartext(operand, "ADD").getData());
   auto result = std::make_unique<CudaCiphertext>(getFactory());
-  getFactory().check(abc_add_plain(getFactory().context(), result->handle, handle, data.data(), data.size(), 1));
+  getFactory().checkResult(abc_add_plain(getFactory().context(), result->handle, handle, data.data(), data.size(), 1), result->handle);
   return result;
 }
 std::unique_ptr<AbstractCiphertext> CudaCiphertext::subtractPlain(const ICleartext &operand) const {
   auto data = widen(intCleartext(operand, "SUB").getData());
   auto result = std::make_unique<CudaCiphertext>(getFactory());
-  getFactory().check(abc_sub_plain(getFactory().context(), result->handle, handle, data.data(), data.size(), 1));
+  getFactory().checkResult(abc_sub_plain(getFactory().context(), result->handle, handle, data.data(), data.size(), 1), result->handle);
   return result;
 }
 std::unique_ptr<AbstractCiphertext> CudaCiphertext::multiplyPlain(const ICleartext &operand) const {
   const auto &cleartextInt = intCleartext(operand, "MULTIPLY");
   auto result = std::make_unique<CudaCiphertext>(getFactory());
   if (cleartextInt.allEqual(-1)) {  // negate fast path (SealCiphertext.cpp:156-157)
-    getFactory().check(abc_negate(getFactory().context(), result->handle, handle));
+    getFactory().checkResult(abc_negate(getFactory().context(), result->handle, handle), result->handle);
   } else {
     auto data = widen(cleartextInt.getData());
-    getFactory().check(abc_mul_plain(getFactory().context(), result->handle, handle, data.data(), data.size(), 1));
+    getFactory().checkResult(abc_mul_plain(getFactory().context(), result->handle, handle, data.data(), data.size(), 1), result->handle);
   }
   return result;
 }
 void CudaCiphertext::addPlainInplace(const ICleartext &operand) {
   auto data = widen(intCleartext(operand, "ADD").getData());
-  getFactory().check(abc_add_plain(getFactory().context(), handle, handle, data.data(), data.size(), 1));
+  getFactory().checkResult(abc_add_plain(getFactory().context(), handle, handle, data.data(), data.size(), 1), handle);
 }
 void CudaCiphertext::subtractPlainInplace(const ICleartext &operand) {
   auto data = widen(intCleartext(operand, "SUBTRACT").getData());
-  getFactory().check(abc_sub_plain(getFactory().context(), handle, handle, data.data(), data.size(), 1));
+  getFactory().checkResult(abc_sub_plain(getFactory().context(), handle, handle, data.data(), data.size(), 1), handle);
 }
 void CudaCiphertext::multiplyPlainInplace(const ICleartext &operand) {
   const auto &cleartextInt = intCleartext(operand, "MULTIPLY");
   if (cleartextInt.allEqual(-1)) {
-    getFactory().check(abc_negate(getFactory().context(), handle, handle));
+    getFactory().checkResult(abc_negate(getFactory().context(), handle, handle), handle);
   } else {
     auto data = widen(cleartextInt.getData());
-    getFactory().check(abc_mul_plain(getFactory().context(), handle, handle, data.data(), data.size(), 1));
+    getFactory().checkResult(abc_mul_plain(getFactory().context(), handle, handle, data.data(), data.size(), 1), handle);
   }
 }
 

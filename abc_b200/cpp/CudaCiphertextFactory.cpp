@@ -7,6 +7,7 @@
 // places.  The rest (batch tables, pinned staging, SEAL streams, createPlaintext handles) has no counterpart there.
 #include "CudaCiphertextFactory.h"
 
+#include <cstdlib>
 #include <sstream>
 #include <stdexcept>
 
@@ -16,6 +17,15 @@
 
 void CudaCiphertextFactory::check(int status) const {
   if (status != ABC_OK) throw std::runtime_error(abc_last_error(ctx));
+}
+
+void CudaCiphertextFactory::checkResult(int status, const abc_ct *result) const {
+  check(status);
+  if (!st->throwOnTransparent) return;
+  std::vector<int32_t> flags(abc_batch(ctx));
+  check(abc_is_transparent(ctx, result, flags.data()));
+  for (int32_t f : flags)
+    if (f) throw std::logic_error("result ciphertext is transparent");  // SEAL 3.6.5 Evaluator, same type and text
 }
 
 void CudaCiphertextFactory::setup(int device, unsigned int batch, uint64_t seed) {
@@ -32,6 +42,7 @@ void CudaCiphertextFactory::setup(int device, unsigned int batch, uint64_t seed)
   }
   st->ctx = ctx;
   check(abc_keygen(ctx));
+  if (const char *e = std::getenv("ABC_THROW_ON_TRANSPARENT")) st->throwOnTransparent = std::atoi(e) != 0;
 }
 
 // The reference's factory draws its keys from SEAL's randomly seeded PRNG; seed 0 asks the library for the same

@@ -46,6 +46,7 @@ class CudaCiphertextFactory : public AbstractCiphertextFactory {
     size_t nextBatchTable = 0;
     int64_t *pinnedOut = nullptr;                    // page-locked 2 x batch * N slots: decryptCiphertextBatchPinned
     unsigned pinnedNext = 0;
+    bool throwOnTransparent = false;                 // setThrowOnTransparent
     ~State();
   };
   std::shared_ptr<State> st = std::make_shared<State>();
@@ -119,6 +120,14 @@ class CudaCiphertextFactory : public AbstractCiphertextFactory {
   [[nodiscard]] abc_ctx *context() const { return ctx; }
   /// Throws std::runtime_error(abc_last_error) when status != 0 (the reference's error convention).
   void check(int status) const;
+  /// check(status), then — if setThrowOnTransparent(true) — SEAL's verdict on the result of an evaluator op.
+  void checkResult(int status, const abc_ct *result) const;
+  /// Mirror SEAL's SEAL_THROW_ON_TRANSPARENT_CIPHERTEXT (its default build option): every evaluator op whose result has
+  /// an all-zero c1 (`x --- x`, `x *** 0`) throws std::logic_error("result ciphertext is transparent").  Off by default:
+  /// the test is a device reduction and a host synchronisation after EVERY op, which serialises the stream the backend
+  /// otherwise keeps full.  Also switched on by the environment variable ABC_THROW_ON_TRANSPARENT=1.  With a lock-step
+  /// batch the op throws if any instance's result is transparent.
+  void setThrowOnTransparent(bool on) const { st->throwOnTransparent = on; }
 };
 
 #endif  // ABC_B200_CPP_CUDACIPHERTEXTFACTORY_H_

@@ -12,11 +12,15 @@
 //                              registered with the factory (setBatchInputs), every instance is checked against the plain
 //                              evaluation, and the L2Distance line reports the metric of bench.py's end-to-end leg
 //                              (mul+relin + rotate ops/s, encrypt and decrypt included)
+//   abc_driver demo <output_filename> [N] [--batch B]
+//                              the reference's `ast_demo demo <output_filename>` (examples/main.cpp:33-46): one CSV row
+//                              t_keygen,t_input_encryption,t_computation,t_decryption (ms) of the L2Distance ladder
 // Prints one line per case and a JSON summary; exit code 1 on any mismatch.
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <functional>
+#include <fstream>
 #include <iostream>
 #include <random>
 #include <sstream>
@@ -246,6 +250,34 @@ void runKats() {
                    "int i = 19;\nsecret int result = __input0__ --- i;\nreturn result;", "y = result;", in0);
     report("a16.visitor `cipher --- plain`", prefixEquals(r["y"], {24, -18, -18, 3, -8, -12}));
   }
+  {
+    // SEAL (SEAL_THROW_ON_TRANSPARENT_CIPHERTEXT, its default) throws std::logic_error on a result whose c1 is
+    // zero.  Off by default here (a host synchronisation per op); setThrowOnTransparent(true) mirrors it.
+    auto c = f.createCiphertext(data1);
+    auto d = c->clone();
+    auto z = c->subtract(*d);
+    checkCiphertextData(f, *z, {0, 0, 0, 0, 0, 0}, "transparent.default: x --- x is an encryption of zero, no throw");
+    f.setThrowOnTransparent(true);
+    int threw = 0;
+    try { c->subtract(*d); } catch (std::logic_error &e) { threw += std::string(e.what()) == "result ciphertext is transparent"; }
+    try { auto a = c->clone(); a->subtractInplace(*d); } catch (std::logic_error &) { ++threw; }
+    try { Cleartext<int> zero(std::vector<int>{0}); c->multiplyPlain(zero); } catch (std::logic_error &) { ++threw; }
+    report("transparent.mirrored: x --- x, subtractInplace, x *** 0 throw std::logic_error(\"result ciphertext is transparent\")", threw == 3);
+    bool ok = true;
+    try {
+      auto r = c->add(*d); auto m = c->multiply(*d); auto t = c->rotateRows(3);
+      Cleartext<int> two(std::vector<int>{2}); auto p = c->multiplyPlain(two);
+    } catch (std::logic_error &) { ok = false; }
+    report("transparent.mirrored: ordinary results pass the check", ok);
+    // through the interpreter: RuntimeVisitor clones every variable read (RuntimeVisitor.cpp:436), so `x --- x` reaches it
+    threw = 0;
+    try {
+      runProgram(f, "secret int __input0__ = {43,  1,   1,  22, 11, 7};", "secret int result = __input0__ --- __input0__;\nreturn result;",
+                 "y = result;", in0);
+    } catch (std::logic_error &) { ++threw; }
+    report("transparent.mirrored: visitor `x --- x` throws std::logic_error", threw == 1);
+    f.setThrowOnTransparent(false);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ lock-step batch
@@ -469,6 +501,63 @@ void runProgramsBatch(unsigned N, unsigned B, int steps) {
   }
   std::cout << "launches=" << f.launchCount() << std::endl;
 }
+
+// ------------------------------------------------------------------------------------------------ demo
+// The reference's `ast_demo demo <output_filename>` (examples/main.cpp:33-46) writes one CSV row
+// `t_keygen,t_input_encryption,t_computation,t_decryption` (ms; a placeholder row there).  Here the row is measured: the
+// L2Distance ladder through the unmodified RuntimeVisitor on the CUDA factory, the stream drained after every phase.
+void runDemo(const std::string &filename, unsigned N, unsigned B) {
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const size_t n = N / 2;
+  const int64_t t = N <= 8192 ? 1032193 : 786433;
+  auto centre = [&](int64_t v) { v %= t; if (v < 0) v += t; return v > t / 2 ? v - t : v; };
+  std::vector<int64_t> tx((size_t)B * n), ty((size_t)B * n);
+  for (unsigned b = 0; b < B; ++b) {
+    auto x = randomVector(n, 4673838 + 2 * b), y = randomVector(n, 4673839 + 2 * b);
+    for (size_t i = 0; i < n; ++i) { tx[b * n + i] = x[i]; ty[b * n + i] = y[i]; }
+  }
+  std::stringstream ladder;
+  ladder << "secret int d = x --- y;\nsecret int s = d *** d;\n";
+  for (size_t k = n / 2; k >= 1; k /= 2) ladder << "s = s +++ rotate(s, " << k << ");\n";
+  ladder << "return s;\n";
+  BatchProgram prog("secret int x = {0};\nsecret int y = {0};", ladder.str(), "s = s;", {{"x", true}, {"y", true}});
+  const auto t0 = now();
+  CudaCiphertextFactory f(N, 0, B, 0);          // setupSealContext: parameters, sk / pk / relin / Galois keys
+  f.synchronize();
+  const auto t1 = now();
+  f.setBatchInputs({tx, ty});
+  double phase[3] = {0, 0, 0};
+  bool ok = true;
+  for (int rep = 0; rep < 2; ++rep) {            // the second walk is the one reported (the first grows the scratch slots)
+    f.rewindBatchInputs();
+    const auto a = now();
+    RuntimeVisitor srv(f, *prog.astInput, prog.tainted);
+    f.synchronize();
+    const auto b = now();
+    srv.executeAst(*prog.astProgram);
+    f.synchronize();
+    const auto c = now();
+    auto output = srv.getOutput(*prog.astOutput);
+    const int64_t *out = nullptr;
+    for (const auto &[identifier, value] : output)
+      if (auto ciphertext = dynamic_cast<AbstractCiphertext *>(value.get())) out = f.decryptCiphertextBatchPinned(*ciphertext);
+    const auto d = now();
+    phase[0] = ms(a, b); phase[1] = ms(b, c); phase[2] = ms(c, d);
+    for (unsigned i = 0; i < B && ok && out; ++i) {
+      int64_t want = 0;
+      for (size_t j = 0; j < n; ++j) want += (tx[i * n + j] - ty[i * n + j]) * (tx[i * n + j] - ty[i * n + j]);
+      ok = out[(size_t)i * N] == centre(want);
+    }
+    ok = ok && out;
+  }
+  std::ofstream file(filename);
+  file << "t_keygen,t_input_encryption,t_computation,t_decryption\n"
+       << ms(t0, t1) << "," << phase[0] << "," << phase[1] << "," << phase[2] << std::endl;
+  report("demo.L2Distance N=" + std::to_string(N) + " B=" + std::to_string(B) + " -> " + filename, ok && file.good(),
+         "ms: keygen " + std::to_string(ms(t0, t1)) + ", input encryption " + std::to_string(phase[0]) + ", computation " +
+             std::to_string(phase[1]) + ", decryption " + std::to_string(phase[2]));
+}
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -485,7 +574,15 @@ int main(int argc, char **argv) {
       if (batch) runProgramsBatch(N, batch, steps);
       else runPrograms(N);
     }
-    else { std::cerr << "usage: abc_driver kats|programs [N]" << std::endl; return 2; }
+    else if (mode == "demo") {
+      if (argc < 3) { std::cerr << "usage: abc_driver demo <output_filename> [N] [--batch B]" << std::endl; return 2; }
+      const unsigned N = argc > 3 ? (unsigned)std::stoul(argv[3]) : 8192;
+      unsigned batch = 1;
+      for (int i = 4; i + 1 < argc; i += 2)
+        if (std::string(argv[i]) == "--batch") batch = (unsigned)std::stoul(argv[i + 1]);
+      runDemo(argv[2], N, batch);
+    }
+    else { std::cerr << "usage: abc_driver kats | programs [N] [--batch B --steps K] | demo <output_filename> [N] [--batch B]" << std::endl; return 2; }
   } catch (const std::exception &e) {
     std::cout << "[FAIL] uncaught exception: " << e.what() << std::endl;
     ++failures;

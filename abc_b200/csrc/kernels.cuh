@@ -439,6 +439,18 @@ __global__ void __launch_bounds__(1024) k_peak_butterfly(u64 *out, int iters, u6
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ y0 ^ x1 ^ y1 ^ x2 ^ y2 ^ x3 ^ y3;
 }
 
+// Ciphertext::is_transparent (SEAL 3.6.5 ciphertext.h: every polynomial after c0 is zero), per instance: nonzero[inst] is
+// set when any word of c1 is non-zero.  ct [B][2][L][N]; limbs [l0, l1) of c1 are looked at (limb-sharded: the owned ones).
+// grid: (chunks, B).
+__global__ void __launch_bounds__(256) k_c1_nonzero(const u64 *__restrict__ ct, int N, int L, int l0, int l1, int *__restrict__ nonzero) {
+  const int inst = blockIdx.y;
+  const u64 *c1 = ct + ((size_t)inst * 2 + 1) * L * N + (size_t)l0 * N;
+  const size_t words = (size_t)(l1 - l0) * N;
+  u64 acc = 0;
+  for (size_t w = (size_t)blockIdx.x * 256 + threadIdx.x; w < words; w += (size_t)gridDim.x * 256) acc |= c1[w];
+  if (__syncthreads_or(acc != 0) && threadIdx.x == 0) nonzero[inst] = 1;
+}
+
 // Decryptor::invariant_noise_budget, the multi-precision part: x [B][L][N] = c0 + c1*s.  Per coefficient: CRT-compose
 // t*x (RNSBase::compose_array: sum_i [t x_i (Q/q_i)^-1]_{q_i} * (Q/q_i) mod Q), centre it
 // (poly_infty_norm_coeffmod), take its bit length; the block's maximum goes to bits[inst] (atomicMax).

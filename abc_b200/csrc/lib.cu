@@ -1855,6 +1855,33 @@ abc_status abc_noise_budget(abc_ctx *c, const abc_ct *ct, int32_t *out_bits) {
   return check_ks_fault(c);
 }
 
+// Ciphertext::is_transparent per instance (SEAL's Evaluator throws std::logic_error "result ciphertext is transparent" on
+// such results when built with SEAL_THROW_ON_TRANSPARENT_CIPHERTEXT, its default).  Synchronises: the C++
+// drop-in calls it after every op only when the factory was asked to mirror that behaviour.
+abc_status abc_is_transparent(abc_ctx *c, const abc_ct *ct, int32_t *out_flags) {
+  NvtxOp nvtx_("abc_is_transparent");
+  if (!valid_ct(c, ct)) return fail(c, ABC_ERR_PARAM, "invalid ciphertext handle");
+  CHECK_POISON(c);
+  CK(cudaSetDevice(c->device));
+  TRY(ct_resolve(c, ct));
+  const int N = c->N, L = c->L, B = c->B;
+  const int l0 = c->own_lo, l1 = c->own_hi;   // limb-sharded: this rank's verdict covers the limbs it owns
+  int *d_nz = nullptr;
+  CK(cudaMallocAsync((void **)&d_nz, (size_t)B * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(d_nz, 0, (size_t)B * sizeof(int), c->stream));
+  {
+    Launch l(c, "c1_nonzero");
+    k_c1_nonzero<<<dim3(std::max(1, std::min(64, (l1 - l0) * N / 2048)), B), 256, 0, c->stream>>>(ct->b->d, N, L, l0, l1, d_nz);
+    CK(cudaGetLastError());
+  }
+  std::vector<int> nz(B);
+  CK(cudaMemcpyAsync(nz.data(), d_nz, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  sfree(c, d_nz);
+  for (int i = 0; i < B; ++i) out_flags[i] = nz[i] ? 0 : 1;
+  return check_ks_fault(c);
+}
+
 // Decryptor::decrypt + BatchEncoder::decode, enqueued: the slots land in out_slots (pinned host memory for a truly
 // asynchronous copy) once abc_decrypt_wait / abc_sync returns.  The device-side result sits in one of two buffers and
 // leaves on the context's D2H stream, so the copy overlaps the kernels of the ops enqueued after this call.

@@ -54,3 +54,21 @@ def test_a16_and_unsupported_ops_are_in_the_kats():
     _, out = run("kats")
     assert "[ ok ] a16.Cleartext<int>::subtract_inplace(ciphertext)" in out
     assert out.count("[ ok ] unsupported.") >= 15
+
+
+def test_transparent_results_throw_like_seal_when_asked_to():
+    """SURVEY A.8b: std::logic_error("result ciphertext is transparent") from the C++ drop-in (setThrowOnTransparent),
+    through factory ops and through the reference's RuntimeVisitor; off by default."""
+    _, out = run("kats")
+    assert out.count("[ ok ] transparent.") == 4
+
+
+def test_demo_csv_breakdown(tmp_path):
+    """The reference demo's CSV schema (examples/main.cpp:41), measured: one row of four phase times in ms."""
+    target = tmp_path / "demo.csv"
+    summary, _ = run("demo", str(target), "8192", "--batch", "8")
+    assert summary["cases"] == 1
+    header, row = target.read_text().strip().splitlines()
+    assert header == "t_keygen,t_input_encryption,t_computation,t_decryption"
+    vals = [float(v) for v in row.split(",")]
+    assert len(vals) == 4 and all(v > 0 for v in vals)

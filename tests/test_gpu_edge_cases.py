@@ -105,6 +105,28 @@ def test_error_behaviour():
         f.close(); g.close()
 
 
+def test_transparent_results_are_detected_per_instance():
+    """SURVEY A.8b: SEAL throws std::logic_error on results whose c1 is zero (x --- x on clones, x *** 0); the C-ABI
+    reports them (abc_is_transparent), the C++ drop-in throws when asked to (abc_driver kats, `transparent.*`)."""
+    from abc_b200 import CudaCiphertextFactory
+    f = CudaCiphertextFactory(4096, seed=SEED, batch=3, galois_steps=[1])
+    try:
+        x = f.createCiphertext(np.arange(3 * 8).reshape(3, 8))
+        assert not x.isTransparent().any()
+        assert x.subtract(x.clone()).isTransparent().all()
+        assert x.multiplyPlain([0]).isTransparent().all()
+        assert not x.add(x).isTransparent().any()
+        assert not x.multiply(x).isTransparent().any()
+        assert not x.rotateRows(1).isTransparent().any()          # a deferred handle is resolved first
+        # one instance only: instance 1 of y equals instance 1 of x, the others differ
+        w = x.export()
+        w2 = w.copy(); w2[0, 1, 0, 5] ^= np.uint64(1); w2[2, 1, f.L - 1, 4095] ^= np.uint64(1)
+        d = f.importCiphertext(w2).subtract(x)
+        assert list(d.isTransparent()) == [False, True, False]
+    finally:
+        f.close()
+
+
 def test_key_import_round_trip():
     """abc_key_import: keys produced elsewhere (the oracle here; SEAL's raw key data has the same layout)."""
     from abc_b200 import CudaCiphertextFactory, KEY_GALOIS, KEY_PUBLIC, KEY_RELIN, KEY_SECRET
