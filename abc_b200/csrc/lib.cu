@@ -15,6 +15,7 @@ typedef struct { char internal[128]; } ncclUniqueId;
 #include <sys/random.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -79,6 +80,10 @@ struct abc_ctx {
   int ks1_skew = 40;                             // ABC_KS1_SKEW: single-launch key switch, special units run this far ahead
   int idx_t = 0;
   std::vector<void *> owned;  // device allocations freed at destroy
+  // released ciphertext buffers, ready for reuse on c->stream (salloc / sfree); at most blk_cache_limit bytes are parked
+  std::vector<std::pair<size_t, u64 *>> blk_free;
+  std::map<void *, size_t> blk_live;
+  size_t blk_free_words = 0, blk_cache_limit = (size_t)32 << 30;
   u32 *d_index_map = nullptr;
   int *rm_ct = nullptr;     // [3L]  w % L
   int *rm_key = nullptr;    // [2k]  w % k
@@ -197,9 +202,22 @@ abc_status check_ks_fault(abc_ctx *c) {
 #define CHECK_POISON(c) do { if ((c)->faulted) return fail((c), ABC_ERR_CUDA, kFaultMsg); } while (0)
 
 // NVTX range around one ABI call ("abc_mul_relin", "abc_rotate_rows", ...): what nsys / ncu --nvtx group kernels by
+// ABC_HOST_TRACE=<ms>: every ABI call, launch and stream-ordered allocation whose HOST side took longer than that is
+// reported on stderr (the device-side work is asynchronous: a slow one is a blocking driver call or a descheduled thread)
+static double host_trace_ms() {
+  static const double thr = [] { const char *e = getenv("ABC_HOST_TRACE"); return e ? atof(e) : -1.0; }();
+  return thr;
+}
 struct NvtxOp {
-  explicit NvtxOp(const char *name) { nvtxRangePushA(name); }
-  ~NvtxOp() { nvtxRangePop(); }
+  const char *name; std::chrono::steady_clock::time_point t0;
+  explicit NvtxOp(const char *n) : name(n) { nvtxRangePushA(n); if (host_trace_ms() >= 0) t0 = std::chrono::steady_clock::now(); }
+  ~NvtxOp() {
+    nvtxRangePop();
+    if (host_trace_ms() >= 0) {
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      if (ms > host_trace_ms()) fprintf(stderr, "[abc_b200 host] %-28s %9.3f ms\n", name, ms);
+    }
+  }
 };
 struct Launch {
   abc_ctx *c; const char *name; cudaEvent_t a = nullptr, b = nullptr;
@@ -217,18 +235,62 @@ struct Launch {
   }
 };
 
+// Ciphertext buffers come in two or three sizes per context and are allocated and dropped by every op, so released
+// blocks are kept on a per-context free list and handed out again without a driver call.  cudaMallocAsync, although
+// stream-ordered, was measured to BLOCK the host for 1.5 ... 216 ms now and then (first allocations after a
+// synchronisation, `ABC_HOST_TRACE`), which is what made end-to-end steps stall on a device that was waiting for work.
+// Reuse is safe under the rule the stream-ordered free already relied on: a buffer is released only after everything
+// that touches it has been enqueued on (or joined into) c->stream, and the next user is enqueued on c->stream.
+static bool release_parked(abc_ctx *c) {
+  if (c->blk_free.empty()) return false;
+  for (auto &b : c->blk_free) cudaFreeAsync(b.second, c->stream);
+  c->blk_free.clear(); c->blk_free_words = 0;
+  return true;
+}
 abc_status salloc(abc_ctx *c, u64 **p, size_t words) {
-  CK(cudaMallocAsync((void **)p, words * sizeof(u64), c->stream));
+  for (size_t i = c->blk_free.size(); i-- > 0;)
+    if (c->blk_free[i].first == words) {
+      *p = c->blk_free[i].second;
+      c->blk_free.erase(c->blk_free.begin() + (long)i);
+      c->blk_free_words -= words;
+      c->blk_live[*p] = words;
+      return ABC_OK;
+    }
+  NvtxOp nvtx_("cudaMallocAsync");
+  cudaError_t e = cudaMallocAsync((void **)p, words * sizeof(u64), c->stream);
+  if (e != cudaSuccess && release_parked(c)) {   // out of memory with blocks of other sizes parked: give them back, retry
+    cudaGetLastError();
+    e = cudaMallocAsync((void **)p, words * sizeof(u64), c->stream);
+  }
+  CK(e);
+  c->blk_live[*p] = words;
   return ABC_OK;
 }
-void sfree(abc_ctx *c, void *p) { if (p) cudaFreeAsync(p, c->stream); }
+void sfree(abc_ctx *c, void *p) {
+  if (!p) return;
+  auto it = c->blk_live.find(p);
+  if (it == c->blk_live.end()) { cudaFreeAsync(p, c->stream); return; }   // not a salloc block (small per-call arrays)
+  const size_t words = it->second;
+  c->blk_live.erase(it);
+  if (c->blk_free.size() < 24 && (c->blk_free_words + words) * sizeof(u64) <= c->blk_cache_limit) {
+    c->blk_free.emplace_back(words, (u64 *)p);
+    c->blk_free_words += words;
+  } else {
+    cudaFreeAsync(p, c->stream);
+  }
+}
 enum { SC_T = 0, SC_ACC, SC_X, SC_OUT3, SC_U, SC_TMP, SC_DECX, SC_DECP, SC_P, SC_NK, SC_ENTT, SC_COMM_SEND, SC_COMM_ALL, SC_Y, SC_SX, SC_XCH, SC_XI, SC_NSLOTS };
 static_assert(SC_NSLOTS <= 32, "abc_ctx::sc_ptr / sc_words hold 32 slots");
 abc_status scratch(abc_ctx *c, int slot, u64 **p, size_t words) {
   if (c->sc_words[slot] < words) {
     if (c->sc_ptr[slot]) cudaFreeAsync(c->sc_ptr[slot], c->stream);
     c->sc_ptr[slot] = nullptr; c->sc_words[slot] = 0;
-    CK(cudaMallocAsync((void **)&c->sc_ptr[slot], words * sizeof(u64), c->stream));
+    cudaError_t e = cudaMallocAsync((void **)&c->sc_ptr[slot], words * sizeof(u64), c->stream);
+    if (e != cudaSuccess && release_parked(c)) {
+      cudaGetLastError();
+      e = cudaMallocAsync((void **)&c->sc_ptr[slot], words * sizeof(u64), c->stream);
+    }
+    CK(e);
     c->sc_words[slot] = words;
   }
   *p = c->sc_ptr[slot];
@@ -426,6 +488,7 @@ abc_status build_tables(abc_ctx *c) {
   if (const char *e = getenv("ABC_KS_RED")) c->ks_red = atoi(e);
   if (const char *e = getenv("ABC_KS14_SPLIT")) c->ks14 = atoi(e);
   if (const char *e = getenv("ABC_KS_PERSIST")) c->ks_persist = atoi(e);
+  if (const char *e = getenv("ABC_BLOCK_CACHE_MIB")) c->blk_cache_limit = (size_t)atoll(e) << 20;   // 0: every release goes to the driver
   cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device);
   if (const char *e = getenv("ABC_KS_SPLIT_MAXB")) c->ks_split_maxb = atoi(e);
   if (const char *e = getenv("ABC_BEHZ_FUSED")) c->behz_fused = atoi(e) != 0;
@@ -1487,6 +1550,7 @@ void abc_ctx_destroy(abc_ctx *c) {
   for (void *p : c->owned) cudaFree(p);
   if (c->flush_buf) cudaFree(c->flush_buf);
   for (u64 *p : c->sc_ptr) if (p) cudaFree(p);
+  for (auto &b : c->blk_free) cudaFree(b.second);
   for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
