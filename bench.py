@@ -679,12 +679,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--ref-instances-per-core", type=int, default=8)
-    ap.add_argument("--workload", default="l2distance", choices=["l2distance", "deep_chain"],
-                    help="deep_chain: BASELINE.json configs[4], N=65536 multiplicative chain, RNS limbs sharded over the ranks")
+    ap.add_argument("--workload", default="l2distance", choices=["l2distance", "deep_chain", "stencil10k"],
+                    help="deep_chain: BASELINE.json configs[4], N=65536 multiplicative chain, RNS limbs sharded over the ranks; "
+                         "stencil10k: configs[3], 10 000 BoxBlur / GxKernel instances sharded over the ranks (tools/stencil10k_bench.py, "
+                         "one JSON line per program)")
     ap.add_argument("--depth", type=int, default=8, help="deep_chain: (mul+relin, rotate) pairs per step")
     args = ap.parse_args()
     if args.workload == "deep_chain":
         return run_deep_chain(args)
+    if args.workload == "stencil10k":
+        from tools import stencil10k_bench
+        sys.argv = [sys.argv[0], "--passes", str(max(1, args.steps))]
+        return stencil10k_bench.main()
     if args.impl == "reference":
         run_reference(args)
     else:
