@@ -55,6 +55,7 @@ SYMBOLS = {
     "abc_decrypt_decode_async": (i32, [vp, vp, vp]),
     "abc_decrypt_wait": (i32, [vp]),
     "abc_set_encrypt_nonce": (i32, [vp, u64]),
+    "abc_set_rng_key": (i32, [vp, vp]),
     "abc_noise_budget": (i32, [vp, vp, vp]),
     "abc_is_transparent": (i32, [vp, vp, vp]),
     "abc_add": (i32, [vp, vp, vp, vp]),

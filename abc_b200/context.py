@@ -149,6 +149,14 @@ class CudaCiphertextFactory:
     def set_encrypt_nonce(self, nonce):
         self._ck(self._lib.abc_set_encrypt_nonce(self._h, nonce))
 
+    def set_rng_key(self, key32):
+        """The sampler's 32-byte ChaCha20 key from the caller (abc_set_rng_key): call on a factory built with
+        keygen=False, then keygen()."""
+        if len(key32) != 32:
+            raise AbcError("rng key must be 32 bytes")
+        buf = (C.c_ubyte * 32)(*key32)
+        self._ck(self._lib.abc_set_rng_key(self._h, buf))
+
     # -- ciphertext creation (AbstractCiphertextFactory.h:19-38)
     def _slots(self, data):
         """Returns (int64 array, n per instance, broadcast flag)."""

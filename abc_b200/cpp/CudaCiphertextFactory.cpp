@@ -28,7 +28,7 @@ void CudaCiphertextFactory::checkResult(int status, const abc_ct *result) const 
     if (f) throw std::logic_error("result ciphertext is transparent");  // SEAL 3.6.5 Evaluator, same type and text
 }
 
-void CudaCiphertextFactory::setup(int device, unsigned int batch, uint64_t seed) {
+void CudaCiphertextFactory::setup(int device, unsigned int batch, uint64_t seed, const uint8_t *rngKey32) {
   // SealCiphertextFactory::setupSealContext (src/runtime/SealCiphertextFactory.cpp:72-100): BFVDefault(N),
   // Batching(N, 20), then secret/public/Galois/relin keys.  n_primes = 0 and plain_modulus = 0 select the
   // same SEAL defaults inside the library.
@@ -41,8 +41,15 @@ void CudaCiphertextFactory::setup(int device, unsigned int batch, uint64_t seed)
     throw std::runtime_error(std::string("CudaCiphertextFactory: ") + abc_last_error(nullptr));
   }
   st->ctx = ctx;
+  if (rngKey32) check(abc_set_rng_key(ctx, rngKey32));
   check(abc_keygen(ctx));
   if (const char *e = std::getenv("ABC_THROW_ON_TRANSPARENT")) st->throwOnTransparent = std::atoi(e) != 0;
+}
+
+CudaCiphertextFactory::CudaCiphertextFactory(unsigned int numElementsPerCiphertextSlot, int device, unsigned int batch,
+                                             const std::array<uint8_t, 32> &rngKey)
+    : ciphertextSlotSize(numElementsPerCiphertextSlot) {
+  setup(device, batch, 0, rngKey.data());
 }
 
 // The reference's factory draws its keys from SEAL's randomly seeded PRNG; seed 0 asks the library for the same

@@ -9,6 +9,7 @@
 #define ABC_B200_CPP_CUDACIPHERTEXTFACTORY_H_
 
 #include <cstdint>
+#include <array>
 #include <memory>
 #include <string>
 #include <vector>
@@ -53,7 +54,7 @@ class CudaCiphertextFactory : public AbstractCiphertextFactory {
   abc_ctx *ctx = nullptr;                            // = st->ctx
   void releaseBatchTables() const;
 
-  void setup(int device, unsigned int batch, uint64_t seed);
+  void setup(int device, unsigned int batch, uint64_t seed, const uint8_t *rngKey32 = nullptr);
 
  public:
   CudaCiphertextFactory();
@@ -61,6 +62,10 @@ class CudaCiphertextFactory : public AbstractCiphertextFactory {
   explicit CudaCiphertextFactory(unsigned int numElementsPerCiphertextSlot);
   /// Extended constructor: device ordinal, instances per handle (lock-step batch), sampler seed.
   CudaCiphertextFactory(unsigned int numElementsPerCiphertextSlot, int device, unsigned int batch, uint64_t seed);
+  /// The same with the sampler's 256-bit ChaCha20 key supplied by the caller (32 bytes of its own entropy): the way to give
+  /// the per-GPU factories of one job the same keys without a guessable 64-bit seed.
+  CudaCiphertextFactory(unsigned int numElementsPerCiphertextSlot, int device, unsigned int batch,
+                        const std::array<uint8_t, 32> &rngKey);
   ~CudaCiphertextFactory() = default;
   /// A copy shares the device context (keys, stream) with the original; the context goes when the last copy — and the last
   /// ciphertext created through it — is gone.  One host thread at a time per context (copies included).

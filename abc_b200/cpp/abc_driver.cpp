@@ -16,6 +16,7 @@
 //                              the reference's `ast_demo demo <output_filename>` (examples/main.cpp:33-46): one CSV row
 //                              t_keygen,t_input_encryption,t_computation,t_decryption (ms) of the L2Distance ladder
 // Prints one line per case and a JSON summary; exit code 1 on any mismatch.
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -249,6 +250,21 @@ void runKats() {
     r = runProgram(f, "secret int __input0__ = {43,  1,   1,  22, 11, 7};",
                    "int i = 19;\nsecret int result = __input0__ --- i;\nreturn result;", "y = result;", in0);
     report("a16.visitor `cipher --- plain`", prefixEquals(r["y"], {24, -18, -18, 3, -8, -12}));
+  }
+  {
+    // two factories built from the same caller-supplied 32-byte sampler key hold the same secret key: a ciphertext saved by
+    // one (SEAL stream) decrypts under the other; a factory with an OS-drawn key cannot decrypt it
+    std::array<uint8_t, 32> rngKey{};
+    for (size_t i = 0; i < rngKey.size(); ++i) rngKey[i] = (uint8_t)(101 * i + 7);
+    CudaCiphertextFactory a(4096, 0, 1, rngKey), b(4096, 0, 1, rngKey), other(4096);
+    auto ct = a.createCiphertext(data1);
+    auto stream = a.saveCiphertext(*ct);
+    auto viaB = b.loadCiphertext(stream);
+    checkCiphertextData(b, *viaB, data1, "rngkey.same 32-byte sampler key on two factories: ciphertext of one decrypts under the other");
+    auto viaOther = other.loadCiphertext(stream);
+    std::vector<int64_t> garbage;
+    other.decryptCiphertext(*viaOther, garbage);
+    report("rngkey.a factory with an OS-drawn key does not decrypt it", !prefixEquals(garbage, data1));
   }
   {
     // SEAL (SEAL_THROW_ON_TRANSPARENT_CIPHERTEXT, its default) throws std::logic_error on a result whose c1 is

@@ -254,13 +254,13 @@ __global__ void __launch_bounds__(256) k_plain_addsub(u64 *__restrict__ dst, con
 // Encryption tail (Encryptor::encrypt_zero_internal + RNSTool::divide_and_round_q_last_inplace +
 // multiply_add_plain_with_scaling_variant; SealCiphertextFactory.cpp:12).
 // tmp [inst][2][k][N] = INTT(pk_j * NTT(u)) in coefficient form.  Adds e_j ~ CBD, divides by p with
-// rounding, adds the scaled plaintext to component 0.  grid: (N/256, 2, B)
+// rounding, adds the scaled plaintext to component 0.  rnd [inst][3][N]: the words of the encryption's streams
+// (DOM_ENC, nonce0 + inst, b = 0 (u), 1 (e_0), 2 (e_1)) from k_rng_fill.  grid: (N/256, 2, B)
 __global__ void __launch_bounds__(256) k_enc_finish(const u64 *__restrict__ tmp, const u64 *__restrict__ plain,
-                                                    long long plain_is, u64 *__restrict__ ct, u64 seed, u64 nonce0,
+                                                    long long plain_is, u64 *__restrict__ ct, const u64 *__restrict__ rnd,
                                                     const DevConst *__restrict__ C, int N, int L, int k) {
   const int n = blockIdx.x * 256 + threadIdx.x, comp = blockIdx.y, inst = blockIdx.z;
-  const u64 h = stream_key(seed, 4 /*DOM_ENC*/, nonce0 + (u64)inst, 1 + (u64)comp);
-  const int e = sample_cbd(h, (u64)n);
+  const int e = cbd_of(rnd[((size_t)inst * 3 + 1 + comp) * N + n]);
   const u64 *tp = tmp + ((size_t)inst * 2 + comp) * k * N + n;
   u64 last = add_mod(tp[(size_t)L * N], small_to_mod(e, C->p), C->p);
   last = add_mod(last, C->p_half, C->p);
@@ -309,18 +309,31 @@ __global__ void __launch_bounds__(128) k_dec_finish(const u64 *__restrict__ x, u
 // ------------------------------------------------------------------------------------------------
 // Key generation helpers (KeyGenerator; SealCiphertextFactory.cpp:89-93)
 // uniform a_i mod q_i for all key-level limbs of one polynomial.  grid: (N/256, k)
-__global__ void __launch_bounds__(256) k_sample_uniform(u64 *__restrict__ dst, u64 seed, u64 domain, u64 a,
+// (SEAL sample_poly_uniform: rejection above the largest multiple of q; retry j of coefficient n is word n + j * 2^24)
+__global__ void __launch_bounds__(256) k_sample_uniform(u64 *__restrict__ dst, RngKey key, u64 domain, u64 a,
                                                         u64 b_base, const DevConst *__restrict__ C, int N) {
   const int n = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
   const u64 q = C->q[i];
-  const u64 h = stream_key(seed, domain, a, ((b_base | (u64)i) << 2) | 0);
+  const RngStream rs = rng_stream(key, domain, a, ((b_base | (u64)i) << 2) | 0);
   const u64 max_random = ~0ULL, max_multiple = max_random - (max_random % q) - 1;
   u64 r;
   for (u64 attempt = 0;; ++attempt) {
-    r = mix64(h ^ ((u64)n | (attempt << 32)));
+    r = rng_word(rs, (u64)n | (attempt << 24));
     if (r < max_multiple) break;
   }
   dst[(size_t)i * N + n] = r % q;
+}
+// The words of `streams` sampler streams per instance, generated once: dst [inst][streams][N], stream s of instance inst =
+// rng_stream(key, domain, a0 + inst, b0 + s); one ChaCha20 block (8 words) per thread.  grid: (N/8/128, streams, B)
+__global__ void __launch_bounds__(128) k_rng_fill(u64 *__restrict__ dst, RngKey key, u64 domain, u64 a0, u64 b0, int N) {
+  const int blk = blockIdx.x * 128 + threadIdx.x, s = blockIdx.y, inst = blockIdx.z;
+  if (blk * 8 >= N) return;
+  const RngStream rs = rng_stream(key, domain, a0 + (u64)inst, b0 + (u64)s);
+  u64 w[8];
+  chacha20_block(rs, (u32)blk, w);
+  ulonglong2 *o = reinterpret_cast<ulonglong2 *>(dst + ((size_t)inst * gridDim.y + s) * N + (size_t)blk * 8);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = make_ulonglong2(w[2 * i], w[2 * i + 1]);
 }
 // c0 = -(a*s + e) [+ factor * newkey at limb J]  (encrypt_zero_symmetric + generate_one_kswitch_key)
 // key block layout [2][k][N]: c0 rows then c1 = a rows.  grid: (N/256, k)

@@ -62,6 +62,9 @@ struct abc_ctx {
   // so two contexts that share a key seed (one factory per GPU) never reuse (u, e0, e1); abc_set_encrypt_nonce makes the
   // stream reproducible (salt 0) for parity tests.
   u64 enc_salt = 0;
+  // the sampler's 256-bit ChaCha20 key (modarith.cuh): 32 bytes from the OS generator, or expanded from an explicit seed
+  // (tests; the same keys on every GPU of a job), or set by abc_set_rng_key
+  RngKey rng_key{};
   std::vector<u64> primes, bsk;
   DevConst hC;
   DevConst *dC = nullptr;
@@ -279,7 +282,7 @@ void sfree(abc_ctx *c, void *p) {
     cudaFreeAsync(p, c->stream);
   }
 }
-enum { SC_T = 0, SC_ACC, SC_X, SC_OUT3, SC_U, SC_TMP, SC_DECX, SC_DECP, SC_P, SC_NK, SC_ENTT, SC_COMM_SEND, SC_COMM_ALL, SC_Y, SC_SX, SC_XCH, SC_XI, SC_NSLOTS };
+enum { SC_T = 0, SC_ACC, SC_X, SC_OUT3, SC_U, SC_TMP, SC_DECX, SC_DECP, SC_P, SC_NK, SC_ENTT, SC_COMM_SEND, SC_COMM_ALL, SC_Y, SC_SX, SC_XCH, SC_XI, SC_RND, SC_NSLOTS };
 static_assert(SC_NSLOTS <= 32, "abc_ctx::sc_ptr / sc_words hold 32 slots");
 abc_status scratch(abc_ctx *c, int slot, u64 **p, size_t words) {
   if (c->sc_words[slot] < words) {
@@ -322,6 +325,13 @@ abc_status launch_limb(abc_ctx *c, int combo, int ar, const LimbJob &job, int W,
   return ABC_OK;
 }
 LimbJob blank_job() { LimbJob j; memset(&j, 0, sizeof j); return j; }
+// explicit 64-bit seed -> sampler key (part of the sampler definition: DESIGN.md "Sampler")
+RngKey rng_key_from_seed(u64 seed) {
+  RngKey key{};
+  key.k[0] = (u32)seed; key.k[1] = (u32)(seed >> 32);
+  key.k[2] = 0x2d636261u; key.k[3] = 0x30303262u;   // "abc-b200"
+  return key;
+}
 
 #define DISPATCH_L(c, EXPR)                                                        \
   switch ((c)->L) {                                                                \
@@ -1373,12 +1383,18 @@ abc_status encrypt_device(abc_ctx *c, const u64 *plain, int broadcast, u64 *ct) 
   const int N = c->N, L = c->L, k = c->k, B = c->B;
   const u64 nonce0 = c->enc_salt + c->enc_nonce * (u64)B;
   c->enc_nonce++;
-  u64 *u = nullptr, *tmp = nullptr;
+  u64 *u = nullptr, *tmp = nullptr, *rnd = nullptr;
   TRY(scratch(c, SC_U, &u, (size_t)B * k * N));
   TRY(scratch(c, SC_TMP, &tmp, (size_t)B * 2 * k * N));
+  TRY(scratch(c, SC_RND, &rnd, (size_t)B * 3 * N));
+  {  // the three streams of every instance (u, e_0, e_1), one ChaCha20 block per thread; the k limb rows of u then read them
+    Launch l(c, "enc_rng_fill");
+    k_rng_fill<<<dim3((N / 8 + 127) / 128, 3, B), 128, 0, c->stream>>>(rnd, c->rng_key, DOM_ENC, nonce0, 0, N);
+    CK(cudaGetLastError());
+  }
   LimbJob j = blank_job();
   j.dst = u; j.dst_is = (long long)k * N; j.rowmod = c->rm_key;
-  j.seed = c->seed; j.domain = DOM_ENC; j.a0 = nonce0; j.b = 0;
+  j.rng = c->rng_key; j.domain = DOM_ENC; j.a0 = nonce0; j.b = 0; j.rnd = rnd; j.rnd_is = (long long)3 * N;
   TRY(launch_limb(c, LIMB_TERNARY_FWD, c->ar_q, j, k, B, "enc_sample_u_ntt"));
   j = blank_job();
   j.src = u; j.src_is = (long long)k * N; j.rowsrc = c->rm_key;
@@ -1387,8 +1403,7 @@ abc_status encrypt_device(abc_ctx *c, const u64 *plain, int broadcast, u64 *ct) 
   TRY(launch_limb(c, LIMB_MUL_INV, c->ar_q, j, 2 * k, B, "enc_mul_pk_intt"));
   {
     Launch l(c, "enc_finish");
-    k_enc_finish<<<dim3(N / 256, 2, B), 256, 0, c->stream>>>(tmp, plain, broadcast ? 0 : N, ct, c->seed, nonce0, c->dC, N,
-                                                           L, k);
+    k_enc_finish<<<dim3(N / 256, 2, B), 256, 0, c->stream>>>(tmp, plain, broadcast ? 0 : N, ct, rnd, c->dC, N, L, k);
     CK(cudaGetLastError());
   }
   return ABC_OK;
@@ -1423,12 +1438,12 @@ abc_status gen_key_block(abc_ctx *c, u64 *blk, u64 dom, u64 a_id, u64 b_base, co
   const int N = c->N, k = c->k;
   {
     Launch l(c, "keygen_uniform");
-    k_sample_uniform<<<dim3(N / 256, k), 256, 0, c->stream>>>(blk + (size_t)k * N, c->seed, dom, a_id, b_base, c->dC, N);
+    k_sample_uniform<<<dim3(N / 256, k), 256, 0, c->stream>>>(blk + (size_t)k * N, c->rng_key, dom, a_id, b_base, c->dC, N);
     CK(cudaGetLastError());
   }
   LimbJob j = blank_job();
   j.dst = e_ntt; j.dst_is = 0; j.rowmod = c->rm_key;
-  j.seed = c->seed; j.domain = dom; j.a0 = a_id; j.b = (b_base << 2) | 1;
+  j.rng = c->rng_key; j.domain = dom; j.a0 = a_id; j.b = (b_base << 2) | 1;
   TRY(launch_limb(c, LIMB_CBD_FWD, c->ar_q, j, k, 1, "keygen_noise_ntt"));
   {
     Launch l(c, "keygen_finish");
@@ -1491,11 +1506,12 @@ abc_status abc_ctx_create(const abc_params *p, abc_ctx **out) {
   while ((1ull << logN) < N) ++logN;
   if ((1ull << logN) != N || logN < 12 || logN > 16) return bail(ABC_ERR_PARAM, "poly_degree must be a power of two in [4096, 65536]");
   c->N = (int)N; c->logN = logN; c->B = p->batch ? (int)p->batch : 1; c->seed = p->seed;
-  {  // seed 0 = not reproducible: key seed and encryption salt from the OS generator
-    u64 r[2] = {0, 0};
+  {  // seed 0 = not reproducible: the sampler key and the encryption salt come from the OS generator
+    u64 r[5] = {0, 0, 0, 0, 0};
     if (getrandom(r, sizeof r, 0) != (ssize_t)sizeof r) return bail(ABC_ERR_STATE, "getrandom failed: no entropy for keys / encryption randomness");
-    if (c->seed == 0) c->seed = r[0] | 1ull;
-    c->enc_salt = r[1];
+    c->enc_salt = r[4];
+    if (c->seed == 0) memcpy(c->rng_key.k, r, 32);
+    else c->rng_key = rng_key_from_seed(c->seed);
   }
   try {
     if (p->n_primes == 0) c->primes = hm::bfv_default_primes(N);
@@ -1621,7 +1637,7 @@ static abc_status keygen_impl(abc_ctx *c, const std::vector<u32> &elts) {
   if (!c->d_pk) CK(cudaMalloc((void **)&c->d_pk, (size_t)2 * k * N * 8));
   if (!c->d_relin) CK(cudaMalloc((void **)&c->d_relin, kw * 8));
   LimbJob j = blank_job();
-  j.dst = c->d_sk; j.rowmod = c->rm_key; j.seed = c->seed; j.domain = DOM_SK;
+  j.dst = c->d_sk; j.rowmod = c->rm_key; j.rng = c->rng_key; j.domain = DOM_SK;
   TRY(launch_limb(c, LIMB_TERNARY_FWD, c->ar_q, j, k, 1, "keygen_sk_ntt"));
   u64 *nk = nullptr, *e_ntt = nullptr;
   TRY(scratch(c, SC_NK, &nk, (size_t)k * N));
@@ -1855,6 +1871,13 @@ abc_status abc_encode_encrypt(abc_ctx *c, const int64_t *slots, size_t n, int br
   abc_status s = abc_encrypt_pt(c, pt, out);
   abc_pt_free(pt);
   return s;
+}
+// The sampler key from the caller (32 bytes of its own entropy): what gives every GPU of a job the same keys without
+// falling back to a 64-bit seed.  Takes effect for the next abc_keygen and for the encryptions that follow.
+abc_status abc_set_rng_key(abc_ctx *c, const uint8_t *key32) {
+  if (!key32) return fail(c, ABC_ERR_PARAM, "null key");
+  memcpy(c->rng_key.k, key32, 32);
+  return ABC_OK;
 }
 abc_status abc_set_encrypt_nonce(abc_ctx *c, uint64_t nonce) { c->enc_nonce = nonce; c->enc_salt = 0; return ABC_OK; }
 

@@ -28,8 +28,11 @@ struct LimbJob {
   int n;                                      // coefficients per limb (row stride); = kernel N except in TAIL mode
   int sub;                                    // TAIL mode: log2(blocks per limb); blockIdx.x = row << sub | block
   int prefetch_ahead;                         // > 0: L2-prefetch the source row of the CTA this many blocks ahead
-  // sampler (PRE_TERNARY / PRE_CBD): stream = stream_key(seed, domain, a0 + inst, b)
-  u64 seed, domain, a0, b;
+  // sampler (PRE_TERNARY / PRE_CBD): stream = rng_stream(rng, domain, a0 + inst, b) (modarith.cuh); rnd, if set, holds the
+  // stream's words already generated (k_rng_fill): word idx of instance inst at rnd[inst * rnd_is + idx]
+  RngKey rng;
+  u64 domain, a0, b;
+  const u64 *rnd; long long rnd_is;
   // PRE_ENCODE / POST_DECODE
   const long long *slots_in; long long *slots_out; const u32 *index_map; int n_slots; long long slots_is;
   // PRE_PLAIN_LIFT
@@ -93,25 +96,24 @@ enum {
 };
 
 __device__ __forceinline__ u64 small_to_mod(int v, u64 q) { return v < 0 ? q - (u64)(-v) : (u64)v; }
-__device__ __forceinline__ int sample_ternary(u64 h, u64 idx) {
-  u64 r = mix64(h ^ idx);
-  return (int)(((r >> 32) * 3) >> 32) - 1;
-}
-__device__ __forceinline__ int sample_cbd(u64 h, u64 idx) {
-  u64 r = mix64(h ^ idx);
-  return __popcll(r & 0x1fffffULL) - __popcll((r >> 21) & 0x1fffffULL);
-}
 
 // ---- pre-op: coefficients (2*e2, 2*e2+1) of source row `srow`, ready for the forward transform (< q)
 // h = sampler stream key (sampling modes); n = coefficients per limb
 template <int PRE>
 __device__ __forceinline__ ulonglong2 limb_load_pair(const LimbJob &job, const ModInfo &M, const ModInfo *__restrict__ mods,
-                                                     int n, int inst, int srow, int e2, u64 h) {
+                                                     int n, int inst, int srow, int e2, const RngStream &rs) {
   const u64 q = M.q;
   ulonglong2 v;
   if (PRE == PRE_TERNARY || PRE == PRE_CBD) {
-    const int a = (PRE == PRE_TERNARY) ? sample_ternary(h, (u64)(2 * e2)) : sample_cbd(h, (u64)(2 * e2));
-    const int b = (PRE == PRE_TERNARY) ? sample_ternary(h, (u64)(2 * e2 + 1)) : sample_cbd(h, (u64)(2 * e2 + 1));
+    u64 r0, r1;
+    if (job.rnd) {
+      const ulonglong2 w = reinterpret_cast<const ulonglong2 *>(job.rnd + (size_t)inst * job.rnd_is)[e2];
+      r0 = w.x; r1 = w.y;
+    } else {
+      rng_word_pair(rs, (u64)e2, r0, r1);
+    }
+    const int a = (PRE == PRE_TERNARY) ? ternary_of(r0) : cbd_of(r0);
+    const int b = (PRE == PRE_TERNARY) ? ternary_of(r1) : cbd_of(r1);
     v.x = small_to_mod(a, q); v.y = small_to_mod(b, q);
   } else if (PRE == PRE_GALOIS_REDUCE) {
     // GaloisTool::apply_galois as a gather (negation is modulo the SOURCE limb's prime), then the ModUp reduction
@@ -583,9 +585,10 @@ __device__ __forceinline__ void limb_body(const LimbJob &job, const ModInfo *__r
       sm[swz((int)job.index_map[e])] = v < 0 ? q + (u64)v : (u64)v;
     }
   } else {
-    const u64 h = (PRE == PRE_TERNARY || PRE == PRE_CBD) ? stream_key(job.seed, job.domain, job.a0 + (u64)inst, job.b) : 0;
+    RngStream rs;
+    if (PRE == PRE_TERNARY || PRE == PRE_CBD) rs = rng_stream(job.rng, job.domain, job.a0 + (u64)inst, job.b);
     for (int e2 = tid; e2 < D::N / 2; e2 += D::T)
-      *reinterpret_cast<ulonglong2 *>(&sm[swz_pair(tid, e2)]) = limb_load_pair<PRE>(job, M, mods, n, inst, srow, eoff + e2, h);
+      *reinterpret_cast<ulonglong2 *>(&sm[swz_pair(tid, e2)]) = limb_load_pair<PRE>(job, M, mods, n, inst, srow, eoff + e2, rs);
   }
   if (!LINSRC) __syncthreads();
   // T[inst][I][0..L) is dead once both components' rows have read it (the barrier above: every thread of this row has).
@@ -745,11 +748,12 @@ __global__ void __launch_bounds__(256) k_head_fwd(LimbJob job, const ModInfo *__
   const u64 q = M.q, q2 = 2 * q;
   const int drow = job.rowdst ? job.rowdst[w] : w;
   const int srow = job.rowsrc ? job.rowsrc[w] : drow;
-  const u64 h = (PRE == PRE_TERNARY || PRE == PRE_CBD) ? stream_key(job.seed, job.domain, job.a0 + (u64)inst, job.b) : 0;
+  RngStream rs;
+  if (PRE == PRE_TERNARY || PRE == PRE_CBD) rs = rng_stream(job.rng, job.domain, job.a0 + (u64)inst, job.b);
   u64 x[R], y[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    ulonglong2 v = limb_load_pair<PRE>(job, M, mods, n, inst, srow, c2 + r * stride2, h);
+    ulonglong2 v = limb_load_pair<PRE>(job, M, mods, n, inst, srow, c2 + r * stride2, rs);
     x[r] = v.x; y[r] = v.y;
   }
 #pragma unroll

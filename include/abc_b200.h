@@ -39,12 +39,12 @@ typedef struct abc_params {
   uint64_t plain_modulus;   /* t; 0 -> SEAL PlainModulus::Batching(N, 20) */
   int32_t device;           /* CUDA device ordinal */
   uint32_t batch;           /* independent instances per handle (>= 1) */
-  uint64_t seed;            /* key sampler seed; 0 = draw one from the OS generator (getrandom).  A fixed seed makes the
-                             * keys reproducible by anyone who knows it: tests and multi-GPU key sharing only.
-                             * Encryption randomness is salted per context from the OS either way (see
-                             * abc_set_encrypt_nonce).  The sampler itself is a counter-based statistical generator,
-                             * NOT a CSPRNG: production keys should be generated by SEAL and
-                             * imported (abc_key_import / abc_seal_key_load). */
+  uint64_t seed;            /* 0 = the sampler's 256-bit key is drawn from the OS generator (getrandom), like the
+                             * reference's randomly seeded SEAL PRNG.  A non-zero seed is EXPANDED to the key, which
+                             * makes the keys reproducible by anyone who knows those 64 bits: tests, and the same keys
+                             * on every GPU of a job when abc_set_rng_key is not used.  Encryption randomness is
+                             * additionally salted per context from the OS (see abc_set_encrypt_nonce).  The sampler
+                             * is the ChaCha20 key stream. */
 } abc_params;
 
 /* --- context: replaces SealCiphertextFactory::setupSealContext (src/runtime/SealCiphertextFactory.cpp:72-100)
@@ -128,6 +128,12 @@ abc_status abc_is_transparent(abc_ctx *ctx, const abc_ct *ct, int32_t *out_flags
  * a key seed, e.g. one factory per GPU, never repeat randomness).  This call sets the counter AND zeroes the salt: the
  * encryptions that follow are reproducible — for parity tests against the oracle only. */
 abc_status abc_set_encrypt_nonce(abc_ctx *ctx, uint64_t nonce);
+/* The sampler's 256-bit key, supplied by the caller (32 bytes of its own entropy) instead of the OS-drawn one or the
+ * expansion of a 64-bit `seed`: what gives every GPU of a job the same keys at full key strength.  Call before
+ * abc_keygen; it also keys the encryptions that follow.  Keys, u and the error polynomials are the ChaCha20 key stream
+ * under this key (one stream per key / encryption / component), mapped to SEAL's distributions (uniform mod q_i with
+ * rejection, ternary, centred binomial 21 - 21). */
+abc_status abc_set_rng_key(abc_ctx *ctx, const uint8_t *key32);
 
 /* --- ciphertext-ciphertext ops.  dst may alias a (the *Inplace variants of the reference).
  * add/sub: Evaluator::add/sub          (src/runtime/SealCiphertext.cpp:90-100,113-119)

@@ -198,7 +198,8 @@ struct obfv_ctx {
   u64 neg_inv_q_mod_mtilde, q_mod_bsk[MAXK], inv_mtilde_mod_bsk[MAXK], inv_q_mod_bsk[MAXK];
   u64 inv_punct_B[MAXK], punct_B_mod_q[MAXK][MAXK], punct_B_mod_msk[MAXK], inv_B_mod_msk, B_mod_q[MAXK];
   /* keys */
-  u64 seed; u64 *sk, *pk, *relin; u64 **galois; /* galois indexed by (elt-1)/2 */
+  u64 seed; u32 rng_key[8]; int rng_key_set; /* sampler key: expanded from seed unless obfv_set_rng_key was called */
+  u64 *sk, *pk, *relin; u64 **galois; /* galois indexed by (elt-1)/2 */
 };
 
 static const u64 DEF_4096[] = {0xffffee001ULL, 0xffffc4001ULL, 0x1ffffe0001ULL};
@@ -379,36 +380,70 @@ void obfv_ntt_inv(const obfv_ctx *c, size_t idx, u64 *limb) { ntt_inv(tab_for(c,
 
 /* ------------------------------------------------------------------ sampler (our own spec; SEAL's
  * Blake2xb/SHAKE stream is randomly seeded and cannot be matched, only the distributions are SEAL's:
- * sample_poly_ternary, sample_poly_cbd (SEAL 3.6 default noise), sample_poly_uniform — util/rlwe.cpp) */
-static inline u64 mix64(u64 z) {
-  z += 0x9e3779b97f4a7c15ULL;
-  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
-  z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
-  return z ^ (z >> 31);
+ * sample_poly_ternary, sample_poly_cbd (SEAL 3.6 default noise), sample_poly_uniform — util/rlwe.cpp).
+ * Randomness = the ChaCha20 key stream (20 rounds, RFC 8439 state layout) under a 256-bit key:
+ *   state = "expand 32-byte k" | key[8] | block counter | nonce (domain | b << 4, a lo, a hi)
+ *   word idx of stream (domain, a, b) = 32-bit words 2*(idx & 7), 2*(idx & 7) + 1 of block idx >> 3.
+ * A 64-bit seed (tests) expands to the key (seed lo, seed hi, "abc-", "b200", 0, 0, 0, 0). */
+typedef struct { u32 key[8]; u32 n0, n1, n2; u32 have; u32 ctr; u64 w[8]; } rng_stream_t;
+static void rng_key_from_seed(u64 seed, u32 key[8]) {
+  memset(key, 0, 32);
+  key[0] = (u32)seed; key[1] = (u32)(seed >> 32); key[2] = 0x2d636261u; key[3] = 0x30303262u;
 }
-static inline u64 stream_key(u64 seed, u64 domain, u64 a, u64 b) {
-  u64 h = mix64(seed ^ (domain * 0xd6e8feb86659fd93ULL));
-  h = mix64(h ^ a);
-  return mix64(h ^ b);
+static rng_stream_t rng_stream(const u32 key[8], u64 domain, u64 a, u64 b) {
+  rng_stream_t s;
+  memcpy(s.key, key, 32);
+  s.n0 = (u32)domain | ((u32)b << 4); s.n1 = (u32)a; s.n2 = (u32)(a >> 32);
+  s.have = 0; s.ctr = 0;
+  return s;
 }
-u64 obfv_rng(u64 seed, u64 domain, u64 a, u64 b, u64 idx) { return mix64(stream_key(seed, domain, a, b) ^ idx); }
+static inline u32 rotl32(u32 x, int r) { return (x << r) | (x >> (32 - r)); }
+#define QR(a, b, c, d) \
+  a += b; d ^= a; d = rotl32(d, 16); c += d; b ^= c; b = rotl32(b, 12); \
+  a += b; d ^= a; d = rotl32(d, 8);  c += d; b ^= c; b = rotl32(b, 7);
+static void chacha20_block(rng_stream_t *s, u32 counter) {
+  u32 in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u}, x[16];
+  memcpy(in + 4, s->key, 32);
+  in[12] = counter; in[13] = s->n0; in[14] = s->n1; in[15] = s->n2;
+  memcpy(x, in, sizeof x);
+  for (int r = 0; r < 10; r++) {
+    QR(x[0], x[4], x[8], x[12]) QR(x[1], x[5], x[9], x[13]) QR(x[2], x[6], x[10], x[14]) QR(x[3], x[7], x[11], x[15])
+    QR(x[0], x[5], x[10], x[15]) QR(x[1], x[6], x[11], x[12]) QR(x[2], x[7], x[8], x[13]) QR(x[3], x[4], x[9], x[14])
+  }
+  for (int i = 0; i < 8; i++) s->w[i] = (u64)(x[2 * i] + in[2 * i]) | (u64)(x[2 * i + 1] + in[2 * i + 1]) << 32;
+  s->ctr = counter; s->have = 1;
+}
+#undef QR
+static u64 rng_word(rng_stream_t *s, u64 idx) {
+  const u32 ctr = (u32)(idx >> 3);
+  if (!s->have || s->ctr != ctr) chacha20_block(s, ctr);
+  return s->w[idx & 7];
+}
+/* test hook: word idx of stream (domain, a, b) under the key a seed expands to; with key32 != NULL under that key */
+u64 obfv_rng(u64 seed, const unsigned char *key32, u64 domain, u64 a, u64 b, u64 idx) {
+  u32 key[8];
+  if (key32) memcpy(key, key32, 32); else rng_key_from_seed(seed, key);
+  rng_stream_t s = rng_stream(key, domain, a, b);
+  return rng_word(&s, idx);
+}
 
 enum { DOM_SK = 1, DOM_PK = 2, DOM_KSK = 3, DOM_ENC = 4 };
 
 /* ternary: {0,1,2} -> {-1,0,+1}; returns signed */
-static inline int sample_ternary(u64 h, u64 idx) {
-  u64 r = mix64(h ^ idx);
+static inline int sample_ternary(rng_stream_t *h, u64 idx) {
+  u64 r = rng_word(h, idx);
   return (int)(((r >> 32) * 3) >> 32) - 1;
 }
 /* centred binomial, 21 - 21 bits (SEAL sample_poly_cbd) */
-static inline int sample_cbd(u64 h, u64 idx) {
-  u64 r = mix64(h ^ idx);
+static inline int sample_cbd(rng_stream_t *h, u64 idx) {
+  u64 r = rng_word(h, idx);
   return __builtin_popcountll(r & 0x1fffffULL) - __builtin_popcountll((r >> 21) & 0x1fffffULL);
 }
-static inline u64 sample_uniform(u64 h, u64 idx, u64 q) {
+/* SEAL sample_poly_uniform: rejection above the largest multiple of q; retry j of coefficient idx is word idx + j * 2^24 */
+static inline u64 sample_uniform(rng_stream_t *h, u64 idx, u64 q) {
   const u64 max_random = ~(u64)0, max_multiple = max_random - (max_random % q) - 1;
   for (u64 attempt = 0;; attempt++) {
-    u64 r = mix64(h ^ (idx | (attempt << 32)));
+    u64 r = rng_word(h, idx | (attempt << 24));
     if (r < max_multiple) return r % q;
   }
 }
@@ -444,11 +479,12 @@ static void encrypt_zero_symmetric(const obfv_ctx *c, u64 dom, u64 a_id, u64 b_b
   const size_t N = c->N, k = c->k;
   u64 *c0 = out, *c1 = out + k * N;
   u64 *e = malloc(N * 8);
-  const u64 he = stream_key(c->seed, dom, a_id, (b_base << 2) | 1);
+  rng_stream_t he = rng_stream(c->rng_key, dom, a_id, (b_base << 2) | 1);
   for (size_t i = 0; i < k; i++) {
-    const u64 q = c->q[i], ha = stream_key(c->seed, dom, a_id, ((b_base | i) << 2) | 0);
-    for (size_t j = 0; j < N; j++) c1[i * N + j] = sample_uniform(ha, j, q);
-    for (size_t j = 0; j < N; j++) e[j] = small_to_mod(sample_cbd(he, j), q);
+    const u64 q = c->q[i];
+    rng_stream_t ha = rng_stream(c->rng_key, dom, a_id, ((b_base | i) << 2) | 0);
+    for (size_t j = 0; j < N; j++) c1[i * N + j] = sample_uniform(&ha, j, q);
+    for (size_t j = 0; j < N; j++) e[j] = small_to_mod(sample_cbd(&he, j), q);
     ntt_fwd(&c->nq[i], e, N);
     for (size_t j = 0; j < N; j++) {
       u64 v = addmod(mulmod(c->sk[i * N + j], c1[i * N + j], q), e[j], q);
@@ -513,13 +549,14 @@ u32 obfv_elt_from_step(const obfv_ctx *c, int step) {
 static void keygen_impl(obfv_ctx *c, u64 seed, const u32 *elts, size_t ne) {
   const size_t N = c->N, k = c->k, L = c->L;
   c->seed = seed;
+  if (!c->rng_key_set) rng_key_from_seed(seed, c->rng_key);
   free(c->sk); free(c->pk); free(c->relin);
   for (size_t i = 0; i < N; i++) { free(c->galois[i]); c->galois[i] = NULL; }
   /* secret key: ternary, NTT form at key level (KeyGenerator::generate_sk) */
   c->sk = malloc(k * N * 8);
-  const u64 hs = stream_key(seed, DOM_SK, 0, 0);
+  rng_stream_t hs = rng_stream(c->rng_key, DOM_SK, 0, 0);
   for (size_t i = 0; i < k; i++) {
-    for (size_t j = 0; j < N; j++) c->sk[i * N + j] = small_to_mod(sample_ternary(hs, j), c->q[i]);
+    for (size_t j = 0; j < N; j++) c->sk[i * N + j] = small_to_mod(sample_ternary(&hs, j), c->q[i]);
     ntt_fwd(&c->nq[i], c->sk + i * N, N);
   }
   /* public key (generate_pk) */
@@ -541,6 +578,8 @@ static void keygen_impl(obfv_ctx *c, u64 seed, const u32 *elts, size_t ne) {
   }
   free(nk);
 }
+/* the sampler key itself (32 bytes) instead of a 64-bit seed: mirrors abc_set_rng_key */
+void obfv_set_rng_key(obfv_ctx *c, const unsigned char *key32) { memcpy(c->rng_key, key32, 32); c->rng_key_set = 1; }
 void obfv_keygen(obfv_ctx *c, u64 seed) {
   u32 elts[64]; size_t ne = obfv_galois_elts(c, elts, 64);
   keygen_impl(c, seed, elts, ne);
@@ -575,20 +614,20 @@ static void scale_plain_addsub(const obfv_ctx *c, const u64 *plain, u64 *c0, int
 void obfv_encrypt(const obfv_ctx *c, const u64 *plain, u64 nonce, u64 *ct) {
   const size_t N = c->N, k = c->k, L = c->L;
   u64 *u = malloc(k * N * 8), *tmp = malloc(2 * k * N * 8);
-  const u64 hu = stream_key(c->seed, DOM_ENC, nonce, 0);
+  rng_stream_t hu = rng_stream(c->rng_key, DOM_ENC, nonce, 0);
   for (size_t i = 0; i < k; i++) {
-    for (size_t j = 0; j < N; j++) u[i * N + j] = small_to_mod(sample_ternary(hu, j), c->q[i]);
+    for (size_t j = 0; j < N; j++) u[i * N + j] = small_to_mod(sample_ternary(&hu, j), c->q[i]);
     ntt_fwd(&c->nq[i], u + i * N, N);
   }
   for (size_t pidx = 0; pidx < 2; pidx++) {
-    const u64 he = stream_key(c->seed, DOM_ENC, nonce, 1 + pidx);
+    rng_stream_t he = rng_stream(c->rng_key, DOM_ENC, nonce, 1 + pidx);
     for (size_t i = 0; i < k; i++) {
       const u64 q = c->q[i];
       u64 *d = tmp + (pidx * k + i) * N;
       const u64 *pkp = c->pk + (pidx * k + i) * N;
       for (size_t j = 0; j < N; j++) d[j] = bmul(u[i * N + j], pkp[j], &c->bq[i]);
       ntt_inv(&c->nq[i], d, N);
-      for (size_t j = 0; j < N; j++) d[j] = addmod(d[j], small_to_mod(sample_cbd(he, j), q), q);
+      for (size_t j = 0; j < N; j++) d[j] = addmod(d[j], small_to_mod(sample_cbd(&he, j), q), q);
     }
     /* RNSTool::divide_and_round_q_last_inplace */
     u64 *last = tmp + (pidx * k + L) * N;

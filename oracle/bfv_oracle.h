@@ -96,7 +96,9 @@ void obfv_behz_scale(const obfv_ctx *c, const uint64_t *in_q, const uint64_t *in
 void obfv_switch_key(const obfv_ctx *c, uint64_t *ct2, const uint64_t *target, const uint64_t *key);
 
 /* sampler (shared spec with the CUDA library, documented in DESIGN.md) */
-uint64_t obfv_rng(uint64_t seed, uint64_t domain, uint64_t a, uint64_t b, uint64_t idx);
+uint64_t obfv_rng(uint64_t seed, const unsigned char *key32, uint64_t domain, uint64_t a, uint64_t b, uint64_t idx);
+/* the sampler's 32-byte ChaCha20 key itself instead of the expansion of a 64-bit seed (mirror of abc_set_rng_key) */
+void obfv_set_rng_key(obfv_ctx *c, const unsigned char *key32);
 
 #ifdef __cplusplus
 }

@@ -64,7 +64,8 @@ def _load():
         "obfv_behz_lift": (None, [vp, u64p, u64p]),
         "obfv_behz_scale": (None, [vp, u64p, u64p, u64p]),
         "obfv_switch_key": (None, [vp, u64p, u64p, vp]),
-        "obfv_rng": (u64, [u64, u64, u64, u64, u64]),
+        "obfv_rng": (u64, [u64, vp, u64, u64, u64, u64]),
+        "obfv_set_rng_key": (None, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, name)
@@ -92,9 +93,10 @@ class Oracle:
     """SEAL-3.6.5-restatement BFV context.  Mirrors what SealCiphertextFactory sets up
     (/root/reference/src/runtime/SealCiphertextFactory.cpp:72-100)."""
 
-    def __init__(self, N, primes=None, t=0, seed=None, galois_steps=None, aux=None):
+    def __init__(self, N, primes=None, t=0, seed=None, galois_steps=None, aux=None, rng_key=None):
         """aux = (bits, count): test hook, BEHZ auxiliary base of `count` + 1 primes of `bits` bits instead of SEAL's
-        61-bit ones (obfv_create_aux); None = SEAL's base."""
+        61-bit ones (obfv_create_aux); None = SEAL's base.  rng_key: the sampler's 32-byte ChaCha20 key itself (mirror of
+        abc_set_rng_key); otherwise the key is expanded from `seed`."""
         L_ = lib()
         arr = None if primes is None else np.asarray(primes, dtype=np.uint64)
         ptr, n = (None, 0) if arr is None else (arr.ctypes.data, len(arr))
@@ -111,6 +113,13 @@ class Oracle:
         self.primes = [int(v) for v in q]
         self.ct_words = 2 * self.L * N
         self.seed = None
+        if rng_key is not None:
+            if len(rng_key) != 32:
+                raise ValueError("rng_key must be 32 bytes")
+            self._rng_key = (C.c_ubyte * 32)(*rng_key)
+            L_.obfv_set_rng_key(self._c, self._rng_key)
+            if seed is None:
+                seed = 0
         if seed is not None:
             self.keygen(seed, galois_steps)
 

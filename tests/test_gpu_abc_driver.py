@@ -72,3 +72,8 @@ def test_demo_csv_breakdown(tmp_path):
     assert header == "t_keygen,t_input_encryption,t_computation,t_decryption"
     vals = [float(v) for v in row.split(",")]
     assert len(vals) == 4 and all(v > 0 for v in vals)
+
+
+def test_caller_supplied_sampler_key_shares_keys_between_factories():
+    _, out = run("kats")
+    assert out.count("[ ok ] rngkey.") == 2

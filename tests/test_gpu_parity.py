@@ -70,6 +70,36 @@ def test_keygen_bit_exact(which, pair4096, pair8192):
         assert np.array_equal(f.export_key(KEY_GALOIS, e), o.galois_key(e)), "galois key %d" % e
 
 
+def test_caller_supplied_rng_key_matches_oracle():
+    """abc_set_rng_key: the sampler's 32-byte ChaCha20 key from the caller (the oracle's key stream is pinned to RFC 8439 in
+    tests/test_oracle.py); keys and an encryption under it are word for word the oracle's, and differ under another key."""
+    from abc_b200 import CudaCiphertextFactory, KEY_GALOIS, KEY_PUBLIC, KEY_RELIN, KEY_SECRET
+    from oracle.bfv_oracle import Oracle
+    key = bytes((37 * i + 11) % 256 for i in range(32))
+    o = Oracle(4096, rng_key=key, galois_steps=[1, -2])
+    f = CudaCiphertextFactory(4096, keygen=False, batch=2)
+    g = CudaCiphertextFactory(4096, keygen=False)
+    try:
+        f.set_rng_key(key)
+        f.keygen([1, -2])
+        assert np.array_equal(f.export_key(KEY_SECRET), o.secret_key())
+        assert np.array_equal(f.export_key(KEY_PUBLIC), o.public_key())
+        assert np.array_equal(f.export_key(KEY_RELIN), o.relin_key())
+        for step in (1, -2):
+            e = f.elt_from_step(step)
+            assert np.array_equal(f.export_key(KEY_GALOIS, e), o.galois_key(e))
+        data = np.arange(2 * 9).reshape(2, 9) - 4
+        f.set_encrypt_nonce(21)
+        ct = f.createCiphertext(data).export()
+        for i in range(2):
+            assert np.array_equal(ct[i], o.encrypt_slots(data[i], 21 * 2 + i))
+        g.set_rng_key(bytes(32))
+        g.keygen([1, -2])
+        assert not np.array_equal(g.export_key(KEY_SECRET), o.secret_key())
+    finally:
+        f.close(); g.close()
+
+
 @pytest.mark.parametrize("which", ["4096", "8192"])
 def test_encrypt_decrypt_bit_exact(which, pair4096, pair8192):
     f, o = pair4096 if which == "4096" else pair8192

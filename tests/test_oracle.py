@@ -211,6 +211,37 @@ def test_sampler_distributions(oracle4096):
     assert np.abs(ev).max() <= 21 and 2.5 < ev.std() < 4.0
 
 
+def test_sampler_key_stream_is_chacha20_rfc8439():
+    """The sampler's randomness is the ChaCha20 key stream: RFC 8439 section 2.3.2 (key 00..1f, nonce 00:00:00:09 00:00:00:4a
+    00:00:00:00, block counter 1).  In the sampler's terms (DESIGN.md "Sampler") the nonce words are (domain | b << 4, a lo,
+    a hi) and word idx of a stream sits in block idx >> 3, so that block is words 8..15 of stream (domain 0, a = 0x4a000000,
+    b = 0x09000000 >> 4)."""
+    import ctypes as C
+    from oracle.bfv_oracle import lib
+    key = (C.c_ubyte * 32)(*range(32))
+    block = bytes.fromhex(
+        "10f1e7e4d13b5915500fdd1fa32071c4" "c7d1f4c733c068030422aa9ac3d46c4e"
+        "d2826446079faa0914c2d705d98b02a2" "b5129cd1de164eb9cbd083e8a2503c4e")
+    want = np.frombuffer(block, dtype="<u8")
+    got = [lib().obfv_rng(0, key, 0, 0x4a000000, 0x09000000 >> 4, 8 + j) for j in range(8)]
+    assert got == [int(v) for v in want]
+    # a 64-bit seed expands to the key (seed lo, seed hi, "abc-", "b200", 0, 0, 0, 0)
+    seed = 0x1122334455667788
+    key2 = (C.c_ubyte * 32)(*(seed.to_bytes(8, "little") + b"abc-b200" + bytes(16)))
+    assert lib().obfv_rng(seed, None, 4, 77, 1, 5) == lib().obfv_rng(0, key2, 4, 77, 1, 5)
+    # distinct streams, distinct words
+    assert len({lib().obfv_rng(seed, None, d, a, b, 0) for d in (1, 2, 3, 4) for a in (0, 1) for b in (0, 1, 2)}) == 24
+
+
+def test_explicit_rng_key_replaces_the_seed():
+    key = bytes(range(100, 132))
+    a = Oracle(4096, rng_key=key, galois_steps=[1])
+    b = Oracle(4096, rng_key=key, seed=999, galois_steps=[1])       # the seed no longer matters
+    c = Oracle(4096, seed=0, galois_steps=[1])
+    assert np.array_equal(a.secret_key(), b.secret_key()) and np.array_equal(a.public_key(), b.public_key())
+    assert not np.array_equal(a.secret_key(), c.secret_key())
+
+
 def test_noise_budget_tracks_decryptability(oracle4096):
     """invariant_noise_budget (SealCiphertext::noiseBits): positive while decryption is exact, shrinking with every
     multiplication, 0 once the noise has overrun q/t (N=4096: 72-bit q, 20-bit t, two multiplications fit)."""
