@@ -127,6 +127,38 @@ def test_transparent_results_are_detected_per_instance():
         f.close()
 
 
+@pytest.mark.parametrize("limit_mib", ["0", "1", None])
+def test_buffer_free_list_limits_do_not_change_results(limit_mib, monkeypatch):
+    """Ciphertext buffers are recycled through a per-context free list (lib.cu: salloc / sfree).  With the list disabled
+    (ABC_BLOCK_CACHE_MIB=0: every release goes to the driver), with a limit that parks one small block at most, and with
+    the default, a program that allocates and drops handles of both buffer sizes gives the oracle's coefficients."""
+    from abc_b200 import CudaCiphertextFactory
+    from oracle.bfv_oracle import Oracle
+    if limit_mib is not None:
+        monkeypatch.setenv("ABC_BLOCK_CACHE_MIB", limit_mib)
+    o = Oracle(4096, seed=SEED)
+    f = CudaCiphertextFactory(4096, seed=SEED, batch=2)
+    try:
+        rng = np.random.default_rng(12)
+        d = rng.integers(-50, 51, size=(2, 32), dtype=np.int64)
+        f.set_encrypt_nonce(3)
+        x = f.createCiphertext(d)
+        w = [o.encrypt_slots(d[i], 3 * 2 + i) for i in range(2)]
+        for rep in range(6):                       # handles of the previous round are dropped while new ones are made
+            y = x.multiply(x)
+            z = y.rotateRows(3).add(x)
+            x = z.subtract(y.clone())
+            for i in range(2):
+                yw = o.mul_relin(w[i], w[i])
+                w[i] = o.sub(o.add(o.rotate_rows(yw, 3), w[i]), yw)
+            del y, z
+        got = x.export()
+        for i in range(2):
+            assert np.array_equal(got[i], w[i])
+    finally:
+        f.close()
+
+
 def test_key_import_round_trip():
     """abc_key_import: keys produced elsewhere (the oracle here; SEAL's raw key data has the same layout)."""
     from abc_b200 import CudaCiphertextFactory, KEY_GALOIS, KEY_PUBLIC, KEY_RELIN, KEY_SECRET
