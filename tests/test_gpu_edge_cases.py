@@ -326,3 +326,17 @@ def test_bench_batch_identical_instances_agree():
         assert np.array_equal(f.decryptCiphertext(s)[B - 1], o.decrypt_slots(s_w))
     finally:
         f.close()
+
+
+def test_key_switch_grids_survive_gpu_time_slicing():
+    """Three processes share the GPU (their contexts are time-sliced, resident CTAs are preempted in the middle of their
+    flag waits) while each loops over the chained and the half-limb-row key switch: every result equals the first one and
+    the oracle's, no sticky fault (tools/timeslice_check.py).  The evidence asked for where compute-sanitizer is not
+    available: the dependency-ordered grids do not rest on exclusive use of the device."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "timeslice_check.py"), "--procs", "3", "--seconds", "6"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "timeslice_check ok" in p.stdout, p.stdout[-3000:] + p.stderr[-2000:]
