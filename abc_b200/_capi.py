@@ -89,6 +89,7 @@ SYMBOLS = {
     "abc_timer_stop": (i32, [vp, f32p]),
     "abc_flush_l2": (i32, [vp, sz]),
     "abc_launch_count": (u64, [vp]),
+    "abc_key_switch_count": (u64, [vp]),
     "abc_profile_enable": (i32, [vp, i32]),
     "abc_profile_json": (C.c_char_p, [vp]),
     "abc_measure_int_peak": (i32, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -289,6 +289,9 @@ class CudaCiphertextFactory:
     def launch_count(self):
         return int(self._lib.abc_launch_count(self._h))
 
+    def key_switch_count(self):
+        return int(self._lib.abc_key_switch_count(self._h))
+
     def profile_enable(self, on=True):
         self._ck(self._lib.abc_profile_enable(self._h, int(on)))
 

@@ -39,6 +39,7 @@ struct ProfRec { const char *name; cudaEvent_t a, b; };
 enum { DOM_SK = 1, DOM_PK = 2, DOM_KSK = 3, DOM_ENC = 4 };
 }  // namespace
 
+struct CtBuf;
 struct abc_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -75,6 +76,15 @@ struct abc_ctx {
   int ks_skew = 8;                               // ABC_KS_SKEW: special-prime rows run this many instances ahead
   bool no_square = false;                        // ABC_NO_SQUARE: multiply(x, x) takes the general path
   bool lazy_rotate = true;                       // ABC_EAGER_ROTATE: rotate_rows runs its last key switch immediately
+  // Intermediate results of multi-step (NAF) rotations, by (source buffer, Galois element): rotate(x, 63) and
+  // rotate(x, -65) both start with the step -1 of x, and rotate(x, -1) itself is that buffer (a 3x3 stencil needs 8 key
+  // switches instead of 12).  An entry holds a reference on both buffers, so neither can be written in place or
+  // reused while it is cached (copy-on-write); entries whose source nobody else holds are dropped.  ABC_ROT_CACHE=n
+  // entries (default 4, 0 = off).
+  struct RotCacheEntry { CtBuf *src; u32 elt; CtBuf *res; uint64_t stamp; };
+  std::vector<RotCacheEntry> rot_cache;
+  uint64_t rot_stamp = 0, rot_cache_hits = 0, key_switches = 0;
+  int rot_cache_max = 4;
   bool ks_unmerged = false, ks_unfused = false;  // ABC_KS_UNMERGED / ABC_KS_UNFUSED: A/B switches for the key-switch tail
   bool ks_no_discard = false;                    // ABC_KS_NO_DISCARD: leave the consumed ModUp rows to L2's write-back
   bool ks_no_image = false;                      // ABC_KS_NO_IMAGE: ModUp rows stored element by element instead of as bulk-copied images
@@ -174,6 +184,7 @@ struct CtBuf {
   CtBuf *sum = nullptr, *other = nullptr;  // deferred difference: value = sum - other
 };
 struct abc_ct { abc_ctx *ctx; CtBuf *b; };
+extern "C" { static void rot_cache_clear(abc_ctx *c); }   // defined with the handle layer below
 struct abc_pt { abc_ctx *ctx; u64 *d; int broadcast; };
 
 namespace {
@@ -245,6 +256,7 @@ struct Launch {
 // Reuse is safe under the rule the stream-ordered free already relied on: a buffer is released only after everything
 // that touches it has been enqueued on (or joined into) c->stream, and the next user is enqueued on c->stream.
 static bool release_parked(abc_ctx *c) {
+  rot_cache_clear(c);   // cached rotation results are memory we can do without
   if (c->blk_free.empty()) return false;
   for (auto &b : c->blk_free) cudaFreeAsync(b.second, c->stream);
   c->blk_free.clear(); c->blk_free_words = 0;
@@ -506,6 +518,7 @@ abc_status build_tables(abc_ctx *c) {
   if (const char *e = getenv("ABC_KS1_THREADS")) c->ks1_threads = atoi(e);
   if (const char *e = getenv("ABC_KS1_SKEW")) c->ks1_skew = atoi(e) < 0 ? 0 : atoi(e);
   c->lazy_rotate = getenv("ABC_EAGER_ROTATE") == nullptr;
+  if (const char *e = getenv("ABC_ROT_CACHE")) c->rot_cache_max = atoi(e);
   c->no_square = getenv("ABC_NO_SQUARE") != nullptr;
   if (const char *e = getenv("ABC_KS_SKEW")) c->ks_skew = atoi(e) < 0 ? 0 : atoi(e);
   {
@@ -965,6 +978,7 @@ abc_status keyswitch(abc_ctx *c, const u64 *target, long long target_is, const u
   // gather_ct (limb-sharded contexts): the ciphertext block whose c1 is `target`; its limbs are all-gathered in front of
   // ModUp.  With overlap on, the exchange runs on the communication stream while the ModUp rows whose source limb is
   // local are already transforming; the rows fed by remote limbs follow once it has landed.
+  ++c->key_switches;
   const int N = c->N, L = c->L, k = c->k, B = c->B;
   u64 *T = nullptr, *acc = nullptr;
   // exact-double class: the whole key switch can be one launch (ksfused.cu), nothing but INTT_p(acc_L) goes through HBM.
@@ -1553,6 +1567,7 @@ void abc_ctx_destroy(abc_ctx *c) {
   if (!c) return;
   if (c->live_handles > 0) { c->zombie = true; return; }   // completed by the last handle's free
   cudaSetDevice(c->device);
+  rot_cache_clear(c);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm_stream) { cudaStreamSynchronize(c->comm_stream); cudaStreamDestroy(c->comm_stream); }
   if (c->comm_ready) cudaEventDestroy(c->comm_ready);
@@ -1751,6 +1766,37 @@ static void ct_share(abc_ct *dst, CtBuf *b) {
   buf_unref(dst->ctx, dst->b);
   dst->b = b;
 }
+// ---- rotation cache (abc_ctx::rot_cache)
+static void rot_cache_drop(abc_ctx *c, size_t i) {
+  abc_ctx::RotCacheEntry e = c->rot_cache[i];
+  c->rot_cache.erase(c->rot_cache.begin() + (long)i);
+  buf_unref(c, e.res);
+  buf_unref(c, e.src);
+}
+// entries whose source buffer only the cache still holds can never hit again
+static void rot_cache_purge(abc_ctx *c) {
+  for (size_t i = c->rot_cache.size(); i-- > 0;)
+    if (c->rot_cache[i].src->refs == 1) rot_cache_drop(c, i);
+}
+static void rot_cache_clear(abc_ctx *c) {
+  while (!c->rot_cache.empty()) rot_cache_drop(c, c->rot_cache.size() - 1);
+}
+static CtBuf *rot_cache_find(abc_ctx *c, const CtBuf *src, u32 elt) {
+  for (auto &e : c->rot_cache)
+    if (e.src == src && e.elt == elt) { e.stamp = ++c->rot_stamp; ++c->rot_cache_hits; return e.res; }
+  return nullptr;
+}
+static void rot_cache_put(abc_ctx *c, CtBuf *src, u32 elt, CtBuf *res) {
+  if (c->rot_cache_max <= 0) return;
+  if ((int)c->rot_cache.size() >= c->rot_cache_max) {   // least recently used goes
+    size_t lru = 0;
+    for (size_t i = 1; i < c->rot_cache.size(); ++i) if (c->rot_cache[i].stamp < c->rot_cache[lru].stamp) lru = i;
+    rot_cache_drop(c, lru);
+  }
+  ++src->refs; ++res->refs;
+  c->rot_cache.push_back({src, elt, res, ++c->rot_stamp});
+}
+
 // Materialise a deferred rotation: every clone sharing the buffer sees the result.
 static abc_status buf_resolve(abc_ctx *c, CtBuf *b) {
   if (b->d) return ABC_OK;
@@ -1790,6 +1836,7 @@ void abc_ct_free(abc_ct *ct) {
   abc_ctx *c = ct->ctx;
   buf_unref(c, ct->b);
   delete ct;
+  rot_cache_purge(c);
   handle_released(c);
 }
 size_t abc_ct_words(const abc_ctx *c) { return (size_t)c->B * ct_words1(c); }
@@ -2114,10 +2161,18 @@ static abc_status rotate_impl(abc_ctx *c, abc_ct *dst, const abc_ct *a, int step
   // The last Galois step is deferred (see CtBuf) unless an addend is given or the context is limb-sharded; the steps
   // before it run now.  Each key switch writes a fresh buffer (its gathers read the previous one).
   const bool defer = !addend && c->lazy_rotate && c->world == 1;
+  const bool cached = c->rot_cache_max > 0 && c->world == 1;
   CtBuf *cur = a->b;
   ++cur->refs;
   for (size_t pi = 0; pi < plan.size(); ++pi) {
     const bool last = pi + 1 == plan.size();
+    if (cached && !(last && addend))
+      if (CtBuf *hit = rot_cache_find(c, cur, plan[pi])) {   // this step of this buffer exists already
+        ++hit->refs;
+        buf_unref(c, cur);
+        cur = hit;
+        continue;
+      }
     if (last && defer) {
       CtBuf *nb = new CtBuf; nb->src = cur; nb->elt = plan[pi];  // takes over the reference held on cur
       buf_unref(c, dst->b);
@@ -2130,9 +2185,11 @@ static abc_status rotate_impl(abc_ctx *c, abc_ct *dst, const abc_ct *a, int step
       s = apply_galois(c, cur->d, out, plan[pi], (addend && last) ? addend->b->d : nullptr);
       if (s != ABC_OK) sfree(c, out);
     }
+    if (s != ABC_OK) { buf_unref(c, cur); return s; }
+    CtBuf *nb = new CtBuf; nb->d = out;
+    if (cached && !last) rot_cache_put(c, cur, plan[pi], nb);   // the shared prefix of the NAF chains of one source
     buf_unref(c, cur);
-    if (s != ABC_OK) return s;
-    cur = new CtBuf; cur->d = out;
+    cur = nb;
   }
   buf_unref(c, dst->b);  // released stream-ordered: after the kernels that read it
   dst->b = cur;
@@ -2316,6 +2373,7 @@ abc_status abc_flush_l2(abc_ctx *c, size_t bytes) {
   return ABC_OK;
 }
 uint64_t abc_launch_count(const abc_ctx *c) { return c->launches; }
+uint64_t abc_key_switch_count(const abc_ctx *c) { return c->key_switches; }
 abc_status abc_profile_enable(abc_ctx *c, int on) {
   CK(cudaStreamSynchronize(c->stream));
   for (auto &r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

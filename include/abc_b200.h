@@ -202,6 +202,9 @@ abc_status abc_timer_stop(abc_ctx *ctx, float *ms);            /* synchronises *
 abc_status abc_flush_l2(abc_ctx *ctx, size_t bytes);
 /* kernels launched by this context so far */
 uint64_t abc_launch_count(const abc_ctx *ctx);
+/* key switches run so far (relinearisations and Galois steps): what deferred rotations, rotate-and-add fusion and the
+ * rotation-prefix cache save shows here */
+uint64_t abc_key_switch_count(const abc_ctx *ctx);
 /* per-kernel-family device time: enable, then read {name, launches, total ms} rows as a JSON string */
 abc_status abc_profile_enable(abc_ctx *ctx, int on);
 const char *abc_profile_json(abc_ctx *ctx);

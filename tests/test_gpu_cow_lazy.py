@@ -152,3 +152,56 @@ def test_noise_budget_matches_oracle(pair):
         seen.append(m.noiseBits())
         assert seen[-1] == o.noise_budget(mw)
     assert seen[0] < a.noiseBits() and seen[-1] == 0
+
+
+def test_rotation_prefix_cache_saves_key_switches_and_never_goes_stale(pair, monkeypatch):
+    """rotate(x, 63) = step -1 then step 64 (SEAL's NAF order, low digit first), rotate(x, -65) = step -1 then step -64,
+    and rotate(x, -1) is that first step itself: the library keeps the intermediate buffer per (source buffer, Galois
+    element), so the eight rotations of a 3x3 stencil cost 8 key switches instead of 12 — with the same coefficients — and a
+    source that is written afterwards (copy-on-write: the cache holds a reference) never yields a stale result."""
+    from abc_b200 import CudaCiphertextFactory
+    f, o = pair
+    rng = np.random.default_rng(9)
+    a, aw = fresh(f, o, rng, 71)
+    b, bw = fresh(f, o, rng, 72)
+    steps = (-65, -64, -63, -1, 1, 63, 64, 65)
+
+    def stencil(fac, img):
+        acc = None
+        for k in steps:
+            r = img.rotateRows(k)
+            if acc is None:
+                acc = r
+            else:
+                acc.addInplace(r)
+        return acc
+
+    want = None
+    for k in steps:
+        r = o.rotate_rows(aw, k)
+        want = r if want is None else o.add(want, r)
+    n0 = f.key_switch_count()
+    got = stencil(f, a)
+    assert eq(got, want)
+    with_cache = f.key_switch_count() - n0
+    monkeypatch.setenv("ABC_ROT_CACHE", "0")              # the same without the cache
+    h = CudaCiphertextFactory(f.N, seed=SEED)
+    try:
+        a2 = h.importCiphertext(a.export())
+        n1 = h.key_switch_count()
+        got2 = stencil(h, a2)
+        without = h.key_switch_count() - n1
+        assert np.array_equal(got2.export(), got.export())
+    finally:
+        h.close()
+    assert (with_cache, without) == (8, 12)
+    # staleness: the cached prefix belongs to the OLD buffer of `a`
+    a.addInplace(b)                                                   # writes a (a new buffer: the cache pinned the old one)
+    aw2 = o.add(aw, bw)
+    assert eq(a.rotateRows(63), o.rotate_rows(aw2, 63))
+    assert eq(a.rotateRows(-1), o.rotate_rows(aw2, -1))
+    c = a.clone()
+    c.rotateRowsInplace(-65)                                          # shares a's cached prefix (same buffer), then diverges
+    assert eq(c, o.rotate_rows(aw2, -65)) and eq(a, aw2)
+    a.negateInplace()
+    assert eq(a.rotateRows(63), o.rotate_rows(o.negate(aw2), 63))
