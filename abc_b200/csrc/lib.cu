@@ -942,7 +942,8 @@ abc_status allgather_columns(abc_ctx *c, u64 *base, size_t rows, size_t inst_str
 __global__ void k_key_to_f64(const u64 *__restrict__ in, double *__restrict__ out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
 }
-void drop_key_f64(abc_ctx *c) {
+void drop_key_f64(abc_ctx *c) {   // keys are about to change
+  rot_cache_clear(c);             // cached rotation prefixes were computed under the old keys
   if (c->key_f64.empty()) return;
   cudaStreamSynchronize(c->stream);
   for (auto &kv : c->key_f64) cudaFree(kv.second);
