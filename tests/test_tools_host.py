@@ -1,0 +1,40 @@
+"""Host-side checkers used by the GPU benches, pinned on the CPU: the stencil expectation of tools/stencil10k_bench.py
+against a restatement of the reference's naiveBoxBlur / naiveGxKernel (test/end-to-end/BoxBlurTest.cpp:21-38,
+GxKernelTest.cpp:20-37), and its NAF key-switch count against the oracle's rotation plan."""
+import numpy as np
+
+from tools import stencil10k_bench as sb
+
+
+def naive_stencil(img, w):
+    """The reference's loops, including the index arithmetic: ((x+i)*imgSize + (y+j)) is an int that converts to size_t
+    before `% img.size()` (2^64 = 0 mod 4096, so negative indices wrap cyclically)."""
+    size = int(np.ceil(np.sqrt(len(img))))
+    out = list(img)
+    for x in range(size):
+        for y in range(size):
+            value = 0
+            for j in (-1, 0, 1):
+                for i in (-1, 0, 1):
+                    idx = (((x + i) * size + (y + j)) % (1 << 64)) % len(img)
+                    value += w[i + 1][j + 1] * img[idx]
+            out[size * x + y] = value
+    return out
+
+
+def test_stencil_expectation_is_the_references_naive_functions():
+    rng = np.random.default_rng(5)
+    imgs = rng.integers(0, 1025, size=(2, sb.SIZE * sb.SIZE), dtype=np.int64)
+    for w in (sb.BOX, sb.GX):
+        got = sb.expected(imgs, w)
+        for b in range(2):
+            assert list(got[b]) == naive_stencil([int(v) for v in imgs[b]], w)
+
+
+def test_naf_weight_is_the_oracles_key_switch_count(oracle4096):
+    o = oracle4096
+    # (steps whose NAF has a digit N/2 are left out: that digit is the identity on a row and SEAL skips it)
+    for step in list(range(-130, 131)) + [-1023, 1023, 511, -767, 341, -683]:
+        assert sb.naf_weight(step) == o.rotate_keyswitch_count(step), step
+    assert sb.key_switches(sb.BOX) == 12 and sb.key_switches(sb.GX) == 10
+    assert [k for k, _ in sb.taps(sb.BOX)] == [-65, -64, -63, -1, 0, 1, 63, 64, 65]
