@@ -38,3 +38,27 @@ def test_naf_weight_is_the_oracles_key_switch_count(oracle4096):
         assert sb.naf_weight(step) == o.rotate_keyswitch_count(step), step
     assert sb.key_switches(sb.BOX) == 12 and sb.key_switches(sb.GX) == 10
     assert [k for k, _ in sb.taps(sb.BOX)] == [-65, -64, -63, -1, 0, 1, 63, 64, 65]
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` needs no GPU: the reference's RuntimeVisitor over the CPU port, one JSON line with the
+    keys of the bench contract (impl, metric, unit, value, config identical to our arm's, cpu_baseline, e2e with zero copy
+    bytes).  Tiny sample: one instance per host process, one step."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-instances-per-core", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    r = json.loads(lines[0])
+    assert r["impl"] == "reference" and r["higher_is_better"] is True and r["unit"] == "ops/s" and r["value"] > 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert key in r
+    assert r["config"]["workload"].startswith("l2distance_batched") and "batch_per_gpu" in r["config"]
+    assert r["cpu_baseline"]["kind"] in ("port", "reference") and r["cpu_baseline"]["cores"] >= 1
+    assert r["cpu_baseline"]["value"] == r["value"]
+    assert r["e2e"] == {"value": r["value"], "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
