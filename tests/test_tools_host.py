@@ -62,3 +62,35 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert r["cpu_baseline"]["kind"] in ("port", "reference") and r["cpu_baseline"]["cores"] >= 1
     assert r["cpu_baseline"]["value"] == r["value"]
     assert r["e2e"] == {"value": r["value"], "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_product_host_number_theory_matches_the_oracle(tmp_path):
+    """abc_b200/csrc/hostmath.hpp is what abc_ctx_create builds its tables from (SEAL's default primes, the plain modulus,
+    minimal primitive 2N-th roots, the 61-bit auxiliary primes, inverses, Barrett ratios).  Compiled alone with g++ (no
+    GPU) and compared with the oracle, N = 4096 ... 32768."""
+    import os
+    import subprocess
+    from oracle.bfv_oracle import Oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "hostmath_probe")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(root, "tests", "host", "hostmath_probe.cpp")], check=True)
+    for N in (4096, 8192, 16384, 32768):
+        out = subprocess.run([exe, str(N)], capture_output=True, text=True, check=True).stdout.split("\n")
+        vals = {}
+        for line in out:
+            if line:
+                k, *v = line.split()
+                vals.setdefault(k, []).append([int(x) for x in v])
+        o = Oracle(N)
+        assert vals["k"][0][0] == o.k
+        assert [q[0] for q in vals["q"]] == o.primes
+        assert vals["t"][0][0] == o.t
+        assert [p[0] for p in vals["psi"]] == [o.psi(i) for i in range(o.k)]
+        msk, gamma, B = o.aux_primes()
+        aux = [a[0] for a in vals["aux"]]
+        assert set(B) | {msk} <= set(aux) or aux[:len(B)] == B        # SEAL takes its base from this prime sequence
+        q0, q1 = o.primes[0], o.primes[1]
+        assert vals["inv"][0][0] == pow(q0 % q1, -1, q1)
+        hi, lo = vals["barrett"][0]
+        assert (hi << 64 | lo) == (1 << 128) // q0
+        assert vals["brev"][0][0] == int("{:013b}".format(0x1234)[::-1], 2)
