@@ -301,3 +301,16 @@ def test_behz_product_does_not_depend_on_the_auxiliary_base():
             assert np.array_equal(x, y), "auxiliary base %r changes the product" % (aux,)
     small = Oracle(N, seed=SEED, aux=(44, 1))      # 88 bits: below the rule
     assert not all(np.array_equal(x, y) for x, y in zip(want, products(small)))
+
+
+def test_oracle_regression_digests():
+    """tests/golden/oracle_vectors.json: coefficient-level digests of the oracle's own outputs (keys and encryption under
+    the ChaCha20 sampler, every op).  Pins the oracle against accidental change; says nothing about SEAL."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_oracle_vectors", os.path.join(here, "golden", "make_oracle_vectors.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(here, "golden", "oracle_vectors.json")))
+    for n in (4096, 8192):
+        assert mod.vectors(n) == want[str(n)], "oracle output changed at N = %d" % n
