@@ -339,4 +339,6 @@ def test_key_switch_grids_survive_gpu_time_slicing():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = subprocess.run([sys.executable, os.path.join(root, "tools", "timeslice_check.py"), "--procs", "3", "--seconds", "6"],
                        capture_output=True, text=True, timeout=600)
+    if p.returncode == 0 and "timeslice_check skipped" in p.stdout:
+        pytest.skip("the device does not admit several processes (exclusive compute mode)")
     assert p.returncode == 0 and "timeslice_check ok" in p.stdout, p.stdout[-3000:] + p.stderr[-2000:]
